@@ -1,0 +1,410 @@
+/*
+ * dcsim_b200.cu — sm_100a kernels and the C-ABI of include/dcsim_b200.h.
+ *
+ * Kernels
+ *   dcsim_advance_kernel   one warp per replica; stages the replica's state block HBM -> shared memory,
+ *                          runs the event engine of dcsim_core.cuh, stages it back, writes the summary row.
+ *   dcsim_reduce_kernel    [n_replicas][K] summaries -> DCSIM_AGG_K doubles (the only cross-GPU payload).
+ *
+ * Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false (see __graft_entry__.build()).
+ * -fmad=false matters: the reference is CPython float arithmetic, one rounding per operation.
+ */
+#include <cuda_runtime.h>
+
+#include <new>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "dcsim_core.cuh"
+
+#define DCSIM_MAX_WARPS_PER_CTA 4
+
+extern __shared__ __align__(16) char dcsim_smem[];
+
+__global__ void __launch_bounds__(DCSIM_MAX_WARPS_PER_CTA * 32)
+dcsim_advance_kernel(const __grid_constant__ dcsim_kparams_t P, unsigned long long* __restrict__ events_total) {
+  const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31u);
+  const int wpc = (int)(blockDim.x >> 5);
+  const uint64_t r = (uint64_t)blockIdx.x * (uint64_t)wpc + (uint64_t)warp;
+  if (r >= P.n_replicas) return; /* whole warps leave together */
+  const int bytes = P.L.total_bytes;
+  char* blk = dcsim_smem + (size_t)warp * (size_t)bytes;
+  char* home = P.state + r * (uint64_t)bytes;
+  const bool fresh = reinterpret_cast<const dcsim_hdr_t*>(home)->initialized == 0u;
+  if (!fresh) { /* resume: coalesced 16-byte loads of the replica's block */
+    const uint4* src = reinterpret_cast<const uint4*>(home);
+    uint4* dst = reinterpret_cast<uint4*>(blk);
+    for (int i = lane; i < bytes / 16; i += 32) dst[i] = src[i];
+  }
+  __syncwarp();
+  const uint32_t n = dcsim_replica_step(&P, r, blk, fresh);
+  __syncwarp();
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(blk);
+    uint4* dst = reinterpret_cast<uint4*>(home);
+    for (int i = lane; i < bytes / 16; i += 32) dst[i] = src[i];
+  }
+  if (lane == 0 && n) atomicAdd(events_total, (unsigned long long)n);
+}
+
+/* Aggregates the summaries; every block reduces a slice, then one atomicAdd per component. */
+__global__ void dcsim_reduce_kernel(const double* __restrict__ summary, uint64_t n, double* __restrict__ out) {
+  double acc[DCSIM_AGG_K];
+#pragma unroll
+  for (int k = 0; k < DCSIM_AGG_K; ++k) acc[k] = 0.0;
+  for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x) {
+    const double* s = summary + r * DCSIM_SUMMARY_K;
+    const double fin = s[DCSIM_S_JOBS_FINISHED], e = s[DCSIM_S_TOTAL_ENERGY_J];
+    const double ml = fin > 0.0 ? s[DCSIM_S_LAT_SUM] / fin : 0.0;
+    acc[DCSIM_A_REPLICAS] += 1.0;
+    acc[DCSIM_A_FAILED] += (s[DCSIM_S_STATUS] != 0.0 || s[DCSIM_S_DONE] == 0.0) ? 1.0 : 0.0;
+    acc[DCSIM_A_EVENTS] += s[DCSIM_S_EVENTS];
+    acc[DCSIM_A_JOBS] += fin;
+    acc[DCSIM_A_ENERGY] += e;
+    acc[DCSIM_A_ENERGY_SQ] += e * e;
+    acc[DCSIM_A_LAT_SUM] += s[DCSIM_S_LAT_SUM];
+    acc[DCSIM_A_MEANLAT_SUM] += ml;
+    acc[DCSIM_A_MEANLAT_SQ] += ml * ml;
+    acc[DCSIM_A_RNG_WORDS] += s[DCSIM_S_RNG_WORDS];
+  }
+#pragma unroll
+  for (int k = 0; k < DCSIM_AGG_K; ++k) {
+    double v = acc[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31u) == 0u && v != 0.0) atomicAdd(out + k, v);
+  }
+}
+
+/* ================================================================================================
+ * C-ABI
+ * ============================================================================================== */
+struct dcsim {
+  dcsim_spec_t spec;
+  dcsim_layout_t L;
+  uint64_t n_replicas, seed0;
+  int device, sm_count, warps_per_cta, ctas, smem_bytes, regs, resident_warps;
+  cudaStream_t stream, own_stream;
+  char* d_state;
+  char* d_queues;
+  double* d_summary;
+  unsigned long long* d_events;
+  uint32_t* d_counts;
+  dcsim_trace_rec_t* d_trace;
+  dcsim_job_rec_t* d_jobs;
+  dcsim_cluster_rec_t* d_cluster;
+  uint32_t trace_cap, jobs_cap, cluster_cap;
+  int64_t trace_replica, log_replica;
+  int launches;
+  unsigned long long events_seen;
+  char err[512];
+};
+
+static thread_local char g_create_err[512] = "";
+
+static int set_err(dcsim_t* h, int code, const char* fmt, const char* a = "", long long b = 0) {
+  char* dst = h ? h->err : g_create_err;
+  snprintf(dst, 512, fmt, a, b);
+  return code;
+}
+
+#define CUDA_TRY(h, call)                                                                  \
+  do {                                                                                     \
+    cudaError_t e_ = (call);                                                               \
+    if (e_ != cudaSuccess)                                                                 \
+      return set_err(h, e_ == cudaErrorMemoryAllocation ? DCSIM_E_NOMEM : DCSIM_E_CUDA,    \
+                     "CUDA error: %s (line %lld)", cudaGetErrorString(e_), (long long)__LINE__); \
+  } while (0)
+
+extern "C" {
+
+size_t dcsim_sizeof_spec(void) { return sizeof(dcsim_spec_t); }
+uint32_t dcsim_abi_version(void) { return DCSIM_ABI_VERSION; }
+int dcsim_summary_k(void) { return DCSIM_SUMMARY_K; }
+
+static int validate_spec(const dcsim_spec_t* sp) {
+  if (sp->magic != DCSIM_SPEC_MAGIC) return set_err(NULL, DCSIM_E_INVALID, "spec: bad magic%s%lld");
+  if (sp->abi_version != DCSIM_ABI_VERSION) return set_err(NULL, DCSIM_E_INVALID, "spec: ABI version mismatch%s%lld");
+  if (sp->spec_bytes != sizeof(dcsim_spec_t)) return set_err(NULL, DCSIM_E_INVALID, "spec: struct size mismatch (producer says %s%lld bytes)", "", sp->spec_bytes);
+  if (sp->n_dc < 1 || sp->n_dc > DCSIM_MAX_DC || sp->n_ing < 1 || sp->n_ing > DCSIM_MAX_ING)
+    return set_err(NULL, DCSIM_E_INVALID, "spec: n_dc / n_ing out of range%s%lld");
+  if (!(sp->log_interval > 0.0)) return set_err(NULL, DCSIM_E_INVALID, "spec: log_interval must be > 0%s%lld");
+  if (sp->policy_name != DCSIM_POLICY_ENERGY_AWARE && sp->policy_name != DCSIM_POLICY_PERF_FIRST)
+    return set_err(NULL, DCSIM_E_INVALID, "Unknown policy name%s%lld"); /* policy.py:41 */
+  for (int k = 0; k < 2; ++k) {
+    const dcsim_arrival_t* a = &sp->arr[k];
+    if (a->mode < DCSIM_ARR_OFF || a->mode > DCSIM_ARR_SINUSOID) return set_err(NULL, DCSIM_E_INVALID, "Unknown mode%s%lld"); /* arrivals.py:33 */
+    if (a->mode == DCSIM_ARR_SINUSOID && !(a->rate > 0.0 && a->period > 0.0))
+      return set_err(NULL, DCSIM_E_INVALID, "sinusoid arrivals need rate > 0 and period > 0%s%lld");
+    if (a->mode == DCSIM_ARR_SINUSOID && (a->amp > 1.0 || a->amp < -1.0))
+      return set_err(NULL, DCSIM_E_INVALID, "sinusoid arrivals with |amp| > 1 never terminate in the reference (arrivals.py:41-45)%s%lld");
+  }
+  for (int d = 0; d < sp->n_dc; ++d) {
+    const dcsim_dc_t* c = &sp->dc[d];
+    if (c->total_gpus < 0 || c->n_freq < 1 || c->n_freq > DCSIM_MAX_FREQ)
+      return set_err(NULL, DCSIM_E_INVALID, "spec: DC %s%lld has bad total_gpus / n_freq", "", d);
+  }
+  if (sp->algo == DCSIM_ALGO_CAP_GREEDY && sp->power_cap > 0.0)
+    return set_err(NULL, DCSIM_E_UNSUPPORTED, "algo=cap_greedy with power_cap>0 (per-job DVFS re-scheduling, SIM:248-315) is not on the device path yet%s%lld");
+  if (sp->algo < DCSIM_ALGO_DEFAULT || sp->algo > DCSIM_ALGO_CAP_GREEDY)
+    return set_err(NULL, DCSIM_E_UNSUPPORTED, "spec: unknown algo id %s%lld", "", sp->algo);
+  return DCSIM_OK;
+}
+
+int dcsim_create(const void* spec_blob, size_t spec_bytes, uint64_t n_replicas, uint64_t base_seed,
+                 uint64_t first_replica_id, int device, dcsim_t** out) {
+  if (!out) return set_err(NULL, DCSIM_E_INVALID, "create: out is NULL%s%lld");
+  *out = NULL;
+  if (!spec_blob || spec_bytes != sizeof(dcsim_spec_t))
+    return set_err(NULL, DCSIM_E_INVALID, "create: spec blob must be %s%lld bytes", "", (long long)sizeof(dcsim_spec_t));
+  if (n_replicas == 0) return set_err(NULL, DCSIM_E_INVALID, "create: n_replicas must be > 0%s%lld");
+  dcsim_spec_t sp;
+  memcpy(&sp, spec_blob, sizeof(sp));
+  int rc = validate_spec(&sp);
+  if (rc != DCSIM_OK) return rc;
+
+  dcsim_t* h = new (std::nothrow) dcsim();
+  if (!h) return set_err(NULL, DCSIM_E_NOMEM, "create: host allocation failed%s%lld");
+  memset(h, 0, sizeof(*h));
+  h->spec = sp;
+  dcsim_make_layout(&h->spec, &h->L);
+  h->n_replicas = n_replicas;
+  h->seed0 = base_seed + first_replica_id;
+  h->device = device;
+  h->trace_replica = -1;
+  h->log_replica = -1;
+
+#define CREATE_TRY(call)                                                                  \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess) {                                                              \
+      rc = set_err(NULL, e_ == cudaErrorMemoryAllocation ? DCSIM_E_NOMEM : DCSIM_E_CUDA,  \
+                   "CUDA error in create: %s (line %lld)", cudaGetErrorString(e_), (long long)__LINE__); \
+      dcsim_destroy(h);                                                                   \
+      return rc;                                                                          \
+    }                                                                                     \
+  } while (0)
+
+  CREATE_TRY(cudaSetDevice(device));
+  int smem_optin = 0;
+  CREATE_TRY(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
+  CREATE_TRY(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  int wpc = smem_optin / h->L.total_bytes;
+  if (wpc > DCSIM_MAX_WARPS_PER_CTA) wpc = DCSIM_MAX_WARPS_PER_CTA;
+  if (wpc < 1) {
+    rc = set_err(NULL, DCSIM_E_UNSUPPORTED, "state block of %s%lld bytes does not fit one CTA's shared memory; lower cap_run / cap_xfer", "", h->L.total_bytes);
+    dcsim_destroy(h);
+    return rc;
+  }
+  h->warps_per_cta = wpc;
+  h->smem_bytes = wpc * h->L.total_bytes;
+  h->ctas = (int)((n_replicas + (uint64_t)wpc - 1) / (uint64_t)wpc);
+  CREATE_TRY(cudaFuncSetAttribute(dcsim_advance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
+  cudaFuncAttributes fa;
+  CREATE_TRY(cudaFuncGetAttributes(&fa, dcsim_advance_kernel));
+  h->regs = fa.numRegs;
+  int blocks_per_sm = 0;
+  CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, dcsim_advance_kernel, wpc * 32, h->smem_bytes));
+  h->resident_warps = blocks_per_sm * wpc;
+
+  CREATE_TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  h->stream = h->own_stream;
+  const size_t state_bytes = (size_t)n_replicas * (size_t)h->L.total_bytes;
+  const size_t queue_bytes = (size_t)n_replicas * (size_t)h->L.queue_bytes;
+  CREATE_TRY(cudaMalloc(&h->d_state, state_bytes));
+  CREATE_TRY(cudaMalloc(&h->d_queues, queue_bytes ? queue_bytes : 16));
+  CREATE_TRY(cudaMalloc(&h->d_summary, (size_t)n_replicas * DCSIM_SUMMARY_K * sizeof(double)));
+  CREATE_TRY(cudaMalloc(&h->d_events, sizeof(unsigned long long)));
+  CREATE_TRY(cudaMalloc(&h->d_counts, 4 * sizeof(uint32_t)));
+  CREATE_TRY(cudaMemsetAsync(h->d_state, 0, state_bytes, h->stream)); /* hdr.initialized == 0 => fresh replica */
+  CREATE_TRY(cudaMemsetAsync(h->d_summary, 0, (size_t)n_replicas * DCSIM_SUMMARY_K * sizeof(double), h->stream));
+  CREATE_TRY(cudaMemsetAsync(h->d_events, 0, sizeof(unsigned long long), h->stream));
+  CREATE_TRY(cudaMemsetAsync(h->d_counts, 0, 4 * sizeof(uint32_t), h->stream));
+  CREATE_TRY(cudaStreamSynchronize(h->stream));
+#undef CREATE_TRY
+  *out = h;
+  return DCSIM_OK;
+}
+
+int dcsim_set_stream(dcsim_t* h, void* cuda_stream) {
+  if (!h) return DCSIM_E_INVALID;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  return DCSIM_OK;
+}
+
+int dcsim_set_trace(dcsim_t* h, uint64_t replica, uint32_t capacity) {
+  if (!h) return DCSIM_E_INVALID;
+  if (h->launches) return set_err(h, DCSIM_E_STATE, "set_trace must precede the first advance%s%lld");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  if (h->d_trace) { cudaFree(h->d_trace); h->d_trace = NULL; }
+  h->trace_cap = 0; h->trace_replica = -1;
+  if (capacity == 0) return DCSIM_OK;
+  if (replica >= h->n_replicas) return set_err(h, DCSIM_E_INVALID, "set_trace: replica out of range%s%lld");
+  CUDA_TRY(h, cudaMalloc(&h->d_trace, (size_t)capacity * sizeof(dcsim_trace_rec_t)));
+  h->trace_cap = capacity; h->trace_replica = (int64_t)replica;
+  return DCSIM_OK;
+}
+
+int dcsim_set_logging(dcsim_t* h, uint64_t replica, uint32_t job_capacity, uint32_t cluster_capacity) {
+  if (!h) return DCSIM_E_INVALID;
+  if (h->launches) return set_err(h, DCSIM_E_STATE, "set_logging must precede the first advance%s%lld");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  if (h->d_jobs) { cudaFree(h->d_jobs); h->d_jobs = NULL; }
+  if (h->d_cluster) { cudaFree(h->d_cluster); h->d_cluster = NULL; }
+  h->jobs_cap = h->cluster_cap = 0; h->log_replica = -1;
+  if (job_capacity == 0 && cluster_capacity == 0) return DCSIM_OK;
+  if (replica >= h->n_replicas) return set_err(h, DCSIM_E_INVALID, "set_logging: replica out of range%s%lld");
+  if (job_capacity) CUDA_TRY(h, cudaMalloc(&h->d_jobs, (size_t)job_capacity * sizeof(dcsim_job_rec_t)));
+  if (cluster_capacity) CUDA_TRY(h, cudaMalloc(&h->d_cluster, (size_t)cluster_capacity * sizeof(dcsim_cluster_rec_t)));
+  h->jobs_cap = job_capacity; h->cluster_cap = cluster_capacity; h->log_replica = (int64_t)replica;
+  return DCSIM_OK;
+}
+
+int dcsim_advance(dcsim_t* h, uint64_t max_events_per_replica, uint64_t* total_events_out) {
+  if (!h) return DCSIM_E_INVALID;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  dcsim_kparams_t P;
+  memset(&P, 0, sizeof(P));
+  P.spec = h->spec;
+  P.L = h->L;
+  P.rec.trace = h->d_trace; P.rec.jobs = h->d_jobs; P.rec.cluster = h->d_cluster; P.rec.counts = h->d_counts;
+  P.rec.trace_cap = h->trace_cap; P.rec.jobs_cap = h->jobs_cap; P.rec.cluster_cap = h->cluster_cap;
+  P.rec.trace_replica = h->trace_replica; P.rec.log_replica = h->log_replica;
+  P.n_replicas = h->n_replicas;
+  P.seed0 = h->seed0;
+  P.max_events = max_events_per_replica;
+  P.state = h->d_state; P.queues = h->d_queues; P.summary = h->d_summary;
+  P.end_eps = h->spec.end_time + 1e-9; /* SIM:161 */
+  dcsim_advance_kernel<<<h->ctas, h->warps_per_cta * 32, h->smem_bytes, h->stream>>>(P, h->d_events);
+  CUDA_TRY(h, cudaGetLastError());
+  h->launches++;
+  if (total_events_out) {
+    unsigned long long total = 0;
+    CUDA_TRY(h, cudaMemcpyAsync(&total, h->d_events, sizeof(total), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    *total_events_out = (uint64_t)(total - h->events_seen);
+    h->events_seen = total;
+  }
+  return DCSIM_OK;
+}
+
+int dcsim_fetch_summary(dcsim_t* h, double* out, size_t out_bytes) {
+  if (!h || !out) return DCSIM_E_INVALID;
+  const size_t need = (size_t)h->n_replicas * DCSIM_SUMMARY_K * sizeof(double);
+  if (out_bytes < need) return set_err(h, DCSIM_E_INVALID, "fetch_summary: buffer too small (need %s%lld bytes)", "", (long long)need);
+  if (!h->launches) return set_err(h, DCSIM_E_STATE, "fetch_summary before the first advance%s%lld");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  CUDA_TRY(h, cudaMemcpyAsync(out, h->d_summary, need, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return DCSIM_OK;
+}
+
+int dcsim_summary_device_ptr(dcsim_t* h, void** dev_ptr_out) {
+  if (!h || !dev_ptr_out) return DCSIM_E_INVALID;
+  *dev_ptr_out = h->d_summary;
+  return DCSIM_OK;
+}
+
+int dcsim_all_done(dcsim_t* h, int* done_out) {
+  if (!h || !done_out) return DCSIM_E_INVALID;
+  if (!h->launches) { *done_out = 0; return DCSIM_OK; }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  double* agg = NULL;
+  CUDA_TRY(h, cudaMalloc(&agg, DCSIM_AGG_K * sizeof(double)));
+  int rc = dcsim_reduce_summary(h, agg);
+  double host[DCSIM_AGG_K];
+  if (rc == DCSIM_OK) {
+    cudaError_t e = cudaMemcpyAsync(host, agg, sizeof(host), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) rc = set_err(h, DCSIM_E_CUDA, "CUDA error: %s%lld", cudaGetErrorString(e));
+  }
+  cudaFree(agg);
+  if (rc != DCSIM_OK) return rc;
+  /* DCSIM_A_FAILED counts replicas that are not done OR stopped on a capacity overflow; the latter never
+   * finish, so report "done" once nothing is still running */
+  *done_out = 0;
+  {
+    /* not-done and status==0  <=> still running */
+    size_t need = (size_t)h->n_replicas * DCSIM_SUMMARY_K;
+    double* s = (double*)malloc(need * sizeof(double));
+    if (!s) return set_err(h, DCSIM_E_NOMEM, "all_done: host allocation failed%s%lld");
+    rc = dcsim_fetch_summary(h, s, need * sizeof(double));
+    if (rc == DCSIM_OK) {
+      int running = 0;
+      for (uint64_t r = 0; r < h->n_replicas && !running; ++r)
+        if (s[r * DCSIM_SUMMARY_K + DCSIM_S_DONE] == 0.0 && s[r * DCSIM_SUMMARY_K + DCSIM_S_STATUS] == 0.0) running = 1;
+      *done_out = !running;
+    }
+    free(s);
+  }
+  return rc;
+}
+
+int dcsim_reduce_summary(dcsim_t* h, double* dev_out) {
+  if (!h || !dev_out) return DCSIM_E_INVALID;
+  if (!h->launches) return set_err(h, DCSIM_E_STATE, "reduce_summary before the first advance%s%lld");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  CUDA_TRY(h, cudaMemsetAsync(dev_out, 0, DCSIM_AGG_K * sizeof(double), h->stream));
+  int blocks = (int)((h->n_replicas + 255) / 256);
+  if (blocks > 4 * h->sm_count) blocks = 4 * h->sm_count;
+  dcsim_reduce_kernel<<<blocks, 256, 0, h->stream>>>(h->d_summary, h->n_replicas, dev_out);
+  CUDA_TRY(h, cudaGetLastError());
+  return DCSIM_OK;
+}
+
+static int fetch_records(dcsim_t* h, const void* dev, size_t rec_bytes, uint32_t dev_cap, int which, void* out,
+                         uint32_t capacity, uint32_t* n_out) {
+  if (!h || !n_out) return DCSIM_E_INVALID;
+  *n_out = 0;
+  if (!dev) return DCSIM_OK;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  uint32_t counts[4];
+  CUDA_TRY(h, cudaMemcpyAsync(counts, h->d_counts, sizeof(counts), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  uint32_t n = counts[which] < dev_cap ? counts[which] : dev_cap;
+  if (n > capacity) n = capacity;
+  if (n && out) {
+    CUDA_TRY(h, cudaMemcpyAsync(out, dev, (size_t)n * rec_bytes, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  }
+  *n_out = n;
+  return DCSIM_OK;
+}
+
+int dcsim_fetch_trace(dcsim_t* h, dcsim_trace_rec_t* out, uint32_t capacity, uint32_t* n_out) {
+  return fetch_records(h, h ? h->d_trace : NULL, sizeof(dcsim_trace_rec_t), h ? h->trace_cap : 0, 0, out, capacity, n_out);
+}
+int dcsim_fetch_job_log(dcsim_t* h, dcsim_job_rec_t* out, uint32_t capacity, uint32_t* n_out) {
+  return fetch_records(h, h ? h->d_jobs : NULL, sizeof(dcsim_job_rec_t), h ? h->jobs_cap : 0, 1, out, capacity, n_out);
+}
+int dcsim_fetch_cluster_log(dcsim_t* h, dcsim_cluster_rec_t* out, uint32_t capacity, uint32_t* n_out) {
+  return fetch_records(h, h ? h->d_cluster : NULL, sizeof(dcsim_cluster_rec_t), h ? h->cluster_cap : 0, 2, out, capacity, n_out);
+}
+
+int dcsim_launch_info(dcsim_t* h, dcsim_launch_info_t* out) {
+  if (!h || !out) return DCSIM_E_INVALID;
+  memset(out, 0, sizeof(*out));
+  out->warps_per_cta = h->warps_per_cta; out->ctas = h->ctas; out->smem_bytes_per_cta = h->smem_bytes;
+  out->regs_per_thread = h->regs; out->resident_warps_per_sm = h->resident_warps; out->sm_count = h->sm_count;
+  out->cap_xfer = h->L.cap_xfer; out->cap_run = h->L.cap_run; out->cap_q_inf = h->L.cap_q[0]; out->cap_q_trn = h->L.cap_q[1];
+  out->kernel_launches = h->launches;
+  out->hbm_bytes_state = (uint64_t)h->n_replicas * (uint64_t)h->L.total_bytes;
+  out->hbm_bytes_queues = (uint64_t)h->n_replicas * h->L.queue_bytes;
+  return DCSIM_OK;
+}
+
+const char* dcsim_last_error(const dcsim_t* h) { return h ? h->err : g_create_err; }
+
+void dcsim_destroy(dcsim_t* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->own_stream) { cudaStreamSynchronize(h->stream); }
+  cudaFree(h->d_state); cudaFree(h->d_queues); cudaFree(h->d_summary); cudaFree(h->d_events); cudaFree(h->d_counts);
+  cudaFree(h->d_trace); cudaFree(h->d_jobs); cudaFree(h->d_cluster);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+}
+
+} /* extern "C" */

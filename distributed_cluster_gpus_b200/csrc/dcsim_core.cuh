@@ -1,0 +1,951 @@
+/*
+ * dcsim_core.cuh — the per-replica event engine of the B200 batched simulator.
+ *
+ * One warp owns one Monte-Carlo replica of the reference's multi-DC event loop
+ * (simcore/simulator_paper_multi.py:412-480 and the leaves it calls; citations are relative to the
+ * reference tree).  The replica's whole working set — pending-event candidates, in-flight transfers,
+ * running-job records, per-DC accumulators, a 128-word Philox window — is a "state block" that the warp
+ * stages in shared memory for the duration of a launch; only the unbounded FIFO queues live in HBM.
+ *
+ * How the 32 lanes are used
+ *   - pop-min: the pending events are kept as 32 *candidates* (one per DC = earliest job_finish of that DC,
+ *     one per (ingress, job type) = its next arrival, one for the earliest in-flight transfer, one for the
+ *     log tick); every lane loads one candidate and three REDUX.MIN (hi word, lo word, seq) find the winner;
+ *   - the per-event sweep over all DCs (SIM:429-437) runs one DC per lane;
+ *   - pool rescans, order-preserving compaction of the running set, Philox refill (one block per lane),
+ *     state load/store run strided across the warp;
+ *   - the handlers themselves are strictly sequential per replica (the RNG stream is consumed in order)
+ *     and run on lane 0 out of shared memory.
+ *
+ * All arithmetic that defines results is FP64 and is written so that, compiled with -fmad=false, every
+ * + - * / happens in the reference's order with one rounding each.  log/exp/pow/sin come from CUDA's
+ * libdevice (<= 2 ulp from glibc's), which is why parity with the reference is asserted at 1e-9 relative
+ * and exact event/job/RNG-word counts rather than bit-for-bit.
+ *
+ * The file compiles two ways:
+ *   - nvcc, sm_100a: DCSIM_LANES = 32, warp collectives are real (csrc/dcsim_b200.cu);
+ *   - g++ with -DDCSIM_HOST_EMU (tests/hostemu/, TEST-ONLY): DCSIM_LANES = 1, collectives are identities.
+ *     It exists so the handler logic can be checked against the oracle where there is no GPU; it is not
+ *     linked into, or reachable from, the product library.
+ */
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/dcsim_b200.h"
+
+#ifdef DCSIM_HOST_EMU
+#define DCSIM_DEV static inline
+#define DCSIM_LANES 1
+static inline int dcsim_lane() { return 0; }
+static inline void dcsim_warp_sync() {}
+static inline uint32_t dcsim_warp_min_u32(uint32_t x) { return x; }
+static inline uint32_t dcsim_warp_ballot(bool p) { return p ? 1u : 0u; }
+static inline uint32_t dcsim_bcast_u32(uint32_t x, int) { return x; }
+static inline int dcsim_ffs(uint32_t x) { return __builtin_ffs((int)x); }
+static inline uint32_t dcsim_hi(double x) { uint64_t u; memcpy(&u, &x, 8); return (uint32_t)(u >> 32); }
+static inline uint32_t dcsim_lo(double x) { uint64_t u; memcpy(&u, &x, 8); return (uint32_t)u; }
+static inline uint32_t dcsim_mulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+static inline int dcsim_bit_length(uint32_t n) { return 32 - __builtin_clz(n); }
+#define DCSIM_INF (__builtin_inf())
+#else
+#define DCSIM_DEV __device__ __forceinline__
+#define DCSIM_LANES 32
+DCSIM_DEV int dcsim_lane() { return (int)(threadIdx.x & 31u); }
+DCSIM_DEV void dcsim_warp_sync() { __syncwarp(); }
+DCSIM_DEV uint32_t dcsim_warp_min_u32(uint32_t x) { return __reduce_min_sync(0xffffffffu, x); }
+DCSIM_DEV uint32_t dcsim_warp_ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
+DCSIM_DEV uint32_t dcsim_bcast_u32(uint32_t x, int src) { return __shfl_sync(0xffffffffu, x, src); }
+DCSIM_DEV int dcsim_ffs(uint32_t x) { return __ffs((int)x); }
+DCSIM_DEV uint32_t dcsim_hi(double x) { return (uint32_t)__double2hiint(x); }
+DCSIM_DEV uint32_t dcsim_lo(double x) { return (uint32_t)__double2loint(x); }
+DCSIM_DEV uint32_t dcsim_mulhi(uint32_t a, uint32_t b) { return __umulhi(a, b); }
+DCSIM_DEV int dcsim_bit_length(uint32_t n) { return 32 - __clz((int)n); }
+#define DCSIM_INF (__longlong_as_double(0x7ff0000000000000LL))
+#endif
+
+/* ---- candidate slots (the event set, one slot per lane) -------------------------------------- */
+enum {
+  CAND_DC0 = 0,      /* + d   : earliest job_finish among DC d's running jobs */
+  CAND_STREAM0 = 8,  /* + 2*ingress + jtype : next arrival of that stream */
+  CAND_XFER = 24,    /* earliest in-flight xfer_done */
+  CAND_LOG = 25,     /* the log tick */
+  CAND_N = 32
+};
+enum { KIND_ARR_INF = 0, KIND_ARR_TRN = 1, KIND_XFER = 2, KIND_FINISH = 3, KIND_LOG = 4 };
+
+enum { /* per-DC f64 arrays inside the state block, each DCSIM_MAX_DC long */
+  DF_ENERGY = 0, DF_LAST_E_T, DF_UTIL_TIME, DF_UTIL_LAST, DF_UTIL_BEGIN, DF_ACC_UNIT, DF_CUR_FREQ, DF_POWER, DF_N
+};
+enum { /* per-DC i32 arrays */
+  DI_BUSY = 0, DI_NRUN, DI_QH_INF, DI_QT_INF, DI_QH_TRN, DI_QT_TRN, DI_FMIN_SLOT, DI_N
+};
+
+#define DCSIM_RNG_WINDOW 128u /* Philox words staged per refill: one block per lane */
+#define DCSIM_RNG_MARGIN 24u  /* refill when fewer than this many staged words remain at an arrival */
+/* A rejection loop that has not accepted after this many draws stops the replica with DCSIM_ST_RNG_RUNAWAY
+ * instead of spinning (the reference would spin: e.g. arrivals.py:41-45 under a clipped lambda). */
+#define DCSIM_REJECTION_LIMIT 65536
+
+/* Persistent scalars of a replica (first bytes of its state block). */
+struct dcsim_hdr_t {
+  double now, lat_sum, lat_sum_inf, lat_sum_trn, last_t;
+  uint32_t n_events, seq, jid, rng_pos;
+  uint32_t n_xfer, status, done, initialized;
+  uint32_t n_fin_inf, n_fin_trn, ev_arr, ev_xfer;
+  uint32_t ev_fin, ev_log, max_xfer, max_run;
+  uint32_t max_q, xmin_slot, bandit_t, _pad;
+};
+
+/* Byte offsets of the arrays inside a state block; computed once per handle on the host. */
+struct dcsim_layout_t {
+  int32_t cand_t, cand_seq;
+  int32_t dc_f64, dc_i32;
+  int32_t xf_t, xf_size, xf_seq, xf_meta, xf_jid;
+  int32_t rn_t, rn_pw, rn_tpt, rn_start, rn_size, rn_f, rn_seq, rn_meta, rn_jid;
+  int32_t rng_buf;
+  int32_t bandit_n, bandit_s;
+  int32_t total_bytes;
+  int32_t cap_xfer, cap_run;
+  int32_t cap_q[2];        /* FIFO entries per DC: [0]=inference [1]=training */
+  int32_t _pad;
+  uint64_t queue_bytes;    /* HBM bytes of one replica's FIFOs */
+};
+
+static inline int32_t dcsim_align16(int32_t x) { return (x + 15) & ~15; }
+
+/* Host-side: sizes the state block from the spec's capacities. */
+static inline void dcsim_make_layout(const dcsim_spec_t* sp, dcsim_layout_t* L) {
+  memset(L, 0, sizeof(*L));
+  const int D = DCSIM_MAX_DC;
+  int32_t cx = sp->cap_xfer > 0 ? sp->cap_xfer : 64;
+  int32_t cr = sp->cap_run > 0 ? sp->cap_run : 16;
+  cx = (cx + 3) & ~3;
+  cr = (cr + 3) & ~3;
+  L->cap_xfer = cx;
+  L->cap_run = cr;
+  L->cap_q[0] = sp->cap_q_inf > 0 ? sp->cap_q_inf : 4096;
+  L->cap_q[1] = sp->cap_q_trn > 0 ? sp->cap_q_trn : 512;
+  int32_t o = dcsim_align16((int32_t)sizeof(dcsim_hdr_t));
+  L->cand_t = o; o += CAND_N * 8;
+  L->cand_seq = o; o += CAND_N * 4;
+  L->dc_f64 = o; o += DF_N * D * 8;
+  L->dc_i32 = o; o = dcsim_align16(o + DI_N * D * 4);
+  L->xf_t = o; o += cx * 8;
+  L->xf_size = o; o += cx * 8;
+  L->xf_seq = o; o += cx * 4;
+  L->xf_meta = o; o += cx * 4;
+  L->xf_jid = o; o = dcsim_align16(o + cx * 4);
+  const int32_t nr = sp->n_dc * cr;
+  L->rn_t = o; o += nr * 8;
+  L->rn_pw = o; o += nr * 8;
+  L->rn_tpt = o; o += nr * 8;
+  L->rn_start = o; o += nr * 8;
+  L->rn_size = o; o += nr * 8;
+  L->rn_f = o; o += nr * 8;
+  L->rn_seq = o; o += nr * 4;
+  L->rn_meta = o; o += nr * 4;
+  L->rn_jid = o; o = dcsim_align16(o + nr * 4);
+  L->rng_buf = o; o += (int32_t)DCSIM_RNG_WINDOW * 4;
+  if (sp->xfer_rule == DCSIM_START_BANDIT || sp->deq_rule == DCSIM_START_BANDIT) {
+    L->bandit_s = o; o += sp->n_dc * 2 * DCSIM_MAX_FREQ * 8;
+    L->bandit_n = o; o += sp->n_dc * 2 * DCSIM_MAX_FREQ * 4;
+  }
+  L->total_bytes = dcsim_align16(o);
+  L->queue_bytes = (uint64_t)sp->n_dc * ((uint64_t)L->cap_q[0] + (uint64_t)L->cap_q[1]) * 16ull;
+}
+
+/* One FIFO entry in HBM: the part of a Job that survives queueing (models.py:5-27). */
+struct alignas(16) dcsim_qent_t {
+  double size;
+  uint32_t jid;
+  uint32_t ing;
+};
+
+/* Optional recorders for ONE replica of the batch (the CSV wire formats; debug trace). */
+struct dcsim_recorders_t {
+  dcsim_trace_rec_t* trace;
+  dcsim_job_rec_t* jobs;
+  dcsim_cluster_rec_t* cluster;
+  uint32_t* counts; /* [0]=trace rows, [1]=job rows, [2]=cluster rows (device memory) */
+  uint32_t trace_cap, jobs_cap, cluster_cap, _pad;
+  int64_t trace_replica; /* local replica index, -1 = none */
+  int64_t log_replica;
+};
+
+/* Everything a launch needs.  Passed as ONE __grid_constant__ kernel parameter, so the scenario is read
+ * through the constant cache and never competes with the state blocks for shared memory / L1. */
+struct dcsim_kparams_t {
+  dcsim_spec_t spec;
+  dcsim_layout_t L;
+  dcsim_recorders_t rec;
+  uint64_t n_replicas;
+  uint64_t seed0;       /* Philox key of local replica 0 (base_seed + first_replica_id) */
+  uint64_t max_events;  /* per replica per launch; 0 = run to the end */
+  char* state;          /* [n_replicas][L.total_bytes] */
+  char* queues;         /* [n_replicas][L.queue_bytes] */
+  double* summary;      /* [n_replicas][DCSIM_SUMMARY_K] */
+  double end_eps;       /* end_time + 1e-9, the _schedule cut-off (SIM:161) */
+};
+
+/* ---- small typed views ------------------------------------------------------------------------ */
+template <typename T>
+DCSIM_DEV T* dcsim_at(char* blk, int32_t off) { return reinterpret_cast<T*>(blk + off); }
+
+struct dcsim_ctx_t {
+  const dcsim_kparams_t* P;
+  char* blk;             /* this replica's state block (shared memory on the GPU) */
+  char* q;               /* this replica's FIFOs (HBM) */
+  dcsim_hdr_t* H;
+  int lane;
+  bool is_traced, is_logged;
+  /* Philox stream */
+  uint32_t key0, key1;
+  uint32_t rng_base;     /* stream index of rng_buf[0]; multiple of 4 */
+  uint32_t rng_valid;    /* words staged (0 or DCSIM_RNG_WINDOW) */
+  uint32_t sblk[4];      /* slow path: one block computed by lane 0 alone */
+  uint32_t sblk_idx;
+};
+
+#define DCF(c, which) (dcsim_at<double>((c).blk, (c).P->L.dc_f64) + (which) * DCSIM_MAX_DC)
+#define DCI(c, which) (dcsim_at<int32_t>((c).blk, (c).P->L.dc_i32) + (which) * DCSIM_MAX_DC)
+#define CAND_T(c) (dcsim_at<double>((c).blk, (c).P->L.cand_t))
+#define CAND_SEQ(c) (dcsim_at<uint32_t>((c).blk, (c).P->L.cand_seq))
+
+/* ================================================================================================
+ * Philox4x32-10 stream; definition shared with oracle/philox_random.py
+ * ============================================================================================== */
+DCSIM_DEV void dcsim_philox_block(uint32_t k0, uint32_t k1, uint32_t b, uint32_t out[4]) {
+  uint32_t c0 = b, c1 = 0u, c2 = 0u, c3 = 0u; /* block index < 2^30 here: rng_pos is 32-bit */
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = dcsim_mulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = dcsim_mulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+/* Warp-uniform.  Makes sure at least DCSIM_RNG_MARGIN staged words are ahead of rng_pos: every lane
+ * computes one block of the window [pos & ~3, +128). */
+DCSIM_DEV void dcsim_rng_ensure(dcsim_ctx_t& c, uint32_t pos) {
+  if (c.rng_valid && pos >= c.rng_base && pos + DCSIM_RNG_MARGIN <= c.rng_base + DCSIM_RNG_WINDOW) return;
+  dcsim_warp_sync();
+  const uint32_t base = pos & ~3u;
+  uint32_t* buf = dcsim_at<uint32_t>(c.blk, c.P->L.rng_buf);
+  for (uint32_t b = (uint32_t)c.lane; b < DCSIM_RNG_WINDOW / 4u; b += DCSIM_LANES) {
+    uint32_t w[4];
+    dcsim_philox_block(c.key0, c.key1, (base >> 2) + b, w);
+    buf[4 * b + 0] = w[0]; buf[4 * b + 1] = w[1]; buf[4 * b + 2] = w[2]; buf[4 * b + 3] = w[3];
+  }
+  c.rng_base = base;
+  c.rng_valid = DCSIM_RNG_WINDOW;
+  dcsim_warp_sync();
+}
+
+/* Lane 0 only.  Next word of the stream. */
+DCSIM_DEV uint32_t dcsim_rng_word(dcsim_ctx_t& c) {
+  const uint32_t pos = c.H->rng_pos;
+  c.H->rng_pos = pos + 1u;
+  const uint32_t idx = pos - c.rng_base;
+  if (c.rng_valid && idx < DCSIM_RNG_WINDOW) return dcsim_at<uint32_t>(c.blk, c.P->L.rng_buf)[idx];
+  const uint32_t b = pos >> 2; /* rare: a handler out-ran the window (long rejection run) */
+  if (b != c.sblk_idx) { dcsim_philox_block(c.key0, c.key1, b, c.sblk); c.sblk_idx = b; }
+  return c.sblk[pos & 3u];
+}
+
+/* CPython genrand_res53 (Modules/_randommodule.c): 53-bit uniform on [0,1) from two words */
+DCSIM_DEV double dcsim_rng_random(dcsim_ctx_t& c) {
+  const uint32_t a = dcsim_rng_word(c) >> 5, b = dcsim_rng_word(c) >> 6;
+  return ((double)a * 67108864.0 + (double)b) * (1.0 / 9007199254740992.0);
+}
+
+/* random.py:242-250 via random.choice (SIM:576): k = n.bit_length(); redraw until < n */
+DCSIM_DEV int dcsim_rng_randbelow(dcsim_ctx_t& c, int n) {
+  const int k = dcsim_bit_length((uint32_t)n);
+  uint32_t v = dcsim_rng_word(c) >> (32 - k);
+  for (int it = 0; v >= (uint32_t)n; ++it) {
+    if (it >= DCSIM_REJECTION_LIMIT) { c.H->status |= DCSIM_ST_RNG_RUNAWAY; return 0; }
+    v = dcsim_rng_word(c) >> (32 - k);
+  }
+  return (int)v;
+}
+
+/* random.py:617 */
+DCSIM_DEV double dcsim_expovariate(dcsim_ctx_t& c, double lambd) { return -log(1.0 - dcsim_rng_random(c)) / lambd; }
+
+/* random.py:541-549 (Kinderman-Monahan) */
+DCSIM_DEV double dcsim_normalvariate(dcsim_ctx_t& c, double mu, double sigma) {
+  const double NV = c.P->spec.nv_magicconst;
+  double z = 0.0;
+  for (int it = 0;; ++it) {
+    if (it >= DCSIM_REJECTION_LIMIT) { c.H->status |= DCSIM_ST_RNG_RUNAWAY; break; }
+    const double u1 = dcsim_rng_random(c);
+    const double u2 = 1.0 - dcsim_rng_random(c);
+    z = NV * (u1 - 0.5) / u2;
+    const double zz = z * z / 4.0;
+    if (zz <= -log(u2)) break;
+  }
+  return mu + z * sigma;
+}
+
+/* ================================================================================================
+ * Model leaves, evaluated in registers at job start
+ * ============================================================================================== */
+/* f**3 as CPython computes it (libm pow(f, 3.0), correctly rounded for every f this path sees):
+ * error-free products via fma, one final rounding. */
+DCSIM_DEV double dcsim_cube(double f) {
+  const double p = f * f, pe = fma(f, f, -p);
+  const double q = p * f, qe = fma(p, f, -q);
+  return q + (qe + pe * f);
+}
+
+/* energy_paper.py:4-12   n * (alpha_p f^3 + beta_p f + gamma_p) */
+DCSIM_DEV double dcsim_task_power(int n, double f_ghz, const dcsim_coeffs_t& k) {
+  const double f = f_ghz > 0.0 ? f_ghz : 0.0;
+  const double per_gpu = k.alpha_p * dcsim_cube(f) + k.beta_p * f + k.gamma_p;
+  return (double)(n > 0 ? n : 0) * per_gpu;
+}
+
+/* latency_paper.py:4-9 */
+DCSIM_DEV double dcsim_step_time(int n_gpus, double f_ghz, const dcsim_coeffs_t& k) {
+  const int n = n_gpus > 1 ? n_gpus : 1;
+  const double f = f_ghz > 1e-9 ? f_ghz : 1e-9;
+  const double base = k.alpha_t + k.beta_t / f;
+  if (n == 1) return base;
+  return (base + k.gamma_t * (double)n) / (double)n;
+}
+
+/* arrivals.py:5-11 */
+DCSIM_DEV double dcsim_sample_size(dcsim_ctx_t& c, int jt) {
+  const dcsim_spec_t& sp = c.P->spec;
+  if (jt == DCSIM_JT_INFERENCE) {
+    const double x = 1.0 - dcsim_rng_random(c);
+    const double u = x > sp.uniform_floor ? x : sp.uniform_floor;
+    return sp.pareto_xm / pow(u, sp.pareto_inv_alpha);
+  }
+  const double v = exp(dcsim_normalvariate(c, sp.lognorm_mu, sp.lognorm_sigma));
+  return v > sp.lognorm_floor ? v : sp.lognorm_floor;
+}
+
+/* arrivals.py:25-48.  Returns the inter-arrival gap, +inf for a dead stream. */
+DCSIM_DEV double dcsim_next_interarrival(dcsim_ctx_t& c, int jt, double t) {
+  const dcsim_arrival_t& a = c.P->spec.arr[jt];
+  if (a.mode == DCSIM_ARR_POISSON) return a.rate <= 0.0 ? DCSIM_INF : dcsim_expovariate(c, a.rate);
+  if (a.mode == DCSIM_ARR_SINUSOID) {
+    const double abs_amp = a.amp < 0.0 ? -a.amp : a.amp;
+    const double max_rate = a.rate * (1.0 + abs_amp);
+    for (int it = 0;; ++it) {
+      if (it >= DCSIM_REJECTION_LIMIT) { c.H->status |= DCSIM_ST_RNG_RUNAWAY; return DCSIM_INF; }
+      const double w = dcsim_expovariate(c, max_rate);
+      const double tc = t + w;
+      double lam = a.rate * (1.0 + a.amp * sin(c.P->spec.two_pi * fmod(tc, a.period) / a.period));
+      lam = lam > 0.0 ? lam : 0.0;
+      if (dcsim_rng_random(c) <= lam / max_rate) return w;
+    }
+  }
+  return DCSIM_INF;
+}
+
+/* ================================================================================================
+ * Event-set primitives
+ * ============================================================================================== */
+/* Strided arg-min over (t[i], seq[i]), i < n, in (t, seq) lexicographic order (SIM:163: heap key).
+ * Times are >= 0, so their IEEE bit patterns order like unsigned integers and the reduction is three
+ * REDUX.MIN.U32.  Returns the winning index to every lane, -1 if every entry is +inf / n == 0. */
+DCSIM_DEV int dcsim_argmin_ts(const double* t, const uint32_t* seq, int n, int lane, double* t_out, uint32_t* seq_out) {
+  uint32_t bh = 0x7ff00000u, bl = 0u, bs = 0xffffffffu;
+  int bi = -1;
+  for (int i = lane; i < n; i += DCSIM_LANES) {
+    const double ti = t[i];
+    const uint32_t h = dcsim_hi(ti), l = dcsim_lo(ti), s = seq[i];
+    if (h < bh || (h == bh && (l < bl || (l == bl && s < bs)))) { bh = h; bl = l; bs = s; bi = i; }
+  }
+  const uint32_t mh = dcsim_warp_min_u32(bh);
+  if (mh >= 0x7ff00000u) return -1;
+  const uint32_t ml = dcsim_warp_min_u32(bh == mh ? bl : 0xffffffffu);
+  const bool m = (bh == mh) && (bl == ml);
+  const uint32_t ms = dcsim_warp_min_u32(m ? bs : 0xffffffffu);
+  const uint32_t votes = dcsim_warp_ballot(m && bs == ms && bi >= 0);
+  const int src = dcsim_ffs(votes) - 1;
+  const int win = (int)dcsim_bcast_u32((uint32_t)bi, src);
+#ifdef DCSIM_HOST_EMU
+  *t_out = t[win];
+#else
+  *t_out = __hiloint2double((int)mh, (int)ml);
+#endif
+  *seq_out = ms;
+  return win;
+}
+
+/* SIM:160-163: an event later than end_time + 1e-9 (or at +inf) is never scheduled and takes no seq. */
+DCSIM_DEV bool dcsim_schedulable(const dcsim_ctx_t& c, double t) { return !(t == DCSIM_INF) && !(t > c.P->end_eps); }
+
+/* Lane 0.  Re-derives DC d's estimated power exactly as SIM:168-179 does on every event:
+ * running jobs summed in dict (= start) order from 0.0, then the idle term. */
+DCSIM_DEV void dcsim_refresh_power(dcsim_ctx_t& c, int d) {
+  const dcsim_dc_t& cfg = c.P->spec.dc[d];
+  const int n = DCI(c, DI_NRUN)[d];
+  const double* pw = dcsim_at<double>(c.blk, c.P->L.rn_pw) + d * c.P->L.cap_run;
+  double p_active = 0.0;
+  for (int i = 0; i < n; ++i) p_active += pw[i];
+  const int idle = cfg.total_gpus - DCI(c, DI_BUSY)[d];
+  const double p_idle = (double)idle * (cfg.power_gating ? cfg.p_sleep : cfg.p_idle);
+  DCF(c, DF_POWER)[d] = p_active + p_idle;
+}
+
+/* Warp.  Earliest job_finish among DC d's running records -> candidate slot d. */
+DCSIM_DEV void dcsim_rescan_dc(dcsim_ctx_t& c, int d) {
+  dcsim_warp_sync();
+  const int n = DCI(c, DI_NRUN)[d];
+  const int off = d * c.P->L.cap_run;
+  double t; uint32_t s;
+  const int k = dcsim_argmin_ts(dcsim_at<double>(c.blk, c.P->L.rn_t) + off, dcsim_at<uint32_t>(c.blk, c.P->L.rn_seq) + off,
+                                n, c.lane, &t, &s);
+  if (c.lane == 0) {
+    CAND_T(c)[CAND_DC0 + d] = k >= 0 ? t : DCSIM_INF;
+    CAND_SEQ(c)[CAND_DC0 + d] = k >= 0 ? s : 0xffffffffu;
+    DCI(c, DI_FMIN_SLOT)[d] = k;
+  }
+  dcsim_warp_sync();
+}
+
+/* Warp.  Earliest in-flight transfer -> candidate slot CAND_XFER. */
+DCSIM_DEV void dcsim_rescan_xfer(dcsim_ctx_t& c) {
+  dcsim_warp_sync();
+  double t; uint32_t s;
+  const int k = dcsim_argmin_ts(dcsim_at<double>(c.blk, c.P->L.xf_t), dcsim_at<uint32_t>(c.blk, c.P->L.xf_seq),
+                                (int)c.H->n_xfer, c.lane, &t, &s);
+  if (c.lane == 0) {
+    CAND_T(c)[CAND_XFER] = k >= 0 ? t : DCSIM_INF;
+    CAND_SEQ(c)[CAND_XFER] = k >= 0 ? s : 0xffffffffu;
+    c.H->xmin_slot = (uint32_t)k;
+  }
+  dcsim_warp_sync();
+}
+
+/* Warp.  Removes running record `k` of DC d keeping the others in start order (dict semantics, models.py:60). */
+DCSIM_DEV void dcsim_running_erase(dcsim_ctx_t& c, int d, int k) {
+  dcsim_warp_sync();
+  const dcsim_layout_t& L = c.P->L;
+  const int n = DCI(c, DI_NRUN)[d];
+  const int off = d * L.cap_run;
+  double* f64s[6] = {dcsim_at<double>(c.blk, L.rn_t) + off, dcsim_at<double>(c.blk, L.rn_pw) + off,
+                     dcsim_at<double>(c.blk, L.rn_tpt) + off, dcsim_at<double>(c.blk, L.rn_start) + off,
+                     dcsim_at<double>(c.blk, L.rn_size) + off, dcsim_at<double>(c.blk, L.rn_f) + off};
+  uint32_t* u32s[3] = {dcsim_at<uint32_t>(c.blk, L.rn_seq) + off, dcsim_at<uint32_t>(c.blk, L.rn_meta) + off,
+                       dcsim_at<uint32_t>(c.blk, L.rn_jid) + off};
+  for (int j0 = k; j0 < n - 1; j0 += DCSIM_LANES) {
+    const int j = j0 + c.lane;
+    const bool act = j < n - 1;
+    double a[6]; uint32_t b[3];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) a[q] = act ? f64s[q][j + 1] : 0.0;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) b[q] = act ? u32s[q][j + 1] : 0u;
+    dcsim_warp_sync();
+    if (act) {
+#pragma unroll
+      for (int q = 0; q < 6; ++q) f64s[q][j] = a[q];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) u32s[q][j] = b[q];
+    }
+    dcsim_warp_sync();
+  }
+  if (c.lane == 0) DCI(c, DI_NRUN)[d] = n - 1;
+  dcsim_warp_sync();
+}
+
+/* ---- HBM FIFOs (dc.q_inf / dc.q_train, models.py:61-62) --------------------------------------- */
+DCSIM_DEV dcsim_qent_t* dcsim_queue_base(const dcsim_ctx_t& c, int d, int jt) {
+  const dcsim_layout_t& L = c.P->L;
+  const uint64_t per_dc = (uint64_t)L.cap_q[0] + (uint64_t)L.cap_q[1];
+  return reinterpret_cast<dcsim_qent_t*>(c.q) + (uint64_t)d * per_dc + (jt ? (uint64_t)L.cap_q[0] : 0ull);
+}
+DCSIM_DEV int dcsim_queue_len(dcsim_ctx_t& c, int d, int jt) {
+  return DCI(c, jt ? DI_QT_TRN : DI_QT_INF)[d] - DCI(c, jt ? DI_QH_TRN : DI_QH_INF)[d];
+}
+DCSIM_DEV void dcsim_enqueue(dcsim_ctx_t& c, int d, int jt, double size, uint32_t jid, uint32_t ing) {
+  const int cap = c.P->L.cap_q[jt];
+  int32_t* tail = DCI(c, jt ? DI_QT_TRN : DI_QT_INF) + d;
+  const int len = dcsim_queue_len(c, d, jt);
+  if (len >= cap) { c.H->status |= DCSIM_ST_QUEUE_OVERFLOW; return; }
+  dcsim_qent_t e; e.size = size; e.jid = jid; e.ing = ing;
+  dcsim_queue_base(c, d, jt)[(uint32_t)(*tail) % (uint32_t)cap] = e;
+  *tail += 1;
+  if ((uint32_t)(len + 1) > c.H->max_q) c.H->max_q = (uint32_t)(len + 1);
+}
+DCSIM_DEV dcsim_qent_t dcsim_dequeue(dcsim_ctx_t& c, int d, int jt) {
+  int32_t* head = DCI(c, jt ? DI_QH_TRN : DI_QH_INF) + d;
+  const dcsim_qent_t e = dcsim_queue_base(c, d, jt)[(uint32_t)(*head) % (uint32_t)c.P->L.cap_q[jt]];
+  *head += 1;
+  return e;
+}
+
+/* ================================================================================================
+ * Handlers (lane 0)
+ * ============================================================================================== */
+/* policy.py:16-41: returns the GPU count and rewrites dc.current_freq */
+DCSIM_DEV int dcsim_policy_select(dcsim_ctx_t& c, int d, int jt) {
+  const dcsim_spec_t& sp = c.P->spec;
+  double* cur = DCF(c, DF_CUR_FREQ) + d;
+  const int free_g = sp.dc[d].total_gpus - DCI(c, DI_BUSY)[d];
+  int g = free_g > 0 ? (free_g < sp.max_gpus_per_job ? free_g : sp.max_gpus_per_job) : 0;
+  if (jt == DCSIM_JT_INFERENCE) {
+    *cur = sp.dvfs_high;
+  } else if (sp.policy_name == DCSIM_POLICY_PERF_FIRST) {
+    const double cand = dcsim_queue_len(c, d, 0) > 0 ? sp.dvfs_high : sp.dc[d].default_freq;
+    *cur = cand > *cur ? cand : *cur;
+  } else if (sp.train_scale_out_low_freq && free_g >= 2) {
+    *cur = sp.dvfs_low;
+  } else {
+    *cur = sp.dvfs_low > *cur ? sp.dvfs_low : *cur;
+  }
+  return g > 1 ? g : 1;
+}
+
+/* learners.py:20-36 */
+DCSIM_DEV double dcsim_bandit_select(dcsim_ctx_t& c, int d, int jt) {
+  const dcsim_dc_t& cfg = c.P->spec.dc[d];
+  const uint32_t* N = dcsim_at<uint32_t>(c.blk, c.P->L.bandit_n) + (d * 2 + jt) * DCSIM_MAX_FREQ;
+  const double* S = dcsim_at<double>(c.blk, c.P->L.bandit_s) + (d * 2 + jt) * DCSIM_MAX_FREQ;
+  c.H->bandit_t += 1u;
+  for (int i = 0; i < cfg.n_freq; ++i)
+    if (N[i] < 1u) return cfg.freq_levels[i];
+  double best_ucb = -1e9, best_f = cfg.freq_levels[0];
+  const double two_log_t = 2.0 * log((double)c.H->bandit_t);
+  for (int i = 0; i < cfg.n_freq; ++i) {
+    const double n = (double)N[i];
+    const double ucb = S[i] / n + sqrt(two_log_t / n);
+    if (ucb > best_ucb) { best_ucb = ucb; best_f = cfg.freq_levels[i]; }
+  }
+  return best_f;
+}
+
+/* SIM:680-699 (_start_job, use_dc_freq) and SIM:960-980 (_start_job_with_nf): allocate, stamp, push job_finish. */
+DCSIM_DEV void dcsim_start_job(dcsim_ctx_t& c, int d, int jt, double size, uint32_t jid, uint32_t ing, int n, double f) {
+  const dcsim_layout_t& L = c.P->L;
+  const dcsim_coeffs_t& k = c.P->spec.dc[d].coeffs[jt];
+  int32_t* nrun = DCI(c, DI_NRUN) + d;
+  const int slot = *nrun;
+  if (slot >= L.cap_run) { c.H->status |= DCSIM_ST_RUN_OVERFLOW; return; }
+  DCI(c, DI_BUSY)[d] += n;
+  const double T_unit = dcsim_step_time(n, f, k);
+  const double t_fin = c.H->now + size * T_unit;
+  const int i = d * L.cap_run + slot;
+  const bool ok = dcsim_schedulable(c, t_fin);
+  const uint32_t seq = ok ? c.H->seq++ : 0xffffffffu;
+  dcsim_at<double>(c.blk, L.rn_t)[i] = ok ? t_fin : DCSIM_INF; /* a dropped finish holds its GPUs for ever */
+  dcsim_at<uint32_t>(c.blk, L.rn_seq)[i] = seq;
+  dcsim_at<double>(c.blk, L.rn_pw)[i] = dcsim_task_power(n, f, k);
+  dcsim_at<double>(c.blk, L.rn_tpt)[i] = 1.0 / T_unit; /* SIM:956 */
+  dcsim_at<double>(c.blk, L.rn_start)[i] = c.H->now;
+  dcsim_at<double>(c.blk, L.rn_size)[i] = size;
+  dcsim_at<double>(c.blk, L.rn_f)[i] = f;
+  dcsim_at<uint32_t>(c.blk, L.rn_meta)[i] = (uint32_t)n | ((uint32_t)jt << 16) | (ing << 17);
+  dcsim_at<uint32_t>(c.blk, L.rn_jid)[i] = jid;
+  *nrun = slot + 1;
+  if ((uint32_t)(slot + 1) > c.H->max_run) c.H->max_run = (uint32_t)(slot + 1);
+  if (ok) { /* incremental update of DC d's earliest finish */
+    const double ct = CAND_T(c)[CAND_DC0 + d];
+    if (t_fin < ct || (t_fin == ct && seq < CAND_SEQ(c)[CAND_DC0 + d])) {
+      CAND_T(c)[CAND_DC0 + d] = t_fin; CAND_SEQ(c)[CAND_DC0 + d] = seq; DCI(c, DI_FMIN_SLOT)[d] = slot;
+    }
+  }
+}
+
+/* SIM:982-984  int((now % 86400) // 3600), CPython float_rem / float_floor_div for positive operands */
+DCSIM_DEV int dcsim_current_hour(double now) {
+  const double x = fmod(now, 86400.0);
+  const double mod = fmod(x, 3600.0);
+  const double div = (x - mod) / 3600.0;
+  double fl = floor(div);
+  if (div - fl > 0.5) fl += 1.0;
+  return (int)fl;
+}
+
+/* The start rules of SIM:603-676 (at xfer_done) and SIM:892-927 (dequeue loop). */
+DCSIM_DEV void dcsim_start_by_rule(dcsim_ctx_t& c, int rule, bool at_xfer, int d, int jt, double size, uint32_t jid, uint32_t ing) {
+  const dcsim_spec_t& sp = c.P->spec;
+  const int free_g = sp.dc[d].total_gpus - DCI(c, DI_BUSY)[d];
+  if (rule == DCSIM_START_NF_LUT) {
+    const dcsim_nf_t nf = at_xfer ? sp.dc[d].nf_xfer[jt][dcsim_current_hour(c.H->now)] : sp.dc[d].nf_deq[jt];
+    int n = nf.n < free_g ? nf.n : free_g; /* SIM:962 */
+    n = n > 1 ? n : 1;
+    dcsim_start_job(c, d, jt, size, jid, ing, n, nf.f);
+  } else if (rule == DCSIM_START_BANDIT) {
+    int n = free_g < sp.max_gpus_per_job ? free_g : sp.max_gpus_per_job;
+    const double f = dcsim_bandit_select(c, d, jt);
+    n = n < free_g ? n : free_g;
+    n = n > 1 ? n : 1;
+    dcsim_start_job(c, d, jt, size, jid, ing, n, f);
+  } else {
+    const int g = dcsim_policy_select(c, d, jt);
+    dcsim_start_job(c, d, jt, size, jid, ing, g, DCF(c, DF_CUR_FREQ)[d]); /* SIM:689,696: f = dc.current_freq */
+  }
+}
+
+/* SIM:537-592 */
+DCSIM_DEV void dcsim_handle_arrival(dcsim_ctx_t& c, int stream) {
+  const dcsim_spec_t& sp = c.P->spec;
+  const dcsim_layout_t& L = c.P->L;
+  dcsim_hdr_t* H = c.H;
+  const int jt = stream & 1, ing = stream >> 1;
+  const uint32_t jid = ++H->jid;
+  const double size = dcsim_sample_size(c, jt);
+  int dc_sel = 0;
+  if (sp.route_rule == DCSIM_ROUTE_ECO) { /* SIM:544-553: strict <, first DC wins */
+    double best = sp.dc[0].eco_e_unit[jt] * size;
+    for (int d = 1; d < sp.n_dc; ++d) {
+      const double score = sp.dc[d].eco_e_unit[jt] * size;
+      if (score < best) { best = score; dc_sel = d; }
+    }
+  } else {
+    dc_sel = dcsim_rng_randbelow(c, sp.n_dc); /* SIM:575-576 */
+  }
+  const double t_x = H->now + sp.transfer_s[ing][dc_sel][jt];
+  if (dcsim_schedulable(c, t_x)) { /* SIM:580-588 */
+    const uint32_t slot = H->n_xfer;
+    if ((int)slot >= L.cap_xfer) {
+      H->status |= DCSIM_ST_XFER_OVERFLOW;
+    } else {
+      const uint32_t seq = H->seq++;
+      dcsim_at<double>(c.blk, L.xf_t)[slot] = t_x;
+      dcsim_at<double>(c.blk, L.xf_size)[slot] = size;
+      dcsim_at<uint32_t>(c.blk, L.xf_seq)[slot] = seq;
+      dcsim_at<uint32_t>(c.blk, L.xf_meta)[slot] = (uint32_t)dc_sel | ((uint32_t)jt << 3) | ((uint32_t)ing << 4);
+      dcsim_at<uint32_t>(c.blk, L.xf_jid)[slot] = jid;
+      H->n_xfer = slot + 1u;
+      if (slot + 1u > H->max_xfer) H->max_xfer = slot + 1u;
+      const double ct = CAND_T(c)[CAND_XFER];
+      if (t_x < ct || (t_x == ct && seq < CAND_SEQ(c)[CAND_XFER])) {
+        CAND_T(c)[CAND_XFER] = t_x; CAND_SEQ(c)[CAND_XFER] = seq; H->xmin_slot = slot;
+      }
+    }
+  }
+  const double t_a = H->now + dcsim_next_interarrival(c, jt, H->now); /* SIM:591-592 */
+  if (dcsim_schedulable(c, t_a)) {
+    CAND_T(c)[CAND_STREAM0 + stream] = t_a;
+    CAND_SEQ(c)[CAND_STREAM0 + stream] = H->seq++;
+  } else {
+    CAND_T(c)[CAND_STREAM0 + stream] = DCSIM_INF;
+    CAND_SEQ(c)[CAND_STREAM0 + stream] = 0xffffffffu;
+  }
+}
+
+/* SIM:595-678 (lane 0 part): consume pool entry `slot`, start the job or queue it. */
+DCSIM_DEV void dcsim_handle_xfer(dcsim_ctx_t& c, int slot) {
+  const dcsim_spec_t& sp = c.P->spec;
+  const dcsim_layout_t& L = c.P->L;
+  dcsim_hdr_t* H = c.H;
+  double* xt = dcsim_at<double>(c.blk, L.xf_t); double* xs = dcsim_at<double>(c.blk, L.xf_size);
+  uint32_t* xq = dcsim_at<uint32_t>(c.blk, L.xf_seq); uint32_t* xm = dcsim_at<uint32_t>(c.blk, L.xf_meta);
+  uint32_t* xj = dcsim_at<uint32_t>(c.blk, L.xf_jid);
+  const double size = xs[slot];
+  const uint32_t meta = xm[slot], jid = xj[slot];
+  const int d = (int)(meta & 7u), jt = (int)((meta >> 3) & 1u);
+  const uint32_t ing = meta >> 4;
+  const uint32_t last = H->n_xfer - 1u; /* unordered pool: move the last entry into the hole */
+  xt[slot] = xt[last]; xs[slot] = xs[last]; xq[slot] = xq[last]; xm[slot] = xm[last]; xj[slot] = xj[last];
+  H->n_xfer = last;
+  if (sp.dc[d].total_gpus - DCI(c, DI_BUSY)[d] > 0) {
+    dcsim_start_by_rule(c, sp.xfer_rule, true, d, jt, size, jid, ing);
+    dcsim_refresh_power(c, d);
+  } else {
+    dcsim_enqueue(c, d, jt, size, jid, ing); /* SIM:678 */
+  }
+}
+
+/* SIM:701-927 minus RL/elastic branches (lane 0 part, after the record was read and before it is erased). */
+DCSIM_DEV void dcsim_finish_account(dcsim_ctx_t& c, int d, int slot) {
+  const dcsim_spec_t& sp = c.P->spec;
+  const dcsim_layout_t& L = c.P->L;
+  dcsim_hdr_t* H = c.H;
+  const int i = d * L.cap_run + slot;
+  const uint32_t meta = dcsim_at<uint32_t>(c.blk, L.rn_meta)[i];
+  const int g = (int)(meta & 0xffffu), jt = (int)((meta >> 16) & 1u);
+  int32_t* busy = DCI(c, DI_BUSY) + d;
+  *busy = *busy - g > 0 ? *busy - g : 0; /* SIM:707 */
+  const double now = H->now;
+  DCF(c, DF_ACC_UNIT)[d] += dcsim_at<double>(c.blk, L.rn_tpt)[i] * fmod(now, sp.log_interval); /* SIM:711 */
+  const double lat = now - dcsim_at<double>(c.blk, L.rn_start)[i]; /* SIM:820 */
+  H->lat_sum += lat;
+  if (jt == DCSIM_JT_INFERENCE) { H->lat_sum_inf += lat; H->n_fin_inf++; } else { H->lat_sum_trn += lat; H->n_fin_trn++; }
+  const double f_used = dcsim_at<double>(c.blk, L.rn_f)[i];
+  if (c.is_logged && c.P->rec.jobs) { /* job_log.csv row, SIM:815-823 */
+    const uint32_t r = c.P->rec.counts[1];
+    if (r < c.P->rec.jobs_cap) {
+      dcsim_job_rec_t* o = c.P->rec.jobs + r;
+      o->jid = dcsim_at<uint32_t>(c.blk, L.rn_jid)[i]; o->ingress = (uint8_t)(meta >> 17); o->jtype = (uint8_t)jt;
+      o->dc = (uint8_t)d; o->n_gpus = (uint8_t)g; o->size = dcsim_at<double>(c.blk, L.rn_size)[i];
+      o->f_used = f_used; o->start_s = dcsim_at<double>(c.blk, L.rn_start)[i]; o->finish_s = now;
+    }
+    c.P->rec.counts[1] = r + 1u;
+  }
+  if (sp.deq_rule == DCSIM_START_BANDIT) { /* learners.py:38-42 with cost = E_pred (SIM:716, 826-827) */
+    const dcsim_dc_t& cfg = sp.dc[d];
+    const double E_pred = dcsim_at<double>(c.blk, L.rn_pw)[i] * dcsim_step_time(g, f_used, cfg.coeffs[jt]);
+    for (int q = 0; q < cfg.n_freq; ++q) {
+      if (cfg.freq_levels[q] == f_used) {
+        dcsim_at<uint32_t>(c.blk, L.bandit_n)[(d * 2 + jt) * DCSIM_MAX_FREQ + q] += 1u;
+        dcsim_at<double>(c.blk, L.bandit_s)[(d * 2 + jt) * DCSIM_MAX_FREQ + q] += -E_pred;
+        break;
+      }
+    }
+  }
+}
+
+/* SIM:840-927: start queued jobs while GPUs are free, inference first when inf_priority. */
+DCSIM_DEV void dcsim_dequeue_loop(dcsim_ctx_t& c, int d) {
+  const dcsim_spec_t& sp = c.P->spec;
+  while (sp.dc[d].total_gpus - DCI(c, DI_BUSY)[d] > 0 && c.H->status == 0u) {
+    int jt;
+    if (sp.inf_priority && dcsim_queue_len(c, d, 0) > 0) jt = 0;
+    else if (dcsim_queue_len(c, d, 1) > 0) jt = 1;
+    else break;
+    const dcsim_qent_t e = dcsim_dequeue(c, d, jt);
+    dcsim_start_by_rule(c, sp.deq_rule, false, d, jt, e.size, e.jid, e.ing);
+  }
+}
+
+/* SIM:929-949 + the :221-225 heuristic of _control.  DC-parallel: one DC per lane. */
+DCSIM_DEV void dcsim_handle_log(dcsim_ctx_t& c) {
+  const dcsim_spec_t& sp = c.P->spec;
+  const dcsim_layout_t& L = c.P->L;
+  const double interval = sp.log_interval;
+  for (int d = c.lane; d < sp.n_dc; d += DCSIM_LANES) {
+    if (sp.control_lower_idle && DCI(c, DI_BUSY)[d] == 0 && sp.dc[d].n_freq > 0) {
+      double m = sp.dc[d].freq_levels[0];
+      for (int q = 1; q < sp.dc[d].n_freq; ++q) m = sp.dc[d].freq_levels[q] < m ? sp.dc[d].freq_levels[q] : m;
+      DCF(c, DF_CUR_FREQ)[d] = m;
+    }
+  }
+  dcsim_warp_sync();
+  for (int d = c.lane; d < sp.n_dc; d += DCSIM_LANES) {
+    const int n = DCI(c, DI_NRUN)[d];
+    const double* tpt = dcsim_at<double>(c.blk, L.rn_tpt) + d * L.cap_run;
+    const uint32_t* meta = dcsim_at<uint32_t>(c.blk, L.rn_meta) + d * L.cap_run;
+    double acc = DCF(c, DF_ACC_UNIT)[d];
+    int run_inf = 0;
+    for (int i = 0; i < n; ++i) { acc += tpt[i] * interval; run_inf += ((meta[i] >> 16) & 1u) ? 0 : 1; } /* SIM:941-942 */
+    DCF(c, DF_ACC_UNIT)[d] = acc;
+    if (c.is_logged && c.P->rec.cluster) { /* cluster_log.csv row, SIM:944-948; rows of one tick are DC-ordered */
+      const uint32_t r = c.P->rec.counts[2] + (uint32_t)d;
+      if (r < c.P->rec.cluster_cap) {
+        dcsim_cluster_rec_t* o = c.P->rec.cluster + r;
+        o->time_s = c.H->now; o->freq = DCF(c, DF_CUR_FREQ)[d]; o->util_gpu_time = DCF(c, DF_UTIL_TIME)[d];
+        o->util_begin_ts = DCF(c, DF_UTIL_BEGIN)[d]; o->acc_job_unit = acc; o->power_w = DCF(c, DF_POWER)[d];
+        o->energy_j = DCF(c, DF_ENERGY)[d]; o->dc = d; o->busy = DCI(c, DI_BUSY)[d]; o->run_total = n;
+        o->run_inf = run_inf; o->q_inf = dcsim_queue_len(c, d, 0); o->q_train = dcsim_queue_len(c, d, 1);
+      }
+    }
+  }
+  dcsim_warp_sync();
+  if (c.lane == 0) {
+    if (c.is_logged && c.P->rec.cluster) c.P->rec.counts[2] += (uint32_t)sp.n_dc;
+    const double t = c.H->now + interval; /* SIM:949 */
+    if (dcsim_schedulable(c, t)) { CAND_T(c)[CAND_LOG] = t; CAND_SEQ(c)[CAND_LOG] = c.H->seq++; }
+    else { CAND_T(c)[CAND_LOG] = DCSIM_INF; CAND_SEQ(c)[CAND_LOG] = 0xffffffffu; }
+  }
+  dcsim_warp_sync();
+}
+
+/* ================================================================================================
+ * Replica life cycle
+ * ============================================================================================== */
+/* SIM:31-157, the parts that touch simulation state: zeroed DCs at default_freq, one pending arrival per
+ * (ingress, job type) in dict order inf-then-trn, then the first log tick. */
+DCSIM_DEV void dcsim_replica_init(dcsim_ctx_t& c) {
+  const dcsim_spec_t& sp = c.P->spec;
+  const dcsim_layout_t& L = c.P->L;
+  for (int i = c.lane; i < L.total_bytes / 4; i += DCSIM_LANES) dcsim_at<uint32_t>(c.blk, 0)[i] = 0u;
+  dcsim_warp_sync();
+  for (int i = c.lane; i < CAND_N; i += DCSIM_LANES) { CAND_T(c)[i] = DCSIM_INF; CAND_SEQ(c)[i] = 0xffffffffu; }
+  for (int d = c.lane; d < sp.n_dc; d += DCSIM_LANES) {
+    DCF(c, DF_CUR_FREQ)[d] = sp.dc[d].default_freq; /* models.py:76 */
+    DCI(c, DI_FMIN_SLOT)[d] = -1;
+    DCF(c, DF_POWER)[d] = (double)sp.dc[d].total_gpus * (sp.dc[d].power_gating ? sp.dc[d].p_sleep : sp.dc[d].p_idle);
+  }
+  dcsim_warp_sync();
+  c.rng_valid = 0u; c.rng_base = 0u; c.sblk_idx = 0xffffffffu;
+  for (int s = 0; s < 2 * sp.n_ing; ++s) { /* SIM:154-156 */
+    dcsim_rng_ensure(c, c.H->rng_pos);
+    if (c.lane == 0) {
+      const double t = 0.0 + dcsim_next_interarrival(c, s & 1, 0.0);
+      if (dcsim_schedulable(c, t)) { CAND_T(c)[CAND_STREAM0 + s] = t; CAND_SEQ(c)[CAND_STREAM0 + s] = c.H->seq++; }
+    }
+    dcsim_warp_sync();
+  }
+  if (c.lane == 0) {
+    const double t = 0.0 + sp.log_interval; /* SIM:157 */
+    if (dcsim_schedulable(c, t)) { CAND_T(c)[CAND_LOG] = t; CAND_SEQ(c)[CAND_LOG] = c.H->seq++; }
+    c.H->xmin_slot = 0xffffffffu;
+    c.H->initialized = 1u;
+  }
+  dcsim_warp_sync();
+}
+
+/* SIM:469-475: util to end_time, then accrue_energy(end_time) WITHOUT power_fn => models.py:82-91. */
+DCSIM_DEV void dcsim_replica_tail(dcsim_ctx_t& c) {
+  const dcsim_spec_t& sp = c.P->spec;
+  const double end = sp.end_time;
+  for (int d = c.lane; d < sp.n_dc; d += DCSIM_LANES) {
+    const dcsim_dc_t& cfg = sp.dc[d];
+    const int busy = DCI(c, DI_BUSY)[d];
+    const double ul = DCF(c, DF_UTIL_LAST)[d];
+    if (0.0 < ul && ul < end) {
+      DCF(c, DF_UTIL_TIME)[d] += (double)busy * (end - ul);
+      DCF(c, DF_UTIL_LAST)[d] = end;
+    }
+    const double le = DCF(c, DF_LAST_E_T)[d];
+    if (le == 0.0) {
+      DCF(c, DF_LAST_E_T)[d] = end;
+    } else {
+      double dt = end - le; dt = dt > 0.0 ? dt : 0.0;
+      const double f = DCF(c, DF_CUR_FREQ)[d];
+      const double fa = cfg.alpha == 3.0 ? dcsim_cube(f) : pow(f, cfg.alpha);
+      const double p_active = (double)busy * (cfg.p_idle + cfg.p_peak * fa);
+      const double p_idle = (double)(cfg.total_gpus - busy) * (cfg.power_gating ? cfg.p_sleep : cfg.p_idle);
+      DCF(c, DF_ENERGY)[d] += (p_active + p_idle) * dt;
+      DCF(c, DF_LAST_E_T)[d] = end;
+    }
+  }
+  dcsim_warp_sync();
+}
+
+/* SIM:423-467: the event loop.  Returns the number of events processed by this call. */
+DCSIM_DEV uint32_t dcsim_replica_run(dcsim_ctx_t& c) {
+  const dcsim_spec_t& sp = c.P->spec;
+  const dcsim_layout_t& L = c.P->L;
+  const uint64_t budget = c.P->max_events;
+  uint32_t done_here = 0u;
+  bool finished = false;
+  for (;;) {
+    if (budget && done_here >= budget) break;
+    if (c.H->status != 0u) break; /* a capacity overflowed: stop and report, never guess */
+    double t; uint32_t seq;
+    const int win = dcsim_argmin_ts(CAND_T(c), CAND_SEQ(c), CAND_N, c.lane, &t, &seq);
+    if (win < 0) { finished = true; break; }      /* `while self.event_q` */
+    if (t > sp.end_time) { finished = true; break; } /* SIM:427 */
+
+    for (int d = c.lane; d < sp.n_dc; d += DCSIM_LANES) { /* SIM:429-437 */
+      const double ul = DCF(c, DF_UTIL_LAST)[d];
+      if (ul == 0.0) {
+        DCF(c, DF_UTIL_LAST)[d] = t; DCF(c, DF_UTIL_BEGIN)[d] = t;
+      } else {
+        double dt = t - ul; dt = dt > 0.0 ? dt : 0.0;
+        DCF(c, DF_UTIL_TIME)[d] += (double)DCI(c, DI_BUSY)[d] * dt;
+        DCF(c, DF_UTIL_LAST)[d] = t;
+      }
+      const double le = DCF(c, DF_LAST_E_T)[d]; /* models.py:100-106 */
+      if (le == 0.0) {
+        DCF(c, DF_LAST_E_T)[d] = t;
+      } else {
+        double dt = t - le; dt = dt > 0.0 ? dt : 0.0;
+        DCF(c, DF_ENERGY)[d] += DCF(c, DF_POWER)[d] * dt;
+        DCF(c, DF_LAST_E_T)[d] = t;
+      }
+    }
+    ++done_here;
+    const int kind = win < CAND_STREAM0 ? KIND_FINISH : (win < CAND_XFER ? (win & 1) : (win == CAND_XFER ? KIND_XFER : KIND_LOG));
+    if (c.lane == 0) {
+      c.H->now = t; c.H->last_t = t; c.H->n_events++;
+      if (c.is_traced && c.P->rec.trace) {
+        const uint32_t r = c.P->rec.counts[0];
+        if (r < c.P->rec.trace_cap) { c.P->rec.trace[r].t = t; c.P->rec.trace[r].seq = seq; c.P->rec.trace[r].kind = (uint32_t)kind; }
+        c.P->rec.counts[0] = r + 1u;
+      }
+    }
+    dcsim_warp_sync();
+
+    if (kind == KIND_ARR_INF || kind == KIND_ARR_TRN) {
+      dcsim_rng_ensure(c, c.H->rng_pos);
+      if (c.lane == 0) { c.H->ev_arr++; dcsim_handle_arrival(c, win - CAND_STREAM0); }
+      dcsim_warp_sync();
+    } else if (kind == KIND_XFER) {
+      if (c.lane == 0) { c.H->ev_xfer++; dcsim_handle_xfer(c, (int)c.H->xmin_slot); }
+      dcsim_rescan_xfer(c);
+    } else if (kind == KIND_FINISH) {
+      const int d = win - CAND_DC0;
+      const int slot = DCI(c, DI_FMIN_SLOT)[d];
+      if (c.lane == 0) { c.H->ev_fin++; dcsim_finish_account(c, d, slot); }
+      dcsim_running_erase(c, d, slot);
+      if (c.lane == 0) { dcsim_dequeue_loop(c, d); dcsim_refresh_power(c, d); }
+      dcsim_rescan_dc(c, d);
+    } else {
+      if (c.lane == 0) c.H->ev_log++;
+      dcsim_handle_log(c);
+    }
+  }
+  (void)L;
+  if (finished && c.H->done == 0u) {
+    dcsim_replica_tail(c);
+    if (c.lane == 0) c.H->done = 1u;
+    dcsim_warp_sync();
+  }
+  return done_here;
+}
+
+/* Writes the replica's row of the summary array (layout: include/dcsim_b200.h). */
+DCSIM_DEV void dcsim_write_summary(dcsim_ctx_t& c, double* out) {
+  const dcsim_spec_t& sp = c.P->spec;
+  const dcsim_hdr_t* H = c.H;
+  dcsim_warp_sync();
+  for (int i = c.lane; i < DCSIM_SUMMARY_K; i += DCSIM_LANES) out[i] = 0.0;
+  dcsim_warp_sync();
+  if (c.lane == 0) {
+    double tot = 0.0;
+    for (int d = 0; d < sp.n_dc; ++d) tot += DCF(c, DF_ENERGY)[d];
+    out[DCSIM_S_STATUS] = (double)H->status;
+    out[DCSIM_S_EVENTS] = (double)H->n_events;
+    out[DCSIM_S_JOBS_FINISHED] = (double)(H->n_fin_inf + H->n_fin_trn);
+    out[DCSIM_S_JOBS_CREATED] = (double)H->jid;
+    out[DCSIM_S_TOTAL_ENERGY_J] = tot;
+    out[DCSIM_S_LAT_SUM] = H->lat_sum;
+    out[DCSIM_S_LAT_SUM_INF] = H->lat_sum_inf; out[DCSIM_S_FIN_INF] = (double)H->n_fin_inf;
+    out[DCSIM_S_LAT_SUM_TRN] = H->lat_sum_trn; out[DCSIM_S_FIN_TRN] = (double)H->n_fin_trn;
+    out[DCSIM_S_RNG_WORDS] = (double)H->rng_pos;
+    out[DCSIM_S_LAST_T] = H->last_t;
+    out[DCSIM_S_SEQ] = (double)H->seq;
+    out[DCSIM_S_EV_ARRIVAL] = (double)H->ev_arr; out[DCSIM_S_EV_XFER] = (double)H->ev_xfer;
+    out[DCSIM_S_EV_FINISH] = (double)H->ev_fin; out[DCSIM_S_EV_LOG] = (double)H->ev_log;
+    out[DCSIM_S_DONE] = (double)H->done;
+    out[DCSIM_S_MAX_XFER] = (double)H->max_xfer; out[DCSIM_S_MAX_RUN] = (double)H->max_run;
+    out[DCSIM_S_MAX_Q] = (double)H->max_q;
+  }
+  for (int d = c.lane; d < sp.n_dc; d += DCSIM_LANES) {
+    double* o = out + DCSIM_S_DC0 + d * DCSIM_S_DC_STRIDE;
+    o[DCSIM_SD_ENERGY_J] = DCF(c, DF_ENERGY)[d];
+    o[DCSIM_SD_UTIL_GPU_TIME] = DCF(c, DF_UTIL_TIME)[d];
+    o[DCSIM_SD_ACC_JOB_UNIT] = DCF(c, DF_ACC_UNIT)[d];
+    o[DCSIM_SD_BUSY] = (double)DCI(c, DI_BUSY)[d];
+    o[DCSIM_SD_CURRENT_FREQ] = DCF(c, DF_CUR_FREQ)[d];
+    o[DCSIM_SD_Q_INF] = (double)dcsim_queue_len(c, d, 0);
+    o[DCSIM_SD_Q_TRN] = (double)dcsim_queue_len(c, d, 1);
+    o[DCSIM_SD_RUNNING] = (double)DCI(c, DI_NRUN)[d];
+  }
+}
+
+/* One replica, one launch: (init |) resume -> run -> summary.  `blk` is the working copy of the state
+ * block (shared memory on the GPU), already loaded unless `fresh`. */
+DCSIM_DEV uint32_t dcsim_replica_step(const dcsim_kparams_t* P, uint64_t r, char* blk, bool fresh) {
+  dcsim_ctx_t c;
+  c.P = P; c.blk = blk; c.H = reinterpret_cast<dcsim_hdr_t*>(blk); c.lane = dcsim_lane();
+  c.q = P->queues + r * P->L.queue_bytes;
+  c.is_traced = ((int64_t)r == P->rec.trace_replica);
+  c.is_logged = ((int64_t)r == P->rec.log_replica);
+  const uint64_t key = P->seed0 + r;
+  c.key0 = (uint32_t)key; c.key1 = (uint32_t)(key >> 32);
+  c.rng_valid = 0u; c.rng_base = 0u; c.sblk_idx = 0xffffffffu;
+  c.sblk[0] = c.sblk[1] = c.sblk[2] = c.sblk[3] = 0u;
+  if (fresh) dcsim_replica_init(c);
+  uint32_t n = 0u;
+  if (c.H->done == 0u) n = dcsim_replica_run(c);
+  dcsim_write_summary(c, P->summary + r * DCSIM_SUMMARY_K);
+  dcsim_warp_sync();
+  return n;
+}

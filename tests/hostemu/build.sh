@@ -1,0 +1,7 @@
+#!/bin/sh
+# TEST-ONLY build of the single-lane host emulation (see hostemu.cpp).
+set -e
+cd "$(dirname "$0")"
+mkdir -p _build
+g++ -O2 -fPIC -shared -std=gnu++17 -ffp-contract=off -fno-fast-math -Wall -Wno-unused-function -Wno-unknown-pragmas \
+    -o _build/libdcsim_hostemu.so hostemu.cpp -lm

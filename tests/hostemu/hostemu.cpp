@@ -1,0 +1,59 @@
+/*
+ * TEST-ONLY.  Single-lane host build of distributed_cluster_gpus_b200/csrc/dcsim_core.cuh
+ * (DCSIM_LANES = 1; warp collectives are identities).  Lets the CPU test-suite run the *device source's*
+ * handler logic, state-block layout, Philox window, FIFO rings and resume path against the oracle where no
+ * GPU exists.  It is not part of, linked into, or reachable from the product library — the product fails
+ * loudly without CUDA.  What it cannot show (lane mapping, __syncwarp placement, REDUX) is what the
+ * `-m gpu` parity tests are for.
+ */
+#define DCSIM_HOST_EMU 1
+#include "../../distributed_cluster_gpus_b200/csrc/dcsim_core.cuh"
+
+#include <stdlib.h>
+
+extern "C" {
+
+size_t hostemu_sizeof_spec(void) { return sizeof(dcsim_spec_t); }
+
+/* Runs n replicas; each advance call processes `chunk_events` events per replica (0 = to the end) and the
+ * state block round-trips through "HBM" between calls exactly as the kernel's stage-in/stage-out does.
+ * trace/job/cluster recorders apply to `rec_replica` (-1 = none); counts[3] receives the row counts. */
+long long hostemu_run_batch(const void* spec_blob, size_t spec_bytes, uint64_t n_replicas, uint64_t seed0,
+                            uint64_t chunk_events, double* out_summaries, int64_t rec_replica,
+                            dcsim_trace_rec_t* trace, uint32_t trace_cap, dcsim_job_rec_t* jobs, uint32_t jobs_cap,
+                            dcsim_cluster_rec_t* cluster, uint32_t cluster_cap, uint32_t* counts, int32_t* layout_out) {
+  if (!spec_blob || spec_bytes != sizeof(dcsim_spec_t)) return -1;
+  dcsim_kparams_t* P = (dcsim_kparams_t*)calloc(1, sizeof(dcsim_kparams_t));
+  memcpy(&P->spec, spec_blob, sizeof(dcsim_spec_t));
+  if (P->spec.magic != DCSIM_SPEC_MAGIC) { free(P); return -1; }
+  dcsim_make_layout(&P->spec, &P->L);
+  if (layout_out) { layout_out[0] = P->L.total_bytes; layout_out[1] = P->L.cap_xfer; layout_out[2] = P->L.cap_run;
+                    layout_out[3] = P->L.cap_q[0]; layout_out[4] = P->L.cap_q[1]; }
+  uint32_t local_counts[4] = {0, 0, 0, 0};
+  P->rec.trace = trace; P->rec.jobs = jobs; P->rec.cluster = cluster; P->rec.counts = counts ? counts : local_counts;
+  P->rec.trace_cap = trace_cap; P->rec.jobs_cap = jobs_cap; P->rec.cluster_cap = cluster_cap;
+  P->rec.trace_replica = trace ? rec_replica : -1; P->rec.log_replica = (jobs || cluster) ? rec_replica : -1;
+  if (counts) counts[0] = counts[1] = counts[2] = 0;
+  P->n_replicas = n_replicas; P->seed0 = seed0; P->max_events = chunk_events;
+  P->end_eps = P->spec.end_time + 1e-9;
+  P->state = (char*)calloc(n_replicas, (size_t)P->L.total_bytes);
+  P->queues = (char*)calloc(n_replicas, (size_t)P->L.queue_bytes + 16);
+  P->summary = out_summaries;
+  char* work = (char*)malloc((size_t)P->L.total_bytes);
+  long long total = 0;
+  for (uint64_t r = 0; r < n_replicas; ++r) {
+    char* home = P->state + r * (uint64_t)P->L.total_bytes;
+    for (int guard = 0; guard < 100000000; ++guard) {
+      const bool fresh = ((dcsim_hdr_t*)home)->initialized == 0u;
+      if (!fresh) memcpy(work, home, (size_t)P->L.total_bytes); /* stage in */
+      total += dcsim_replica_step(P, r, work, fresh);
+      memcpy(home, work, (size_t)P->L.total_bytes);             /* stage out */
+      const dcsim_hdr_t* H = (const dcsim_hdr_t*)home;
+      if (H->done || H->status || chunk_events == 0) break;
+    }
+  }
+  free(work); free(P->state); free(P->queues); free(P);
+  return total;
+}
+
+} /* extern "C" */

@@ -1,0 +1,58 @@
+"""TEST-ONLY ctypes access to the single-lane host build of the device core (tests/hostemu/hostemu.cpp)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_DIR = os.path.join(_HERE, "hostemu")
+_SO = os.path.join(_DIR, "_build", "libdcsim_hostemu.so")
+_CORE = os.path.join(_HERE, "..", "distributed_cluster_gpus_b200", "csrc", "dcsim_core.cuh")
+_HDR = os.path.join(_HERE, "..", "include", "dcsim_b200.h")
+SUMMARY_K = 24 + 8 * 8
+TRACE_DTYPE = np.dtype([("t", "<f8"), ("seq", "<u4"), ("kind", "<u4")])
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        srcs = (os.path.join(_DIR, "hostemu.cpp"), _CORE, _HDR)
+        if not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
+            subprocess.run([os.path.join(_DIR, "build.sh")], check=True, capture_output=True)
+        L = C.CDLL(_SO)
+        L.hostemu_sizeof_spec.restype = C.c_size_t
+        L.hostemu_run_batch.restype = C.c_longlong
+        L.hostemu_run_batch.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p,
+                                        C.c_int64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p,
+                                        C.c_uint32, C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def run_batch(spec_bytes, n_replicas, seed0, chunk_events=0, trace_cap=0, rec_replica=-1, job_dtype=None,
+              jobs_cap=0, cluster_dtype=None, cluster_cap=0):
+    out = np.zeros((n_replicas, SUMMARY_K))
+    buf = C.create_string_buffer(spec_bytes, len(spec_bytes))
+    trace = np.zeros(max(trace_cap, 1), dtype=TRACE_DTYPE)
+    jobs = np.zeros(max(jobs_cap, 1), dtype=job_dtype) if job_dtype is not None else None
+    cluster = np.zeros(max(cluster_cap, 1), dtype=cluster_dtype) if cluster_dtype is not None else None
+    counts = np.zeros(4, dtype=np.uint32)
+    layout = np.zeros(8, dtype=np.int32)
+    total = lib().hostemu_run_batch(buf, len(spec_bytes), n_replicas, seed0 & (2**64 - 1), chunk_events,
+                                    out.ctypes.data, rec_replica,
+                                    trace.ctypes.data if trace_cap else None, trace_cap,
+                                    jobs.ctypes.data if jobs is not None and jobs_cap else None, jobs_cap,
+                                    cluster.ctypes.data if cluster is not None and cluster_cap else None, cluster_cap,
+                                    counts.ctypes.data, layout.ctypes.data)
+    if total < 0:
+        raise ValueError("hostemu rejected the spec blob")
+    res = {"summary": out, "events": int(total), "trace": trace[:min(int(counts[0]), trace_cap)],
+           "layout": {"total_bytes": int(layout[0]), "cap_xfer": int(layout[1]), "cap_run": int(layout[2]),
+                      "cap_q_inf": int(layout[3]), "cap_q_trn": int(layout[4])}}
+    if jobs is not None:
+        res["jobs"] = jobs[:min(int(counts[1]), jobs_cap)]
+    if cluster is not None:
+        res["cluster"] = cluster[:min(int(counts[2]), cluster_cap)]
+    return res
