@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py — simulated events/sec of the batched multi-DC event engine (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps 3 --warmup 3            # this repo's CUDA path
+    python bench.py --impl reference --gpus 1 --steps 3 --warmup 3   # the reference algorithm on host cores
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W               # N>1: one rank per GPU, weak scaling
+
+A "step" = one full pass of the hot path over one batch: every one of the R replicas per GPU is simulated from
+t = 0 to end_time (reset -> advance kernel -> on-device summary reduction [-> one NCCL all-reduce of 16 doubles]).
+Workload (config.workload) = BASELINE.json configs[2]: 4 DC x 64 sim-GPUs, sinusoid inference (rate 10, amp 0.6,
+period 3600 s) + Poisson training (rate 1) per ingress, default_policy/energy_aware, 65 536 replicas per GPU,
+120 simulated seconds (~17 k events per replica).
+
+JSON keys beyond the base contract:
+  roofline      algorithmic HBM bytes (96 + 76*D per event) / advance-kernel time vs measured HBM peak
+  cpu_baseline  the oracle (C restatement of the reference loop) on the box's host cores, bounded sample
+  e2e           same metric through the drop-in MultiIngressPaperSimulator(...).run() — host spec in, kernel,
+                summaries + CSV rows back in host memory — timed on the host clock
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+from distributed_cluster_gpus_b200 import scenarios as SC, sharding, spec as S  # noqa: E402
+
+METRIC = "simulated events/sec, 4-DC x 64-sim-GPU, 65536 replicas per GPU"
+UNIT = "events/s"
+HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def workload(args):
+    sc = dict(SC.BY_NAME[args.scenario]) if args.scenario in SC.BY_NAME else dict(SC.CFG3)
+    if args.duration:
+        sc["duration"] = float(args.duration)
+    return sc
+
+
+def config_dict(sc, args, world, extra=None):
+    cfg = {"workload": f"{sc['n_dc']} DC x {sc['gpus_per_dc']} sim-GPUs, inf {sc['inf']['mode']} rate {sc['inf']['rate']} "
+                       f"amp {sc['inf']['amp']} period {sc['inf']['period']}s + trn {sc['trn']['mode']} rate {sc['trn']['rate']} "
+                       f"per ingress, algo {sc['algo']}/{sc['policy']}, {sc['duration']:.0f} simulated s",
+           "scenario": sc["name"], "replicas_per_gpu": args.replicas, "replicas_total": args.replicas * world,
+           "sim_duration_s": sc["duration"], "parallelism": f"replica-sharded x{world} (no data-path collective)",
+           "l2": "working set (state blocks + FIFO rings, GBs) is far larger than the 126 MB L2; no flush needed"}
+    cfg.update(extra or {})
+    return cfg
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+def measured_traffic():
+    """dram bytes per advance launch from the committed ncu capture of this same command, if one exists."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc, self.thread = gpu_index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, pw, reasons = [], [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for row in self.rows:
+            parts = [p.strip() for p in row.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1])); smax.append(float(parts[2])); pw.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on host cores (the reference is pure Python and cannot travel)
+# ---------------------------------------------------------------------------------------------------
+def oracle_rate(sc, n_replicas, threads, seed=123):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_lib
+    oracle_lib.build()
+    blob = SC.to_spec(sc).to_bytes()
+    t0 = time.perf_counter()
+    _, events = oracle_lib.run_batch(blob, n_replicas, seed, 0, oracle_lib.RNG_PHILOX, threads)
+    dt = time.perf_counter() - t0
+    return events, dt
+
+
+def cpu_baseline(sc, target_s=12.0):
+    cores = os.cpu_count() or 1
+    oracle_rate(sc, cores, cores)                            # load + page in
+    ev, dt = oracle_rate(sc, cores, cores)                   # calibration: one replica per thread
+    n = int(max(cores, min(16384, cores * max(1.0, target_s / max(dt, 1e-3)))))
+    n -= n % cores
+    ev, dt = oracle_rate(sc, n, cores, seed=1000)
+    return {"value": ev / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} replicas of the same workload ({ev} events) in {dt:.1f} s on {cores} threads; "
+                      "oracle/dcsim_oracle.c = C restatement of the reference's Python loop (the Python original "
+                      "measured 7-20 k events/s/core on this scenario, tests/golden/*.json ref_wall_s)"}
+
+
+def run_reference_arm(args, world, rank):
+    if rank != 0:
+        return
+    sc = workload(args)
+    cores = os.cpu_count() or 1
+    oracle_rate(sc, cores, cores)                                              # load + page in
+    ev, dt = oracle_rate(sc, cores, cores)                                     # calibration: one replica per thread
+    n = int(max(cores, min(8192, cores * max(1.0, 8.0 / max(dt, 1e-3)))))     # ~8 s of CPU work per step
+    n -= n % cores
+    for _ in range(args.warmup):
+        oracle_rate(sc, max(cores, n // 8), cores)
+    t0 = time.perf_counter()
+    events = 0
+    for i in range(args.steps):
+        e, _ = oracle_rate(sc, n, cores, seed=123 + i * n)
+        events += e
+    total = time.perf_counter() - t0
+    value = events / total
+    sample = f"{n} replicas per step ({events // max(args.steps, 1)} events) on {cores} host threads, oracle port of the reference loop"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * total / max(args.steps, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(sc, args, world, {"sample_replicas_per_step": n}),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_b200(args, world, rank, local_rank):
+    import torch
+    import torch.distributed as dist
+    from distributed_cluster_gpus_b200.engine import BatchedEngine
+    from distributed_cluster_gpus_b200.configs import paper_config as pc
+    from distributed_cluster_gpus_b200.simcore.simulator_paper_multi import MultiIngressPaperSimulator
+    import logging
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    sc = workload(args)
+    sp = SC.to_spec(sc)
+    R = args.replicas
+    first = rank * R
+    stream = torch.cuda.current_stream()
+    eng = BatchedEngine(sp, R, base_seed=123, first_replica_id=first, device=local_rank, cuda_stream=stream.cuda_stream)
+    info = eng.launch_info()
+    agg = torch.zeros((args.steps + args.warmup + 1, S.AGG_K), dtype=torch.float64, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(i, k0=None, k1=None):
+        eng.reset(123 + i * R * world, first)
+        if k0 is not None:
+            k0.record(stream)
+        eng.advance(0, sync=False)
+        if k1 is not None:
+            k1.record(stream)
+        eng.reduce_into(agg[i].data_ptr())
+        if world > 1:
+            dist.all_reduce(agg[i], op=dist.ReduceOp.SUM)          # the run's only collective: 16 doubles over NVLink
+
+    for i in range(args.warmup):
+        one_step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    k0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    k1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0.record(stream)
+    for j in range(args.steps):
+        one_step(args.warmup + j, k0[j], k1[j])
+    t1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    elapsed_ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device="cuda")
+    kernel_ms = [a.elapsed_time(b) for a, b in zip(k0, k1)]
+    if world > 1:
+        dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
+    elapsed_s = float(elapsed_ms.item()) / 1000.0
+    steps_agg = agg[args.warmup: args.warmup + args.steps].cpu().numpy()       # already summed over ranks
+    events_total = float(steps_agg[:, S.A_EVENTS].sum())
+    failed = float(steps_agg[:, S.A_FAILED].sum())
+    if world > 1:
+        pass
+    else:
+        pass
+    value = events_total / elapsed_s
+
+    # ---- roofline of the dominant kernel (advance), this rank ------------------------------------
+    local_events_per_launch = events_total / args.steps / world
+    b_alg = 96 + 76 * sc["n_dc"]
+    kms = sum(kernel_ms) / len(kernel_ms)
+    achieved = local_events_per_launch * b_alg / (kms / 1000.0) / 1e9
+    peak, peak_src = hbm_peak()
+    traffic = measured_traffic()
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+                "kernel": "dcsim_advance_kernel", "kernel_ms": kms, "events_per_launch": local_events_per_launch,
+                "algorithmic_bytes_per_event": b_alg, "peak_source": peak_src,
+                "note": "path is warp-serial-latency bound, not HBM bound (SURVEY.md §8d); see DESIGN.md for the "
+                        "secondary bound (issue slots) and profiles/ for ncu evidence",
+                "events_per_s_per_resident_warp": local_events_per_launch / (kms / 1000.0) / max(1, info["resident_warps_per_sm"] * info["sm_count"])}
+
+    # ---- e2e through the drop-in public API (host buffers in and out) -----------------------------
+    kw = SC.build_inputs(sc)
+    log_dir = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else "/tmp", f"dcsim_bench_{os.getpid()}")
+    eng.close()
+    e2e_steps = max(1, min(args.steps, 2))
+
+    def e2e_step(i):
+        kw_i = SC.build_inputs(sc)
+        sim = MultiIngressPaperSimulator(router_policy=pc.build_router_policy(), logger=logging.getLogger("bench"),
+                                         sim_duration=sc["duration"], log_interval=sc["log_interval"], log_path=log_dir,
+                                         rng_seed=5000 + i * R * world, algo=sc["algo"], show_progress=False,
+                                         replicas=R, device=local_rank, first_replica_id=first, **kw_i)
+        sim.run()
+        vec = torch.from_numpy(sharding.aggregate_rows(sim.summary)).cuda()
+        sharding.allreduce_aggregate(vec)
+        return vec.cpu().numpy(), sim
+
+    e2e_step(-1)                                                               # warm the allocator / page tables
+    barrier()
+    w0 = time.perf_counter()
+    e2e_events = 0.0
+    for i in range(e2e_steps):
+        a, sim = e2e_step(i)
+        e2e_events += a[S.A_EVENTS]
+    barrier()
+    w = torch.tensor([time.perf_counter() - w0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(w, op=dist.ReduceOp.MAX)
+    e2e_value = e2e_events / float(w.item())
+    csv_bytes = sum(os.path.getsize(p) for p in (sim.cluster_log_path, sim.job_log_path) if os.path.exists(p))
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(len(sp.to_bytes()) + 512),
+           "d2h_bytes_per_step": int(R * S.SUMMARY_K * 8 + csv_bytes), "steps": e2e_steps,
+           "api": "MultiIngressPaperSimulator(..., replicas=R).run(): flatten -> dcsim_create -> dcsim_advance -> "
+                  "dcsim_fetch_summary -> DataCenter write-back + cluster_log.csv/job_log.csv of replica 0",
+           "ms_per_step": 1000.0 * float(w.item()) / e2e_steps}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1000.0 * elapsed_s / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config_dict(sc, args, world, {"events_per_step": events_total / args.steps,
+                                                        "failed_replicas": failed, "launch": info}),
+                "roofline": roofline, "cpu_baseline": cpu_baseline(sc) if world == 1 and not args.no_cpu_baseline else None,
+                "e2e": e2e, "gpu_launches": 2 * args.steps, "clocks": clocks, "impl": "b200"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--replicas", type=int, default=65536, help="replicas per GPU")
+    ap.add_argument("--scenario", type=str, default="cfg3_4x64_sinusoid_120s")
+    ap.add_argument("--duration", type=float, default=None, help="override the scenario's simulated seconds")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, world, rank)
+        return
+    run_b200(args, world, rank, local_rank)
+
+
+if __name__ == "__main__":
+    main()

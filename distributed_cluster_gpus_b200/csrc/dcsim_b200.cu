@@ -226,6 +226,16 @@ int dcsim_create(const void* spec_blob, size_t spec_bytes, uint64_t n_replicas, 
   return DCSIM_OK;
 }
 
+int dcsim_reset(dcsim_t* h, uint64_t base_seed, uint64_t first_replica_id) {
+  if (!h) return DCSIM_E_INVALID;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  /* hdr.initialized == 0 marks a fresh replica; the FIFOs need no clearing (head == tail == 0) */
+  CUDA_TRY(h, cudaMemsetAsync(h->d_state, 0, (size_t)h->n_replicas * (size_t)h->L.total_bytes, h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_counts, 0, 4 * sizeof(uint32_t), h->stream));
+  h->seed0 = base_seed + first_replica_id;
+  return DCSIM_OK;
+}
+
 int dcsim_set_stream(dcsim_t* h, void* cuda_stream) {
   if (!h) return DCSIM_E_INVALID;
   CUDA_TRY(h, cudaSetDevice(h->device));

@@ -86,7 +86,7 @@ enum { /* per-DC i32 arrays */
 #define DCSIM_RNG_MARGIN 24u  /* refill when fewer than this many staged words remain at an arrival */
 /* A rejection loop that has not accepted after this many draws stops the replica with DCSIM_ST_RNG_RUNAWAY
  * instead of spinning (the reference would spin: e.g. arrivals.py:41-45 under a clipped lambda). */
-#define DCSIM_REJECTION_LIMIT 65536
+#define DCSIM_REJECTION_LIMIT (1 << 24)
 
 /* Persistent scalars of a replica (first bytes of its state block). */
 struct dcsim_hdr_t {

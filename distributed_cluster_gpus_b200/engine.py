@@ -1,0 +1,165 @@
+"""BatchedEngine — thin owner of one ``dcsim_t`` handle (one CUDA device, one stream, R replicas)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+from . import spec as S
+
+TRACE_DTYPE = np.dtype([("t", "<f8"), ("seq", "<u4"), ("kind", "<u4")])
+JOB_DTYPE = np.dtype([("jid", "<u4"), ("ingress", "u1"), ("jtype", "u1"), ("dc", "u1"), ("n_gpus", "u1"),
+                      ("size", "<f8"), ("f_used", "<f8"), ("start_s", "<f8"), ("finish_s", "<f8")], align=True)
+CLUSTER_DTYPE = np.dtype([("time_s", "<f8"), ("freq", "<f8"), ("util_gpu_time", "<f8"), ("util_begin_ts", "<f8"),
+                          ("acc_job_unit", "<f8"), ("power_w", "<f8"), ("energy_j", "<f8"), ("dc", "<i4"),
+                          ("busy", "<i4"), ("run_total", "<i4"), ("run_inf", "<i4"), ("q_inf", "<i4"),
+                          ("q_train", "<i4")], align=True)
+assert TRACE_DTYPE.itemsize == C.sizeof(S.TraceRec) and JOB_DTYPE.itemsize == C.sizeof(S.JobRec)
+assert CLUSTER_DTYPE.itemsize == C.sizeof(S.ClusterRec)
+
+
+class BatchedEngine:
+    """R independent replicas of one scenario on one GPU.
+
+    Replica r uses Philox key ``base_seed + first_replica_id + r`` — the key the reference would be given as
+    ``rng_seed`` — so results do not depend on how replicas are sharded over GPUs.
+    """
+
+    def __init__(self, spec: S.Spec, n_replicas: int, base_seed: int, first_replica_id: int = 0, device: int = 0,
+                 cuda_stream: int = 0):
+        self._lib = N.load()
+        self._h = C.c_void_p()
+        self.n_replicas = int(n_replicas)
+        self.spec = spec
+        blob = spec.to_bytes()
+        self._blob = C.create_string_buffer(blob, len(blob))
+        N.check(self._lib.dcsim_create(self._blob, len(blob), self.n_replicas, base_seed & (2**64 - 1),
+                                       first_replica_id, device, C.byref(self._h)))
+        if cuda_stream:
+            self.set_stream(cuda_stream)
+        self._trace_cap = self._jobs_cap = self._cluster_cap = 0
+
+    # -- configuration ---------------------------------------------------------------------------
+    def set_stream(self, cuda_stream: int):
+        N.check(self._lib.dcsim_set_stream(self._h, C.c_void_p(cuda_stream)), self._h)
+
+    def reset(self, base_seed: int, first_replica_id: int = 0):
+        """All replicas back to t = 0 with new keys; allocations are kept."""
+        N.check(self._lib.dcsim_reset(self._h, base_seed & (2**64 - 1), first_replica_id), self._h)
+
+    def set_trace(self, replica: int, capacity: int):
+        N.check(self._lib.dcsim_set_trace(self._h, replica, capacity), self._h)
+        self._trace_cap = capacity
+
+    def set_logging(self, replica: int, job_capacity: int, cluster_capacity: int):
+        N.check(self._lib.dcsim_set_logging(self._h, replica, job_capacity, cluster_capacity), self._h)
+        self._jobs_cap, self._cluster_cap = job_capacity, cluster_capacity
+
+    # -- run -------------------------------------------------------------------------------------
+    def advance(self, max_events_per_replica: int = 0, sync: bool = True) -> int:
+        """Every replica processes up to ``max_events_per_replica`` more events (0 = to end_time).
+        With ``sync`` returns the number of events this call processed; otherwise launches and returns -1."""
+        if sync:
+            total = C.c_uint64(0)
+            N.check(self._lib.dcsim_advance(self._h, max_events_per_replica, C.byref(total)), self._h)
+            return int(total.value)
+        N.check(self._lib.dcsim_advance(self._h, max_events_per_replica, None), self._h)
+        return -1
+
+    def all_done(self) -> bool:
+        d = C.c_int(0)
+        N.check(self._lib.dcsim_all_done(self._h, C.byref(d)), self._h)
+        return bool(d.value)
+
+    def summary(self, out=None) -> np.ndarray:
+        """[n_replicas, SUMMARY_K] float64; ``out`` may be a (pinned) preallocated array."""
+        if out is None:
+            out = np.empty((self.n_replicas, S.SUMMARY_K), dtype=np.float64)
+        N.check(self._lib.dcsim_fetch_summary(self._h, C.c_void_p(out.ctypes.data), out.nbytes), self._h)
+        return out
+
+    def fetch_summary_into(self, host_ptr: int, nbytes: int):
+        N.check(self._lib.dcsim_fetch_summary(self._h, C.c_void_p(host_ptr), nbytes), self._h)
+
+    def summary_device_ptr(self) -> int:
+        p = C.c_void_p()
+        N.check(self._lib.dcsim_summary_device_ptr(self._h, C.byref(p)), self._h)
+        return int(p.value)
+
+    def reduce_into(self, device_ptr: int):
+        """Writes the AGG_K-vector (spec.A_*) to device memory; the caller all-reduces it."""
+        N.check(self._lib.dcsim_reduce_summary(self._h, C.c_void_p(device_ptr)), self._h)
+
+    # -- recorders -------------------------------------------------------------------------------
+    def _fetch(self, fn, dtype, cap):
+        arr = np.zeros(max(cap, 1), dtype=dtype)
+        n = C.c_uint32(0)
+        N.check(fn(self._h, C.c_void_p(arr.ctypes.data), cap, C.byref(n)), self._h)
+        return arr[: n.value]
+
+    def trace(self):
+        return self._fetch(self._lib.dcsim_fetch_trace, TRACE_DTYPE, self._trace_cap)
+
+    def job_log(self):
+        return self._fetch(self._lib.dcsim_fetch_job_log, JOB_DTYPE, self._jobs_cap)
+
+    def cluster_log(self):
+        return self._fetch(self._lib.dcsim_fetch_cluster_log, CLUSTER_DTYPE, self._cluster_cap)
+
+    def launch_info(self) -> dict:
+        li = S.LaunchInfo()
+        N.check(self._lib.dcsim_launch_info(self._h, C.byref(li)), self._h)
+        return {name: int(getattr(li, name)) for name, _ in S.LaunchInfo._fields_ if not name.startswith("_")}
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.dcsim_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+STATUS_NAMES = {S.ST_XFER_OVERFLOW: "in-flight transfer pool", S.ST_RUN_OVERFLOW: "running set",
+                S.ST_QUEUE_OVERFLOW: "FIFO queue", S.ST_STALE_OVERFLOW: "stale-event pool",
+                S.ST_RNG_RUNAWAY: "rejection-sampling runaway"}
+
+
+def describe_status(bits: int) -> str:
+    return ", ".join(name for bit, name in STATUS_NAMES.items() if bits & bit) or "ok"
+
+
+def run_to_completion(spec_factory, n_replicas, base_seed, first_replica_id=0, device=0, cuda_stream=0,
+                      max_retries=3, configure=None):
+    """Runs all replicas to end_time.  A replica that overflowed a capacity is never trusted: the whole batch
+    is re-run with that capacity raised (``spec_factory(caps)`` rebuilds the blob).  Returns (engine, summary)."""
+    caps = {}
+    for attempt in range(max_retries + 1):
+        sp = spec_factory(dict(caps))
+        eng = BatchedEngine(sp, n_replicas, base_seed, first_replica_id, device, cuda_stream)
+        if configure:
+            configure(eng)
+        eng.advance(0)
+        summ = eng.summary()
+        bits = int(np.bitwise_or.reduce(summ[:, S.S_STATUS].astype(np.int64)))
+        if bits == 0:
+            return eng, summ
+        eng.close()
+        if bits & S.ST_RNG_RUNAWAY or attempt == max_retries:
+            raise RuntimeError(f"replicas stopped: {describe_status(bits)}")
+        g_max = max(sp.dc[d].total_gpus for d in range(sp.n_dc))
+        if bits & S.ST_RUN_OVERFLOW:
+            caps["cap_run"] = g_max
+        if bits & S.ST_XFER_OVERFLOW:
+            caps["cap_xfer"] = 2 * sp.cap_xfer
+        if bits & S.ST_QUEUE_OVERFLOW:
+            caps["cap_q_inf"], caps["cap_q_trn"] = 2 * sp.cap_q_inf, 2 * sp.cap_q_trn
+    raise AssertionError("unreachable")

@@ -224,6 +224,10 @@ int dcsim_summary_k(void);
 int dcsim_create(const void* spec_blob, size_t spec_bytes, uint64_t n_replicas, uint64_t base_seed,
                  uint64_t first_replica_id, int device, dcsim_t** out);
 
+/* Returns every replica to its freshly-constructed state with new keys (base_seed + first_replica_id + r),
+ * keeping all device allocations.  Asynchronous on the handle's stream. */
+int dcsim_reset(dcsim_t* h, uint64_t base_seed, uint64_t first_replica_id);
+
 /* Launch on a caller-provided cudaStream_t (e.g. torch's current stream) instead of the handle's own. */
 int dcsim_set_stream(dcsim_t* h, void* cuda_stream);
 

@@ -1,0 +1,88 @@
+"""The DEVICE SOURCE (csrc/dcsim_core.cuh) compiled single-lane for the host (tests/hostemu, test-only) against
+the oracle.  On the same libm the two must agree bit for bit on the whole 88-double summary — this pins the
+handler logic, the state-block layout, the Philox window / slow path, the FIFO rings and the resume path
+before any GPU time is spent.  Lane mapping and warp collectives are covered by the -m gpu tests."""
+import numpy as np
+import pytest
+
+from conftest import golden_names
+from distributed_cluster_gpus_b200 import scenarios as SC, spec as S
+
+DEVICE_SUPPORTED = [n for n in golden_names() if not n.startswith("cap_greedy")]
+HIGH_WATER = (S.S_MAX_XFER, S.S_MAX_RUN, S.S_MAX_Q)
+
+
+def _same(a, b):
+    a, b = a.copy(), b.copy()
+    for col in HIGH_WATER:  # the oracle's heap counts xfers differently from the device pool's high-water mark
+        a[..., col] = b[..., col] = 0
+    return np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("name", DEVICE_SUPPORTED)
+def test_device_core_equals_oracle(oracle, hostemu, name):
+    sc = SC.BY_NAME[name]
+    if sc["duration"] > 300 and sc["n_dc"] >= 4:
+        sc = dict(sc, duration=150.0)
+    blob = SC.to_spec(sc).to_bytes()
+    want, total = oracle.run_batch(blob, 3, 1000, 7)
+    got = hostemu.run_batch(blob, 3, 1000 + 7)
+    assert got["events"] == total
+    assert np.all(got["summary"][:, S.S_STATUS] == 0)
+    assert _same(got["summary"], want), np.argwhere(got["summary"] != want)[:10]
+
+
+@pytest.mark.parametrize("chunk", [1, 7, 1000])
+def test_resume_is_invariant(oracle, hostemu, chunk):
+    """advance() in chunks (state block staged out and in between launches) == one advance to the end."""
+    sc = dict(SC.CFG3, duration=25.0 if chunk == 1 else 60.0)
+    blob = SC.to_spec(sc).to_bytes()
+    whole = hostemu.run_batch(blob, 2, 5)
+    parts = hostemu.run_batch(blob, 2, 5, chunk_events=chunk)
+    assert np.array_equal(whole["summary"], parts["summary"])
+    assert whole["events"] == parts["events"]
+
+
+def test_trace_matches_oracle(oracle, hostemu):
+    blob = SC.to_spec(SC.BY_NAME["sweep_joint_nf"]).to_bytes()
+    sim = oracle.OracleSim(blob, 321, trace_cap=5000)
+    sim.advance(5000)
+    want = sim.trace()
+    got = hostemu.run_batch(blob, 2, 320, trace_cap=5000, rec_replica=1)["trace"]
+    assert len(got) == len(want) == 5000
+    assert np.array_equal(got["t"], want["t"]) and np.array_equal(got["seq"], want["seq"])
+    assert np.array_equal(got["kind"], want["kind"])
+
+
+def test_job_and_cluster_logs_match_oracle(oracle, hostemu):
+    from distributed_cluster_gpus_b200.engine import CLUSTER_DTYPE, JOB_DTYPE
+    blob = SC.to_spec(SC.BY_NAME["ragged_3dc_12_5_40"]).to_bytes()
+    sim = oracle.OracleSim(blob, 11, joblog_cap=20000, clog_cap=2000)
+    sim.advance(0)
+    got = hostemu.run_batch(blob, 1, 11, rec_replica=0, job_dtype=JOB_DTYPE, jobs_cap=20000,
+                            cluster_dtype=CLUSTER_DTYPE, cluster_cap=2000)
+    wj, wc = sim.job_log(), sim.cluster_log()
+    assert len(got["jobs"]) == len(wj) > 20 and len(got["cluster"]) == len(wc) > 100
+    for f in JOB_DTYPE.names:
+        assert np.array_equal(got["jobs"][f], wj[f]), f
+    for f in CLUSTER_DTYPE.names:
+        assert np.array_equal(got["cluster"][f], wc[f]), f
+
+
+def test_capacity_overflow_is_reported_not_hidden(hostemu):
+    sc = SC.CFG3
+    for caps, bit in (({"cap_xfer": 4}, S.ST_XFER_OVERFLOW), ({"cap_run": 4}, S.ST_RUN_OVERFLOW),
+                      ({"cap_q_inf": 16}, S.ST_QUEUE_OVERFLOW)):
+        out = hostemu.run_batch(SC.to_spec(sc, caps=caps).to_bytes(), 1, 3)["summary"][0]
+        assert int(out[S.S_STATUS]) & bit and int(out[S.S_DONE]) == 0
+
+
+def test_rng_window_slow_path(oracle, hostemu):
+    """D = 1 makes random.choice reject half its draws and sinusoid near a trough rejects most candidates:
+    long rejection runs out-run the 128-word window and exercise the single-lane slow path."""
+    sc = SC.scenario("slowpath", 1, 64, dict(mode="sinusoid", rate=30.0, amp=1.0, period=20.0),
+                     dict(mode="sinusoid", rate=3.0, amp=0.9, period=7.0), 120.0)
+    blob = SC.to_spec(sc).to_bytes()
+    want, _ = oracle.run_batch(blob, 2, 77)
+    got = hostemu.run_batch(blob, 2, 77)["summary"]
+    assert _same(got, want)

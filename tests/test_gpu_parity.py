@@ -1,0 +1,201 @@
+"""Parity tests proper: the sm_100a kernel through the C-ABI against the oracle and the reference fixtures.
+
+Bar (BASELINE.json north_star): exact event / job / RNG-word counts; per-replica total energy and mean job
+latency within 1e-9 relative.  Every float of the summary is held to the same 1e-9.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import golden_names, has_cuda, load_golden
+from distributed_cluster_gpus_b200 import scenarios as SC, sharding, spec as S
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not has_cuda(), reason="needs a CUDA device")]
+
+RTOL = 1e-9
+COUNT_COLS = (S.S_STATUS, S.S_EVENTS, S.S_JOBS_FINISHED, S.S_JOBS_CREATED, S.S_FIN_INF, S.S_FIN_TRN, S.S_RNG_WORDS,
+              S.S_SEQ, S.S_EV_ARRIVAL, S.S_EV_XFER, S.S_EV_FINISH, S.S_EV_LOG, S.S_DONE)
+FLOAT_COLS = (S.S_TOTAL_ENERGY_J, S.S_LAT_SUM, S.S_LAT_SUM_INF, S.S_LAT_SUM_TRN, S.S_LAST_T)
+DEVICE_SUPPORTED = [n for n in golden_names() if not n.startswith("cap_greedy")]
+
+
+def engine_cls():
+    from distributed_cluster_gpus_b200.engine import BatchedEngine
+    return BatchedEngine
+
+
+def assert_rows_match(got, want, n_dc, rtol=RTOL):
+    for col in COUNT_COLS:
+        assert np.array_equal(got[:, col], want[:, col]), f"count column {col}: {got[:, col]} vs {want[:, col]}"
+    worst = 0.0
+    cols = list(FLOAT_COLS)
+    for d in range(n_dc):
+        b = S.S_DC0 + d * S.S_DC_STRIDE
+        cols += [b + S.SD_ENERGY_J, b + S.SD_UTIL_GPU_TIME, b + S.SD_ACC_JOB_UNIT, b + S.SD_CURRENT_FREQ]
+        for k in (S.SD_BUSY, S.SD_Q_INF, S.SD_Q_TRN, S.SD_RUNNING):
+            assert np.array_equal(got[:, b + k], want[:, b + k]), f"dc{d} field {k}"
+    for col in cols:
+        denom = np.maximum(np.abs(want[:, col]), 1e-300)
+        rel = np.max(np.where(want[:, col] == got[:, col], 0.0, np.abs(got[:, col] - want[:, col]) / denom))
+        assert rel <= rtol, f"float column {col}: rel err {rel:.3e}"
+        worst = max(worst, rel)
+    return worst
+
+
+@pytest.mark.parametrize("name", DEVICE_SUPPORTED)
+def test_kernel_matches_oracle(oracle, name):
+    sc = SC.BY_NAME[name]
+    sp = SC.to_spec(sc)
+    n = 8 if sc["duration"] * sc["n_dc"] <= 2400 else 3
+    with engine_cls()(sp, n, base_seed=123, first_replica_id=0) as eng:
+        total = eng.advance(0)
+        got = eng.summary()
+    want, want_total = oracle.run_batch(sp.to_bytes(), n, 123, 0, n_threads=os.cpu_count() or 1)
+    assert total == want_total
+    worst = assert_rows_match(got, want, sc["n_dc"])
+    print(f"{name}: {n} replicas, {total} events, worst float rel err {worst:.2e}")
+
+
+@pytest.mark.parametrize("name", ["cfg1_1x4_poisson_5000s", "cfg2_1x64_poisson_600s", "cfg3_4x64_sinusoid_120s",
+                                  "cfg5_8x256_sinusoid_60s", "sweep_joint_nf", "sweep_carbon_cost", "sweep_eco_route",
+                                  "sweep_bandit"])
+def test_kernel_matches_reference_fixture(name):
+    """Straight against the reference's own numbers (fixture = reference + injected Philox), no oracle in between."""
+    doc = load_golden(name)
+    sc = doc["scenario"]
+    runs = {r["seed"]: r for r in doc["runs"] if r["rng"] == "philox"}
+    with engine_cls()(SC.to_spec(sc), 2, base_seed=123) as eng:      # replicas 0,1 -> seeds 123,124
+        eng.advance(0)
+        got = eng.summary()
+    for r, seed in enumerate((123, 124)):
+        run = runs[seed]
+        assert int(got[r, S.S_EVENTS]) == run["events"] and int(got[r, S.S_JOBS_FINISHED]) == run["jobs_finished"]
+        assert int(got[r, S.S_RNG_WORDS]) == run["rng_words"] and int(got[r, S.S_SEQ]) == run["seq_pushed"]
+        e_ref = float.fromhex(run["total_energy_j"])
+        assert abs(got[r, S.S_TOTAL_ENERGY_J] - e_ref) <= RTOL * abs(e_ref)
+        if run["jobs_finished"]:
+            m_ref = float.fromhex(run["mean_latency_s"])
+            assert abs(got[r, S.S_LAT_SUM] / got[r, S.S_JOBS_FINISHED] - m_ref) <= RTOL * abs(m_ref)
+
+
+@pytest.mark.parametrize("chunk", [1, 13, 4096])
+def test_resume_is_invariant_on_device(chunk):
+    sp = SC.to_spec(dict(SC.CFG3, duration=10.0 if chunk == 1 else 40.0))
+    with engine_cls()(sp, 5, base_seed=9) as eng:
+        eng.advance(0)
+        whole = eng.summary()
+    with engine_cls()(sp, 5, base_seed=9) as eng:
+        guard = 0
+        while not eng.all_done():
+            eng.advance(chunk)
+            guard += 1
+            assert guard < 20000
+        parts = eng.summary()
+    assert np.array_equal(whole, parts)
+
+
+def test_trace_and_logs_match_oracle(oracle):
+    sp = SC.to_spec(SC.BY_NAME["ragged_3dc_12_5_40"])
+    with engine_cls()(sp, 4, base_seed=40) as eng:
+        eng.set_trace(2, 6000)
+        eng.set_logging(2, 20000, 2000)
+        eng.advance(0)
+        tr, jobs, cl = eng.trace(), eng.job_log(), eng.cluster_log()
+    sim = oracle.OracleSim(sp.to_bytes(), 42, trace_cap=6000, joblog_cap=20000, clog_cap=2000)
+    sim.advance(0)
+    wt, wj, wc = sim.trace(), sim.job_log(), sim.cluster_log()
+    assert len(tr) == len(wt) and np.array_equal(tr["kind"], wt["kind"]) and np.array_equal(tr["seq"], wt["seq"])
+    np.testing.assert_allclose(tr["t"], wt["t"], rtol=1e-12, atol=0)
+    assert len(jobs) == len(wj) and len(cl) == len(wc)
+    for f in ("jid", "ingress", "jtype", "dc", "n_gpus"):
+        assert np.array_equal(jobs[f], wj[f]), f
+    for f in ("size", "f_used", "start_s", "finish_s"):
+        np.testing.assert_allclose(jobs[f], wj[f], rtol=1e-12)
+    for f in ("dc", "busy", "run_total", "run_inf", "q_inf", "q_train"):
+        assert np.array_equal(cl[f], wc[f]), f
+    for f in ("time_s", "freq", "util_gpu_time", "util_begin_ts", "acc_job_unit", "power_w", "energy_j"):
+        np.testing.assert_allclose(cl[f], wc[f], rtol=1e-9)
+
+
+def test_full_size_batch_properties(oracle):
+    """BASELINE size (65 536 replicas, 4 DC x 64) on a short horizon: every replica finishes cleanly, the batch is
+    deterministic, a random sample agrees with the oracle, results do not depend on the batch a replica is in,
+    and the on-device reduction equals the host aggregate."""
+    import torch
+    sp = SC.to_spec(dict(SC.CFG3, duration=12.0))
+    n = 65536
+    with engine_cls()(sp, n, base_seed=1000) as eng:
+        total = eng.advance(0)
+        big = eng.summary()
+        agg_t = torch.zeros(S.AGG_K, dtype=torch.float64, device="cuda")
+        eng.reduce_into(agg_t.data_ptr())
+        torch.cuda.synchronize()
+        agg = agg_t.cpu().numpy()
+        eng.reset(1000)
+        assert eng.advance(0) == total
+        assert np.array_equal(eng.summary(), big)                      # deterministic, reset is clean
+    assert np.all(big[:, S.S_STATUS] == 0) and np.all(big[:, S.S_DONE] == 1)
+    assert big[:, S.S_EVENTS].sum() == total
+    host = sharding.aggregate_rows(big)
+    assert agg[S.A_REPLICAS] == n and agg[S.A_FAILED] == 0 and agg[S.A_EVENTS] == total
+    np.testing.assert_allclose(agg, host, rtol=1e-11)
+    rng = np.random.default_rng(0)
+    sample = np.sort(rng.choice(n, 64, replace=False))
+    for r in sample[:8]:                                               # sharding invariance: same id, different batch
+        with engine_cls()(sp, 3, base_seed=1000, first_replica_id=int(r)) as eng:
+            eng.advance(0)
+            assert np.array_equal(eng.summary()[0], big[r])
+    want = np.stack([oracle.run_batch(sp.to_bytes(), 1, 1000, int(r))[0][0] for r in sample])
+    assert_rows_match(big[sample], want, 4)
+    words = big[:, S.S_RNG_WORDS]
+    assert words.min() > 0 and len(np.unique(big[:, S.S_TOTAL_ENERGY_J])) > n * 0.99   # replicas really differ
+
+
+def test_capacity_overflow_surfaces_and_engine_retries():
+    from distributed_cluster_gpus_b200.engine import run_to_completion
+    sc = dict(SC.CFG3, duration=30.0)
+    with engine_cls()(SC.to_spec(sc, caps={"cap_run": 4}), 2, base_seed=1) as eng:
+        eng.advance(0)
+        s = eng.summary()
+    assert np.all(s[:, S.S_STATUS].astype(int) & S.ST_RUN_OVERFLOW) and np.all(s[:, S.S_DONE] == 0)
+    first = {"n": 0}
+
+    def factory(caps):
+        first["n"] += 1
+        return SC.to_spec(sc, caps=caps if caps else {"cap_run": 4})
+    eng, summ = run_to_completion(factory, 2, 1)
+    eng.close()
+    assert first["n"] == 2 and np.all(summ[:, S.S_STATUS] == 0) and np.all(summ[:, S.S_DONE] == 1)
+
+
+def test_drop_in_simulator_and_csvs(tmp_path, oracle):
+    import csv
+    import logging
+    from distributed_cluster_gpus_b200.configs import paper_config as pc
+    from distributed_cluster_gpus_b200.simcore.simulator_paper_multi import MultiIngressPaperSimulator
+    sc = SC.BY_NAME["ragged_3dc_12_5_40"]
+    kw = SC.build_inputs(sc)
+    sim = MultiIngressPaperSimulator(router_policy=pc.build_router_policy(), logger=logging.getLogger("t"),
+                                     sim_duration=sc["duration"], log_interval=sc["log_interval"], log_path=str(tmp_path),
+                                     rng_seed=77, algo=sc["algo"], show_progress=False, replicas=16, **kw)
+    sim.run()
+    want, _ = oracle.run_batch(SC.to_spec(sc).to_bytes(), 16, 77)
+    assert_rows_match(sim.summary, want, sc["n_dc"])
+    for d, dc in enumerate(kw["dcs"].values()):                        # DataCenters are the result carriers
+        assert abs(dc.energy_joules - want[0, S.S_DC0 + d * 8]) <= RTOL * abs(want[0, S.S_DC0 + d * 8])
+        assert dc.busy_gpus == int(want[0, S.S_DC0 + d * 8 + S.SD_BUSY])
+    rows = list(csv.reader(open(tmp_path / "job_log.csv")))
+    assert rows[0][:4] == ["jid", "ingress", "type", "size"] and len(rows) - 1 == int(want[0, S.S_JOBS_FINISHED])
+    crow = list(csv.reader(open(tmp_path / "cluster_log.csv")))
+    assert crow[0][0] == "time_s" and len(crow) - 1 == int(want[0, S.S_EV_LOG]) * sc["n_dc"]
+
+
+def test_unsupported_and_invalid_specs_fail_loudly():
+    from distributed_cluster_gpus_b200 import _native
+    with pytest.raises(_native.DcsimError, match="cap_greedy"):
+        engine_cls()(SC.to_spec(SC.BY_NAME["cap_greedy_4x64"]), 1, 0)
+    sp = SC.to_spec(SC.CFG1)
+    sp.n_dc = 0
+    with pytest.raises(_native.DcsimError):
+        engine_cls()(sp, 1, 0)
