@@ -198,7 +198,8 @@ def run_b200(args, world, rank, local_rank):
     sp = SC.to_spec(sc)
     R = args.replicas
     first = rank * R
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()              # explicit (non-default) stream: its handle is what the C-ABI launches on,
+    torch.cuda.set_stream(stream)             # so torch.cuda.Event timing brackets exactly our kernels
     eng = BatchedEngine(sp, R, base_seed=123, first_replica_id=first, device=local_rank, cuda_stream=stream.cuda_stream)
     info = eng.launch_info()
     agg = torch.zeros((args.steps + args.warmup + 1, S.AGG_K), dtype=torch.float64, device="cuda")
@@ -274,7 +275,8 @@ def run_b200(args, world, rank, local_rank):
         sim = MultiIngressPaperSimulator(router_policy=pc.build_router_policy(), logger=logging.getLogger("bench"),
                                          sim_duration=sc["duration"], log_interval=sc["log_interval"], log_path=log_dir,
                                          rng_seed=5000 + i * R * world, algo=sc["algo"], show_progress=False,
-                                         replicas=R, device=local_rank, first_replica_id=first, **kw_i)
+                                         replicas=R, device=local_rank, first_replica_id=first,
+                                         cuda_stream=stream.cuda_stream, **kw_i)
         sim.run()
         vec = torch.from_numpy(sharding.aggregate_rows(sim.summary)).cuda()
         sharding.allreduce_aggregate(vec)
