@@ -265,6 +265,16 @@ def run_b200(args, world, rank, local_rank):
                 "events_per_s_per_resident_warp": local_events_per_launch / (kms / 1000.0) / max(1, info["resident_warps_per_sm"] * info["sm_count"])}
 
     # ---- e2e through the drop-in public API (host buffers in and out) -----------------------------
+    if args.no_e2e:
+        eng.close()
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                              "ms_per_step": 1000.0 * elapsed_s / args.steps, "kernel_ms": kms, "launch": info,
+                              "clocks": clocks, "tuning_run": True}), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     kw = SC.build_inputs(sc)
     log_dir = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else "/tmp", f"dcsim_bench_{os.getpid()}")
     eng.close()
@@ -325,6 +335,7 @@ def main():
     ap.add_argument("--scenario", type=str, default="cfg3_4x64_sinusoid_120s")
     ap.add_argument("--duration", type=float, default=None, help="override the scenario's simulated seconds")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="tuning runs only: skip the end-to-end leg")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

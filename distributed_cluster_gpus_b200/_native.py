@@ -9,7 +9,8 @@ import os
 from . import spec as S
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libdcsim_b200.so")
+# DCSIM_B200_LIB selects another build of the SAME CUDA library (tuning experiments); never a different backend.
+LIB_PATH = os.environ.get("DCSIM_B200_LIB") or os.path.join(_HERE, "csrc", "libdcsim_b200.so")
 
 OK, E_INVALID, E_CUDA, E_NOMEM, E_STATE, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 

@@ -22,7 +22,11 @@
 
 extern __shared__ __align__(16) char dcsim_smem[];
 
-__global__ void __launch_bounds__(DCSIM_MAX_WARPS_PER_CTA * 32)
+#ifndef DCSIM_MIN_CTAS_PER_SM
+#define DCSIM_MIN_CTAS_PER_SM 8 /* 8 CTAs x 4 warps = 32 warps/SM -> ptxas keeps the kernel within 64 registers */
+#endif
+
+__global__ void __launch_bounds__(DCSIM_MAX_WARPS_PER_CTA * 32, DCSIM_MIN_CTAS_PER_SM)
 dcsim_advance_kernel(const __grid_constant__ dcsim_kparams_t P, unsigned long long* __restrict__ events_total) {
   const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31u);
   const int wpc = (int)(blockDim.x >> 5);

@@ -76,11 +76,21 @@ enum {
 enum { KIND_ARR_INF = 0, KIND_ARR_TRN = 1, KIND_XFER = 2, KIND_FINISH = 3, KIND_LOG = 4 };
 
 enum { /* per-DC f64 arrays inside the state block, each DCSIM_MAX_DC long */
-  DF_ENERGY = 0, DF_LAST_E_T, DF_UTIL_TIME, DF_UTIL_LAST, DF_UTIL_BEGIN, DF_ACC_UNIT, DF_CUR_FREQ, DF_POWER, DF_N
+  DF_ENERGY = 0,
+  DF_LAST_T,     /* util_last_ts (SIM:430-436) AND last_energy_time (models.py:100-106): both are 0.0 until the
+                    first event and are set to t on every event, so one slot carries both */
+  DF_UTIL_TIME, DF_UTIL_BEGIN, DF_ACC_UNIT, DF_CUR_FREQ, DF_POWER, DF_N
 };
-enum { /* per-DC i32 arrays */
-  DI_BUSY = 0, DI_NRUN, DI_QH_INF, DI_QT_INF, DI_QH_TRN, DI_QT_TRN, DI_FMIN_SLOT, DI_N
+enum { /* per-DC i32 arrays; FIFO rings are (head index, length) so no modulo is needed */
+  DI_BUSY = 0, DI_NRUN, DI_QH_INF, DI_QN_INF, DI_QH_TRN, DI_QN_TRN, DI_FMIN_SLOT, DI_N
 };
+
+/* One DC per lane on the GPU (32 lanes >= DCSIM_MAX_DC); a plain loop in the single-lane host build. */
+#if DCSIM_LANES >= DCSIM_MAX_DC
+#define DCSIM_FOR_EACH_DC(d, c, n) for (int d = (c).lane, once_ = 1; once_ && d < (n); once_ = 0)
+#else
+#define DCSIM_FOR_EACH_DC(d, c, n) for (int d = 0; d < (n); ++d)
+#endif
 
 #define DCSIM_RNG_WINDOW 128u /* Philox words staged per refill: one block per lane */
 #define DCSIM_RNG_MARGIN 24u  /* refill when fewer than this many staged words remain at an arrival */
@@ -202,16 +212,19 @@ struct dcsim_ctx_t {
   bool is_traced, is_logged;
   /* Philox stream */
   uint32_t key0, key1;
-  uint32_t rng_base;     /* stream index of rng_buf[0]; multiple of 4 */
-  uint32_t rng_valid;    /* words staged (0 or DCSIM_RNG_WINDOW) */
-  uint32_t sblk[4];      /* slow path: one block computed by lane 0 alone */
-  uint32_t sblk_idx;
+  uint32_t rng_base;     /* warp-uniform: stream index of rng_buf[0] (multiple of 4); rng_pos + 1 = nothing staged */
+  /* Hot scalars kept in registers; lane 0's copy is authoritative (only lane 0 runs handlers) and is written
+   * back to the header when the launch ends. */
+  uint32_t rng_pos;      /* words consumed */
+  uint32_t seq;          /* successful pushes (SIM:163) */
+  double now;            /* warp-uniform */
 };
 
 #define DCF(c, which) (dcsim_at<double>((c).blk, (c).P->L.dc_f64) + (which) * DCSIM_MAX_DC)
 #define DCI(c, which) (dcsim_at<int32_t>((c).blk, (c).P->L.dc_i32) + (which) * DCSIM_MAX_DC)
 #define CAND_T(c) (dcsim_at<double>((c).blk, (c).P->L.cand_t))
 #define CAND_SEQ(c) (dcsim_at<uint32_t>((c).blk, (c).P->L.cand_seq))
+#define RNG_BUF(c) (dcsim_at<uint32_t>((c).blk, (c).P->L.rng_buf))
 
 /* ================================================================================================
  * Philox4x32-10 stream; definition shared with oracle/philox_random.py
@@ -230,32 +243,40 @@ DCSIM_DEV void dcsim_philox_block(uint32_t k0, uint32_t k1, uint32_t b, uint32_t
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-/* Warp-uniform.  Makes sure at least DCSIM_RNG_MARGIN staged words are ahead of rng_pos: every lane
- * computes one block of the window [pos & ~3, +128). */
+/* Warp-uniform.  Makes sure at least DCSIM_RNG_MARGIN staged words are ahead of `pos`: every lane
+ * computes one block of the window [pos & ~3, +128).  Ends with a warp sync when it refilled. */
 DCSIM_DEV void dcsim_rng_ensure(dcsim_ctx_t& c, uint32_t pos) {
-  if (c.rng_valid && pos >= c.rng_base && pos + DCSIM_RNG_MARGIN <= c.rng_base + DCSIM_RNG_WINDOW) return;
-  dcsim_warp_sync();
+  if (pos - c.rng_base <= DCSIM_RNG_WINDOW - DCSIM_RNG_MARGIN) return; /* unsigned: also false when nothing is staged */
   const uint32_t base = pos & ~3u;
-  uint32_t* buf = dcsim_at<uint32_t>(c.blk, c.P->L.rng_buf);
+  uint32_t* buf = RNG_BUF(c);
   for (uint32_t b = (uint32_t)c.lane; b < DCSIM_RNG_WINDOW / 4u; b += DCSIM_LANES) {
     uint32_t w[4];
     dcsim_philox_block(c.key0, c.key1, (base >> 2) + b, w);
     buf[4 * b + 0] = w[0]; buf[4 * b + 1] = w[1]; buf[4 * b + 2] = w[2]; buf[4 * b + 3] = w[3];
   }
   c.rng_base = base;
-  c.rng_valid = DCSIM_RNG_WINDOW;
   dcsim_warp_sync();
+}
+
+/* Rare: a handler out-ran the staged window (a long rejection run); lane 0 computes the block alone. */
+#ifndef DCSIM_HOST_EMU
+__device__ __noinline__
+#else
+static
+#endif
+uint32_t dcsim_rng_word_slow(uint32_t k0, uint32_t k1, uint32_t pos) {
+  uint32_t w[4];
+  dcsim_philox_block(k0, k1, pos >> 2, w);
+  const uint32_t j = pos & 3u;
+  return j == 0u ? w[0] : (j == 1u ? w[1] : (j == 2u ? w[2] : w[3]));
 }
 
 /* Lane 0 only.  Next word of the stream. */
 DCSIM_DEV uint32_t dcsim_rng_word(dcsim_ctx_t& c) {
-  const uint32_t pos = c.H->rng_pos;
-  c.H->rng_pos = pos + 1u;
+  const uint32_t pos = c.rng_pos++;
   const uint32_t idx = pos - c.rng_base;
-  if (c.rng_valid && idx < DCSIM_RNG_WINDOW) return dcsim_at<uint32_t>(c.blk, c.P->L.rng_buf)[idx];
-  const uint32_t b = pos >> 2; /* rare: a handler out-ran the window (long rejection run) */
-  if (b != c.sblk_idx) { dcsim_philox_block(c.key0, c.key1, b, c.sblk); c.sblk_idx = b; }
-  return c.sblk[pos & 3u];
+  if (idx < DCSIM_RNG_WINDOW) return RNG_BUF(c)[idx];
+  return dcsim_rng_word_slow(c.key0, c.key1, pos);
 }
 
 /* CPython genrand_res53 (Modules/_randommodule.c): 53-bit uniform on [0,1) from two words */
@@ -320,6 +341,17 @@ DCSIM_DEV double dcsim_step_time(int n_gpus, double f_ghz, const dcsim_coeffs_t&
   return (base + k.gamma_t * (double)n) / (double)n;
 }
 
+/* x % y for x >= 0, y > 0 (what CPython computes with fmod).  q = floor(fl(x/y)) is the true quotient or one
+ * more (rounding is monotone and integers are representable); x - q*y is then the true remainder or a tiny
+ * negative number, both exact in one fma, and the fix-up addition is exact because the true remainder is
+ * representable.  Checked against fmod() on the host build (tests/test_device_core_hostemu.py). */
+DCSIM_DEV double dcsim_mod_pos(double x, double y) {
+  const double q = floor(x / y);
+  double r = fma(-q, y, x);
+  if (r < 0.0) r += y;
+  return r;
+}
+
 /* arrivals.py:5-11 */
 DCSIM_DEV double dcsim_sample_size(dcsim_ctx_t& c, int jt) {
   const dcsim_spec_t& sp = c.P->spec;
@@ -343,7 +375,7 @@ DCSIM_DEV double dcsim_next_interarrival(dcsim_ctx_t& c, int jt, double t) {
       if (it >= DCSIM_REJECTION_LIMIT) { c.H->status |= DCSIM_ST_RNG_RUNAWAY; return DCSIM_INF; }
       const double w = dcsim_expovariate(c, max_rate);
       const double tc = t + w;
-      double lam = a.rate * (1.0 + a.amp * sin(c.P->spec.two_pi * fmod(tc, a.period) / a.period));
+      double lam = a.rate * (1.0 + a.amp * sin(c.P->spec.two_pi * dcsim_mod_pos(tc, a.period) / a.period));
       lam = lam > 0.0 ? lam : 0.0;
       if (dcsim_rng_random(c) <= lam / max_rate) return w;
     }
@@ -400,7 +432,6 @@ DCSIM_DEV void dcsim_refresh_power(dcsim_ctx_t& c, int d) {
 
 /* Warp.  Earliest job_finish among DC d's running records -> candidate slot d. */
 DCSIM_DEV void dcsim_rescan_dc(dcsim_ctx_t& c, int d) {
-  dcsim_warp_sync();
   const int n = DCI(c, DI_NRUN)[d];
   const int off = d * c.P->L.cap_run;
   double t; uint32_t s;
@@ -416,7 +447,6 @@ DCSIM_DEV void dcsim_rescan_dc(dcsim_ctx_t& c, int d) {
 
 /* Warp.  Earliest in-flight transfer -> candidate slot CAND_XFER. */
 DCSIM_DEV void dcsim_rescan_xfer(dcsim_ctx_t& c) {
-  dcsim_warp_sync();
   double t; uint32_t s;
   const int k = dcsim_argmin_ts(dcsim_at<double>(c.blk, c.P->L.xf_t), dcsim_at<uint32_t>(c.blk, c.P->L.xf_seq),
                                 (int)c.H->n_xfer, c.lane, &t, &s);
@@ -430,7 +460,6 @@ DCSIM_DEV void dcsim_rescan_xfer(dcsim_ctx_t& c) {
 
 /* Warp.  Removes running record `k` of DC d keeping the others in start order (dict semantics, models.py:60). */
 DCSIM_DEV void dcsim_running_erase(dcsim_ctx_t& c, int d, int k) {
-  dcsim_warp_sync();
   const dcsim_layout_t& L = c.P->L;
   const int n = DCI(c, DI_NRUN)[d];
   const int off = d * L.cap_run;
@@ -454,7 +483,7 @@ DCSIM_DEV void dcsim_running_erase(dcsim_ctx_t& c, int d, int k) {
 #pragma unroll
       for (int q = 0; q < 3; ++q) u32s[q][j] = b[q];
     }
-    dcsim_warp_sync();
+    if (j0 + DCSIM_LANES < n - 1) dcsim_warp_sync(); /* next chunk reads what this one did not write; keep order */
   }
   if (c.lane == 0) DCI(c, DI_NRUN)[d] = n - 1;
   dcsim_warp_sync();
@@ -466,23 +495,25 @@ DCSIM_DEV dcsim_qent_t* dcsim_queue_base(const dcsim_ctx_t& c, int d, int jt) {
   const uint64_t per_dc = (uint64_t)L.cap_q[0] + (uint64_t)L.cap_q[1];
   return reinterpret_cast<dcsim_qent_t*>(c.q) + (uint64_t)d * per_dc + (jt ? (uint64_t)L.cap_q[0] : 0ull);
 }
-DCSIM_DEV int dcsim_queue_len(dcsim_ctx_t& c, int d, int jt) {
-  return DCI(c, jt ? DI_QT_TRN : DI_QT_INF)[d] - DCI(c, jt ? DI_QH_TRN : DI_QH_INF)[d];
-}
+DCSIM_DEV int dcsim_queue_len(dcsim_ctx_t& c, int d, int jt) { return DCI(c, jt ? DI_QN_TRN : DI_QN_INF)[d]; }
 DCSIM_DEV void dcsim_enqueue(dcsim_ctx_t& c, int d, int jt, double size, uint32_t jid, uint32_t ing) {
   const int cap = c.P->L.cap_q[jt];
-  int32_t* tail = DCI(c, jt ? DI_QT_TRN : DI_QT_INF) + d;
-  const int len = dcsim_queue_len(c, d, jt);
-  if (len >= cap) { c.H->status |= DCSIM_ST_QUEUE_OVERFLOW; return; }
+  int32_t* len = DCI(c, jt ? DI_QN_TRN : DI_QN_INF) + d;
+  const int n = *len;
+  if (n >= cap) { c.H->status |= DCSIM_ST_QUEUE_OVERFLOW; return; }
+  int tail = DCI(c, jt ? DI_QH_TRN : DI_QH_INF)[d] + n;
+  if (tail >= cap) tail -= cap;
   dcsim_qent_t e; e.size = size; e.jid = jid; e.ing = ing;
-  dcsim_queue_base(c, d, jt)[(uint32_t)(*tail) % (uint32_t)cap] = e;
-  *tail += 1;
-  if ((uint32_t)(len + 1) > c.H->max_q) c.H->max_q = (uint32_t)(len + 1);
+  dcsim_queue_base(c, d, jt)[tail] = e;
+  *len = n + 1;
+  if ((uint32_t)(n + 1) > c.H->max_q) c.H->max_q = (uint32_t)(n + 1);
 }
 DCSIM_DEV dcsim_qent_t dcsim_dequeue(dcsim_ctx_t& c, int d, int jt) {
   int32_t* head = DCI(c, jt ? DI_QH_TRN : DI_QH_INF) + d;
-  const dcsim_qent_t e = dcsim_queue_base(c, d, jt)[(uint32_t)(*head) % (uint32_t)c.P->L.cap_q[jt]];
-  *head += 1;
+  const int h = *head;
+  const dcsim_qent_t e = dcsim_queue_base(c, d, jt)[h];
+  *head = h + 1 >= c.P->L.cap_q[jt] ? 0 : h + 1;
+  DCI(c, jt ? DI_QN_TRN : DI_QN_INF)[d] -= 1;
   return e;
 }
 
@@ -535,15 +566,15 @@ DCSIM_DEV void dcsim_start_job(dcsim_ctx_t& c, int d, int jt, double size, uint3
   if (slot >= L.cap_run) { c.H->status |= DCSIM_ST_RUN_OVERFLOW; return; }
   DCI(c, DI_BUSY)[d] += n;
   const double T_unit = dcsim_step_time(n, f, k);
-  const double t_fin = c.H->now + size * T_unit;
+  const double t_fin = c.now + size * T_unit;
   const int i = d * L.cap_run + slot;
   const bool ok = dcsim_schedulable(c, t_fin);
-  const uint32_t seq = ok ? c.H->seq++ : 0xffffffffu;
+  const uint32_t seq = ok ? c.seq++ : 0xffffffffu;
   dcsim_at<double>(c.blk, L.rn_t)[i] = ok ? t_fin : DCSIM_INF; /* a dropped finish holds its GPUs for ever */
   dcsim_at<uint32_t>(c.blk, L.rn_seq)[i] = seq;
   dcsim_at<double>(c.blk, L.rn_pw)[i] = dcsim_task_power(n, f, k);
   dcsim_at<double>(c.blk, L.rn_tpt)[i] = 1.0 / T_unit; /* SIM:956 */
-  dcsim_at<double>(c.blk, L.rn_start)[i] = c.H->now;
+  dcsim_at<double>(c.blk, L.rn_start)[i] = c.now;
   dcsim_at<double>(c.blk, L.rn_size)[i] = size;
   dcsim_at<double>(c.blk, L.rn_f)[i] = f;
   dcsim_at<uint32_t>(c.blk, L.rn_meta)[i] = (uint32_t)n | ((uint32_t)jt << 16) | (ing << 17);
@@ -573,7 +604,7 @@ DCSIM_DEV void dcsim_start_by_rule(dcsim_ctx_t& c, int rule, bool at_xfer, int d
   const dcsim_spec_t& sp = c.P->spec;
   const int free_g = sp.dc[d].total_gpus - DCI(c, DI_BUSY)[d];
   if (rule == DCSIM_START_NF_LUT) {
-    const dcsim_nf_t nf = at_xfer ? sp.dc[d].nf_xfer[jt][dcsim_current_hour(c.H->now)] : sp.dc[d].nf_deq[jt];
+    const dcsim_nf_t nf = at_xfer ? sp.dc[d].nf_xfer[jt][dcsim_current_hour(c.now)] : sp.dc[d].nf_deq[jt];
     int n = nf.n < free_g ? nf.n : free_g; /* SIM:962 */
     n = n > 1 ? n : 1;
     dcsim_start_job(c, d, jt, size, jid, ing, n, nf.f);
@@ -607,13 +638,13 @@ DCSIM_DEV void dcsim_handle_arrival(dcsim_ctx_t& c, int stream) {
   } else {
     dc_sel = dcsim_rng_randbelow(c, sp.n_dc); /* SIM:575-576 */
   }
-  const double t_x = H->now + sp.transfer_s[ing][dc_sel][jt];
+  const double t_x = c.now + sp.transfer_s[ing][dc_sel][jt];
   if (dcsim_schedulable(c, t_x)) { /* SIM:580-588 */
     const uint32_t slot = H->n_xfer;
     if ((int)slot >= L.cap_xfer) {
       H->status |= DCSIM_ST_XFER_OVERFLOW;
     } else {
-      const uint32_t seq = H->seq++;
+      const uint32_t seq = c.seq++;
       dcsim_at<double>(c.blk, L.xf_t)[slot] = t_x;
       dcsim_at<double>(c.blk, L.xf_size)[slot] = size;
       dcsim_at<uint32_t>(c.blk, L.xf_seq)[slot] = seq;
@@ -627,10 +658,10 @@ DCSIM_DEV void dcsim_handle_arrival(dcsim_ctx_t& c, int stream) {
       }
     }
   }
-  const double t_a = H->now + dcsim_next_interarrival(c, jt, H->now); /* SIM:591-592 */
+  const double t_a = c.now + dcsim_next_interarrival(c, jt, c.now); /* SIM:591-592 */
   if (dcsim_schedulable(c, t_a)) {
     CAND_T(c)[CAND_STREAM0 + stream] = t_a;
-    CAND_SEQ(c)[CAND_STREAM0 + stream] = H->seq++;
+    CAND_SEQ(c)[CAND_STREAM0 + stream] = c.seq++;
   } else {
     CAND_T(c)[CAND_STREAM0 + stream] = DCSIM_INF;
     CAND_SEQ(c)[CAND_STREAM0 + stream] = 0xffffffffu;
@@ -670,8 +701,8 @@ DCSIM_DEV void dcsim_finish_account(dcsim_ctx_t& c, int d, int slot) {
   const int g = (int)(meta & 0xffffu), jt = (int)((meta >> 16) & 1u);
   int32_t* busy = DCI(c, DI_BUSY) + d;
   *busy = *busy - g > 0 ? *busy - g : 0; /* SIM:707 */
-  const double now = H->now;
-  DCF(c, DF_ACC_UNIT)[d] += dcsim_at<double>(c.blk, L.rn_tpt)[i] * fmod(now, sp.log_interval); /* SIM:711 */
+  const double now = c.now;
+  DCF(c, DF_ACC_UNIT)[d] += dcsim_at<double>(c.blk, L.rn_tpt)[i] * dcsim_mod_pos(now, sp.log_interval); /* SIM:711 */
   const double lat = now - dcsim_at<double>(c.blk, L.rn_start)[i]; /* SIM:820 */
   H->lat_sum += lat;
   if (jt == DCSIM_JT_INFERENCE) { H->lat_sum_inf += lat; H->n_fin_inf++; } else { H->lat_sum_trn += lat; H->n_fin_trn++; }
@@ -712,43 +743,43 @@ DCSIM_DEV void dcsim_dequeue_loop(dcsim_ctx_t& c, int d) {
   }
 }
 
-/* SIM:929-949 + the :221-225 heuristic of _control.  DC-parallel: one DC per lane. */
+/* SIM:929-949 + the :221-225 heuristic of _control.  DC-parallel: one DC per lane.
+ * Entered with all prior writes visible; leaves with its own writes visible (trailing sync). */
 DCSIM_DEV void dcsim_handle_log(dcsim_ctx_t& c) {
   const dcsim_spec_t& sp = c.P->spec;
   const dcsim_layout_t& L = c.P->L;
   const double interval = sp.log_interval;
-  for (int d = c.lane; d < sp.n_dc; d += DCSIM_LANES) {
-    if (sp.control_lower_idle && DCI(c, DI_BUSY)[d] == 0 && sp.dc[d].n_freq > 0) {
+  const bool rec = c.is_logged && c.P->rec.cluster != nullptr;
+  DCSIM_FOR_EACH_DC(d, c, sp.n_dc) {
+    if (sp.control_lower_idle && DCI(c, DI_BUSY)[d] == 0 && sp.dc[d].n_freq > 0) { /* SIM:221-225, before the rows */
       double m = sp.dc[d].freq_levels[0];
       for (int q = 1; q < sp.dc[d].n_freq; ++q) m = sp.dc[d].freq_levels[q] < m ? sp.dc[d].freq_levels[q] : m;
       DCF(c, DF_CUR_FREQ)[d] = m;
     }
-  }
-  dcsim_warp_sync();
-  for (int d = c.lane; d < sp.n_dc; d += DCSIM_LANES) {
     const int n = DCI(c, DI_NRUN)[d];
     const double* tpt = dcsim_at<double>(c.blk, L.rn_tpt) + d * L.cap_run;
-    const uint32_t* meta = dcsim_at<uint32_t>(c.blk, L.rn_meta) + d * L.cap_run;
     double acc = DCF(c, DF_ACC_UNIT)[d];
-    int run_inf = 0;
-    for (int i = 0; i < n; ++i) { acc += tpt[i] * interval; run_inf += ((meta[i] >> 16) & 1u) ? 0 : 1; } /* SIM:941-942 */
+    for (int i = 0; i < n; ++i) acc += tpt[i] * interval; /* SIM:941-942, running jobs in dict order */
     DCF(c, DF_ACC_UNIT)[d] = acc;
-    if (c.is_logged && c.P->rec.cluster) { /* cluster_log.csv row, SIM:944-948; rows of one tick are DC-ordered */
+    if (rec) { /* cluster_log.csv row, SIM:944-948; the rows of one tick are DC-ordered */
       const uint32_t r = c.P->rec.counts[2] + (uint32_t)d;
       if (r < c.P->rec.cluster_cap) {
+        const uint32_t* meta = dcsim_at<uint32_t>(c.blk, L.rn_meta) + d * L.cap_run;
+        int run_inf = 0;
+        for (int i = 0; i < n; ++i) run_inf += ((meta[i] >> 16) & 1u) ? 0 : 1;
         dcsim_cluster_rec_t* o = c.P->rec.cluster + r;
-        o->time_s = c.H->now; o->freq = DCF(c, DF_CUR_FREQ)[d]; o->util_gpu_time = DCF(c, DF_UTIL_TIME)[d];
+        o->time_s = c.now; o->freq = DCF(c, DF_CUR_FREQ)[d]; o->util_gpu_time = DCF(c, DF_UTIL_TIME)[d];
         o->util_begin_ts = DCF(c, DF_UTIL_BEGIN)[d]; o->acc_job_unit = acc; o->power_w = DCF(c, DF_POWER)[d];
         o->energy_j = DCF(c, DF_ENERGY)[d]; o->dc = d; o->busy = DCI(c, DI_BUSY)[d]; o->run_total = n;
         o->run_inf = run_inf; o->q_inf = dcsim_queue_len(c, d, 0); o->q_train = dcsim_queue_len(c, d, 1);
       }
     }
   }
-  dcsim_warp_sync();
+  if (rec) dcsim_warp_sync(); /* every lane has read counts[2] before lane 0 bumps it */
   if (c.lane == 0) {
-    if (c.is_logged && c.P->rec.cluster) c.P->rec.counts[2] += (uint32_t)sp.n_dc;
-    const double t = c.H->now + interval; /* SIM:949 */
-    if (dcsim_schedulable(c, t)) { CAND_T(c)[CAND_LOG] = t; CAND_SEQ(c)[CAND_LOG] = c.H->seq++; }
+    if (rec) c.P->rec.counts[2] += (uint32_t)sp.n_dc;
+    const double t = c.now + interval; /* SIM:949 */
+    if (dcsim_schedulable(c, t)) { CAND_T(c)[CAND_LOG] = t; CAND_SEQ(c)[CAND_LOG] = c.seq++; }
     else { CAND_T(c)[CAND_LOG] = DCSIM_INF; CAND_SEQ(c)[CAND_LOG] = 0xffffffffu; }
   }
   dcsim_warp_sync();
@@ -765,24 +796,24 @@ DCSIM_DEV void dcsim_replica_init(dcsim_ctx_t& c) {
   for (int i = c.lane; i < L.total_bytes / 4; i += DCSIM_LANES) dcsim_at<uint32_t>(c.blk, 0)[i] = 0u;
   dcsim_warp_sync();
   for (int i = c.lane; i < CAND_N; i += DCSIM_LANES) { CAND_T(c)[i] = DCSIM_INF; CAND_SEQ(c)[i] = 0xffffffffu; }
-  for (int d = c.lane; d < sp.n_dc; d += DCSIM_LANES) {
+  DCSIM_FOR_EACH_DC(d, c, sp.n_dc) {
     DCF(c, DF_CUR_FREQ)[d] = sp.dc[d].default_freq; /* models.py:76 */
     DCI(c, DI_FMIN_SLOT)[d] = -1;
     DCF(c, DF_POWER)[d] = (double)sp.dc[d].total_gpus * (sp.dc[d].power_gating ? sp.dc[d].p_sleep : sp.dc[d].p_idle);
   }
   dcsim_warp_sync();
-  c.rng_valid = 0u; c.rng_base = 0u; c.sblk_idx = 0xffffffffu;
+  c.rng_pos = 0u; c.rng_base = 1u; c.seq = 0u; c.now = 0.0;
   for (int s = 0; s < 2 * sp.n_ing; ++s) { /* SIM:154-156 */
-    dcsim_rng_ensure(c, c.H->rng_pos);
+    dcsim_rng_ensure(c, dcsim_bcast_u32(c.rng_pos, 0));
     if (c.lane == 0) {
       const double t = 0.0 + dcsim_next_interarrival(c, s & 1, 0.0);
-      if (dcsim_schedulable(c, t)) { CAND_T(c)[CAND_STREAM0 + s] = t; CAND_SEQ(c)[CAND_STREAM0 + s] = c.H->seq++; }
+      if (dcsim_schedulable(c, t)) { CAND_T(c)[CAND_STREAM0 + s] = t; CAND_SEQ(c)[CAND_STREAM0 + s] = c.seq++; }
     }
-    dcsim_warp_sync();
+    dcsim_warp_sync(); /* lane 0 is done with the staged words before the next ensure() may overwrite them */
   }
   if (c.lane == 0) {
     const double t = 0.0 + sp.log_interval; /* SIM:157 */
-    if (dcsim_schedulable(c, t)) { CAND_T(c)[CAND_LOG] = t; CAND_SEQ(c)[CAND_LOG] = c.H->seq++; }
+    if (dcsim_schedulable(c, t)) { CAND_T(c)[CAND_LOG] = t; CAND_SEQ(c)[CAND_LOG] = c.seq++; }
     c.H->xmin_slot = 0xffffffffu;
     c.H->initialized = 1u;
   }
@@ -793,34 +824,31 @@ DCSIM_DEV void dcsim_replica_init(dcsim_ctx_t& c) {
 DCSIM_DEV void dcsim_replica_tail(dcsim_ctx_t& c) {
   const dcsim_spec_t& sp = c.P->spec;
   const double end = sp.end_time;
-  for (int d = c.lane; d < sp.n_dc; d += DCSIM_LANES) {
+  DCSIM_FOR_EACH_DC(d, c, sp.n_dc) {
     const dcsim_dc_t& cfg = sp.dc[d];
     const int busy = DCI(c, DI_BUSY)[d];
-    const double ul = DCF(c, DF_UTIL_LAST)[d];
-    if (0.0 < ul && ul < end) {
-      DCF(c, DF_UTIL_TIME)[d] += (double)busy * (end - ul);
-      DCF(c, DF_UTIL_LAST)[d] = end;
-    }
-    const double le = DCF(c, DF_LAST_E_T)[d];
-    if (le == 0.0) {
-      DCF(c, DF_LAST_E_T)[d] = end;
-    } else {
-      double dt = end - le; dt = dt > 0.0 ? dt : 0.0;
+    const double last = DCF(c, DF_LAST_T)[d];
+    if (0.0 < last && last < end) DCF(c, DF_UTIL_TIME)[d] += (double)busy * (end - last); /* SIM:471-474 */
+    if (last != 0.0) { /* models.py:100-106 with power_fn=None */
+      double dt = end - last; dt = dt > 0.0 ? dt : 0.0;
       const double f = DCF(c, DF_CUR_FREQ)[d];
       const double fa = cfg.alpha == 3.0 ? dcsim_cube(f) : pow(f, cfg.alpha);
       const double p_active = (double)busy * (cfg.p_idle + cfg.p_peak * fa);
       const double p_idle = (double)(cfg.total_gpus - busy) * (cfg.power_gating ? cfg.p_sleep : cfg.p_idle);
       DCF(c, DF_ENERGY)[d] += (p_active + p_idle) * dt;
-      DCF(c, DF_LAST_E_T)[d] = end;
     }
+    DCF(c, DF_LAST_T)[d] = end;
   }
   dcsim_warp_sync();
 }
 
-/* SIM:423-467: the event loop.  Returns the number of events processed by this call. */
+/* SIM:423-467: the event loop.  Returns the number of events processed by this call.
+ *
+ * Visibility protocol: every branch ends with a warp sync, so at the top of an iteration all shared-memory
+ * writes of the previous event are visible to every lane; inside a branch a sync separates lane 0's handler
+ * from the warp-parallel step that reads what it wrote. */
 DCSIM_DEV uint32_t dcsim_replica_run(dcsim_ctx_t& c) {
   const dcsim_spec_t& sp = c.P->spec;
-  const dcsim_layout_t& L = c.P->L;
   const uint64_t budget = c.P->max_events;
   uint32_t done_here = 0u;
   bool finished = false;
@@ -829,59 +857,53 @@ DCSIM_DEV uint32_t dcsim_replica_run(dcsim_ctx_t& c) {
     if (c.H->status != 0u) break; /* a capacity overflowed: stop and report, never guess */
     double t; uint32_t seq;
     const int win = dcsim_argmin_ts(CAND_T(c), CAND_SEQ(c), CAND_N, c.lane, &t, &seq);
-    if (win < 0) { finished = true; break; }      /* `while self.event_q` */
+    if (win < 0) { finished = true; break; }         /* `while self.event_q` */
     if (t > sp.end_time) { finished = true; break; } /* SIM:427 */
 
-    for (int d = c.lane; d < sp.n_dc; d += DCSIM_LANES) { /* SIM:429-437 */
-      const double ul = DCF(c, DF_UTIL_LAST)[d];
-      if (ul == 0.0) {
-        DCF(c, DF_UTIL_LAST)[d] = t; DCF(c, DF_UTIL_BEGIN)[d] = t;
+    DCSIM_FOR_EACH_DC(d, c, sp.n_dc) { /* SIM:429-437 + models.py:100-106, state before the event */
+      const double last = DCF(c, DF_LAST_T)[d];
+      if (last == 0.0) {
+        DCF(c, DF_UTIL_BEGIN)[d] = t;
       } else {
-        double dt = t - ul; dt = dt > 0.0 ? dt : 0.0;
+        double dt = t - last; dt = dt > 0.0 ? dt : 0.0;
         DCF(c, DF_UTIL_TIME)[d] += (double)DCI(c, DI_BUSY)[d] * dt;
-        DCF(c, DF_UTIL_LAST)[d] = t;
-      }
-      const double le = DCF(c, DF_LAST_E_T)[d]; /* models.py:100-106 */
-      if (le == 0.0) {
-        DCF(c, DF_LAST_E_T)[d] = t;
-      } else {
-        double dt = t - le; dt = dt > 0.0 ? dt : 0.0;
         DCF(c, DF_ENERGY)[d] += DCF(c, DF_POWER)[d] * dt;
-        DCF(c, DF_LAST_E_T)[d] = t;
       }
+      DCF(c, DF_LAST_T)[d] = t;
     }
     ++done_here;
+    c.now = t;
     const int kind = win < CAND_STREAM0 ? KIND_FINISH : (win < CAND_XFER ? (win & 1) : (win == CAND_XFER ? KIND_XFER : KIND_LOG));
     if (c.lane == 0) {
-      c.H->now = t; c.H->last_t = t; c.H->n_events++;
+      c.H->n_events++;
       if (c.is_traced && c.P->rec.trace) {
         const uint32_t r = c.P->rec.counts[0];
         if (r < c.P->rec.trace_cap) { c.P->rec.trace[r].t = t; c.P->rec.trace[r].seq = seq; c.P->rec.trace[r].kind = (uint32_t)kind; }
         c.P->rec.counts[0] = r + 1u;
       }
     }
-    dcsim_warp_sync();
 
     if (kind == KIND_ARR_INF || kind == KIND_ARR_TRN) {
-      dcsim_rng_ensure(c, c.H->rng_pos);
+      dcsim_rng_ensure(c, dcsim_bcast_u32(c.rng_pos, 0));
       if (c.lane == 0) { c.H->ev_arr++; dcsim_handle_arrival(c, win - CAND_STREAM0); }
       dcsim_warp_sync();
     } else if (kind == KIND_XFER) {
       if (c.lane == 0) { c.H->ev_xfer++; dcsim_handle_xfer(c, (int)c.H->xmin_slot); }
+      dcsim_warp_sync();
       dcsim_rescan_xfer(c);
     } else if (kind == KIND_FINISH) {
       const int d = win - CAND_DC0;
       const int slot = DCI(c, DI_FMIN_SLOT)[d];
       if (c.lane == 0) { c.H->ev_fin++; dcsim_finish_account(c, d, slot); }
-      dcsim_running_erase(c, d, slot);
+      dcsim_running_erase(c, d, slot); /* reads records the accounting did not touch; syncs before it returns */
       if (c.lane == 0) { dcsim_dequeue_loop(c, d); dcsim_refresh_power(c, d); }
+      dcsim_warp_sync();
       dcsim_rescan_dc(c, d);
     } else {
       if (c.lane == 0) c.H->ev_log++;
       dcsim_handle_log(c);
     }
   }
-  (void)L;
   if (finished && c.H->done == 0u) {
     dcsim_replica_tail(c);
     if (c.lane == 0) c.H->done = 1u;
@@ -894,7 +916,6 @@ DCSIM_DEV uint32_t dcsim_replica_run(dcsim_ctx_t& c) {
 DCSIM_DEV void dcsim_write_summary(dcsim_ctx_t& c, double* out) {
   const dcsim_spec_t& sp = c.P->spec;
   const dcsim_hdr_t* H = c.H;
-  dcsim_warp_sync();
   for (int i = c.lane; i < DCSIM_SUMMARY_K; i += DCSIM_LANES) out[i] = 0.0;
   dcsim_warp_sync();
   if (c.lane == 0) {
@@ -917,7 +938,7 @@ DCSIM_DEV void dcsim_write_summary(dcsim_ctx_t& c, double* out) {
     out[DCSIM_S_MAX_XFER] = (double)H->max_xfer; out[DCSIM_S_MAX_RUN] = (double)H->max_run;
     out[DCSIM_S_MAX_Q] = (double)H->max_q;
   }
-  for (int d = c.lane; d < sp.n_dc; d += DCSIM_LANES) {
+  DCSIM_FOR_EACH_DC(d, c, sp.n_dc) {
     double* o = out + DCSIM_S_DC0 + d * DCSIM_S_DC_STRIDE;
     o[DCSIM_SD_ENERGY_J] = DCF(c, DF_ENERGY)[d];
     o[DCSIM_SD_UTIL_GPU_TIME] = DCF(c, DF_UTIL_TIME)[d];
@@ -940,11 +961,16 @@ DCSIM_DEV uint32_t dcsim_replica_step(const dcsim_kparams_t* P, uint64_t r, char
   c.is_logged = ((int64_t)r == P->rec.log_replica);
   const uint64_t key = P->seed0 + r;
   c.key0 = (uint32_t)key; c.key1 = (uint32_t)(key >> 32);
-  c.rng_valid = 0u; c.rng_base = 0u; c.sblk_idx = 0xffffffffu;
-  c.sblk[0] = c.sblk[1] = c.sblk[2] = c.sblk[3] = 0u;
-  if (fresh) dcsim_replica_init(c);
+  if (fresh) {
+    dcsim_replica_init(c);
+  } else { /* resume: hot scalars back into registers */
+    c.rng_pos = c.H->rng_pos; c.seq = c.H->seq; c.now = c.H->now;
+    c.rng_base = c.rng_pos + 1u; /* nothing staged */
+  }
   uint32_t n = 0u;
   if (c.H->done == 0u) n = dcsim_replica_run(c);
+  if (c.lane == 0) { c.H->rng_pos = c.rng_pos; c.H->seq = c.seq; c.H->now = c.now; c.H->last_t = c.H->n_events ? c.now : 0.0; }
+  dcsim_warp_sync();
   dcsim_write_summary(c, P->summary + r * DCSIM_SUMMARY_K);
   dcsim_warp_sync();
   return n;
