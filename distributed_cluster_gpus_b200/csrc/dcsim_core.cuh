@@ -65,6 +65,14 @@ DCSIM_DEV int dcsim_bit_length(uint32_t n) { return 32 - __clz((int)n); }
 #define DCSIM_INF (__longlong_as_double(0x7ff0000000000000LL))
 #endif
 
+DCSIM_DEV double dcsim_bcast_f64(double x, int src) {
+#ifdef DCSIM_HOST_EMU
+  (void)src; return x;
+#else
+  return __hiloint2double((int)dcsim_bcast_u32(dcsim_hi(x), src), (int)dcsim_bcast_u32(dcsim_lo(x), src));
+#endif
+}
+
 /* ---- candidate slots (the event set, one slot per lane) -------------------------------------- */
 enum {
   CAND_DC0 = 0,      /* + d   : earliest job_finish among DC d's running jobs */
@@ -93,7 +101,10 @@ enum { /* per-DC i32 arrays; FIFO rings are (head index, length) so no modulo is
 #endif
 
 #define DCSIM_RNG_WINDOW 128u /* Philox words staged per refill: one block per lane */
-#define DCSIM_RNG_MARGIN 24u  /* refill when fewer than this many staged words remain at an arrival */
+#define DCSIM_RNG_MARGIN 64u  /* refill when fewer than this many staged words remain at an arrival: covers one
+                                 arrival's speculative look-ahead (2 size + 16 route + 8x4 thinning words) */
+#define DCSIM_SPEC_ROUTE (DCSIM_LANES < 16 ? DCSIM_LANES : 16) /* lanes trying random.choice draws at once */
+#define DCSIM_SPEC_THIN (DCSIM_LANES < 8 ? DCSIM_LANES : 8)    /* lanes trying thinning candidates at once */
 /* A rejection loop that has not accepted after this many draws stops the replica with DCSIM_ST_RNG_RUNAWAY
  * instead of spinning (the reference would spin: e.g. arrivals.py:41-45 under a clipped lambda). */
 #define DCSIM_REJECTION_LIMIT (1 << 24)
@@ -277,6 +288,16 @@ DCSIM_DEV uint32_t dcsim_rng_word(dcsim_ctx_t& c) {
   const uint32_t idx = pos - c.rng_base;
   if (idx < DCSIM_RNG_WINDOW) return RNG_BUF(c)[idx];
   return dcsim_rng_word_slow(c.key0, c.key1, pos);
+}
+
+/* Any lane.  Word at absolute stream position `pos` without consuming it (speculative look-ahead). */
+DCSIM_DEV uint32_t dcsim_rng_peek(const dcsim_ctx_t& c, uint32_t pos) {
+  const uint32_t idx = pos - c.rng_base;
+  if (idx < DCSIM_RNG_WINDOW) return RNG_BUF(c)[idx];
+  return dcsim_rng_word_slow(c.key0, c.key1, pos);
+}
+DCSIM_DEV double dcsim_u53(uint32_t w0, uint32_t w1) { /* genrand_res53 on two given words */
+  return ((double)(w0 >> 5) * 67108864.0 + (double)(w1 >> 6)) * (1.0 / 9007199254740992.0);
 }
 
 /* CPython genrand_res53 (Modules/_randommodule.c): 53-bit uniform on [0,1) from two words */
@@ -620,51 +641,120 @@ DCSIM_DEV void dcsim_start_by_rule(dcsim_ctx_t& c, int rule, bool at_xfer, int d
   }
 }
 
-/* SIM:537-592 */
+/* SIM:537-592, whole warp.  Draw order is the reference's: size -> route -> next inter-arrival (App. A.7).
+ * The two rejection loops that dominate the draws — random.choice's bit rejection (random.py:242-250) and the
+ * sinusoid "thinning" (arrivals.py:41-45) — are evaluated SPECULATIVELY: lane j computes candidate j from the
+ * words candidate j would consume (the Philox window is indexable), a ballot picks the first accepting lane,
+ * and the stream position advances by exactly what the sequential loop would have consumed.
+ * On entry c.rng_pos is warp-uniform and >= DCSIM_RNG_MARGIN words are staged; on exit it is uniform again. */
 DCSIM_DEV void dcsim_handle_arrival(dcsim_ctx_t& c, int stream) {
   const dcsim_spec_t& sp = c.P->spec;
   const dcsim_layout_t& L = c.P->L;
   dcsim_hdr_t* H = c.H;
   const int jt = stream & 1, ing = stream >> 1;
-  const uint32_t jid = ++H->jid;
-  const double size = dcsim_sample_size(c, jt);
-  int dc_sel = 0;
-  if (sp.route_rule == DCSIM_ROUTE_ECO) { /* SIM:544-553: strict <, first DC wins */
-    double best = sp.dc[0].eco_e_unit[jt] * size;
-    for (int d = 1; d < sp.n_dc; ++d) {
-      const double score = sp.dc[d].eco_e_unit[jt] * size;
-      if (score < best) { best = score; dc_sel = d; }
-    }
-  } else {
-    dc_sel = dcsim_rng_randbelow(c, sp.n_dc); /* SIM:575-576 */
+  double size = 0.0;
+  uint32_t jid = 0u;
+  if (c.lane == 0) { /* SIM:539-540 */
+    jid = ++H->jid;
+    H->ev_arr++;
+    size = dcsim_sample_size(c, jt);
   }
-  const double t_x = c.now + sp.transfer_s[ing][dc_sel][jt];
-  if (dcsim_schedulable(c, t_x)) { /* SIM:580-588 */
-    const uint32_t slot = H->n_xfer;
-    if ((int)slot >= L.cap_xfer) {
-      H->status |= DCSIM_ST_XFER_OVERFLOW;
-    } else {
-      const uint32_t seq = c.seq++;
-      dcsim_at<double>(c.blk, L.xf_t)[slot] = t_x;
-      dcsim_at<double>(c.blk, L.xf_size)[slot] = size;
-      dcsim_at<uint32_t>(c.blk, L.xf_seq)[slot] = seq;
-      dcsim_at<uint32_t>(c.blk, L.xf_meta)[slot] = (uint32_t)dc_sel | ((uint32_t)jt << 3) | ((uint32_t)ing << 4);
-      dcsim_at<uint32_t>(c.blk, L.xf_jid)[slot] = jid;
-      H->n_xfer = slot + 1u;
-      if (slot + 1u > H->max_xfer) H->max_xfer = slot + 1u;
-      const double ct = CAND_T(c)[CAND_XFER];
-      if (t_x < ct || (t_x == ct && seq < CAND_SEQ(c)[CAND_XFER])) {
-        CAND_T(c)[CAND_XFER] = t_x; CAND_SEQ(c)[CAND_XFER] = seq; H->xmin_slot = slot;
+  uint32_t pos = dcsim_bcast_u32(c.rng_pos, 0);
+
+  int dc_sel = 0;
+  if (sp.route_rule == DCSIM_ROUTE_ECO) { /* SIM:544-553: strict <, first DC wins; no draw */
+    if (c.lane == 0) {
+      double best = sp.dc[0].eco_e_unit[jt] * size;
+      for (int d = 1; d < sp.n_dc; ++d) {
+        const double score = sp.dc[d].eco_e_unit[jt] * size;
+        if (score < best) { best = score; dc_sel = d; }
+      }
+    }
+    dc_sel = (int)dcsim_bcast_u32((uint32_t)dc_sel, 0);
+  } else { /* SIM:575-576 random.choice(names): k = n.bit_length(); redraw until < n */
+    const int n = sp.n_dc, k = dcsim_bit_length((uint32_t)n);
+    for (int it = 0;; it += DCSIM_SPEC_ROUTE) {
+      if (it >= DCSIM_REJECTION_LIMIT) { if (c.lane == 0) H->status |= DCSIM_ST_RNG_RUNAWAY; break; }
+      const bool mine = c.lane < DCSIM_SPEC_ROUTE;
+      const uint32_t v = mine ? dcsim_rng_peek(c, pos + (uint32_t)c.lane) >> (32 - k) : 0xffffffffu;
+      const uint32_t votes = dcsim_warp_ballot(mine && v < (uint32_t)n);
+      if (votes) {
+        const int first = dcsim_ffs(votes) - 1;
+        dc_sel = (int)dcsim_bcast_u32(v, first);
+        pos += (uint32_t)first + 1u;
+        break;
+      }
+      pos += DCSIM_SPEC_ROUTE;
+    }
+  }
+
+  if (c.lane == 0) { /* SIM:580-588 */
+    const double t_x = c.now + sp.transfer_s[ing][dc_sel][jt];
+    if (dcsim_schedulable(c, t_x)) {
+      const uint32_t slot = H->n_xfer;
+      if ((int)slot >= L.cap_xfer) {
+        H->status |= DCSIM_ST_XFER_OVERFLOW;
+      } else {
+        const uint32_t seq = c.seq++;
+        dcsim_at<double>(c.blk, L.xf_t)[slot] = t_x;
+        dcsim_at<double>(c.blk, L.xf_size)[slot] = size;
+        dcsim_at<uint32_t>(c.blk, L.xf_seq)[slot] = seq;
+        dcsim_at<uint32_t>(c.blk, L.xf_meta)[slot] = (uint32_t)dc_sel | ((uint32_t)jt << 3) | ((uint32_t)ing << 4);
+        dcsim_at<uint32_t>(c.blk, L.xf_jid)[slot] = jid;
+        H->n_xfer = slot + 1u;
+        if (slot + 1u > H->max_xfer) H->max_xfer = slot + 1u;
+        const double ct = CAND_T(c)[CAND_XFER];
+        if (t_x < ct || (t_x == ct && seq < CAND_SEQ(c)[CAND_XFER])) {
+          CAND_T(c)[CAND_XFER] = t_x; CAND_SEQ(c)[CAND_XFER] = seq; H->xmin_slot = slot;
+        }
       }
     }
   }
-  const double t_a = c.now + dcsim_next_interarrival(c, jt, c.now); /* SIM:591-592 */
-  if (dcsim_schedulable(c, t_a)) {
-    CAND_T(c)[CAND_STREAM0 + stream] = t_a;
-    CAND_SEQ(c)[CAND_STREAM0 + stream] = c.seq++;
-  } else {
-    CAND_T(c)[CAND_STREAM0 + stream] = DCSIM_INF;
-    CAND_SEQ(c)[CAND_STREAM0 + stream] = 0xffffffffu;
+
+  /* SIM:591-592 next inter-arrival of this stream (arrivals.py:35-48) */
+  const dcsim_arrival_t& a = sp.arr[jt];
+  double gap = DCSIM_INF;
+  if (a.mode == DCSIM_ARR_POISSON) {
+    if (a.rate > 0.0) {
+      if (c.lane == 0) gap = -log(1.0 - dcsim_u53(dcsim_rng_peek(c, pos), dcsim_rng_peek(c, pos + 1u))) / a.rate;
+      pos += 2u;
+    }
+  } else if (a.mode == DCSIM_ARR_SINUSOID) {
+    const double abs_amp = a.amp < 0.0 ? -a.amp : a.amp;
+    const double max_rate = a.rate * (1.0 + abs_amp);
+    for (int it = 0;; it += DCSIM_SPEC_THIN) {
+      if (it >= DCSIM_REJECTION_LIMIT) { if (c.lane == 0) H->status |= DCSIM_ST_RNG_RUNAWAY; break; }
+      const bool mine = c.lane < DCSIM_SPEC_THIN;
+      double w = 0.0;
+      bool accept = false;
+      if (mine) {
+        const uint32_t p = pos + 4u * (uint32_t)c.lane;
+        w = -log(1.0 - dcsim_u53(dcsim_rng_peek(c, p), dcsim_rng_peek(c, p + 1u))) / max_rate;
+        const double tc = c.now + w;
+        double lam = a.rate * (1.0 + a.amp * sin(sp.two_pi * dcsim_mod_pos(tc, a.period) / a.period));
+        lam = lam > 0.0 ? lam : 0.0;
+        accept = dcsim_u53(dcsim_rng_peek(c, p + 2u), dcsim_rng_peek(c, p + 3u)) <= lam / max_rate;
+      }
+      const uint32_t votes = dcsim_warp_ballot(mine && accept);
+      if (votes) {
+        const int first = dcsim_ffs(votes) - 1;
+        gap = dcsim_bcast_f64(w, first);
+        pos += 4u * ((uint32_t)first + 1u);
+        break;
+      }
+      pos += 4u * DCSIM_SPEC_THIN;
+    }
+  }
+  c.rng_pos = pos;
+  if (c.lane == 0) {
+    const double t_a = c.now + gap;
+    if (dcsim_schedulable(c, t_a)) {
+      CAND_T(c)[CAND_STREAM0 + stream] = t_a;
+      CAND_SEQ(c)[CAND_STREAM0 + stream] = c.seq++;
+    } else {
+      CAND_T(c)[CAND_STREAM0 + stream] = DCSIM_INF;
+      CAND_SEQ(c)[CAND_STREAM0 + stream] = 0xffffffffu;
+    }
   }
 }
 
@@ -804,12 +894,13 @@ DCSIM_DEV void dcsim_replica_init(dcsim_ctx_t& c) {
   dcsim_warp_sync();
   c.rng_pos = 0u; c.rng_base = 1u; c.seq = 0u; c.now = 0.0;
   for (int s = 0; s < 2 * sp.n_ing; ++s) { /* SIM:154-156 */
-    dcsim_rng_ensure(c, dcsim_bcast_u32(c.rng_pos, 0));
+    dcsim_rng_ensure(c, c.rng_pos);
     if (c.lane == 0) {
       const double t = 0.0 + dcsim_next_interarrival(c, s & 1, 0.0);
       if (dcsim_schedulable(c, t)) { CAND_T(c)[CAND_STREAM0 + s] = t; CAND_SEQ(c)[CAND_STREAM0 + s] = c.seq++; }
     }
-    dcsim_warp_sync(); /* lane 0 is done with the staged words before the next ensure() may overwrite them */
+    c.rng_pos = dcsim_bcast_u32(c.rng_pos, 0); /* uniform again; also orders lane 0's reads before the next refill */
+    dcsim_warp_sync();
   }
   if (c.lane == 0) {
     const double t = 0.0 + sp.log_interval; /* SIM:157 */
@@ -884,8 +975,8 @@ DCSIM_DEV uint32_t dcsim_replica_run(dcsim_ctx_t& c) {
     }
 
     if (kind == KIND_ARR_INF || kind == KIND_ARR_TRN) {
-      dcsim_rng_ensure(c, dcsim_bcast_u32(c.rng_pos, 0));
-      if (c.lane == 0) { c.H->ev_arr++; dcsim_handle_arrival(c, win - CAND_STREAM0); }
+      dcsim_rng_ensure(c, c.rng_pos); /* rng_pos is warp-uniform between arrivals */
+      dcsim_handle_arrival(c, win - CAND_STREAM0);
       dcsim_warp_sync();
     } else if (kind == KIND_XFER) {
       if (c.lane == 0) { c.H->ev_xfer++; dcsim_handle_xfer(c, (int)c.H->xmin_slot); }
