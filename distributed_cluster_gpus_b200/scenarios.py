@@ -63,6 +63,13 @@ GOLDEN_SCENARIOS = [
 ]
 BY_NAME = {s["name"]: s for s in GOLDEN_SCENARIOS}
 
+# scenarios whose reference-written CSV files are kept under tests/golden/csv/ (wire-format tests)
+CSV_SCENARIOS = {
+    "ragged_3dc_12_5_40": BY_NAME["ragged_3dc_12_5_40"],
+    "csv_joint_nf_4x64_20s": scenario("csv_joint_nf_4x64_20s", 4, 64, SIN10, POI(1.0), 20.0, FREQ3, algo="joint_nf", log_interval=2.0),
+    "csv_carbon_cost_2x16": scenario("csv_carbon_cost_2x16", 2, 16, POI(2.0), POI(0.1), 90.0, FREQ8, algo="carbon_cost"),
+}
+
 
 def build_inputs(sc):
     """Scenario -> kwargs of MultiIngressPaperSimulator / spec.flatten (product builders)."""

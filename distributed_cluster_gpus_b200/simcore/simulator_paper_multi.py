@@ -136,34 +136,42 @@ class MultiIngressPaperSimulator:
             dc.util_last_ts = self.end_time
 
     def _write_csvs(self, jobs, cluster):
-        dc_names, ing_names = list(self.dcs), list(self.ingresses)
-        with open(self.cluster_log_path, "w", newline="") as f:       # SIM:413-418, 944-948
-            w = csv.writer(f)
-            w.writerow(CLUSTER_HEADER)
-            for r in cluster:
-                dc = self.dcs[dc_names[r["dc"]]]
-                total = dc.total_gpus
-                busy = int(r["busy"])
-                util_inst = (busy / total) if total else 0.0
-                now = float(r["time_s"])
-                elapsed = max(1e-9, now - (float(r["util_begin_ts"]) or now))
-                util_avg = (float(r["util_gpu_time"]) / (total * elapsed)) if total else 0.0
-                w.writerow([f"{now:.3f}", dc.name, f"{float(r['freq']):.2f}", busy, total - busy,
-                            int(r["run_total"]), int(r["run_inf"]), int(r["run_total"]) - int(r["run_inf"]),
-                            int(r["q_inf"]), int(r["q_train"]), f"{util_inst:.4f}", f"{util_avg:.4f}",
-                            f"{float(r['acc_job_unit']):.4f}", f"{float(r['power_w']):.2f}",
-                            f"{float(r['energy_j']) / 1000.0:.4f}"])
-        with open(self.job_log_path, "w", newline="") as f:           # SIM:419-421, 814-823
-            w = csv.writer(f)
-            w.writerow(JOB_HEADER)
-            for r in jobs:
-                dc_name, ing_name = dc_names[r["dc"]], ing_names[r["ingress"]]
-                jtype = S.JT_NAMES[r["jtype"]]
-                p_c, t_c = self.coeffs_map[(dc_name, jtype)]
-                n, f_used = int(r["n_gpus"]), float(r["f_used"])
-                t_pred, p_pred, e_pred = energy_tuple(n, f_used, p_c, t_c)
-                net_lat = float(self._spec.net_lat_s[r["ingress"]][r["dc"]])
-                start, finish = float(r["start_s"]), float(r["finish_s"])
-                w.writerow([int(r["jid"]), ing_name, jtype, f"{float(r['size']):.4f}", dc_name, f"{f_used:.3f}", n,
-                            f"{net_lat:.4f}", f"{start:.6f}", f"{finish:.6f}", f"{(finish - start):.6f}", "0",
-                            f"{t_pred:.6f}", f"{p_pred:.2f}", f"{e_pred:.2f}"])
+        write_csv_logs(jobs, cluster, self.dcs, list(self.ingresses), self.coeffs_map, self._spec.net_lat_s,
+                       self.cluster_log_path, self.job_log_path)
+
+
+def write_csv_logs(jobs, cluster, dcs, ingress_names, coeffs_map, net_lat_s, cluster_log_path, job_log_path):
+    """cluster_log.csv / job_log.csv with the reference's columns and number formats from the engine's unrounded
+    records (engine.CLUSTER_DTYPE / JOB_DTYPE).  Rows appear in the reference's order: cluster rows per log tick in
+    DC order (SIM:932), job rows in finish order (SIM:814)."""
+    dc_names = list(dcs)
+    with open(cluster_log_path, "w", newline="") as f:       # SIM:413-418, 944-948
+        w = csv.writer(f)
+        w.writerow(CLUSTER_HEADER)
+        for r in cluster:
+            dc = dcs[dc_names[int(r["dc"])]]
+            total = dc.total_gpus
+            busy = int(r["busy"])
+            util_inst = (busy / total) if total else 0.0
+            now = float(r["time_s"])
+            elapsed = max(1e-9, now - (float(r["util_begin_ts"]) or now))
+            util_avg = (float(r["util_gpu_time"]) / (total * elapsed)) if total else 0.0
+            w.writerow([f"{now:.3f}", dc.name, f"{float(r['freq']):.2f}", busy, total - busy,
+                        int(r["run_total"]), int(r["run_inf"]), int(r["run_total"]) - int(r["run_inf"]),
+                        int(r["q_inf"]), int(r["q_train"]), f"{util_inst:.4f}", f"{util_avg:.4f}",
+                        f"{float(r['acc_job_unit']):.4f}", f"{float(r['power_w']):.2f}",
+                        f"{float(r['energy_j']) / 1000.0:.4f}"])
+    with open(job_log_path, "w", newline="") as f:           # SIM:419-421, 814-823
+        w = csv.writer(f)
+        w.writerow(JOB_HEADER)
+        for r in jobs:
+            dc_name, ing_name = dc_names[int(r["dc"])], ingress_names[int(r["ingress"])]
+            jtype = S.JT_NAMES[int(r["jtype"])]
+            p_c, t_c = coeffs_map[(dc_name, jtype)]
+            n, f_used = int(r["n_gpus"]), float(r["f_used"])
+            t_pred, p_pred, e_pred = energy_tuple(n, f_used, p_c, t_c)
+            net_lat = float(net_lat_s[int(r["ingress"])][int(r["dc"])])
+            start, finish = float(r["start_s"]), float(r["finish_s"])
+            w.writerow([int(r["jid"]), ing_name, jtype, f"{float(r['size']):.4f}", dc_name, f"{f_used:.3f}", n,
+                        f"{net_lat:.4f}", f"{start:.6f}", f"{finish:.6f}", f"{(finish - start):.6f}", "0",
+                        f"{t_pred:.6f}", f"{p_pred:.2f}", f"{e_pred:.2f}"])
