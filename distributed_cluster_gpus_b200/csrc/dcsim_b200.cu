@@ -26,6 +26,10 @@ extern __shared__ __align__(16) char dcsim_smem[];
 #define DCSIM_MIN_CTAS_PER_SM 8 /* 8 CTAs x 4 warps = 32 warps/SM -> ptxas keeps the kernel within 64 registers */
 #endif
 
+/* CAP = the power-cap controller (algo = cap_greedy with power_cap > 0: SIM:207-338) is compiled in.  It is a
+ * separate instantiation because merely inlining that cold code costs the common path 17 % (measured,
+ * profiles/r01_variants_ab.md). */
+template <bool CAP>
 __global__ void __launch_bounds__(DCSIM_MAX_WARPS_PER_CTA * 32, DCSIM_MIN_CTAS_PER_SM)
 dcsim_advance_kernel(const __grid_constant__ dcsim_kparams_t P, unsigned long long* __restrict__ events_total) {
   const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31u);
@@ -42,7 +46,7 @@ dcsim_advance_kernel(const __grid_constant__ dcsim_kparams_t P, unsigned long lo
     for (int i = lane; i < bytes / 16; i += 32) dst[i] = src[i];
   }
   __syncwarp();
-  const uint32_t n = dcsim_replica_step(&P, r, blk, fresh);
+  const uint32_t n = dcsim_replica_step<CAP>(&P, r, blk, fresh);
   __syncwarp();
   {
     const uint4* src = reinterpret_cast<const uint4*>(blk);
@@ -148,8 +152,6 @@ static int validate_spec(const dcsim_spec_t* sp) {
     if (c->total_gpus < 0 || c->n_freq < 1 || c->n_freq > DCSIM_MAX_FREQ)
       return set_err(NULL, DCSIM_E_INVALID, "spec: DC %s%lld has bad total_gpus / n_freq", "", d);
   }
-  if (sp->algo == DCSIM_ALGO_CAP_GREEDY && sp->power_cap > 0.0)
-    return set_err(NULL, DCSIM_E_UNSUPPORTED, "algo=cap_greedy with power_cap>0 (per-job DVFS re-scheduling, SIM:248-315) is not on the device path yet%s%lld");
   if (sp->algo < DCSIM_ALGO_DEFAULT || sp->algo > DCSIM_ALGO_CAP_GREEDY)
     return set_err(NULL, DCSIM_E_UNSUPPORTED, "spec: unknown algo id %s%lld", "", sp->algo);
   return DCSIM_OK;
@@ -203,12 +205,17 @@ int dcsim_create(const void* spec_blob, size_t spec_bytes, uint64_t n_replicas, 
   h->warps_per_cta = wpc;
   h->smem_bytes = wpc * h->L.total_bytes;
   h->ctas = (int)((n_replicas + (uint64_t)wpc - 1) / (uint64_t)wpc);
-  CREATE_TRY(cudaFuncSetAttribute(dcsim_advance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
+  const void* kern = h->L.cap_stale ? (const void*)dcsim_advance_kernel<true> : (const void*)dcsim_advance_kernel<false>;
+  CREATE_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
   cudaFuncAttributes fa;
-  CREATE_TRY(cudaFuncGetAttributes(&fa, dcsim_advance_kernel));
+  CREATE_TRY(cudaFuncGetAttributes(&fa, kern));
   h->regs = fa.numRegs;
   int blocks_per_sm = 0;
-  CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, dcsim_advance_kernel, wpc * 32, h->smem_bytes));
+  if (h->L.cap_stale) {
+    CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, dcsim_advance_kernel<true>, wpc * 32, h->smem_bytes));
+  } else {
+    CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, dcsim_advance_kernel<false>, wpc * 32, h->smem_bytes));
+  }
   h->resident_warps = blocks_per_sm * wpc;
 
   CREATE_TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
@@ -291,7 +298,8 @@ int dcsim_advance(dcsim_t* h, uint64_t max_events_per_replica, uint64_t* total_e
   P.max_events = max_events_per_replica;
   P.state = h->d_state; P.queues = h->d_queues; P.summary = h->d_summary;
   P.end_eps = h->spec.end_time + 1e-9; /* SIM:161 */
-  dcsim_advance_kernel<<<h->ctas, h->warps_per_cta * 32, h->smem_bytes, h->stream>>>(P, h->d_events);
+  if (h->L.cap_stale) dcsim_advance_kernel<true><<<h->ctas, h->warps_per_cta * 32, h->smem_bytes, h->stream>>>(P, h->d_events);
+  else dcsim_advance_kernel<false><<<h->ctas, h->warps_per_cta * 32, h->smem_bytes, h->stream>>>(P, h->d_events);
   CUDA_TRY(h, cudaGetLastError());
   h->launches++;
   if (total_events_out) {

@@ -79,9 +79,10 @@ enum {
   CAND_STREAM0 = 8,  /* + 2*ingress + jtype : next arrival of that stream */
   CAND_XFER = 24,    /* earliest in-flight xfer_done */
   CAND_LOG = 25,     /* the log tick */
+  CAND_STALE = 26,   /* earliest superseded job_finish (cap_greedy re-scheduling leaves the old event in the heap, SIM:330-338) */
   CAND_N = 32
 };
-enum { KIND_ARR_INF = 0, KIND_ARR_TRN = 1, KIND_XFER = 2, KIND_FINISH = 3, KIND_LOG = 4 };
+enum { KIND_ARR_INF = 0, KIND_ARR_TRN = 1, KIND_XFER = 2, KIND_FINISH = 3, KIND_LOG = 4, KIND_STALE = 5 };
 
 enum { /* per-DC f64 arrays inside the state block, each DCSIM_MAX_DC long */
   DF_ENERGY = 0,
@@ -116,7 +117,8 @@ struct dcsim_hdr_t {
   uint32_t n_xfer, status, done, initialized;
   uint32_t n_fin_inf, n_fin_trn, ev_arr, ev_xfer;
   uint32_t ev_fin, ev_log, max_xfer, max_run;
-  uint32_t max_q, xmin_slot, bandit_t, _pad;
+  uint32_t max_q, xmin_slot, bandit_t, n_stale;
+  uint32_t smin_slot, _pad[3];
 };
 
 /* Byte offsets of the arrays inside a state block; computed once per handle on the host. */
@@ -127,6 +129,11 @@ struct dcsim_layout_t {
   int32_t rn_t, rn_pw, rn_tpt, rn_start, rn_size, rn_f, rn_seq, rn_meta, rn_jid;
   int32_t rng_buf;
   int32_t bandit_n, bandit_s;
+  /* power-cap controller (algo = cap_greedy with power_cap > 0 only) */
+  int32_t rn_done, rn_upd;           /* per running record: units_done, last_update (models.py:20-21) */
+  int32_t st_t, st_seq;              /* stale job_finish pool */
+  int32_t at_rho, at_fto, at_ref, at_idx; /* DVFS atoms scratch (freq_load_agg.py) */
+  int32_t cap_stale, cap_atoms;
   int32_t total_bytes;
   int32_t cap_xfer, cap_run;
   int32_t cap_q[2];        /* FIFO entries per DC: [0]=inference [1]=training */
@@ -172,6 +179,22 @@ static inline void dcsim_make_layout(const dcsim_spec_t* sp, dcsim_layout_t* L) 
   if (sp->xfer_rule == DCSIM_START_BANDIT || sp->deq_rule == DCSIM_START_BANDIT) {
     L->bandit_s = o; o += sp->n_dc * 2 * DCSIM_MAX_FREQ * 8;
     L->bandit_n = o; o += sp->n_dc * 2 * DCSIM_MAX_FREQ * 4;
+  }
+  if (sp->algo == DCSIM_ALGO_CAP_GREEDY && sp->power_cap > 0.0) {
+    L->cap_stale = sp->cap_stale > 0 ? ((sp->cap_stale + 3) & ~3) : 64;
+    L->cap_atoms = nr * (DCSIM_MAX_FREQ - 1);
+    int max_levels = 1;
+    for (int d = 0; d < sp->n_dc; ++d) max_levels = sp->dc[d].n_freq > max_levels ? sp->dc[d].n_freq : max_levels;
+    L->cap_atoms = (nr * (max_levels - 1) + 3) & ~3;
+    if (L->cap_atoms < 4) L->cap_atoms = 4;
+    L->rn_done = o; o += nr * 8;
+    L->rn_upd = o; o += nr * 8;
+    L->st_t = o; o += L->cap_stale * 8;
+    L->at_rho = o; o += L->cap_atoms * 8;
+    L->at_fto = o; o += L->cap_atoms * 8;
+    L->st_seq = o; o += L->cap_stale * 4;
+    L->at_ref = o; o += L->cap_atoms * 4;
+    L->at_idx = o; o = dcsim_align16(o + L->cap_atoms * 4);
   }
   L->total_bytes = dcsim_align16(o);
   L->queue_bytes = (uint64_t)sp->n_dc * ((uint64_t)L->cap_q[0] + (uint64_t)L->cap_q[1]) * 16ull;
@@ -480,6 +503,7 @@ DCSIM_DEV void dcsim_rescan_xfer(dcsim_ctx_t& c) {
 }
 
 /* Warp.  Removes running record `k` of DC d keeping the others in start order (dict semantics, models.py:60). */
+template <bool CAP>
 DCSIM_DEV void dcsim_running_erase(dcsim_ctx_t& c, int d, int k) {
   const dcsim_layout_t& L = c.P->L;
   const int n = DCI(c, DI_NRUN)[d];
@@ -505,6 +529,17 @@ DCSIM_DEV void dcsim_running_erase(dcsim_ctx_t& c, int d, int k) {
       for (int q = 0; q < 3; ++q) u32s[q][j] = b[q];
     }
     if (j0 + DCSIM_LANES < n - 1) dcsim_warp_sync(); /* next chunk reads what this one did not write; keep order */
+  }
+  if constexpr (CAP) { /* the controller's per-record progress fields travel with the record (cold path) */
+    double* ex[2] = {dcsim_at<double>(c.blk, L.rn_done) + off, dcsim_at<double>(c.blk, L.rn_upd) + off};
+    for (int j0 = k; j0 < n - 1; j0 += DCSIM_LANES) {
+      const int j = j0 + c.lane;
+      const bool act = j < n - 1;
+      const double a0 = act ? ex[0][j + 1] : 0.0, a1 = act ? ex[1][j + 1] : 0.0;
+      dcsim_warp_sync();
+      if (act) { ex[0][j] = a0; ex[1][j] = a1; }
+      dcsim_warp_sync();
+    }
   }
   if (c.lane == 0) DCI(c, DI_NRUN)[d] = n - 1;
   dcsim_warp_sync();
@@ -579,6 +614,7 @@ DCSIM_DEV double dcsim_bandit_select(dcsim_ctx_t& c, int d, int jt) {
 }
 
 /* SIM:680-699 (_start_job, use_dc_freq) and SIM:960-980 (_start_job_with_nf): allocate, stamp, push job_finish. */
+template <bool CAP>
 DCSIM_DEV void dcsim_start_job(dcsim_ctx_t& c, int d, int jt, double size, uint32_t jid, uint32_t ing, int n, double f) {
   const dcsim_layout_t& L = c.P->L;
   const dcsim_coeffs_t& k = c.P->spec.dc[d].coeffs[jt];
@@ -600,6 +636,10 @@ DCSIM_DEV void dcsim_start_job(dcsim_ctx_t& c, int d, int jt, double size, uint3
   dcsim_at<double>(c.blk, L.rn_f)[i] = f;
   dcsim_at<uint32_t>(c.blk, L.rn_meta)[i] = (uint32_t)n | ((uint32_t)jt << 16) | (ing << 17);
   dcsim_at<uint32_t>(c.blk, L.rn_jid)[i] = jid;
+  if constexpr (CAP) { /* SIM:690-692: units_done = 0, last_update = now */
+    dcsim_at<double>(c.blk, L.rn_done)[i] = 0.0;
+    dcsim_at<double>(c.blk, L.rn_upd)[i] = c.now;
+  }
   *nrun = slot + 1;
   if ((uint32_t)(slot + 1) > c.H->max_run) c.H->max_run = (uint32_t)(slot + 1);
   if (ok) { /* incremental update of DC d's earliest finish */
@@ -621,6 +661,7 @@ DCSIM_DEV int dcsim_current_hour(double now) {
 }
 
 /* The start rules of SIM:603-676 (at xfer_done) and SIM:892-927 (dequeue loop). */
+template <bool CAP>
 DCSIM_DEV void dcsim_start_by_rule(dcsim_ctx_t& c, int rule, bool at_xfer, int d, int jt, double size, uint32_t jid, uint32_t ing) {
   const dcsim_spec_t& sp = c.P->spec;
   const int free_g = sp.dc[d].total_gpus - DCI(c, DI_BUSY)[d];
@@ -628,16 +669,16 @@ DCSIM_DEV void dcsim_start_by_rule(dcsim_ctx_t& c, int rule, bool at_xfer, int d
     const dcsim_nf_t nf = at_xfer ? sp.dc[d].nf_xfer[jt][dcsim_current_hour(c.now)] : sp.dc[d].nf_deq[jt];
     int n = nf.n < free_g ? nf.n : free_g; /* SIM:962 */
     n = n > 1 ? n : 1;
-    dcsim_start_job(c, d, jt, size, jid, ing, n, nf.f);
+    dcsim_start_job<CAP>(c, d, jt, size, jid, ing, n, nf.f);
   } else if (rule == DCSIM_START_BANDIT) {
     int n = free_g < sp.max_gpus_per_job ? free_g : sp.max_gpus_per_job;
     const double f = dcsim_bandit_select(c, d, jt);
     n = n < free_g ? n : free_g;
     n = n > 1 ? n : 1;
-    dcsim_start_job(c, d, jt, size, jid, ing, n, f);
+    dcsim_start_job<CAP>(c, d, jt, size, jid, ing, n, f);
   } else {
     const int g = dcsim_policy_select(c, d, jt);
-    dcsim_start_job(c, d, jt, size, jid, ing, g, DCF(c, DF_CUR_FREQ)[d]); /* SIM:689,696: f = dc.current_freq */
+    dcsim_start_job<CAP>(c, d, jt, size, jid, ing, g, DCF(c, DF_CUR_FREQ)[d]); /* SIM:689,696: f = dc.current_freq */
   }
 }
 
@@ -759,6 +800,7 @@ DCSIM_DEV void dcsim_handle_arrival(dcsim_ctx_t& c, int stream) {
 }
 
 /* SIM:595-678 (lane 0 part): consume pool entry `slot`, start the job or queue it. */
+template <bool CAP>
 DCSIM_DEV void dcsim_handle_xfer(dcsim_ctx_t& c, int slot) {
   const dcsim_spec_t& sp = c.P->spec;
   const dcsim_layout_t& L = c.P->L;
@@ -774,7 +816,7 @@ DCSIM_DEV void dcsim_handle_xfer(dcsim_ctx_t& c, int slot) {
   xt[slot] = xt[last]; xs[slot] = xs[last]; xq[slot] = xq[last]; xm[slot] = xm[last]; xj[slot] = xj[last];
   H->n_xfer = last;
   if (sp.dc[d].total_gpus - DCI(c, DI_BUSY)[d] > 0) {
-    dcsim_start_by_rule(c, sp.xfer_rule, true, d, jt, size, jid, ing);
+    dcsim_start_by_rule<CAP>(c, sp.xfer_rule, true, d, jt, size, jid, ing);
     dcsim_refresh_power(c, d);
   } else {
     dcsim_enqueue(c, d, jt, size, jid, ing); /* SIM:678 */
@@ -821,6 +863,7 @@ DCSIM_DEV void dcsim_finish_account(dcsim_ctx_t& c, int d, int slot) {
 }
 
 /* SIM:840-927: start queued jobs while GPUs are free, inference first when inf_priority. */
+template <bool CAP>
 DCSIM_DEV void dcsim_dequeue_loop(dcsim_ctx_t& c, int d) {
   const dcsim_spec_t& sp = c.P->spec;
   while (sp.dc[d].total_gpus - DCI(c, DI_BUSY)[d] > 0 && c.H->status == 0u) {
@@ -829,17 +872,164 @@ DCSIM_DEV void dcsim_dequeue_loop(dcsim_ctx_t& c, int d) {
     else if (dcsim_queue_len(c, d, 1) > 0) jt = 1;
     else break;
     const dcsim_qent_t e = dcsim_dequeue(c, d, jt);
-    dcsim_start_by_rule(c, sp.deq_rule, false, d, jt, e.size, e.jid, e.ing);
+    dcsim_start_by_rule<CAP>(c, sp.deq_rule, false, d, jt, e.size, e.jid, e.ing);
+  }
+}
+
+/* Warp.  Earliest superseded job_finish -> candidate slot CAND_STALE. */
+DCSIM_DEV void dcsim_rescan_stale(dcsim_ctx_t& c) {
+  double t; uint32_t s;
+  const int k = dcsim_argmin_ts(dcsim_at<double>(c.blk, c.P->L.st_t), dcsim_at<uint32_t>(c.blk, c.P->L.st_seq),
+                                (int)c.H->n_stale, c.lane, &t, &s);
+  if (c.lane == 0) {
+    CAND_T(c)[CAND_STALE] = k >= 0 ? t : DCSIM_INF;
+    CAND_SEQ(c)[CAND_STALE] = k >= 0 ? s : 0xffffffffu;
+    c.H->smin_slot = (uint32_t)k;
+  }
+  dcsim_warp_sync();
+}
+
+/* Lane 0.  SIM:317-338 _reschedule_job: bank progress at the old frequency, switch, push a new job_finish and
+ * leave the old one behind as a stale event. */
+DCSIM_DEV void dcsim_reschedule_job(dcsim_ctx_t& c, int d, int slot, double new_f) {
+  const dcsim_layout_t& L = c.P->L;
+  const int i = d * L.cap_run + slot;
+  const uint32_t meta = dcsim_at<uint32_t>(c.blk, L.rn_meta)[i];
+  const int g = (int)(meta & 0xffffu), jt = (int)((meta >> 16) & 1u);
+  const dcsim_coeffs_t& k = c.P->spec.dc[d].coeffs[jt];
+  const double f_old = dcsim_at<double>(c.blk, L.rn_f)[i];
+  const double f_cur = f_old != 0.0 ? f_old : DCF(c, DF_CUR_FREQ)[d];
+  const double total = dcsim_at<double>(c.blk, L.rn_size)[i];
+  const double T0 = dcsim_step_time(g, f_cur, k);
+  const double rate = 1.0 / (T0 > 1e-9 ? T0 : 1e-9);
+  double dt = c.now - dcsim_at<double>(c.blk, L.rn_upd)[i]; dt = dt > 0.0 ? dt : 0.0;
+  const double ud = dcsim_at<double>(c.blk, L.rn_done)[i] + rate * dt;
+  const double done = total < ud ? total : ud;
+  dcsim_at<double>(c.blk, L.rn_done)[i] = done;
+  dcsim_at<double>(c.blk, L.rn_upd)[i] = c.now;
+  dcsim_at<double>(c.blk, L.rn_f)[i] = new_f;
+  double left = total - done; left = left > 0.0 ? left : 0.0;
+  const double T1 = dcsim_step_time(g, new_f, k);
+  const double rate_new = 1.0 / (T1 > 1e-9 ? T1 : 1e-9);
+  const double finish_in = left / (rate_new > 1e-9 ? rate_new : 1e-9);
+  const double t_old = dcsim_at<double>(c.blk, L.rn_t)[i];
+  if (!(t_old == DCSIM_INF)) { /* the superseded event stays in the event set */
+    const uint32_t ns = c.H->n_stale;
+    if ((int)ns >= L.cap_stale) { c.H->status |= DCSIM_ST_STALE_OVERFLOW; }
+    else {
+      dcsim_at<double>(c.blk, L.st_t)[ns] = t_old;
+      dcsim_at<uint32_t>(c.blk, L.st_seq)[ns] = dcsim_at<uint32_t>(c.blk, L.rn_seq)[i];
+      c.H->n_stale = ns + 1u;
+    }
+  }
+  const double t_new = c.now + finish_in;
+  const bool ok = dcsim_schedulable(c, t_new);
+  dcsim_at<double>(c.blk, L.rn_t)[i] = ok ? t_new : DCSIM_INF;
+  dcsim_at<uint32_t>(c.blk, L.rn_seq)[i] = ok ? c.seq++ : 0xffffffffu;
+  dcsim_at<double>(c.blk, L.rn_pw)[i] = dcsim_task_power(g, new_f, k);
+  dcsim_at<double>(c.blk, L.rn_tpt)[i] = 1.0 / T1;
+}
+
+/* Lane 0.  SIM:207-315 for algo = cap_greedy (cap_uniform never changes state: SIM:197-203 compares two identical
+ * estimates).  Atoms are freq_load_agg.py:44-80's DOWN steps; the UP list is built by the reference and never read. */
+DCSIM_DEV void dcsim_control_cap_greedy(dcsim_ctx_t& c) {
+  const dcsim_spec_t& sp = c.P->spec;
+  const dcsim_layout_t& L = c.P->L;
+  double totalP = 0.0;
+  for (int d = 0; d < sp.n_dc; ++d) totalP += DCF(c, DF_POWER)[d];
+  if (totalP <= sp.power_cap - 5.0) return; /* cap_margin hysteresis, SIM:235-237 */
+  double deficit = totalP - sp.power_cap; deficit = deficit > 0.0 ? deficit : 0.0;
+  if (deficit <= 1e-6) return;
+  double* at_rho = dcsim_at<double>(c.blk, L.at_rho);
+  double* at_fto = dcsim_at<double>(c.blk, L.at_fto);
+  uint32_t* at_ref = dcsim_at<uint32_t>(c.blk, L.at_ref);
+  uint32_t* at_idx = dcsim_at<uint32_t>(c.blk, L.at_idx);
+  for (int guard = 10000; deficit > 1e-6 && guard > 0; --guard) {
+    int na = 0, n_tasks = 0;
+#pragma unroll 1
+    for (int d = 0; d < sp.n_dc; ++d) {
+      const dcsim_dc_t& cfg = sp.dc[d];
+      double lv[DCSIM_MAX_FREQ];
+      for (int q = 0; q < cfg.n_freq; ++q) { /* sorted(freq_levels), freq_load_agg.py:45 */
+        const double v = cfg.freq_levels[q];
+        int r = q;
+        while (r > 0 && lv[r - 1] > v) { lv[r] = lv[r - 1]; --r; }
+        lv[r] = v;
+      }
+      const double f_min = lv[0];
+      const int n = DCI(c, DI_NRUN)[d];
+#pragma unroll 1
+      for (int slot = 0; slot < n; ++slot) {
+        const int i = d * L.cap_run + slot;
+        const uint32_t meta = dcsim_at<uint32_t>(c.blk, L.rn_meta)[i];
+        const int g = (int)(meta & 0xffffu), jt = (int)((meta >> 16) & 1u);
+        const dcsim_coeffs_t& k = cfg.coeffs[jt];
+        const double f_job = dcsim_at<double>(c.blk, L.rn_f)[i];
+        const double cur_f = f_job != 0.0 ? f_job : DCF(c, DF_CUR_FREQ)[d];
+        if (cur_f <= f_min + 1e-12) continue;
+        ++n_tasks;
+        int i0 = 0;
+        for (int q = 1; q < cfg.n_freq; ++q) {
+          const double a = lv[q] - cur_f, b = lv[i0] - cur_f;
+          if ((a < 0.0 ? -a : a) < (b < 0.0 ? -b : b)) i0 = q;
+        }
+        const double T0 = dcsim_step_time(g, lv[i0], k);
+        double curV = T0 <= 0.0 ? 0.0 : 1.0 / T0, curP = dcsim_task_power(g, lv[i0], k);
+        for (int q = i0; q > 0; --q) {
+          const double f_to = lv[q - 1];
+          const double T2 = dcsim_step_time(g, f_to, k);
+          const double V2 = T2 <= 0.0 ? 0.0 : 1.0 / T2, P2 = dcsim_task_power(g, f_to, k);
+          double dV = curV - V2; dV = dV > 0.0 ? dV : 0.0;
+          double dP = curP - P2; dP = dP > 0.0 ? dP : 0.0;
+          if (dV > 0.0 && dP >= 0.0 && na < L.cap_atoms) {
+            at_rho[na] = dP / dV; at_fto[na] = f_to; at_ref[na] = ((uint32_t)d << 16) | (uint32_t)slot;
+            ++na;
+          }
+          curV = V2; curP = P2;
+        }
+      }
+    }
+    if (!n_tasks || !na) break;
+    for (int a = 0; a < na; ++a) { /* list.sort(key=rho) is stable: insertion sort on (rho, build order) */
+      const double r = at_rho[a];
+      int q = a;
+      while (q > 0 && at_rho[at_idx[q - 1]] > r) { at_idx[q] = at_idx[q - 1]; --q; }
+      at_idx[q] = (uint32_t)a;
+    }
+    bool applied = false;
+#pragma unroll 1
+    for (int a = 0; a < na; ++a) {
+      if (deficit <= 1e-6) break;
+      const uint32_t id = at_idx[a];
+      const int d = (int)(at_ref[id] >> 16), slot = (int)(at_ref[id] & 0xffffu);
+      const double cur_f = dcsim_at<double>(c.blk, L.rn_f)[d * L.cap_run + slot];
+      if (at_fto[id] >= cur_f - 1e-12) continue; /* SIM:296 */
+      dcsim_reschedule_job(c, d, slot, at_fto[id]);
+      applied = true;
+      dcsim_refresh_power(c, d);
+      totalP = 0.0;
+      for (int e = 0; e < sp.n_dc; ++e) totalP += DCF(c, DF_POWER)[e];
+      deficit = totalP - sp.power_cap; deficit = deficit > 0.0 ? deficit : 0.0;
+      if (deficit <= 1e-6) break;
+    }
+    if (!applied) break;
   }
 }
 
 /* SIM:929-949 + the :221-225 heuristic of _control.  DC-parallel: one DC per lane.
  * Entered with all prior writes visible; leaves with its own writes visible (trailing sync). */
+template <bool CAP>
 DCSIM_DEV void dcsim_handle_log(dcsim_ctx_t& c) {
   const dcsim_spec_t& sp = c.P->spec;
   const dcsim_layout_t& L = c.P->L;
   const double interval = sp.log_interval;
   const bool rec = c.is_logged && c.P->rec.cluster != nullptr;
+  if constexpr (CAP) { /* SIM:464: _control() precedes _handle_log() */
+    if (c.lane == 0) dcsim_control_cap_greedy(c);
+    dcsim_warp_sync();
+    for (int d = 0; d < sp.n_dc; ++d) dcsim_rescan_dc(c, d); /* finish times may have moved */
+    dcsim_rescan_stale(c);
+  }
   DCSIM_FOR_EACH_DC(d, c, sp.n_dc) {
     if (sp.control_lower_idle && DCI(c, DI_BUSY)[d] == 0 && sp.dc[d].n_freq > 0) { /* SIM:221-225, before the rows */
       double m = sp.dc[d].freq_levels[0];
@@ -938,6 +1128,7 @@ DCSIM_DEV void dcsim_replica_tail(dcsim_ctx_t& c) {
  * Visibility protocol: every branch ends with a warp sync, so at the top of an iteration all shared-memory
  * writes of the previous event are visible to every lane; inside a branch a sync separates lane 0's handler
  * from the warp-parallel step that reads what it wrote. */
+template <bool CAP>
 DCSIM_DEV uint32_t dcsim_replica_run(dcsim_ctx_t& c) {
   const dcsim_spec_t& sp = c.P->spec;
   const uint64_t budget = c.P->max_events;
@@ -964,12 +1155,13 @@ DCSIM_DEV uint32_t dcsim_replica_run(dcsim_ctx_t& c) {
     }
     ++done_here;
     c.now = t;
-    const int kind = win < CAND_STREAM0 ? KIND_FINISH : (win < CAND_XFER ? (win & 1) : (win == CAND_XFER ? KIND_XFER : KIND_LOG));
+    const int kind = win < CAND_STREAM0 ? KIND_FINISH
+                     : (win < CAND_XFER ? (win & 1) : (win == CAND_XFER ? KIND_XFER : (win == CAND_LOG ? KIND_LOG : KIND_STALE)));
     if (c.lane == 0) {
       c.H->n_events++;
       if (c.is_traced && c.P->rec.trace) {
         const uint32_t r = c.P->rec.counts[0];
-        if (r < c.P->rec.trace_cap) { c.P->rec.trace[r].t = t; c.P->rec.trace[r].seq = seq; c.P->rec.trace[r].kind = (uint32_t)kind; }
+        if (r < c.P->rec.trace_cap) { c.P->rec.trace[r].t = t; c.P->rec.trace[r].seq = seq; c.P->rec.trace[r].kind = (uint32_t)(kind == KIND_STALE ? KIND_FINISH : kind); }
         c.P->rec.counts[0] = r + 1u;
       }
     }
@@ -979,20 +1171,30 @@ DCSIM_DEV uint32_t dcsim_replica_run(dcsim_ctx_t& c) {
       dcsim_handle_arrival(c, win - CAND_STREAM0);
       dcsim_warp_sync();
     } else if (kind == KIND_XFER) {
-      if (c.lane == 0) { c.H->ev_xfer++; dcsim_handle_xfer(c, (int)c.H->xmin_slot); }
+      if (c.lane == 0) { c.H->ev_xfer++; dcsim_handle_xfer<CAP>(c, (int)c.H->xmin_slot); }
       dcsim_warp_sync();
       dcsim_rescan_xfer(c);
     } else if (kind == KIND_FINISH) {
       const int d = win - CAND_DC0;
       const int slot = DCI(c, DI_FMIN_SLOT)[d];
       if (c.lane == 0) { c.H->ev_fin++; dcsim_finish_account(c, d, slot); }
-      dcsim_running_erase(c, d, slot); /* reads records the accounting did not touch; syncs before it returns */
-      if (c.lane == 0) { dcsim_dequeue_loop(c, d); dcsim_refresh_power(c, d); }
+      dcsim_running_erase<CAP>(c, d, slot); /* reads records the accounting did not touch; syncs before it returns */
+      if (c.lane == 0) { dcsim_dequeue_loop<CAP>(c, d); dcsim_refresh_power(c, d); }
       dcsim_warp_sync();
       dcsim_rescan_dc(c, d);
-    } else {
+    } else if (kind == KIND_LOG) {
       if (c.lane == 0) c.H->ev_log++;
-      dcsim_handle_log(c);
+      dcsim_handle_log<CAP>(c);
+    } else if constexpr (CAP) { /* a superseded job_finish: it advanced the clock and accrued energy, nothing else (SIM:456-461) */
+      if (c.lane == 0) {
+        c.H->ev_fin++;
+        const uint32_t k = c.H->smin_slot, last = c.H->n_stale - 1u;
+        dcsim_at<double>(c.blk, c.P->L.st_t)[k] = dcsim_at<double>(c.blk, c.P->L.st_t)[last];
+        dcsim_at<uint32_t>(c.blk, c.P->L.st_seq)[k] = dcsim_at<uint32_t>(c.blk, c.P->L.st_seq)[last];
+        c.H->n_stale = last;
+      }
+      dcsim_warp_sync();
+      dcsim_rescan_stale(c);
     }
   }
   if (finished && c.H->done == 0u) {
@@ -1044,6 +1246,7 @@ DCSIM_DEV void dcsim_write_summary(dcsim_ctx_t& c, double* out) {
 
 /* One replica, one launch: (init |) resume -> run -> summary.  `blk` is the working copy of the state
  * block (shared memory on the GPU), already loaded unless `fresh`. */
+template <bool CAP>
 DCSIM_DEV uint32_t dcsim_replica_step(const dcsim_kparams_t* P, uint64_t r, char* blk, bool fresh) {
   dcsim_ctx_t c;
   c.P = P; c.blk = blk; c.H = reinterpret_cast<dcsim_hdr_t*>(blk); c.lane = dcsim_lane();
@@ -1059,7 +1262,7 @@ DCSIM_DEV uint32_t dcsim_replica_step(const dcsim_kparams_t* P, uint64_t r, char
     c.rng_base = c.rng_pos + 1u; /* nothing staged */
   }
   uint32_t n = 0u;
-  if (c.H->done == 0u) n = dcsim_replica_run(c);
+  if (c.H->done == 0u) n = dcsim_replica_run<CAP>(c);
   if (c.lane == 0) { c.H->rng_pos = c.rng_pos; c.H->seq = c.seq; c.H->now = c.now; c.H->last_t = c.H->n_events ? c.now : 0.0; }
   dcsim_warp_sync();
   dcsim_write_summary(c, P->summary + r * DCSIM_SUMMARY_K);

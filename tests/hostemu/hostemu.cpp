@@ -46,7 +46,7 @@ long long hostemu_run_batch(const void* spec_blob, size_t spec_bytes, uint64_t n
     for (int guard = 0; guard < 100000000; ++guard) {
       const bool fresh = ((dcsim_hdr_t*)home)->initialized == 0u;
       if (!fresh) memcpy(work, home, (size_t)P->L.total_bytes); /* stage in */
-      total += dcsim_replica_step(P, r, work, fresh);
+      total += P->L.cap_stale ? dcsim_replica_step<true>(P, r, work, fresh) : dcsim_replica_step<false>(P, r, work, fresh);
       memcpy(home, work, (size_t)P->L.total_bytes);             /* stage out */
       const dcsim_hdr_t* H = (const dcsim_hdr_t*)home;
       if (H->done || H->status || chunk_events == 0) break;

@@ -8,7 +8,7 @@ import pytest
 from conftest import golden_names
 from distributed_cluster_gpus_b200 import scenarios as SC, spec as S
 
-DEVICE_SUPPORTED = [n for n in golden_names() if not n.startswith("cap_greedy")]
+DEVICE_SUPPORTED = golden_names()
 HIGH_WATER = (S.S_MAX_XFER, S.S_MAX_RUN, S.S_MAX_Q)
 
 

@@ -17,7 +17,7 @@ RTOL = 1e-9
 COUNT_COLS = (S.S_STATUS, S.S_EVENTS, S.S_JOBS_FINISHED, S.S_JOBS_CREATED, S.S_FIN_INF, S.S_FIN_TRN, S.S_RNG_WORDS,
               S.S_SEQ, S.S_EV_ARRIVAL, S.S_EV_XFER, S.S_EV_FINISH, S.S_EV_LOG, S.S_DONE)
 FLOAT_COLS = (S.S_TOTAL_ENERGY_J, S.S_LAT_SUM, S.S_LAT_SUM_INF, S.S_LAT_SUM_TRN, S.S_LAST_T)
-DEVICE_SUPPORTED = [n for n in golden_names() if not n.startswith("cap_greedy")]
+DEVICE_SUPPORTED = golden_names()
 
 
 def engine_cls():
@@ -193,8 +193,10 @@ def test_drop_in_simulator_and_csvs(tmp_path, oracle):
 
 def test_unsupported_and_invalid_specs_fail_loudly():
     from distributed_cluster_gpus_b200 import _native
-    with pytest.raises(_native.DcsimError, match="cap_greedy"):
-        engine_cls()(SC.to_spec(SC.BY_NAME["cap_greedy_4x64"]), 1, 0)
+    sp = SC.to_spec(SC.CFG1)
+    sp.algo = 99
+    with pytest.raises(_native.DcsimError, match="algo"):
+        engine_cls()(sp, 1, 0)
     sp = SC.to_spec(SC.CFG1)
     sp.n_dc = 0
     with pytest.raises(_native.DcsimError):

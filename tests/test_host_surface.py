@@ -38,7 +38,8 @@ def test_create_rejects_bad_arguments_without_a_gpu():
     buf = C.create_string_buffer(bytes(blob), len(blob))
     assert lib.dcsim_create(buf, len(blob), 1, 0, 0, 0, C.byref(h)) == _native.E_INVALID
     assert b"magic" in lib.dcsim_last_error(None)
-    sp = SC.to_spec(SC.BY_NAME["cap_greedy_4x64"])
+    sp = SC.to_spec(SC.CFG1)
+    sp.algo = 99
     buf = C.create_string_buffer(sp.to_bytes(), C.sizeof(sp))
     assert lib.dcsim_create(buf, C.sizeof(sp), 1, 0, 0, 0, C.byref(h)) == _native.E_UNSUPPORTED
 
