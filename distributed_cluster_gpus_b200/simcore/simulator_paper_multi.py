@@ -8,7 +8,7 @@ include/dcsim_b200.h.  Replica ``r`` is the trajectory the reference would produ
 the CSVs; all replicas are available as ``self.summary`` ([replicas, spec.SUMMARY_K]).
 
 Not on this path (raises): ``algo="chsac_af"`` / ``elastic_scaling`` (online torch agent mutating across events,
-SIM:555-573) and ``algo="cap_greedy"`` with a positive ``power_cap`` (device support pending).
+SIM:555-573).
 """
 import csv
 import os

@@ -201,3 +201,30 @@ def test_unsupported_and_invalid_specs_fail_loudly():
     sp.n_dc = 0
     with pytest.raises(_native.DcsimError):
         engine_cls()(sp, 1, 0)
+
+
+@pytest.mark.parametrize("name", ["cfg1_1x4_poisson_5000s", "cfg2_1x64_poisson_600s", "cfg3_4x64_sinusoid_120s",
+                                  "cfg3_4x64_sinusoid_600s", "cfg5_8x256_sinusoid_60s", "sweep_joint_nf"])
+def test_baseline_configs_64_replica_sample(oracle, name):
+    """>= 64 replicas per BASELINE config, full duration, exact counts + 1e-9 floats."""
+    sc = SC.BY_NAME[name]
+    sp = SC.to_spec(sc)
+    with engine_cls()(sp, 64, base_seed=20260921, first_replica_id=5) as eng:
+        total = eng.advance(0)
+        got = eng.summary()
+    want, want_total = oracle.run_batch(sp.to_bytes(), 64, 20260921, 5, n_threads=os.cpu_count() or 1)
+    assert total == want_total
+    worst = assert_rows_match(got, want, sc["n_dc"])
+    print(f"{name}: 64 replicas, {total} events, worst float rel err {worst:.2e}")
+
+
+def test_cli_runs_a_batch(tmp_path):
+    import json
+    from distributed_cluster_gpus_b200.run_sim_paper import main
+    out = tmp_path / "stats.json"
+    sim = main(["--duration", "30", "--inf-mode", "sinusoid", "--inf-rate", "10", "--inf-period", "3600", "--trn-rate", "1",
+                "--n-dc", "4", "--gpus-per-dc", "64", "--replicas", "256", "--log-path", str(tmp_path / "run" / "x"),
+                "--summary-json", str(out), "--progress", ""])
+    stats = json.load(open(out))
+    assert stats["replicas"] == 256 and stats["events_total"] == sim.summary[:, S.S_EVENTS].sum() > 256 * 1000
+    assert stats["energy_j_ci95"] > 0 and os.path.exists(sim.job_log_path) and os.path.exists(sim.cluster_log_path)
