@@ -195,8 +195,20 @@ int dcsim_create(const void* spec_blob, size_t spec_bytes, uint64_t n_replicas, 
   int smem_optin = 0;
   CREATE_TRY(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
   CREATE_TRY(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-  int wpc = smem_optin / h->L.total_bytes;
-  if (wpc > DCSIM_MAX_WARPS_PER_CTA) wpc = DCSIM_MAX_WARPS_PER_CTA;
+  /* warps per CTA: whichever of 4 / 2 / 1 keeps the most warps resident (each CTA also reserves 1 KB of shared
+   * memory and an SM holds at most 32 CTAs); small state blocks end up at 4 x 8 CTAs, large ones at 1 or 2 */
+  int smem_sm = 0;
+  CREATE_TRY(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device));
+  int wpc = 0, best_warps = 0;
+  for (int cand = DCSIM_MAX_WARPS_PER_CTA; cand >= 1; cand >>= 1) {
+    const long long per_cta = (long long)cand * h->L.total_bytes;
+    if (per_cta > smem_optin) continue;
+    int ctas = (int)(smem_sm / (per_cta + 1024));
+    if (ctas > 32) ctas = 32;
+    int warps = ctas * cand;
+    if (warps > DCSIM_MIN_CTAS_PER_SM * DCSIM_MAX_WARPS_PER_CTA) warps = DCSIM_MIN_CTAS_PER_SM * DCSIM_MAX_WARPS_PER_CTA; /* register bound */
+    if (warps > best_warps) { best_warps = warps; wpc = cand; }
+  }
   if (wpc < 1) {
     rc = set_err(NULL, DCSIM_E_UNSUPPORTED, "state block of %s%lld bytes does not fit one CTA's shared memory; lower cap_run / cap_xfer", "", h->L.total_bytes);
     dcsim_destroy(h);

@@ -541,6 +541,7 @@ DCSIM_DEV void dcsim_running_erase(dcsim_ctx_t& c, int d, int k) {
       dcsim_warp_sync();
     }
   }
+  dcsim_warp_sync(); /* every lane has read n (and finished its copies) before the count changes */
   if (c.lane == 0) DCI(c, DI_NRUN)[d] = n - 1;
   dcsim_warp_sync();
 }
@@ -1153,6 +1154,7 @@ DCSIM_DEV uint32_t dcsim_replica_run(dcsim_ctx_t& c) {
       }
       DCF(c, DF_LAST_T)[d] = t;
     }
+    dcsim_warp_sync(); /* every lane has read its candidate / busy / power before lane 0's handler rewrites them */
     ++done_here;
     c.now = t;
     const int kind = win < CAND_STREAM0 ? KIND_FINISH
@@ -1263,6 +1265,7 @@ DCSIM_DEV uint32_t dcsim_replica_step(const dcsim_kparams_t* P, uint64_t r, char
   }
   uint32_t n = 0u;
   if (c.H->done == 0u) n = dcsim_replica_run<CAP>(c);
+  dcsim_warp_sync();
   if (c.lane == 0) { c.H->rng_pos = c.rng_pos; c.H->seq = c.seq; c.H->now = c.now; c.H->last_t = c.H->n_events ? c.now : 0.0; }
   dcsim_warp_sync();
   dcsim_write_summary(c, P->summary + r * DCSIM_SUMMARY_K);
