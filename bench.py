@@ -318,7 +318,7 @@ def run_b200(args, world, rank, local_rank):
                 "config": config_dict(sc, args, world, {"events_per_step": events_total / args.steps,
                                                         "failed_replicas": failed, "launch": info}),
                 "roofline": roofline, "cpu_baseline": cpu_baseline(sc) if world == 1 and not args.no_cpu_baseline else None,
-                "e2e": e2e, "gpu_launches": 2 * args.steps, "clocks": clocks, "impl": "b200"}
+                "e2e": e2e, "gpu_launches": (3 if info.get("arrivals_prepass") else 2) * args.steps, "clocks": clocks, "impl": "b200"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -29,7 +29,8 @@ extern __shared__ __align__(16) char dcsim_smem[];
 /* CAP = the power-cap controller (algo = cap_greedy with power_cap > 0: SIM:207-338) is compiled in.  It is a
  * separate instantiation because merely inlining that cold code costs the common path 17 % (measured,
  * profiles/r01_variants_ab.md). */
-template <bool CAP>
+/* PRE = arrivals come from the list written by dcsim_arrivals_kernel (no sampling in this kernel). */
+template <bool CAP, bool PRE>
 __global__ void __launch_bounds__(DCSIM_MAX_WARPS_PER_CTA * 32, DCSIM_MIN_CTAS_PER_SM)
 dcsim_advance_kernel(const __grid_constant__ dcsim_kparams_t P, unsigned long long* __restrict__ events_total) {
   const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31u);
@@ -46,7 +47,7 @@ dcsim_advance_kernel(const __grid_constant__ dcsim_kparams_t P, unsigned long lo
     for (int i = lane; i < bytes / 16; i += 32) dst[i] = src[i];
   }
   __syncwarp();
-  const uint32_t n = dcsim_replica_step<CAP>(&P, r, blk, fresh);
+  const uint32_t n = dcsim_replica_step<CAP, PRE>(&P, r, blk, fresh);
   __syncwarp();
   {
     const uint4* src = reinterpret_cast<const uint4*>(blk);
@@ -54,6 +55,17 @@ dcsim_advance_kernel(const __grid_constant__ dcsim_kparams_t P, unsigned long lo
     for (int i = lane; i < bytes / 16; i += 32) dst[i] = src[i];
   }
   if (lane == 0 && n) atomicAdd(events_total, (unsigned long long)n);
+}
+
+/* Arrival pre-pass: one THREAD per replica generates that replica's whole arrival list (instants, sizes, routed
+ * DCs) in the reference's draw order; consecutive threads = consecutive replicas, so all 32 lanes of a warp run the
+ * samplers (pow / log / sin / rejection loops) that the event loop would otherwise run on one lane. */
+#define DCSIM_ARRIVALS_THREADS 128
+extern __shared__ __align__(16) double dcsim_arr_scratch[];
+__global__ void __launch_bounds__(DCSIM_ARRIVALS_THREADS) dcsim_arrivals_kernel(const __grid_constant__ dcsim_kparams_t P) {
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= P.n_replicas) return;
+  dcsim_generate_arrivals(&P, r, dcsim_arr_scratch + threadIdx.x, (int)blockDim.x); /* stream clocks: [stream][thread] */
 }
 
 /* Aggregates the summaries; every block reduces a slice, then one atomicAdd per component. */
@@ -104,6 +116,12 @@ struct dcsim {
   uint32_t trace_cap, jobs_cap, cluster_cap;
   int64_t trace_replica, log_replica;
   int launches;
+  int prepass, arrivals_ready;
+  double* d_arr_t;
+  double* d_arr_size;
+  uint32_t* d_arr_meta;
+  dcsim_arrhdr_t* d_arr_hdr;
+  uint32_t cap_arr;
   unsigned long long events_seen;
   char err[512];
 };
@@ -173,7 +191,12 @@ int dcsim_create(const void* spec_blob, size_t spec_bytes, uint64_t n_replicas, 
   if (!h) return set_err(NULL, DCSIM_E_NOMEM, "create: host allocation failed%s%lld");
   memset(h, 0, sizeof(*h));
   h->spec = sp;
-  dcsim_make_layout(&h->spec, &h->L);
+  { /* DCSIM_PREPASS=0 keeps the samplers inside the event loop (the round-1 v3 kernel); default: pre-pass */
+    const char* e = getenv("DCSIM_PREPASS");
+    h->prepass = !(e && e[0] == '0');
+  }
+  dcsim_make_layout(&h->spec, &h->L, h->prepass);
+  h->cap_arr = (uint32_t)(h->spec.cap_arrivals > 0 ? h->spec.cap_arrivals : 16384);
   h->n_replicas = n_replicas;
   h->seed0 = base_seed + first_replica_id;
   h->device = device;
@@ -217,16 +240,21 @@ int dcsim_create(const void* spec_blob, size_t spec_bytes, uint64_t n_replicas, 
   h->warps_per_cta = wpc;
   h->smem_bytes = wpc * h->L.total_bytes;
   h->ctas = (int)((n_replicas + (uint64_t)wpc - 1) / (uint64_t)wpc);
-  const void* kern = h->L.cap_stale ? (const void*)dcsim_advance_kernel<true> : (const void*)dcsim_advance_kernel<false>;
+  const void* kern = h->L.cap_stale ? (h->prepass ? (const void*)dcsim_advance_kernel<true, true> : (const void*)dcsim_advance_kernel<true, false>)
+                                    : (h->prepass ? (const void*)dcsim_advance_kernel<false, true> : (const void*)dcsim_advance_kernel<false, false>);
   CREATE_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
   cudaFuncAttributes fa;
   CREATE_TRY(cudaFuncGetAttributes(&fa, kern));
   h->regs = fa.numRegs;
   int blocks_per_sm = 0;
-  if (h->L.cap_stale) {
-    CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, dcsim_advance_kernel<true>, wpc * 32, h->smem_bytes));
+  if (h->L.cap_stale && h->prepass) {
+    CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, dcsim_advance_kernel<true, true>, wpc * 32, h->smem_bytes));
+  } else if (h->L.cap_stale) {
+    CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, dcsim_advance_kernel<true, false>, wpc * 32, h->smem_bytes));
+  } else if (h->prepass) {
+    CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, dcsim_advance_kernel<false, true>, wpc * 32, h->smem_bytes));
   } else {
-    CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, dcsim_advance_kernel<false>, wpc * 32, h->smem_bytes));
+    CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, dcsim_advance_kernel<false, false>, wpc * 32, h->smem_bytes));
   }
   h->resident_warps = blocks_per_sm * wpc;
 
@@ -237,6 +265,13 @@ int dcsim_create(const void* spec_blob, size_t spec_bytes, uint64_t n_replicas, 
   CREATE_TRY(cudaMalloc(&h->d_state, state_bytes));
   CREATE_TRY(cudaMalloc(&h->d_queues, queue_bytes ? queue_bytes : 16));
   CREATE_TRY(cudaMalloc(&h->d_summary, (size_t)n_replicas * DCSIM_SUMMARY_K * sizeof(double)));
+  if (h->prepass) {
+    const size_t ne = (size_t)n_replicas * (size_t)h->cap_arr;
+    CREATE_TRY(cudaMalloc(&h->d_arr_t, ne * sizeof(double)));
+    CREATE_TRY(cudaMalloc(&h->d_arr_size, ne * sizeof(double)));
+    CREATE_TRY(cudaMalloc(&h->d_arr_meta, ne * sizeof(uint32_t)));
+    CREATE_TRY(cudaMalloc(&h->d_arr_hdr, (size_t)n_replicas * sizeof(dcsim_arrhdr_t)));
+  }
   CREATE_TRY(cudaMalloc(&h->d_events, sizeof(unsigned long long)));
   CREATE_TRY(cudaMalloc(&h->d_counts, 4 * sizeof(uint32_t)));
   CREATE_TRY(cudaMemsetAsync(h->d_state, 0, state_bytes, h->stream)); /* hdr.initialized == 0 => fresh replica */
@@ -256,6 +291,7 @@ int dcsim_reset(dcsim_t* h, uint64_t base_seed, uint64_t first_replica_id) {
   CUDA_TRY(h, cudaMemsetAsync(h->d_state, 0, (size_t)h->n_replicas * (size_t)h->L.total_bytes, h->stream));
   CUDA_TRY(h, cudaMemsetAsync(h->d_counts, 0, 4 * sizeof(uint32_t), h->stream));
   h->seed0 = base_seed + first_replica_id;
+  h->arrivals_ready = 0;
   return DCSIM_OK;
 }
 
@@ -310,8 +346,22 @@ int dcsim_advance(dcsim_t* h, uint64_t max_events_per_replica, uint64_t* total_e
   P.max_events = max_events_per_replica;
   P.state = h->d_state; P.queues = h->d_queues; P.summary = h->d_summary;
   P.end_eps = h->spec.end_time + 1e-9; /* SIM:161 */
-  if (h->L.cap_stale) dcsim_advance_kernel<true><<<h->ctas, h->warps_per_cta * 32, h->smem_bytes, h->stream>>>(P, h->d_events);
-  else dcsim_advance_kernel<false><<<h->ctas, h->warps_per_cta * 32, h->smem_bytes, h->stream>>>(P, h->d_events);
+  P.arr_t = h->d_arr_t; P.arr_size = h->d_arr_size; P.arr_meta = h->d_arr_meta; P.arr_hdr = h->d_arr_hdr; P.cap_arr = h->cap_arr;
+  const dim3 grid(h->ctas), block(h->warps_per_cta * 32);
+  if (h->prepass) {
+    if (!h->arrivals_ready) { /* once per (re)seeded batch: the arrival lists of all replicas */
+      const int nb = (int)((h->n_replicas + DCSIM_ARRIVALS_THREADS - 1) / DCSIM_ARRIVALS_THREADS);
+      dcsim_arrivals_kernel<<<nb, DCSIM_ARRIVALS_THREADS, 2 * DCSIM_MAX_ING * DCSIM_ARRIVALS_THREADS * sizeof(double), h->stream>>>(P);
+      CUDA_TRY(h, cudaGetLastError());
+      h->arrivals_ready = 1;
+      h->launches++;
+    }
+    if (h->L.cap_stale) dcsim_advance_kernel<true, true><<<grid, block, h->smem_bytes, h->stream>>>(P, h->d_events);
+    else dcsim_advance_kernel<false, true><<<grid, block, h->smem_bytes, h->stream>>>(P, h->d_events);
+  } else {
+    if (h->L.cap_stale) dcsim_advance_kernel<true, false><<<grid, block, h->smem_bytes, h->stream>>>(P, h->d_events);
+    else dcsim_advance_kernel<false, false><<<grid, block, h->smem_bytes, h->stream>>>(P, h->d_events);
+  }
   CUDA_TRY(h, cudaGetLastError());
   h->launches++;
   if (total_events_out) {
@@ -426,6 +476,8 @@ int dcsim_launch_info(dcsim_t* h, dcsim_launch_info_t* out) {
   out->kernel_launches = h->launches;
   out->hbm_bytes_state = (uint64_t)h->n_replicas * (uint64_t)h->L.total_bytes;
   out->hbm_bytes_queues = (uint64_t)h->n_replicas * h->L.queue_bytes;
+  out->arrivals_prepass = h->prepass;
+  out->hbm_bytes_arrivals = h->prepass ? (uint64_t)h->n_replicas * ((uint64_t)h->cap_arr * 20ull + sizeof(dcsim_arrhdr_t)) : 0ull;
   return DCSIM_OK;
 }
 
@@ -437,6 +489,7 @@ void dcsim_destroy(dcsim_t* h) {
   if (h->own_stream) { cudaStreamSynchronize(h->stream); }
   cudaFree(h->d_state); cudaFree(h->d_queues); cudaFree(h->d_summary); cudaFree(h->d_events); cudaFree(h->d_counts);
   cudaFree(h->d_trace); cudaFree(h->d_jobs); cudaFree(h->d_cluster);
+  cudaFree(h->d_arr_t); cudaFree(h->d_arr_size); cudaFree(h->d_arr_meta); cudaFree(h->d_arr_hdr);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
 }

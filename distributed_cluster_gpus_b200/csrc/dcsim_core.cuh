@@ -118,7 +118,7 @@ struct dcsim_hdr_t {
   uint32_t n_fin_inf, n_fin_trn, ev_arr, ev_xfer;
   uint32_t ev_fin, ev_log, max_xfer, max_run;
   uint32_t max_q, xmin_slot, bandit_t, n_stale;
-  uint32_t smin_slot, _pad[3];
+  uint32_t smin_slot, arr_cursor, arr_count, aw_base; /* arrival-list cursor / length / first staged entry */
 };
 
 /* Byte offsets of the arrays inside a state block; computed once per handle on the host. */
@@ -134,6 +134,9 @@ struct dcsim_layout_t {
   int32_t st_t, st_seq;              /* stale job_finish pool */
   int32_t at_rho, at_fto, at_ref, at_idx; /* DVFS atoms scratch (freq_load_agg.py) */
   int32_t cap_stale, cap_atoms;
+  /* arrival pre-pass mode: a 32-entry staging window of the replica's arrival list + per-stream pending seq */
+  int32_t aw_t, aw_size, aw_meta, pend_seq;
+  int32_t prepass;
   int32_t total_bytes;
   int32_t cap_xfer, cap_run;
   int32_t cap_q[2];        /* FIFO entries per DC: [0]=inference [1]=training */
@@ -144,8 +147,9 @@ struct dcsim_layout_t {
 static inline int32_t dcsim_align16(int32_t x) { return (x + 15) & ~15; }
 
 /* Host-side: sizes the state block from the spec's capacities. */
-static inline void dcsim_make_layout(const dcsim_spec_t* sp, dcsim_layout_t* L) {
+static inline void dcsim_make_layout(const dcsim_spec_t* sp, dcsim_layout_t* L, int prepass) {
   memset(L, 0, sizeof(*L));
+  L->prepass = prepass ? 1 : 0;
   const int D = DCSIM_MAX_DC;
   int32_t cx = sp->cap_xfer > 0 ? sp->cap_xfer : 64;
   int32_t cr = sp->cap_run > 0 ? sp->cap_run : 16;
@@ -175,7 +179,14 @@ static inline void dcsim_make_layout(const dcsim_spec_t* sp, dcsim_layout_t* L) 
   L->rn_seq = o; o += nr * 4;
   L->rn_meta = o; o += nr * 4;
   L->rn_jid = o; o = dcsim_align16(o + nr * 4);
-  L->rng_buf = o; o += (int32_t)DCSIM_RNG_WINDOW * 4;
+  if (prepass) { /* no in-kernel sampling: the Philox window gives way to the arrival-list window */
+    L->aw_t = o; o += 32 * 8;
+    L->aw_size = o; o += 32 * 8;
+    L->aw_meta = o; o += 32 * 4;
+    L->pend_seq = o; o += 2 * DCSIM_MAX_ING * 4;
+  } else {
+    L->rng_buf = o; o += (int32_t)DCSIM_RNG_WINDOW * 4;
+  }
   if (sp->xfer_rule == DCSIM_START_BANDIT || sp->deq_rule == DCSIM_START_BANDIT) {
     L->bandit_s = o; o += sp->n_dc * 2 * DCSIM_MAX_FREQ * 8;
     L->bandit_n = o; o += sp->n_dc * 2 * DCSIM_MAX_FREQ * 4;
@@ -218,6 +229,14 @@ struct dcsim_recorders_t {
   int64_t log_replica;
 };
 
+/* Per-replica result of the arrival pre-pass. */
+struct dcsim_arrhdr_t {
+  uint32_t count;      /* arrivals with t <= end_time, i.e. arrival events the loop will process */
+  uint32_t first_mask; /* bit s: stream s's first arrival was schedulable (took a seq at construction, SIM:154-156) */
+  uint32_t rng_words;  /* words the whole run consumes */
+  uint32_t status;     /* DCSIM_ST_* raised while generating */
+};
+
 /* Everything a launch needs.  Passed as ONE __grid_constant__ kernel parameter, so the scenario is read
  * through the constant cache and never competes with the state blocks for shared memory / L1. */
 struct dcsim_kparams_t {
@@ -230,6 +249,12 @@ struct dcsim_kparams_t {
   char* state;          /* [n_replicas][L.total_bytes] */
   char* queues;         /* [n_replicas][L.queue_bytes] */
   double* summary;      /* [n_replicas][DCSIM_SUMMARY_K] */
+  /* arrival lists (pre-pass mode), replica-major SoA: entry k of replica r at [r * cap_arr + k] */
+  double* arr_t;        /* arrival instant */
+  double* arr_size;     /* job size (arrivals.py:5-11) */
+  uint32_t* arr_meta;   /* stream (bits 0-3) | routed DC (4-6) | next arrival of the stream was schedulable (7) */
+  struct dcsim_arrhdr_t* arr_hdr;
+  uint32_t cap_arr, _pad0;
   double end_eps;       /* end_time + 1e-9, the _schedule cut-off (SIM:161) */
 };
 
@@ -425,6 +450,139 @@ DCSIM_DEV double dcsim_next_interarrival(dcsim_ctx_t& c, int jt, double t) {
     }
   }
   return DCSIM_INF;
+}
+
+/* ================================================================================================
+ * Arrival pre-pass (one THREAD per replica)
+ *
+ * In every algo on this path the arrival process does not depend on data-centre state: only arrival handlers
+ * draw random numbers (arrivals.py:8,11,15,44; SIM:576) and routing is random.choice or eco_route's static
+ * E_unit * size score (SIM:544-553, 575-577).  So the replica's whole arrival sequence — instants, sizes, routed
+ * DCs, and which pushes were schedulable — can be generated ahead of the event loop, in the reference's draw order
+ * (arrival events in time order; inside one: size -> route -> next gap), by one thread per replica with all 32
+ * lanes of a warp busy, instead of on one lane of the replica's warp.  The event loop then consumes the list.
+ * ============================================================================================== */
+struct dcsim_trng_t { uint32_t k0, k1, pos, bidx, w0, w1, w2, w3; };
+
+#ifndef DCSIM_HOST_EMU
+__device__ __noinline__
+#else
+static
+#endif
+void dcsim_trng_refill(dcsim_trng_t* g, uint32_t b) {
+  uint32_t w[4];
+  dcsim_philox_block(g->k0, g->k1, b, w);
+  g->w0 = w[0]; g->w1 = w[1]; g->w2 = w[2]; g->w3 = w[3]; g->bidx = b;
+}
+DCSIM_DEV uint32_t dcsim_trng_word(dcsim_trng_t& g) {
+  const uint32_t pos = g.pos++;
+  if ((pos >> 2) != g.bidx) dcsim_trng_refill(&g, pos >> 2);
+  const uint32_t j = pos & 3u;
+  return j == 0u ? g.w0 : (j == 1u ? g.w1 : (j == 2u ? g.w2 : g.w3));
+}
+DCSIM_DEV double dcsim_trng_random(dcsim_trng_t& g) {
+  const uint32_t a = dcsim_trng_word(g), b = dcsim_trng_word(g);
+  return dcsim_u53(a, b);
+}
+
+/* arrivals.py:35-48 with random.py:617; returns the gap (+inf for a dead stream) */
+DCSIM_DEV double dcsim_t_gap(dcsim_trng_t& g, const dcsim_spec_t& sp, int jt, double t, uint32_t* status) {
+  const dcsim_arrival_t& a = sp.arr[jt];
+  if (a.mode == DCSIM_ARR_POISSON) return a.rate <= 0.0 ? DCSIM_INF : -log(1.0 - dcsim_trng_random(g)) / a.rate;
+  if (a.mode == DCSIM_ARR_SINUSOID) {
+    const double abs_amp = a.amp < 0.0 ? -a.amp : a.amp;
+    const double max_rate = a.rate * (1.0 + abs_amp);
+    for (int it = 0;; ++it) {
+      if (it >= DCSIM_REJECTION_LIMIT) { *status |= DCSIM_ST_RNG_RUNAWAY; return DCSIM_INF; }
+      const double w = -log(1.0 - dcsim_trng_random(g)) / max_rate;
+      const double tc = t + w;
+      double lam = a.rate * (1.0 + a.amp * sin(sp.two_pi * dcsim_mod_pos(tc, a.period) / a.period));
+      lam = lam > 0.0 ? lam : 0.0;
+      if (dcsim_trng_random(g) <= lam / max_rate) return w;
+    }
+  }
+  return DCSIM_INF;
+}
+
+/* arrivals.py:5-11 with random.py:541-549, 597 */
+DCSIM_DEV double dcsim_t_size(dcsim_trng_t& g, const dcsim_spec_t& sp, int jt, uint32_t* status) {
+  if (jt == DCSIM_JT_INFERENCE) {
+    const double x = 1.0 - dcsim_trng_random(g);
+    const double u = x > sp.uniform_floor ? x : sp.uniform_floor;
+    return sp.pareto_xm / pow(u, sp.pareto_inv_alpha);
+  }
+  double z = 0.0;
+  for (int it = 0;; ++it) {
+    if (it >= DCSIM_REJECTION_LIMIT) { *status |= DCSIM_ST_RNG_RUNAWAY; break; }
+    const double u1 = dcsim_trng_random(g);
+    const double u2 = 1.0 - dcsim_trng_random(g);
+    z = sp.nv_magicconst * (u1 - 0.5) / u2;
+    const double zz = z * z / 4.0;
+    if (zz <= -log(u2)) break;
+  }
+  const double v = exp(sp.lognorm_mu + z * sp.lognorm_sigma);
+  return v > sp.lognorm_floor ? v : sp.lognorm_floor;
+}
+
+/* One replica's arrival list.  `next_t` is scratch for the 2*n_ing stream clocks, element s at next_t[s * stride]. */
+DCSIM_DEV void dcsim_generate_arrivals(const dcsim_kparams_t* P, uint64_t r, double* next_t, int stride) {
+  const dcsim_spec_t& sp = P->spec;
+  const int n_streams = 2 * sp.n_ing;
+  dcsim_trng_t g;
+  const uint64_t key = P->seed0 + r;
+  g.k0 = (uint32_t)key; g.k1 = (uint32_t)(key >> 32); g.pos = 0u; g.bidx = 0xffffffffu; g.w0 = g.w1 = g.w2 = g.w3 = 0u;
+  uint32_t status = 0u, first_mask = 0u, count = 0u;
+  const double end_eps = P->end_eps;
+  for (int s = 0; s < n_streams; ++s) { /* SIM:154-156 */
+    const double t = 0.0 + dcsim_t_gap(g, sp, s & 1, 0.0, &status);
+    const bool ok = !(t == DCSIM_INF) && !(t > end_eps);
+    next_t[s * stride] = ok ? t : DCSIM_INF;
+    if (ok) first_mask |= 1u << s;
+  }
+  double* out_t = P->arr_t + r * (uint64_t)P->cap_arr;
+  double* out_size = P->arr_size + r * (uint64_t)P->cap_arr;
+  uint32_t* out_meta = P->arr_meta + r * (uint64_t)P->cap_arr;
+  const int k_bits = dcsim_bit_length((uint32_t)sp.n_dc);
+  for (;;) {
+    int s = -1;
+    double t = DCSIM_INF;
+    bool tie = false;
+    for (int q = 0; q < n_streams; ++q) {
+      const double tq = next_t[q * stride];
+      if (tq < t) { t = tq; s = q; tie = false; } else if (tq == t && s >= 0 && !(tq == DCSIM_INF)) tie = true;
+    }
+    if (s < 0 || t > sp.end_time) break; /* heap empty / SIM:427 */
+    if (tie) { status |= DCSIM_ST_ARRIVAL_TIE; break; }
+    if (status) break;
+    const int jt = s & 1;
+    const double size = dcsim_t_size(g, sp, jt, &status); /* draw order: size -> route -> next gap (SIM:540,576,591) */
+    int dc_sel = 0;
+    if (sp.route_rule == DCSIM_ROUTE_ECO) { /* SIM:544-553 */
+      double best = sp.dc[0].eco_e_unit[jt] * size;
+      for (int d = 1; d < sp.n_dc; ++d) {
+        const double score = sp.dc[d].eco_e_unit[jt] * size;
+        if (score < best) { best = score; dc_sel = d; }
+      }
+    } else { /* random.choice: random.py:242-250 */
+      uint32_t v = dcsim_trng_word(g) >> (32 - k_bits);
+      for (int it = 0; v >= (uint32_t)sp.n_dc; ++it) {
+        if (it >= DCSIM_REJECTION_LIMIT) { status |= DCSIM_ST_RNG_RUNAWAY; v = 0u; break; }
+        v = dcsim_trng_word(g) >> (32 - k_bits);
+      }
+      dc_sel = (int)v;
+    }
+    const double tn = t + dcsim_t_gap(g, sp, jt, t, &status);
+    const bool has_next = !(tn == DCSIM_INF) && !(tn > end_eps);
+    next_t[s * stride] = has_next ? tn : DCSIM_INF;
+    if (count >= P->cap_arr) { status |= DCSIM_ST_ARRIVALS_OVERFLOW; break; }
+    out_t[count] = t;
+    out_size[count] = size;
+    out_meta[count] = (uint32_t)s | ((uint32_t)dc_sel << 4) | (has_next ? 0x80u : 0u);
+    ++count;
+  }
+  dcsim_arrhdr_t h;
+  h.count = count; h.first_mask = first_mask; h.rng_words = g.pos; h.status = status;
+  P->arr_hdr[r] = h;
 }
 
 /* ================================================================================================
@@ -800,6 +958,80 @@ DCSIM_DEV void dcsim_handle_arrival(dcsim_ctx_t& c, int stream) {
   }
 }
 
+/* Warp.  Stages entries [base, base+32) of the replica's arrival list into shared memory (coalesced). */
+DCSIM_DEV void dcsim_arrivals_stage(dcsim_ctx_t& c, uint64_t r, uint32_t base) {
+  const dcsim_layout_t& L = c.P->L;
+  const uint64_t off = r * (uint64_t)c.P->cap_arr + base;
+  const uint32_t count = c.H->arr_count;
+  for (uint32_t i = (uint32_t)c.lane; i < 32u; i += DCSIM_LANES) {
+    const bool in = base + i < count;
+    dcsim_at<double>(c.blk, L.aw_t)[i] = in ? c.P->arr_t[off + i] : DCSIM_INF;
+    dcsim_at<double>(c.blk, L.aw_size)[i] = in ? c.P->arr_size[off + i] : 0.0;
+    dcsim_at<uint32_t>(c.blk, L.aw_meta)[i] = in ? c.P->arr_meta[off + i] : 0u;
+  }
+  if (c.lane == 0) c.H->aw_base = base;
+  dcsim_warp_sync();
+}
+
+/* Lane 0.  Publishes list entry `k` as the (single) arrival candidate; its seq is the one its stream was given
+ * when the stream's previous arrival (or the constructor) pushed it. */
+DCSIM_DEV void dcsim_arrival_candidate(dcsim_ctx_t& c, uint32_t k) {
+  const dcsim_layout_t& L = c.P->L;
+  if (k < c.H->arr_count) {
+    const uint32_t i = k - c.H->aw_base;
+    const uint32_t stream = dcsim_at<uint32_t>(c.blk, L.aw_meta)[i] & 15u;
+    CAND_T(c)[CAND_STREAM0] = dcsim_at<double>(c.blk, L.aw_t)[i];
+    CAND_SEQ(c)[CAND_STREAM0] = dcsim_at<uint32_t>(c.blk, L.pend_seq)[stream];
+  } else {
+    CAND_T(c)[CAND_STREAM0] = DCSIM_INF;
+    CAND_SEQ(c)[CAND_STREAM0] = 0xffffffffu;
+  }
+}
+
+/* SIM:537-592 when the arrival list exists: the job's size / DC / "next arrival schedulable" come from the list;
+ * what remains is the xfer_done push and the seq bookkeeping.  Whole warp (the window may need re-staging). */
+DCSIM_DEV void dcsim_handle_arrival_listed(dcsim_ctx_t& c, uint64_t r) {
+  const dcsim_spec_t& sp = c.P->spec;
+  const dcsim_layout_t& L = c.P->L;
+  dcsim_hdr_t* H = c.H;
+  const uint32_t k = H->arr_cursor;
+  if (c.lane == 0) {
+    const uint32_t i = k - H->aw_base;
+    const double size = dcsim_at<double>(c.blk, L.aw_size)[i];
+    const uint32_t meta = dcsim_at<uint32_t>(c.blk, L.aw_meta)[i];
+    const uint32_t stream = meta & 15u;
+    const int jt = (int)(stream & 1u), ing = (int)(stream >> 1), dc_sel = (int)((meta >> 4) & 7u);
+    const uint32_t jid = k + 1u; /* SIM:539: jids count arrivals */
+    H->jid = jid;
+    H->ev_arr++;
+    const double t_x = c.now + sp.transfer_s[ing][dc_sel][jt];
+    if (dcsim_schedulable(c, t_x)) { /* SIM:580-588 */
+      const uint32_t slot = H->n_xfer;
+      if ((int)slot >= L.cap_xfer) {
+        H->status |= DCSIM_ST_XFER_OVERFLOW;
+      } else {
+        const uint32_t seq = c.seq++;
+        dcsim_at<double>(c.blk, L.xf_t)[slot] = t_x;
+        dcsim_at<double>(c.blk, L.xf_size)[slot] = size;
+        dcsim_at<uint32_t>(c.blk, L.xf_seq)[slot] = seq;
+        dcsim_at<uint32_t>(c.blk, L.xf_meta)[slot] = (uint32_t)dc_sel | ((uint32_t)jt << 3) | ((uint32_t)ing << 4);
+        dcsim_at<uint32_t>(c.blk, L.xf_jid)[slot] = jid;
+        H->n_xfer = slot + 1u;
+        if (slot + 1u > H->max_xfer) H->max_xfer = slot + 1u;
+        const double ct = CAND_T(c)[CAND_XFER];
+        if (t_x < ct || (t_x == ct && seq < CAND_SEQ(c)[CAND_XFER])) {
+          CAND_T(c)[CAND_XFER] = t_x; CAND_SEQ(c)[CAND_XFER] = seq; H->xmin_slot = slot;
+        }
+      }
+    }
+    if (meta & 0x80u) dcsim_at<uint32_t>(c.blk, L.pend_seq)[stream] = c.seq++; /* SIM:591-592 push of the next arrival */
+    H->arr_cursor = k + 1u;
+  }
+  dcsim_warp_sync();
+  if (k + 1u - c.H->aw_base >= 32u && k + 1u < c.H->arr_count) dcsim_arrivals_stage(c, r, k + 1u);
+  if (c.lane == 0) dcsim_arrival_candidate(c, k + 1u);
+}
+
 /* SIM:595-678 (lane 0 part): consume pool entry `slot`, start the job or queue it. */
 template <bool CAP>
 DCSIM_DEV void dcsim_handle_xfer(dcsim_ctx_t& c, int slot) {
@@ -1071,7 +1303,8 @@ DCSIM_DEV void dcsim_handle_log(dcsim_ctx_t& c) {
  * ============================================================================================== */
 /* SIM:31-157, the parts that touch simulation state: zeroed DCs at default_freq, one pending arrival per
  * (ingress, job type) in dict order inf-then-trn, then the first log tick. */
-DCSIM_DEV void dcsim_replica_init(dcsim_ctx_t& c) {
+template <bool PRE>
+DCSIM_DEV void dcsim_replica_init(dcsim_ctx_t& c, uint64_t r) {
   const dcsim_spec_t& sp = c.P->spec;
   const dcsim_layout_t& L = c.P->L;
   for (int i = c.lane; i < L.total_bytes / 4; i += DCSIM_LANES) dcsim_at<uint32_t>(c.blk, 0)[i] = 0u;
@@ -1084,6 +1317,24 @@ DCSIM_DEV void dcsim_replica_init(dcsim_ctx_t& c) {
   }
   dcsim_warp_sync();
   c.rng_pos = 0u; c.rng_base = 1u; c.seq = 0u; c.now = 0.0;
+  if constexpr (PRE) { /* the pre-pass already drew everything: hand out the constructor's seqs (SIM:154-157) */
+    if (c.lane == 0) {
+      const dcsim_arrhdr_t ah = c.P->arr_hdr[r];
+      c.H->arr_count = ah.count; c.H->arr_cursor = 0u; c.H->status |= ah.status;
+      c.rng_pos = ah.rng_words;
+      for (int s = 0; s < 2 * sp.n_ing; ++s)
+        if ((ah.first_mask >> s) & 1u) dcsim_at<uint32_t>(c.blk, L.pend_seq)[s] = c.seq++;
+      const double t = 0.0 + sp.log_interval;
+      if (dcsim_schedulable(c, t)) { CAND_T(c)[CAND_LOG] = t; CAND_SEQ(c)[CAND_LOG] = c.seq++; }
+      c.H->xmin_slot = 0xffffffffu;
+      c.H->initialized = 1u;
+    }
+    dcsim_warp_sync();
+    dcsim_arrivals_stage(c, r, 0u);
+    if (c.lane == 0) dcsim_arrival_candidate(c, 0u);
+    dcsim_warp_sync();
+    return;
+  }
   for (int s = 0; s < 2 * sp.n_ing; ++s) { /* SIM:154-156 */
     dcsim_rng_ensure(c, c.rng_pos);
     if (c.lane == 0) {
@@ -1129,8 +1380,8 @@ DCSIM_DEV void dcsim_replica_tail(dcsim_ctx_t& c) {
  * Visibility protocol: every branch ends with a warp sync, so at the top of an iteration all shared-memory
  * writes of the previous event are visible to every lane; inside a branch a sync separates lane 0's handler
  * from the warp-parallel step that reads what it wrote. */
-template <bool CAP>
-DCSIM_DEV uint32_t dcsim_replica_run(dcsim_ctx_t& c) {
+template <bool CAP, bool PRE>
+DCSIM_DEV uint32_t dcsim_replica_run(dcsim_ctx_t& c, uint64_t r) {
   const dcsim_spec_t& sp = c.P->spec;
   const uint64_t budget = c.P->max_events;
   uint32_t done_here = 0u;
@@ -1157,8 +1408,11 @@ DCSIM_DEV uint32_t dcsim_replica_run(dcsim_ctx_t& c) {
     dcsim_warp_sync(); /* every lane has read its candidate / busy / power before lane 0's handler rewrites them */
     ++done_here;
     c.now = t;
-    const int kind = win < CAND_STREAM0 ? KIND_FINISH
-                     : (win < CAND_XFER ? (win & 1) : (win == CAND_XFER ? KIND_XFER : (win == CAND_LOG ? KIND_LOG : KIND_STALE)));
+    int kind = win < CAND_STREAM0 ? KIND_FINISH
+               : (win < CAND_XFER ? (win & 1) : (win == CAND_XFER ? KIND_XFER : (win == CAND_LOG ? KIND_LOG : KIND_STALE)));
+    if constexpr (PRE) { /* one arrival candidate for all streams: the job type is in the list entry */
+      if (win == CAND_STREAM0) kind = (int)(dcsim_at<uint32_t>(c.blk, c.P->L.aw_meta)[c.H->arr_cursor - c.H->aw_base] & 1u);
+    }
     if (c.lane == 0) {
       c.H->n_events++;
       if (c.is_traced && c.P->rec.trace) {
@@ -1169,8 +1423,12 @@ DCSIM_DEV uint32_t dcsim_replica_run(dcsim_ctx_t& c) {
     }
 
     if (kind == KIND_ARR_INF || kind == KIND_ARR_TRN) {
-      dcsim_rng_ensure(c, c.rng_pos); /* rng_pos is warp-uniform between arrivals */
-      dcsim_handle_arrival(c, win - CAND_STREAM0);
+      if constexpr (PRE) {
+        dcsim_handle_arrival_listed(c, r);
+      } else {
+        dcsim_rng_ensure(c, c.rng_pos); /* rng_pos is warp-uniform between arrivals */
+        dcsim_handle_arrival(c, win - CAND_STREAM0);
+      }
       dcsim_warp_sync();
     } else if (kind == KIND_XFER) {
       if (c.lane == 0) { c.H->ev_xfer++; dcsim_handle_xfer<CAP>(c, (int)c.H->xmin_slot); }
@@ -1248,7 +1506,7 @@ DCSIM_DEV void dcsim_write_summary(dcsim_ctx_t& c, double* out) {
 
 /* One replica, one launch: (init |) resume -> run -> summary.  `blk` is the working copy of the state
  * block (shared memory on the GPU), already loaded unless `fresh`. */
-template <bool CAP>
+template <bool CAP, bool PRE>
 DCSIM_DEV uint32_t dcsim_replica_step(const dcsim_kparams_t* P, uint64_t r, char* blk, bool fresh) {
   dcsim_ctx_t c;
   c.P = P; c.blk = blk; c.H = reinterpret_cast<dcsim_hdr_t*>(blk); c.lane = dcsim_lane();
@@ -1258,13 +1516,13 @@ DCSIM_DEV uint32_t dcsim_replica_step(const dcsim_kparams_t* P, uint64_t r, char
   const uint64_t key = P->seed0 + r;
   c.key0 = (uint32_t)key; c.key1 = (uint32_t)(key >> 32);
   if (fresh) {
-    dcsim_replica_init(c);
+    dcsim_replica_init<PRE>(c, r);
   } else { /* resume: hot scalars back into registers */
     c.rng_pos = c.H->rng_pos; c.seq = c.H->seq; c.now = c.H->now;
     c.rng_base = c.rng_pos + 1u; /* nothing staged */
   }
   uint32_t n = 0u;
-  if (c.H->done == 0u) n = dcsim_replica_run<CAP>(c);
+  if (c.H->done == 0u) n = dcsim_replica_run<CAP, PRE>(c, r);
   dcsim_warp_sync();
   if (c.lane == 0) { c.H->rng_pos = c.rng_pos; c.H->seq = c.seq; c.H->now = c.now; c.H->last_t = c.H->n_events ? c.now : 0.0; }
   dcsim_warp_sync();

@@ -130,7 +130,8 @@ class BatchedEngine:
 
 STATUS_NAMES = {S.ST_XFER_OVERFLOW: "in-flight transfer pool", S.ST_RUN_OVERFLOW: "running set",
                 S.ST_QUEUE_OVERFLOW: "FIFO queue", S.ST_STALE_OVERFLOW: "stale-event pool",
-                S.ST_RNG_RUNAWAY: "rejection-sampling runaway"}
+                S.ST_RNG_RUNAWAY: "rejection-sampling runaway", S.ST_ARRIVALS_OVERFLOW: "arrival list",
+                S.ST_ARRIVAL_TIE: "two arrivals at the identical instant"}
 
 
 def describe_status(bits: int) -> str:
@@ -153,13 +154,15 @@ def run_to_completion(spec_factory, n_replicas, base_seed, first_replica_id=0, d
         if bits == 0:
             return eng, summ
         eng.close()
-        if bits & S.ST_RNG_RUNAWAY or attempt == max_retries:
+        if bits & (S.ST_RNG_RUNAWAY | S.ST_ARRIVAL_TIE) or attempt == max_retries:
             raise RuntimeError(f"replicas stopped: {describe_status(bits)}")
         g_max = max(sp.dc[d].total_gpus for d in range(sp.n_dc))
         if bits & S.ST_RUN_OVERFLOW:
             caps["cap_run"] = g_max
         if bits & S.ST_XFER_OVERFLOW:
             caps["cap_xfer"] = 2 * sp.cap_xfer
+        if bits & S.ST_ARRIVALS_OVERFLOW:
+            caps["cap_arrivals"] = 2 * sp.cap_arrivals
         if bits & S.ST_QUEUE_OVERFLOW:
             caps["cap_q_inf"], caps["cap_q_trn"] = 2 * sp.cap_q_inf, 2 * sp.cap_q_trn
     raise AssertionError("unreachable")

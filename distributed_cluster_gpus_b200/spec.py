@@ -35,6 +35,7 @@ S_DC0, S_DC_STRIDE = 24, 8
 SUMMARY_K = 24 + 8 * MAX_DC
 SD_ENERGY_J, SD_UTIL_GPU_TIME, SD_ACC_JOB_UNIT, SD_BUSY, SD_CURRENT_FREQ, SD_Q_INF, SD_Q_TRN, SD_RUNNING = range(8)
 ST_XFER_OVERFLOW, ST_RUN_OVERFLOW, ST_QUEUE_OVERFLOW, ST_STALE_OVERFLOW, ST_RNG_RUNAWAY = 1, 2, 4, 8, 16
+ST_ARRIVALS_OVERFLOW, ST_ARRIVAL_TIE = 32, 64
 A_REPLICAS, A_FAILED, A_EVENTS, A_JOBS, A_ENERGY, A_ENERGY_SQ, A_LAT_SUM, A_MEANLAT_SUM, A_MEANLAT_SQ, A_RNG_WORDS = range(10)
 AGG_K = 16
 
@@ -79,7 +80,7 @@ class Spec(C.Structure):
                 ("net_lat_s", (C.c_double * MAX_DC) * MAX_ING),
                 ("dc", DCSpec * MAX_DC),
                 ("cap_xfer", C.c_int32), ("cap_run", C.c_int32), ("cap_q_inf", C.c_int32),
-                ("cap_q_trn", C.c_int32), ("cap_stale", C.c_int32), ("_pad_tail", C.c_int32)]
+                ("cap_q_trn", C.c_int32), ("cap_stale", C.c_int32), ("cap_arrivals", C.c_int32)]
 
     def to_bytes(self) -> bytes:
         return bytes(memoryview(self).cast("B"))
@@ -106,8 +107,8 @@ class LaunchInfo(C.Structure):
     _fields_ = [("warps_per_cta", C.c_int32), ("ctas", C.c_int32), ("smem_bytes_per_cta", C.c_int32),
                 ("regs_per_thread", C.c_int32), ("resident_warps_per_sm", C.c_int32), ("sm_count", C.c_int32),
                 ("cap_xfer", C.c_int32), ("cap_run", C.c_int32), ("cap_q_inf", C.c_int32), ("cap_q_trn", C.c_int32),
-                ("kernel_launches", C.c_int32), ("_pad", C.c_int32),
-                ("hbm_bytes_state", C.c_uint64), ("hbm_bytes_queues", C.c_uint64)]
+                ("kernel_launches", C.c_int32), ("arrivals_prepass", C.c_int32),
+                ("hbm_bytes_state", C.c_uint64), ("hbm_bytes_queues", C.c_uint64), ("hbm_bytes_arrivals", C.c_uint64)]
 
 
 def _price_for(energy_price, dc_name: str, hour: int) -> float:
@@ -264,8 +265,9 @@ def flatten(ingresses, dcs, graph, arrival_inf, arrival_train, coeffs_map, polic
     cap_q = [_poisson_cap(n_ing * p * float(sim_duration) * share, 32) for p in peak]
     sp.cap_xfer, sp.cap_run, sp.cap_q_inf, sp.cap_q_trn = cap_xfer, max(1, cap_run), cap_q[0], cap_q[1]
     sp.cap_stale = 64 if algo == "cap_greedy" else 0
+    sp.cap_arrivals = _poisson_cap(n_ing * (peak[0] + peak[1]) * float(sim_duration), 64)
     for key, val in (caps or {}).items():
-        if key not in ("cap_xfer", "cap_run", "cap_q_inf", "cap_q_trn", "cap_stale"):
+        if key not in ("cap_xfer", "cap_run", "cap_q_inf", "cap_q_trn", "cap_stale", "cap_arrivals"):
             raise ValueError(f"unknown capacity {key!r}")
         setattr(sp, key, int(val))
     return sp

@@ -135,7 +135,7 @@ typedef struct dcsim_spec {
   int32_t cap_q_inf;           /* FIFO entries per DC, inference */
   int32_t cap_q_trn;           /* FIFO entries per DC, training */
   int32_t cap_stale;           /* stale job_finish events (cap_greedy only) */
-  int32_t _pad_tail;
+  int32_t cap_arrivals;        /* entries of the per-replica arrival list written by the arrival pre-pass */
 } dcsim_spec_t;
 
 /* ---- per-replica summary (row-major [n_replicas][DCSIM_SUMMARY_K] doubles) ------------------ */
@@ -172,7 +172,9 @@ enum { /* offsets inside a per-DC group */
 };
 enum { /* status bits: a replica that overflowed a capacity stops and says so — never silently */
   DCSIM_ST_XFER_OVERFLOW = 1, DCSIM_ST_RUN_OVERFLOW = 2, DCSIM_ST_QUEUE_OVERFLOW = 4,
-  DCSIM_ST_STALE_OVERFLOW = 8, DCSIM_ST_RNG_RUNAWAY = 16
+  DCSIM_ST_STALE_OVERFLOW = 8, DCSIM_ST_RNG_RUNAWAY = 16, DCSIM_ST_ARRIVALS_OVERFLOW = 32,
+  DCSIM_ST_ARRIVAL_TIE = 64 /* two streams drew the very same arrival instant: their order needs the heap's seq,
+                               which the state-independent pre-pass cannot know (probability ~2^-52 per pair) */
 };
 
 /* aggregate vector produced by dcsim_reduce_summary(); the only thing that crosses NVLink */
@@ -265,8 +267,8 @@ int dcsim_fetch_cluster_log(dcsim_t* h, dcsim_cluster_rec_t* out, uint32_t capac
 typedef struct dcsim_launch_info {
   int32_t warps_per_cta, ctas, smem_bytes_per_cta, regs_per_thread;
   int32_t resident_warps_per_sm, sm_count, cap_xfer, cap_run;
-  int32_t cap_q_inf, cap_q_trn, kernel_launches, _pad;
-  uint64_t hbm_bytes_state, hbm_bytes_queues;
+  int32_t cap_q_inf, cap_q_trn, kernel_launches, arrivals_prepass;
+  uint64_t hbm_bytes_state, hbm_bytes_queues, hbm_bytes_arrivals;
 } dcsim_launch_info_t;
 int dcsim_launch_info(dcsim_t* h, dcsim_launch_info_t* out);
 

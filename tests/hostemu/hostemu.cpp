@@ -26,7 +26,10 @@ long long hostemu_run_batch(const void* spec_blob, size_t spec_bytes, uint64_t n
   dcsim_kparams_t* P = (dcsim_kparams_t*)calloc(1, sizeof(dcsim_kparams_t));
   memcpy(&P->spec, spec_blob, sizeof(dcsim_spec_t));
   if (P->spec.magic != DCSIM_SPEC_MAGIC) { free(P); return -1; }
-  dcsim_make_layout(&P->spec, &P->L);
+  const char* pe = getenv("DCSIM_PREPASS");
+  const int prepass = !(pe && pe[0] == '0');
+  dcsim_make_layout(&P->spec, &P->L, prepass);
+  P->cap_arr = (uint32_t)(P->spec.cap_arrivals > 0 ? P->spec.cap_arrivals : 16384);
   if (layout_out) { layout_out[0] = P->L.total_bytes; layout_out[1] = P->L.cap_xfer; layout_out[2] = P->L.cap_run;
                     layout_out[3] = P->L.cap_q[0]; layout_out[4] = P->L.cap_q[1]; }
   uint32_t local_counts[4] = {0, 0, 0, 0};
@@ -39,6 +42,14 @@ long long hostemu_run_batch(const void* spec_blob, size_t spec_bytes, uint64_t n
   P->state = (char*)calloc(n_replicas, (size_t)P->L.total_bytes);
   P->queues = (char*)calloc(n_replicas, (size_t)P->L.queue_bytes + 16);
   P->summary = out_summaries;
+  if (prepass) { /* the arrival pre-pass, one replica after the other */
+    P->arr_t = (double*)calloc(n_replicas * (size_t)P->cap_arr, sizeof(double));
+    P->arr_size = (double*)calloc(n_replicas * (size_t)P->cap_arr, sizeof(double));
+    P->arr_meta = (uint32_t*)calloc(n_replicas * (size_t)P->cap_arr, sizeof(uint32_t));
+    P->arr_hdr = (dcsim_arrhdr_t*)calloc(n_replicas, sizeof(dcsim_arrhdr_t));
+    double clocks[2 * DCSIM_MAX_ING];
+    for (uint64_t r = 0; r < n_replicas; ++r) dcsim_generate_arrivals(P, r, clocks, 1);
+  }
   char* work = (char*)malloc((size_t)P->L.total_bytes);
   long long total = 0;
   for (uint64_t r = 0; r < n_replicas; ++r) {
@@ -46,13 +57,14 @@ long long hostemu_run_batch(const void* spec_blob, size_t spec_bytes, uint64_t n
     for (int guard = 0; guard < 100000000; ++guard) {
       const bool fresh = ((dcsim_hdr_t*)home)->initialized == 0u;
       if (!fresh) memcpy(work, home, (size_t)P->L.total_bytes); /* stage in */
-      total += P->L.cap_stale ? dcsim_replica_step<true>(P, r, work, fresh) : dcsim_replica_step<false>(P, r, work, fresh);
+      total += P->L.cap_stale ? (prepass ? dcsim_replica_step<true, true>(P, r, work, fresh) : dcsim_replica_step<true, false>(P, r, work, fresh))
+                               : (prepass ? dcsim_replica_step<false, true>(P, r, work, fresh) : dcsim_replica_step<false, false>(P, r, work, fresh));
       memcpy(home, work, (size_t)P->L.total_bytes);             /* stage out */
       const dcsim_hdr_t* H = (const dcsim_hdr_t*)home;
       if (H->done || H->status || chunk_events == 0) break;
     }
   }
-  free(work); free(P->state); free(P->queues); free(P);
+  free(work); free(P->state); free(P->queues); free(P->arr_t); free(P->arr_size); free(P->arr_meta); free(P->arr_hdr); free(P);
   return total;
 }
 
