@@ -209,11 +209,14 @@ def run_b200(args, world, rank, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def one_step(i, k0=None, k1=None):
+    def one_step(i, k0=None, k1=None, p0=None):
         eng.reset(123 + i * R * world, first)
+        if p0 is not None:
+            p0.record(stream)
+        eng.prepare()                                               # arrival pre-pass (dcsim_arrivals_kernel)
         if k0 is not None:
             k0.record(stream)
-        eng.advance(0, sync=False)
+        eng.advance(0, sync=False)                                  # event loop (dcsim_advance_kernel)
         if k1 is not None:
             k1.record(stream)
         eng.reduce_into(agg[i].data_ptr())
@@ -227,16 +230,18 @@ def run_b200(args, world, rank, local_rank):
     sampler.start()
     k0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     k1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    p0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t0.record(stream)
     for j in range(args.steps):
-        one_step(args.warmup + j, k0[j], k1[j])
+        one_step(args.warmup + j, k0[j], k1[j], p0[j])
     t1.record(stream)
     barrier()
     clocks = sampler.stop()
     elapsed_ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device="cuda")
     kernel_ms = [a.elapsed_time(b) for a, b in zip(k0, k1)]
+    prepass_ms = sum(a.elapsed_time(b) for a, b in zip(p0, k0)) / args.steps
     if world > 1:
         dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
     elapsed_s = float(elapsed_ms.item()) / 1000.0
@@ -258,7 +263,7 @@ def run_b200(args, world, rank, local_rank):
     traffic = measured_traffic()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
-                "kernel": "dcsim_advance_kernel", "kernel_ms": kms, "events_per_launch": local_events_per_launch,
+                "kernel": "dcsim_advance_kernel", "kernel_ms": kms, "arrivals_prepass_kernel_ms": prepass_ms, "events_per_launch": local_events_per_launch,
                 "algorithmic_bytes_per_event": b_alg, "peak_source": peak_src,
                 "note": "path is warp-serial-latency bound, not HBM bound (SURVEY.md §8d); see DESIGN.md for the "
                         "secondary bound (issue slots) and profiles/ for ncu evidence",
@@ -269,7 +274,7 @@ def run_b200(args, world, rank, local_rank):
         eng.close()
         if rank == 0:
             print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                              "ms_per_step": 1000.0 * elapsed_s / args.steps, "kernel_ms": kms, "launch": info,
+                              "ms_per_step": 1000.0 * elapsed_s / args.steps, "kernel_ms": kms, "prepass_ms": prepass_ms, "launch": info,
                               "clocks": clocks, "tuning_run": True}), flush=True)
         if world > 1:
             dist.barrier()

@@ -17,7 +17,7 @@ OK, E_INVALID, E_CUDA, E_NOMEM, E_STATE, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 # every symbol include/dcsim_b200.h declares
 EXPORTS = (
     "dcsim_sizeof_spec", "dcsim_abi_version", "dcsim_summary_k", "dcsim_create", "dcsim_reset", "dcsim_set_stream",
-    "dcsim_set_trace", "dcsim_set_logging", "dcsim_advance", "dcsim_all_done", "dcsim_fetch_summary",
+    "dcsim_set_trace", "dcsim_set_logging", "dcsim_prepare", "dcsim_advance", "dcsim_all_done", "dcsim_fetch_summary",
     "dcsim_summary_device_ptr", "dcsim_reduce_summary", "dcsim_fetch_trace", "dcsim_fetch_job_log",
     "dcsim_fetch_cluster_log", "dcsim_launch_info", "dcsim_last_error", "dcsim_destroy",
 )
@@ -59,6 +59,8 @@ def load():
     L.dcsim_set_trace.argtypes = [vp, u64, u32]
     L.dcsim_set_logging.restype = i32
     L.dcsim_set_logging.argtypes = [vp, u64, u32, u32]
+    L.dcsim_prepare.restype = i32
+    L.dcsim_prepare.argtypes = [vp]
     L.dcsim_advance.restype = i32
     L.dcsim_advance.argtypes = [vp, u64, C.POINTER(u64)]
     L.dcsim_all_done.restype = i32

@@ -331,31 +331,44 @@ int dcsim_set_logging(dcsim_t* h, uint64_t replica, uint32_t job_capacity, uint3
   return DCSIM_OK;
 }
 
+static void fill_kparams(const dcsim_t* h, dcsim_kparams_t* P, uint64_t max_events) {
+  memset(P, 0, sizeof(*P));
+  P->spec = h->spec;
+  P->L = h->L;
+  P->rec.trace = h->d_trace; P->rec.jobs = h->d_jobs; P->rec.cluster = h->d_cluster; P->rec.counts = h->d_counts;
+  P->rec.trace_cap = h->trace_cap; P->rec.jobs_cap = h->jobs_cap; P->rec.cluster_cap = h->cluster_cap;
+  P->rec.trace_replica = h->trace_replica; P->rec.log_replica = h->log_replica;
+  P->n_replicas = h->n_replicas;
+  P->seed0 = h->seed0;
+  P->max_events = max_events;
+  P->state = h->d_state; P->queues = h->d_queues; P->summary = h->d_summary;
+  P->end_eps = h->spec.end_time + 1e-9; /* SIM:161 */
+  P->arr_t = h->d_arr_t; P->arr_size = h->d_arr_size; P->arr_meta = h->d_arr_meta; P->arr_hdr = h->d_arr_hdr; P->cap_arr = h->cap_arr;
+}
+
+int dcsim_prepare(dcsim_t* h) {
+  if (!h) return DCSIM_E_INVALID;
+  if (!h->prepass || h->arrivals_ready) return DCSIM_OK;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  dcsim_kparams_t P;
+  fill_kparams(h, &P, 0);
+  const int nb = (int)((h->n_replicas + DCSIM_ARRIVALS_THREADS - 1) / DCSIM_ARRIVALS_THREADS);
+  dcsim_arrivals_kernel<<<nb, DCSIM_ARRIVALS_THREADS, 2 * DCSIM_MAX_ING * DCSIM_ARRIVALS_THREADS * sizeof(double), h->stream>>>(P);
+  CUDA_TRY(h, cudaGetLastError());
+  h->arrivals_ready = 1;
+  h->launches++;
+  return DCSIM_OK;
+}
+
 int dcsim_advance(dcsim_t* h, uint64_t max_events_per_replica, uint64_t* total_events_out) {
   if (!h) return DCSIM_E_INVALID;
   CUDA_TRY(h, cudaSetDevice(h->device));
+  int rc = dcsim_prepare(h); /* once per (re)seeded batch: the arrival lists of all replicas */
+  if (rc != DCSIM_OK) return rc;
   dcsim_kparams_t P;
-  memset(&P, 0, sizeof(P));
-  P.spec = h->spec;
-  P.L = h->L;
-  P.rec.trace = h->d_trace; P.rec.jobs = h->d_jobs; P.rec.cluster = h->d_cluster; P.rec.counts = h->d_counts;
-  P.rec.trace_cap = h->trace_cap; P.rec.jobs_cap = h->jobs_cap; P.rec.cluster_cap = h->cluster_cap;
-  P.rec.trace_replica = h->trace_replica; P.rec.log_replica = h->log_replica;
-  P.n_replicas = h->n_replicas;
-  P.seed0 = h->seed0;
-  P.max_events = max_events_per_replica;
-  P.state = h->d_state; P.queues = h->d_queues; P.summary = h->d_summary;
-  P.end_eps = h->spec.end_time + 1e-9; /* SIM:161 */
-  P.arr_t = h->d_arr_t; P.arr_size = h->d_arr_size; P.arr_meta = h->d_arr_meta; P.arr_hdr = h->d_arr_hdr; P.cap_arr = h->cap_arr;
+  fill_kparams(h, &P, max_events_per_replica);
   const dim3 grid(h->ctas), block(h->warps_per_cta * 32);
   if (h->prepass) {
-    if (!h->arrivals_ready) { /* once per (re)seeded batch: the arrival lists of all replicas */
-      const int nb = (int)((h->n_replicas + DCSIM_ARRIVALS_THREADS - 1) / DCSIM_ARRIVALS_THREADS);
-      dcsim_arrivals_kernel<<<nb, DCSIM_ARRIVALS_THREADS, 2 * DCSIM_MAX_ING * DCSIM_ARRIVALS_THREADS * sizeof(double), h->stream>>>(P);
-      CUDA_TRY(h, cudaGetLastError());
-      h->arrivals_ready = 1;
-      h->launches++;
-    }
     if (h->L.cap_stale) dcsim_advance_kernel<true, true><<<grid, block, h->smem_bytes, h->stream>>>(P, h->d_events);
     else dcsim_advance_kernel<false, true><<<grid, block, h->smem_bytes, h->stream>>>(P, h->d_events);
   } else {

@@ -104,6 +104,7 @@ enum { /* per-DC i32 arrays; FIFO rings are (head index, length) so no modulo is
 #define DCSIM_RNG_WINDOW 128u /* Philox words staged per refill: one block per lane */
 #define DCSIM_RNG_MARGIN 64u  /* refill when fewer than this many staged words remain at an arrival: covers one
                                  arrival's speculative look-ahead (2 size + 16 route + 8x4 thinning words) */
+#define DCSIM_ARR_WINDOW 16u   /* arrival-list entries staged in shared memory at a time (pre-pass mode) */
 #define DCSIM_SPEC_ROUTE (DCSIM_LANES < 16 ? DCSIM_LANES : 16) /* lanes trying random.choice draws at once */
 #define DCSIM_SPEC_THIN (DCSIM_LANES < 8 ? DCSIM_LANES : 8)    /* lanes trying thinning candidates at once */
 /* A rejection loop that has not accepted after this many draws stops the replica with DCSIM_ST_RNG_RUNAWAY
@@ -134,7 +135,7 @@ struct dcsim_layout_t {
   int32_t st_t, st_seq;              /* stale job_finish pool */
   int32_t at_rho, at_fto, at_ref, at_idx; /* DVFS atoms scratch (freq_load_agg.py) */
   int32_t cap_stale, cap_atoms;
-  /* arrival pre-pass mode: a 32-entry staging window of the replica's arrival list + per-stream pending seq */
+  /* arrival pre-pass mode: a staging window of the replica's arrival list + per-stream pending seq */
   int32_t aw_t, aw_size, aw_meta, pend_seq;
   int32_t prepass;
   int32_t total_bytes;
@@ -180,9 +181,9 @@ static inline void dcsim_make_layout(const dcsim_spec_t* sp, dcsim_layout_t* L, 
   L->rn_meta = o; o += nr * 4;
   L->rn_jid = o; o = dcsim_align16(o + nr * 4);
   if (prepass) { /* no in-kernel sampling: the Philox window gives way to the arrival-list window */
-    L->aw_t = o; o += 32 * 8;
-    L->aw_size = o; o += 32 * 8;
-    L->aw_meta = o; o += 32 * 4;
+    L->aw_t = o; o += (int32_t)DCSIM_ARR_WINDOW * 8;
+    L->aw_size = o; o += (int32_t)DCSIM_ARR_WINDOW * 8;
+    L->aw_meta = o; o += (int32_t)DCSIM_ARR_WINDOW * 4;
     L->pend_seq = o; o += 2 * DCSIM_MAX_ING * 4;
   } else {
     L->rng_buf = o; o += (int32_t)DCSIM_RNG_WINDOW * 4;
@@ -958,12 +959,12 @@ DCSIM_DEV void dcsim_handle_arrival(dcsim_ctx_t& c, int stream) {
   }
 }
 
-/* Warp.  Stages entries [base, base+32) of the replica's arrival list into shared memory (coalesced). */
+/* Warp.  Stages entries [base, base+DCSIM_ARR_WINDOW) of the replica's arrival list into shared memory (coalesced). */
 DCSIM_DEV void dcsim_arrivals_stage(dcsim_ctx_t& c, uint64_t r, uint32_t base) {
   const dcsim_layout_t& L = c.P->L;
   const uint64_t off = r * (uint64_t)c.P->cap_arr + base;
   const uint32_t count = c.H->arr_count;
-  for (uint32_t i = (uint32_t)c.lane; i < 32u; i += DCSIM_LANES) {
+  for (uint32_t i = (uint32_t)c.lane; i < DCSIM_ARR_WINDOW; i += DCSIM_LANES) {
     const bool in = base + i < count;
     dcsim_at<double>(c.blk, L.aw_t)[i] = in ? c.P->arr_t[off + i] : DCSIM_INF;
     dcsim_at<double>(c.blk, L.aw_size)[i] = in ? c.P->arr_size[off + i] : 0.0;
@@ -994,9 +995,11 @@ DCSIM_DEV void dcsim_handle_arrival_listed(dcsim_ctx_t& c, uint64_t r) {
   const dcsim_spec_t& sp = c.P->spec;
   const dcsim_layout_t& L = c.P->L;
   dcsim_hdr_t* H = c.H;
-  const uint32_t k = H->arr_cursor;
+  /* lane 0 owns cursor / window base (it rewrites them below); the other lanes get them by shuffle */
+  const uint32_t k = dcsim_bcast_u32(c.lane == 0 ? H->arr_cursor : 0u, 0);
+  const uint32_t wbase = dcsim_bcast_u32(c.lane == 0 ? H->aw_base : 0u, 0);
   if (c.lane == 0) {
-    const uint32_t i = k - H->aw_base;
+    const uint32_t i = k - wbase;
     const double size = dcsim_at<double>(c.blk, L.aw_size)[i];
     const uint32_t meta = dcsim_at<uint32_t>(c.blk, L.aw_meta)[i];
     const uint32_t stream = meta & 15u;
@@ -1028,7 +1031,7 @@ DCSIM_DEV void dcsim_handle_arrival_listed(dcsim_ctx_t& c, uint64_t r) {
     H->arr_cursor = k + 1u;
   }
   dcsim_warp_sync();
-  if (k + 1u - c.H->aw_base >= 32u && k + 1u < c.H->arr_count) dcsim_arrivals_stage(c, r, k + 1u);
+  if (k + 1u - wbase >= DCSIM_ARR_WINDOW && k + 1u < c.H->arr_count) dcsim_arrivals_stage(c, r, k + 1u);
   if (c.lane == 0) dcsim_arrival_candidate(c, k + 1u);
 }
 

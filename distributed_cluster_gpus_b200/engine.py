@@ -55,6 +55,10 @@ class BatchedEngine:
         self._jobs_cap, self._cluster_cap = job_capacity, cluster_capacity
 
     # -- run -------------------------------------------------------------------------------------
+    def prepare(self):
+        """Launches the arrival pre-pass (optional; advance() does it when needed)."""
+        N.check(self._lib.dcsim_prepare(self._h), self._h)
+
     def advance(self, max_events_per_replica: int = 0, sync: bool = True) -> int:
         """Every replica processes up to ``max_events_per_replica`` more events (0 = to end_time).
         With ``sync`` returns the number of events this call processed; otherwise launches and returns -1."""

@@ -239,6 +239,14 @@ int dcsim_set_trace(dcsim_t* h, uint64_t replica, uint32_t capacity);
 /* Record job_log / cluster_log rows of one local replica (the CSV wire formats); capacities in rows. */
 int dcsim_set_logging(dcsim_t* h, uint64_t replica, uint32_t job_capacity, uint32_t cluster_capacity);
 
+/* Launches the arrival pre-pass (dcsim_arrivals_kernel) for a freshly created / reset batch if it has not run yet:
+ * one thread per replica draws that replica's whole arrival sequence — inter-arrival gaps (arrivals.py:35-48), job
+ * sizes (arrivals.py:5-11) and routed DCs (simulator_paper_multi.py:544-577) — in the reference's draw order and
+ * writes it as a list the event loop consumes.  Optional: dcsim_advance() calls it when needed; exposed so a
+ * caller can time or overlap it.  Asynchronous on the handle's stream.  No-op when the library was asked to keep
+ * the samplers inside the event loop (environment DCSIM_PREPASS=0). */
+int dcsim_prepare(dcsim_t* h);
+
 /* Replaces MultiIngressPaperSimulator.run (simulator_paper_multi.py:412-480): every replica processes up
  * to max_events_per_replica further events (0 = run to end_time); replicas that reach the end also accrue
  * the tail interval (:469-475).  Asynchronous on the handle's stream unless total_events_out != NULL, in
