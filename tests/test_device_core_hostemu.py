@@ -86,3 +86,24 @@ def test_rng_window_slow_path(oracle, hostemu):
     want, _ = oracle.run_batch(blob, 2, 77)
     got = hostemu.run_batch(blob, 2, 77)["summary"]
     assert _same(got, want)
+
+
+def test_thinning_squeeze_fuzz(oracle, hostemu):
+    """The pre-pass decides thinning candidates from lambda(t) +- eps and only evaluates the reference's expression
+    inside the band.  Random arrival parameters — fast and slow periods, |amp| up to 1, both signs, rates over two
+    decades — must leave every count and float identical to the oracle."""
+    import random as pyrandom
+    rnd = pyrandom.Random(20260921)
+    for case in range(40):
+        inf = dict(mode="sinusoid", rate=10 ** rnd.uniform(-0.5, 1.7), amp=rnd.choice([-1, 1]) * rnd.uniform(0.0, 1.0),
+                   period=10 ** rnd.uniform(0.3, 4.0))
+        trn = dict(mode=rnd.choice(["sinusoid", "poisson"]), rate=10 ** rnd.uniform(-1.5, 0.3),
+                   amp=rnd.uniform(-0.95, 0.95), period=10 ** rnd.uniform(0.5, 3.5))
+        sc = SC.scenario(f"fuzz{case}", rnd.choice([1, 2, 3, 4]), rnd.choice([8, 16, 64]), inf, trn,
+                         duration=rnd.uniform(5.0, 60.0), algo=rnd.choice(["default_policy", "joint_nf", "eco_route"]),
+                         freq_levels=SC.FREQ3)
+        blob = SC.to_spec(sc).to_bytes()
+        want, _ = oracle.run_batch(blob, 2, 1000 + case)
+        got = hostemu.run_batch(blob, 2, 1000 + case)["summary"]
+        assert np.all(got[:, S.S_STATUS] == 0), (case, sc)
+        assert _same(got, want), (case, sc, np.argwhere(got != want)[:6])
