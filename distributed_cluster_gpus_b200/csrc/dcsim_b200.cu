@@ -65,7 +65,9 @@ extern __shared__ __align__(16) double dcsim_arr_scratch[];
 __global__ void __launch_bounds__(DCSIM_ARRIVALS_THREADS) dcsim_arrivals_kernel(const __grid_constant__ dcsim_kparams_t P) {
   const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= P.n_replicas) return;
-  dcsim_generate_arrivals(&P, r, dcsim_arr_scratch + threadIdx.x, (int)blockDim.x); /* stream clocks: [stream][thread] */
+  double* clocks = dcsim_arr_scratch + threadIdx.x;                                     /* [stream][thread] */
+  uint32_t* ring = reinterpret_cast<uint32_t*>(dcsim_arr_scratch + 2 * DCSIM_MAX_ING * blockDim.x) + threadIdx.x; /* [word][thread] */
+  dcsim_generate_arrivals(&P, r, clocks, ring, (int)blockDim.x);
 }
 
 /* Aggregates the summaries; every block reduces a slice, then one atomicAdd per component. */
@@ -353,7 +355,8 @@ int dcsim_prepare(dcsim_t* h) {
   dcsim_kparams_t P;
   fill_kparams(h, &P, 0);
   const int nb = (int)((h->n_replicas + DCSIM_ARRIVALS_THREADS - 1) / DCSIM_ARRIVALS_THREADS);
-  dcsim_arrivals_kernel<<<nb, DCSIM_ARRIVALS_THREADS, 2 * DCSIM_MAX_ING * DCSIM_ARRIVALS_THREADS * sizeof(double), h->stream>>>(P);
+  const size_t scratch = (size_t)DCSIM_ARRIVALS_THREADS * (2 * DCSIM_MAX_ING * sizeof(double) + DCSIM_TRNG_RING * sizeof(uint32_t));
+  dcsim_arrivals_kernel<<<nb, DCSIM_ARRIVALS_THREADS, scratch, h->stream>>>(P);
   CUDA_TRY(h, cudaGetLastError());
   h->arrivals_ready = 1;
   h->launches++;

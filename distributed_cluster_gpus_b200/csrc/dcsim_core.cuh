@@ -463,23 +463,33 @@ DCSIM_DEV double dcsim_next_interarrival(dcsim_ctx_t& c, int jt, double t) {
  * (arrival events in time order; inside one: size -> route -> next gap), by one thread per replica with all 32
  * lanes of a warp busy, instead of on one lane of the replica's warp.  The event loop then consumes the list.
  * ============================================================================================== */
-struct dcsim_trng_t { uint32_t k0, k1, pos, bidx, w0, w1, w2, w3; };
+/* Thread-level Philox stream with a 32-word ring (element i at buf[i * stride]: [word][thread] in shared memory on
+ * the GPU).  The ring is topped up ONCE per arrival, by all lanes of the warp at the same program point; refilling
+ * inside the samplers instead makes 32 out-of-phase lanes drag the warp through the block function at almost every
+ * draw (measured: 43 % of the pre-pass). */
+#define DCSIM_TRNG_RING 32u
+struct dcsim_trng_t { uint32_t k0, k1, pos, filled; uint32_t* buf; int stride; };
 
+DCSIM_DEV void dcsim_trng_block(dcsim_trng_t& g) { /* appends block filled/4 */
+  uint32_t w[4];
+  dcsim_philox_block(g.k0, g.k1, g.filled >> 2, w);
+  const uint32_t i = g.filled & (DCSIM_TRNG_RING - 1u);
+  g.buf[(i + 0u) * g.stride] = w[0]; g.buf[(i + 1u) * g.stride] = w[1];
+  g.buf[(i + 2u) * g.stride] = w[2]; g.buf[(i + 3u) * g.stride] = w[3];
+  g.filled += 4u;
+}
+DCSIM_DEV void dcsim_trng_topup(dcsim_trng_t& g) {
+  while (g.filled - g.pos <= DCSIM_TRNG_RING - 4u) dcsim_trng_block(g);
+}
 #ifndef DCSIM_HOST_EMU
 __device__ __noinline__
 #else
 static
 #endif
-void dcsim_trng_refill(dcsim_trng_t* g, uint32_t b) {
-  uint32_t w[4];
-  dcsim_philox_block(g->k0, g->k1, b, w);
-  g->w0 = w[0]; g->w1 = w[1]; g->w2 = w[2]; g->w3 = w[3]; g->bidx = b;
-}
+void dcsim_trng_dry(dcsim_trng_t* g) { dcsim_trng_block(*g); } /* a sampler out-ran the ring (long rejection run) */
 DCSIM_DEV uint32_t dcsim_trng_word(dcsim_trng_t& g) {
-  const uint32_t pos = g.pos++;
-  if ((pos >> 2) != g.bidx) dcsim_trng_refill(&g, pos >> 2);
-  const uint32_t j = pos & 3u;
-  return j == 0u ? g.w0 : (j == 1u ? g.w1 : (j == 2u ? g.w2 : g.w3));
+  if (g.pos == g.filled) dcsim_trng_dry(&g);
+  return g.buf[(g.pos++ & (DCSIM_TRNG_RING - 1u)) * g.stride];
 }
 DCSIM_DEV double dcsim_trng_random(dcsim_trng_t& g) {
   const uint32_t a = dcsim_trng_word(g), b = dcsim_trng_word(g);
@@ -558,19 +568,21 @@ DCSIM_DEV double dcsim_t_size(dcsim_trng_t& g, const dcsim_spec_t& sp, int jt, u
   return v > sp.lognorm_floor ? v : sp.lognorm_floor;
 }
 
-/* One replica's arrival list.  `next_t` is scratch for the 2*n_ing stream clocks, element s at next_t[s * stride]. */
-DCSIM_DEV void dcsim_generate_arrivals(const dcsim_kparams_t* P, uint64_t r, double* next_t, int stride) {
+/* One replica's arrival list.  `next_t` is scratch for the 2*n_ing stream clocks (element s at next_t[s * stride]),
+ * `ring` for the DCSIM_TRNG_RING staged Philox words (element i at ring[i * stride]). */
+DCSIM_DEV void dcsim_generate_arrivals(const dcsim_kparams_t* P, uint64_t r, double* next_t, uint32_t* ring, int stride) {
   const dcsim_spec_t& sp = P->spec;
   const int n_streams = 2 * sp.n_ing;
   dcsim_trng_t g;
   const uint64_t key = P->seed0 + r;
-  g.k0 = (uint32_t)key; g.k1 = (uint32_t)(key >> 32); g.pos = 0u; g.bidx = 0xffffffffu; g.w0 = g.w1 = g.w2 = g.w3 = 0u;
+  g.k0 = (uint32_t)key; g.k1 = (uint32_t)(key >> 32); g.pos = 0u; g.filled = 0u; g.buf = ring; g.stride = stride;
   uint32_t status = 0u, first_mask = 0u, count = 0u;
   const double end_eps = P->end_eps;
   dcsim_squeeze_t sq[2];
   sq[0] = dcsim_squeeze_setup(sp.arr[0], sp.two_pi);
   sq[1] = dcsim_squeeze_setup(sp.arr[1], sp.two_pi);
   for (int s = 0; s < n_streams; ++s) { /* SIM:154-156 */
+    dcsim_trng_topup(g);
     const double t = 0.0 + dcsim_t_gap(g, sp, sq[s & 1], s & 1, 0.0, &status);
     const bool ok = !(t == DCSIM_INF) && !(t > end_eps);
     next_t[s * stride] = ok ? t : DCSIM_INF;
@@ -591,6 +603,7 @@ DCSIM_DEV void dcsim_generate_arrivals(const dcsim_kparams_t* P, uint64_t r, dou
     if (s < 0 || t > sp.end_time) break; /* heap empty / SIM:427 */
     if (tie) { status |= DCSIM_ST_ARRIVAL_TIE; break; }
     if (status) break;
+    dcsim_trng_topup(g); /* all lanes refill here, together */
     const int jt = s & 1;
     const double size = dcsim_t_size(g, sp, jt, &status); /* draw order: size -> route -> next gap (SIM:540,576,591) */
     int dc_sel = 0;

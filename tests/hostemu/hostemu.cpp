@@ -48,7 +48,8 @@ long long hostemu_run_batch(const void* spec_blob, size_t spec_bytes, uint64_t n
     P->arr_meta = (uint32_t*)calloc(n_replicas * (size_t)P->cap_arr, sizeof(uint32_t));
     P->arr_hdr = (dcsim_arrhdr_t*)calloc(n_replicas, sizeof(dcsim_arrhdr_t));
     double clocks[2 * DCSIM_MAX_ING];
-    for (uint64_t r = 0; r < n_replicas; ++r) dcsim_generate_arrivals(P, r, clocks, 1);
+    uint32_t ring[DCSIM_TRNG_RING];
+    for (uint64_t r = 0; r < n_replicas; ++r) dcsim_generate_arrivals(P, r, clocks, ring, 1);
   }
   char* work = (char*)malloc((size_t)P->L.total_bytes);
   long long total = 0;
