@@ -642,6 +642,23 @@ DCSIM_DEV void dcsim_generate_arrivals(const dcsim_kparams_t* P, uint64_t r, dou
  * Times are >= 0, so their IEEE bit patterns order like unsigned integers and the reduction is three
  * REDUX.MIN.U32.  Returns the winning index to every lane, -1 if every entry is +inf / n == 0. */
 DCSIM_DEV int dcsim_argmin_ts(const double* t, const uint32_t* seq, int n, int lane, double* t_out, uint32_t* seq_out) {
+#if DCSIM_LANES == 32
+  if (n <= 32) { /* the common case (pools rarely hold more than a warp's worth): one entry per lane, no loop */
+    const bool in = lane < n;
+    const double ti = in ? t[lane] : DCSIM_INF;
+    const uint32_t s = in ? seq[lane] : 0xffffffffu;
+    const uint32_t h = dcsim_hi(ti), l = dcsim_lo(ti);
+    const uint32_t mh = dcsim_warp_min_u32(h);
+    if (mh >= 0x7ff00000u) return -1;
+    const uint32_t ml = dcsim_warp_min_u32(h == mh ? l : 0xffffffffu);
+    const bool m = (h == mh) && (l == ml);
+    const uint32_t ms = dcsim_warp_min_u32(m ? s : 0xffffffffu);
+    const uint32_t votes = dcsim_warp_ballot(m && s == ms);
+    *t_out = __hiloint2double((int)mh, (int)ml);
+    *seq_out = ms;
+    return dcsim_ffs(votes) - 1;
+  }
+#endif
   uint32_t bh = 0x7ff00000u, bl = 0u, bs = 0xffffffffu;
   int bi = -1;
   for (int i = lane; i < n; i += DCSIM_LANES) {
@@ -664,6 +681,27 @@ DCSIM_DEV int dcsim_argmin_ts(const double* t, const uint32_t* seq, int n, int l
 #endif
   *seq_out = ms;
   return win;
+}
+
+/* Pop-min over the event set itself: exactly one candidate per lane (CAND_N == 32), so no loop and no index
+ * bookkeeping — two loads, three REDUX.MIN, one ballot.  Returns the winning candidate slot, -1 if all are +inf. */
+DCSIM_DEV int dcsim_argmin_cand(dcsim_ctx_t& c, double* t_out, uint32_t* seq_out) {
+#if DCSIM_LANES == 32
+  const double t = CAND_T(c)[c.lane];
+  const uint32_t s = CAND_SEQ(c)[c.lane];
+  const uint32_t h = dcsim_hi(t), l = dcsim_lo(t);
+  const uint32_t mh = dcsim_warp_min_u32(h);
+  if (mh >= 0x7ff00000u) return -1;
+  const uint32_t ml = dcsim_warp_min_u32(h == mh ? l : 0xffffffffu);
+  const bool m = (h == mh) && (l == ml);
+  const uint32_t ms = dcsim_warp_min_u32(m ? s : 0xffffffffu);
+  const uint32_t votes = dcsim_warp_ballot(m && s == ms);
+  *t_out = __hiloint2double((int)mh, (int)ml);
+  *seq_out = ms;
+  return dcsim_ffs(votes) - 1;
+#else
+  return dcsim_argmin_ts(CAND_T(c), CAND_SEQ(c), CAND_N, c.lane, t_out, seq_out);
+#endif
 }
 
 /* SIM:160-163: an event later than end_time + 1e-9 (or at +inf) is never scheduled and takes no seq. */
@@ -1435,14 +1473,16 @@ DCSIM_DEV void dcsim_replica_tail(dcsim_ctx_t& c) {
 template <bool CAP, bool PRE>
 DCSIM_DEV uint32_t dcsim_replica_run(dcsim_ctx_t& c, uint64_t r) {
   const dcsim_spec_t& sp = c.P->spec;
-  const uint64_t budget = c.P->max_events;
+  /* per-launch event budget as one 32-bit compare: 0 (unlimited) and anything >= 2^32 never trips */
+  const uint32_t budget = (c.P->max_events == 0ull || c.P->max_events > 0xfffffffeull) ? 0xffffffffu : (uint32_t)c.P->max_events;
+  const bool tracing = c.is_traced && c.P->rec.trace != nullptr;
   uint32_t done_here = 0u;
   bool finished = false;
   for (;;) {
-    if (budget && done_here >= budget) break;
+    if (done_here >= budget) break;
     if (c.H->status != 0u) break; /* a capacity overflowed: stop and report, never guess */
     double t; uint32_t seq;
-    const int win = dcsim_argmin_ts(CAND_T(c), CAND_SEQ(c), CAND_N, c.lane, &t, &seq);
+    const int win = dcsim_argmin_cand(c, &t, &seq);
     if (win < 0) { finished = true; break; }         /* `while self.event_q` */
     if (t > sp.end_time) { finished = true; break; } /* SIM:427 */
 
@@ -1465,9 +1505,8 @@ DCSIM_DEV uint32_t dcsim_replica_run(dcsim_ctx_t& c, uint64_t r) {
     if constexpr (PRE) { /* one arrival candidate for all streams: the job type is in the list entry */
       if (win == CAND_STREAM0) kind = (int)(dcsim_at<uint32_t>(c.blk, c.P->L.aw_meta)[c.H->arr_cursor - c.H->aw_base] & 1u);
     }
-    if (c.lane == 0) {
-      c.H->n_events++;
-      if (c.is_traced && c.P->rec.trace) {
+    if (tracing && c.lane == 0) {
+      {
         const uint32_t r = c.P->rec.counts[0];
         if (r < c.P->rec.trace_cap) { c.P->rec.trace[r].t = t; c.P->rec.trace[r].seq = seq; c.P->rec.trace[r].kind = (uint32_t)(kind == KIND_STALE ? KIND_FINISH : kind); }
         c.P->rec.counts[0] = r + 1u;
@@ -1576,7 +1615,10 @@ DCSIM_DEV uint32_t dcsim_replica_step(const dcsim_kparams_t* P, uint64_t r, char
   uint32_t n = 0u;
   if (c.H->done == 0u) n = dcsim_replica_run<CAP, PRE>(c, r);
   dcsim_warp_sync();
-  if (c.lane == 0) { c.H->rng_pos = c.rng_pos; c.H->seq = c.seq; c.H->now = c.now; c.H->last_t = c.H->n_events ? c.now : 0.0; }
+  if (c.lane == 0) {
+    c.H->n_events = c.H->ev_arr + c.H->ev_xfer + c.H->ev_fin + c.H->ev_log; /* every processed event is one of these */
+    c.H->rng_pos = c.rng_pos; c.H->seq = c.seq; c.H->now = c.now; c.H->last_t = c.H->n_events ? c.now : 0.0;
+  }
   dcsim_warp_sync();
   dcsim_write_summary(c, P->summary + r * DCSIM_SUMMARY_K);
   dcsim_warp_sync();
