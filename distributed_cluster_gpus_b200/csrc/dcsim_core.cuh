@@ -1480,7 +1480,9 @@ DCSIM_DEV uint32_t dcsim_replica_run(dcsim_ctx_t& c, uint64_t r) {
   bool finished = false;
   for (;;) {
     if (done_here >= budget) break;
-    if (c.H->status != 0u) break; /* a capacity overflowed: stop and report, never guess */
+    /* a capacity overflowed (or a sampler ran away): stop and report, never guess.  Polled every 16 events — every
+     * capacity check refuses the write on its own, so a replica that overflowed stays memory-safe until it is seen */
+    if ((done_here & 15u) == 0u && c.H->status != 0u) break;
     double t; uint32_t seq;
     const int win = dcsim_argmin_cand(c, &t, &seq);
     if (win < 0) { finished = true; break; }         /* `while self.event_q` */
