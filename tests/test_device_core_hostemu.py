@@ -107,3 +107,16 @@ def test_thinning_squeeze_fuzz(oracle, hostemu):
         got = hostemu.run_batch(blob, 2, 1000 + case)["summary"]
         assert np.all(got[:, S.S_STATUS] == 0), (case, sc)
         assert _same(got, want), (case, sc, np.argwhere(got != want)[:6])
+
+
+@pytest.mark.parametrize("name", ["cfg3_4x64_sinusoid_120s", "sweep_joint_nf", "cap_greedy_4x64", "full_swing_sinusoid_amp1",
+                                  "no_inf_priority_perf_first", "carbon_cost_8h_2x16"])
+def test_in_loop_sampling_mode_equals_oracle(oracle, hostemu, monkeypatch, name):
+    """DCSIM_PREPASS=0: the single-kernel design (samplers inside the event loop, lane-speculative rejection)."""
+    monkeypatch.setenv("DCSIM_PREPASS", "0")
+    blob = SC.to_spec(SC.BY_NAME[name]).to_bytes()
+    want, total = oracle.run_batch(blob, 2, 31)
+    got = hostemu.run_batch(blob, 2, 31)
+    assert got["events"] == total and _same(got["summary"], want)
+    parts = hostemu.run_batch(blob, 2, 31, chunk_events=997)
+    assert np.array_equal(parts["summary"], got["summary"])
