@@ -294,6 +294,7 @@ int dcsim_reset(dcsim_t* h, uint64_t base_seed, uint64_t first_replica_id) {
   CUDA_TRY(h, cudaMemsetAsync(h->d_counts, 0, 4 * sizeof(uint32_t), h->stream));
   h->seed0 = base_seed + first_replica_id;
   h->arrivals_ready = 0;
+  h->launches = 0; /* a reset batch is "fresh": recorders may be re-targeted before its first advance */
   return DCSIM_OK;
 }
 

@@ -1,5 +1,6 @@
 """BatchedEngine — thin owner of one ``dcsim_t`` handle (one CUDA device, one stream, R replicas)."""
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -142,14 +143,49 @@ def describe_status(bits: int) -> str:
     return ", ".join(name for bit, name in STATUS_NAMES.items() if bits & bit) or "ok"
 
 
+# One idle engine is kept after run_to_completion()/release() so that the next run of the SAME scenario shape (same
+# spec blob, replica count, device, stream) re-seeds the existing device allocations (dcsim_reset) instead of
+# freeing and re-allocating tens of GB.  free_cached_engine() drops it.
+_CACHED = {"key": None, "engine": None}
+
+
+def _cache_key(sp, n_replicas, device, cuda_stream):
+    return (sp.to_bytes(), int(n_replicas), int(device), int(cuda_stream), os.environ.get("DCSIM_PREPASS", ""))
+
+
+def acquire_engine(sp, n_replicas, base_seed, first_replica_id=0, device=0, cuda_stream=0):
+    key = _cache_key(sp, n_replicas, device, cuda_stream)
+    if _CACHED["engine"] is not None and _CACHED["key"] == key:
+        eng, _CACHED["engine"], _CACHED["key"] = _CACHED["engine"], None, None
+        eng.set_trace(0, 0)
+        eng.set_logging(0, 0, 0)
+        eng.reset(base_seed, first_replica_id)
+        return eng
+    free_cached_engine()
+    return BatchedEngine(sp, n_replicas, base_seed, first_replica_id, device, cuda_stream)
+
+
+def release_engine(eng, sp, device=0, cuda_stream=0):
+    """Parks a finished engine for reuse (see acquire_engine); any previously parked one is destroyed."""
+    free_cached_engine()
+    _CACHED["engine"], _CACHED["key"] = eng, _cache_key(sp, eng.n_replicas, device, cuda_stream)
+
+
+def free_cached_engine():
+    if _CACHED["engine"] is not None:
+        _CACHED["engine"].close()
+    _CACHED["engine"], _CACHED["key"] = None, None
+
+
 def run_to_completion(spec_factory, n_replicas, base_seed, first_replica_id=0, device=0, cuda_stream=0,
                       max_retries=3, configure=None):
     """Runs all replicas to end_time.  A replica that overflowed a capacity is never trusted: the whole batch
-    is re-run with that capacity raised (``spec_factory(caps)`` rebuilds the blob).  Returns (engine, summary)."""
+    is re-run with that capacity raised (``spec_factory(caps)`` rebuilds the blob).  Returns (engine, summary);
+    hand the engine back with release_engine() (reuse) or close()."""
     caps = {}
     for attempt in range(max_retries + 1):
         sp = spec_factory(dict(caps))
-        eng = BatchedEngine(sp, n_replicas, base_seed, first_replica_id, device, cuda_stream)
+        eng = acquire_engine(sp, n_replicas, base_seed, first_replica_id, device, cuda_stream)
         if configure:
             configure(eng)
         eng.advance(0)

@@ -17,7 +17,7 @@ from typing import Dict, Optional, Tuple, Union
 import numpy as np
 
 from .. import spec as S
-from ..engine import run_to_completion
+from ..engine import release_engine, run_to_completion
 from .arrivals import ArrivalConfig
 from .models import DataCenter
 from .network import Graph, Ingress
@@ -59,7 +59,7 @@ class MultiIngressPaperSimulator:
                  num_fixed_gpus=1, fixed_freq=None,
                  # --- batched-engine additions (keyword only in spirit; defaults reproduce one trajectory) ---
                  replicas: int = 1, device: int = 0, first_replica_id: int = 0, write_logs: bool = True,
-                 cuda_stream: int = 0):
+                 cuda_stream: int = 0, keep_engine: bool = True):
         self.ingresses, self.dcs, self.graph = ingresses, dcs, graph
         self.arr_inf, self.arr_trn = arrival_inf, arrival_train
         self.router_policy = router_policy          # stored, never consulted — as in the reference (SIM:65)
@@ -78,6 +78,7 @@ class MultiIngressPaperSimulator:
         self.show_progress = bool(show_progress)
         self.replicas, self.device, self.first_replica_id = int(replicas), int(device), int(first_replica_id)
         self.write_logs, self.cuda_stream = bool(write_logs), int(cuda_stream)
+        self.keep_engine = bool(keep_engine)   # park the device allocations for the next run of the same shape
         if algo == "chsac_af" or elastic_scaling and algo == "chsac_af":
             raise NotImplementedError("algo=chsac_af is outside the batched path (SIM:555-573)")
         self.cluster_log_path, self.job_log_path = "cluster_log.csv", "job_log.csv"
@@ -118,7 +119,12 @@ class MultiIngressPaperSimulator:
             self._store_replica0(summ[0])
             if self.write_logs:
                 self._write_csvs(eng.job_log(), eng.cluster_log())
-        finally:
+        except BaseException:
+            eng.close()
+            raise
+        if self.keep_engine:
+            release_engine(eng, eng.spec, self.device, self.cuda_stream)   # next run of this shape re-seeds it
+        else:
             eng.close()
         return self
 
