@@ -157,9 +157,9 @@ def acquire_engine(sp, n_replicas, base_seed, first_replica_id=0, device=0, cuda
     key = _cache_key(sp, n_replicas, device, cuda_stream)
     if _CACHED["engine"] is not None and _CACHED["key"] == key:
         eng, _CACHED["engine"], _CACHED["key"] = _CACHED["engine"], None, None
+        eng.reset(base_seed, first_replica_id)   # fresh batch: recorders may be re-targeted again
         eng.set_trace(0, 0)
         eng.set_logging(0, 0, 0)
-        eng.reset(base_seed, first_replica_id)
         return eng
     free_cached_engine()
     return BatchedEngine(sp, n_replicas, base_seed, first_replica_id, device, cuda_stream)
