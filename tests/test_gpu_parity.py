@@ -252,3 +252,29 @@ def test_in_loop_sampling_mode_on_device(oracle, monkeypatch, name):
     a, b = split.copy(), fused.copy()
     a[:, hw] = b[:, hw] = 0
     assert np.array_equal(a, b)
+
+
+def test_parked_engine_is_reseeded_correctly(tmp_path, oracle):
+    """run() parks its device allocations; the next run of the same shape re-seeds them (dcsim_reset) instead of
+    re-allocating.  Results, DataCenter write-back and the CSV rows must be those of a fresh engine."""
+    import csv
+    import logging
+    from distributed_cluster_gpus_b200 import engine as E
+    from distributed_cluster_gpus_b200.configs import paper_config as pc
+    from distributed_cluster_gpus_b200.simcore.simulator_paper_multi import MultiIngressPaperSimulator
+    sc = SC.BY_NAME["ragged_3dc_12_5_40"]
+    blob = SC.to_spec(sc).to_bytes()
+    E.free_cached_engine()
+    for seed in (5, 900, 5):
+        kw = SC.build_inputs(sc)
+        sim = MultiIngressPaperSimulator(router_policy=pc.build_router_policy(), logger=logging.getLogger("t"),
+                                         sim_duration=sc["duration"], log_interval=sc["log_interval"],
+                                         log_path=str(tmp_path / str(seed)), rng_seed=seed, algo=sc["algo"],
+                                         show_progress=False, replicas=8, **kw).run()
+        want, _ = oracle.run_batch(blob, 8, seed)
+        assert_rows_match(sim.summary, want, sc["n_dc"])
+        rows = list(csv.reader(open(sim.job_log_path)))
+        assert len(rows) - 1 == int(want[0, S.S_JOBS_FINISHED])
+        assert E._CACHED["engine"] is not None                      # parked for the next run
+    E.free_cached_engine()
+    assert E._CACHED["engine"] is None
