@@ -192,6 +192,7 @@ def run_b200(args, world, rank, local_rank):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device; there is no CPU fallback")
     torch.cuda.set_device(local_rank)
+    os.environ["NCCL_DEBUG"] = "WARN"         # keep stdout to the one JSON line (no "NCCL version" banner)
     if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     sc = workload(args)
