@@ -38,10 +38,12 @@ dcsim_advance_kernel(const __grid_constant__ dcsim_kparams_t P, unsigned long lo
   const uint64_t r = (uint64_t)blockIdx.x * (uint64_t)wpc + (uint64_t)warp;
   if (r >= P.n_replicas) return; /* whole warps leave together */
   const int bytes = P.L.total_bytes;
-  char* blk = dcsim_smem + (size_t)warp * (size_t)bytes;
   char* home = P.state + r * (uint64_t)bytes;
+  /* normally the block is staged in shared memory; a block too large for that (e.g. one running-job record per GPU
+   * of a 512-GPU DC) is worked on in place — same code, the core only sees a pointer; slower but not refused */
+  char* blk = P.staged ? dcsim_smem + (size_t)warp * (size_t)bytes : home;
   const bool fresh = reinterpret_cast<const dcsim_hdr_t*>(home)->initialized == 0u;
-  if (!fresh) { /* resume: coalesced 16-byte loads of the replica's block */
+  if (P.staged && !fresh) { /* resume: coalesced 16-byte loads of the replica's block */
     const uint4* src = reinterpret_cast<const uint4*>(home);
     uint4* dst = reinterpret_cast<uint4*>(blk);
     for (int i = lane; i < bytes / 16; i += 32) dst[i] = src[i];
@@ -49,7 +51,7 @@ dcsim_advance_kernel(const __grid_constant__ dcsim_kparams_t P, unsigned long lo
   __syncwarp();
   const uint32_t n = dcsim_replica_step<CAP, PRE>(&P, r, blk, fresh);
   __syncwarp();
-  {
+  if (P.staged) {
     const uint4* src = reinterpret_cast<const uint4*>(blk);
     uint4* dst = reinterpret_cast<uint4*>(home);
     for (int i = lane; i < bytes / 16; i += 32) dst[i] = src[i];
@@ -118,7 +120,7 @@ struct dcsim {
   uint32_t trace_cap, jobs_cap, cluster_cap;
   int64_t trace_replica, log_replica;
   int launches;
-  int prepass, arrivals_ready;
+  int prepass, arrivals_ready, staged;
   double* d_arr_t;
   double* d_arr_size;
   uint32_t* d_arr_meta;
@@ -234,13 +236,13 @@ int dcsim_create(const void* spec_blob, size_t spec_bytes, uint64_t n_replicas, 
     if (warps > DCSIM_MIN_CTAS_PER_SM * DCSIM_MAX_WARPS_PER_CTA) warps = DCSIM_MIN_CTAS_PER_SM * DCSIM_MAX_WARPS_PER_CTA; /* register bound */
     if (warps > best_warps) { best_warps = warps; wpc = cand; }
   }
-  if (wpc < 1) {
-    rc = set_err(NULL, DCSIM_E_UNSUPPORTED, "state block of %s%lld bytes does not fit one CTA's shared memory; lower cap_run / cap_xfer", "", h->L.total_bytes);
-    dcsim_destroy(h);
-    return rc;
+  h->staged = 1;
+  if (wpc < 1) { /* the block does not fit a CTA's shared memory: run in place out of HBM/L2 */
+    h->staged = 0;
+    wpc = DCSIM_MAX_WARPS_PER_CTA;
   }
   h->warps_per_cta = wpc;
-  h->smem_bytes = wpc * h->L.total_bytes;
+  h->smem_bytes = h->staged ? wpc * h->L.total_bytes : 0;
   h->ctas = (int)((n_replicas + (uint64_t)wpc - 1) / (uint64_t)wpc);
   const void* kern = h->L.cap_stale ? (h->prepass ? (const void*)dcsim_advance_kernel<true, true> : (const void*)dcsim_advance_kernel<true, false>)
                                     : (h->prepass ? (const void*)dcsim_advance_kernel<false, true> : (const void*)dcsim_advance_kernel<false, false>);
@@ -347,6 +349,7 @@ static void fill_kparams(const dcsim_t* h, dcsim_kparams_t* P, uint64_t max_even
   P->state = h->d_state; P->queues = h->d_queues; P->summary = h->d_summary;
   P->end_eps = h->spec.end_time + 1e-9; /* SIM:161 */
   P->arr_t = h->d_arr_t; P->arr_size = h->d_arr_size; P->arr_meta = h->d_arr_meta; P->arr_hdr = h->d_arr_hdr; P->cap_arr = h->cap_arr;
+  P->staged = (uint32_t)h->staged;
 }
 
 int dcsim_prepare(dcsim_t* h) {

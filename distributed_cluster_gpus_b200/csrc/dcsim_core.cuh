@@ -255,7 +255,8 @@ struct dcsim_kparams_t {
   double* arr_size;     /* job size (arrivals.py:5-11) */
   uint32_t* arr_meta;   /* stream (bits 0-3) | routed DC (4-6) | next arrival of the stream was schedulable (7) */
   struct dcsim_arrhdr_t* arr_hdr;
-  uint32_t cap_arr, _pad0;
+  uint32_t cap_arr;
+  uint32_t staged;      /* 1: state blocks are staged in shared memory; 0: too large for that, run in place in HBM/L2 */
   double end_eps;       /* end_time + 1e-9, the _schedule cut-off (SIM:161) */
 };
 

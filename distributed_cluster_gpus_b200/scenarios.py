@@ -60,6 +60,12 @@ GOLDEN_SCENARIOS = [
     scenario("full_swing_sinusoid_amp1", 2, 32, dict(mode="sinusoid", rate=4.0, amp=1.0, period=60.0), POI(0.3), 300.0, FREQ8),
     scenario("negative_amp_sinusoid", 2, 32, dict(mode="sinusoid", rate=4.0, amp=-0.5, period=45.0), dict(mode="sinusoid", rate=0.3, amp=0.3, period=100.0), 200.0, FREQ8),
     scenario("no_inf_priority_perf_first", 2, 16, POI(4.0), POI(0.5), 200.0, FREQ8, policy="perf_first"),
+    # what `python run_sim_paper.py` runs with its own defaults (run_sim_paper.py:18-112, paper_config.py:39-64):
+    # all 8 DCs with their own GPU counts, sinusoid inference 6/s amp 0.6 period 300 s, Poisson training 0.3/s, 180 s
+    scenario("cli_defaults_8dc_180s", 8, None, dict(mode="sinusoid", rate=6.0, amp=0.6, period=300.0),
+             dict(mode="poisson", rate=0.3, amp=0.0, period=3600.0), 180.0, FREQ8, gpus_list=[16, 32, 256, 16, 128, 16, 512, 512]),
+    scenario("cli_defaults_8dc_joint_nf_60s", 8, None, dict(mode="sinusoid", rate=6.0, amp=0.6, period=300.0),
+             dict(mode="poisson", rate=0.3, amp=0.0, period=3600.0), 60.0, FREQ8, algo="joint_nf", gpus_list=[16, 32, 256, 16, 128, 16, 512, 512]),
 ]
 BY_NAME = {s["name"]: s for s in GOLDEN_SCENARIOS}
 
