@@ -30,7 +30,11 @@ extern __shared__ __align__(16) char dcsim_smem[];
  * separate instantiation because merely inlining that cold code costs the common path 17 % (measured,
  * profiles/r01_variants_ab.md). */
 /* PRE = arrivals come from the list written by dcsim_arrivals_kernel (no sampling in this kernel). */
-template <bool CAP, bool PRE>
+/* STAGED = the replica's state block is staged in shared memory for the launch (the normal case).  When it is
+ * too large for that (e.g. one running-job record per GPU of a 512-GPU DC), the !STAGED instantiation works on it in
+ * place in HBM/L2 — same core, the block is just a pointer — slower but not refused.  A compile-time switch: a
+ * run-time select would turn every state access into a generic load/store (measured -15 %). */
+template <bool CAP, bool PRE, bool STAGED>
 __global__ void __launch_bounds__(DCSIM_MAX_WARPS_PER_CTA * 32, DCSIM_MIN_CTAS_PER_SM)
 dcsim_advance_kernel(const __grid_constant__ dcsim_kparams_t P, unsigned long long* __restrict__ events_total) {
   const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31u);
@@ -39,11 +43,9 @@ dcsim_advance_kernel(const __grid_constant__ dcsim_kparams_t P, unsigned long lo
   if (r >= P.n_replicas) return; /* whole warps leave together */
   const int bytes = P.L.total_bytes;
   char* home = P.state + r * (uint64_t)bytes;
-  /* normally the block is staged in shared memory; a block too large for that (e.g. one running-job record per GPU
-   * of a 512-GPU DC) is worked on in place — same code, the core only sees a pointer; slower but not refused */
-  char* blk = P.staged ? dcsim_smem + (size_t)warp * (size_t)bytes : home;
+  char* blk = STAGED ? dcsim_smem + (size_t)warp * (size_t)bytes : home;
   const bool fresh = reinterpret_cast<const dcsim_hdr_t*>(home)->initialized == 0u;
-  if (P.staged && !fresh) { /* resume: coalesced 16-byte loads of the replica's block */
+  if (STAGED && !fresh) { /* resume: coalesced 16-byte loads of the replica's block */
     const uint4* src = reinterpret_cast<const uint4*>(home);
     uint4* dst = reinterpret_cast<uint4*>(blk);
     for (int i = lane; i < bytes / 16; i += 32) dst[i] = src[i];
@@ -51,7 +53,7 @@ dcsim_advance_kernel(const __grid_constant__ dcsim_kparams_t P, unsigned long lo
   __syncwarp();
   const uint32_t n = dcsim_replica_step<CAP, PRE>(&P, r, blk, fresh);
   __syncwarp();
-  if (P.staged) {
+  if (STAGED) {
     const uint4* src = reinterpret_cast<const uint4*>(blk);
     uint4* dst = reinterpret_cast<uint4*>(home);
     for (int i = lane; i < bytes / 16; i += 32) dst[i] = src[i];
@@ -70,6 +72,16 @@ __global__ void __launch_bounds__(DCSIM_ARRIVALS_THREADS) dcsim_arrivals_kernel(
   double* clocks = dcsim_arr_scratch + threadIdx.x;                                     /* [stream][thread] */
   uint32_t* ring = reinterpret_cast<uint32_t*>(dcsim_arr_scratch + 2 * DCSIM_MAX_ING * blockDim.x) + threadIdx.x; /* [word][thread] */
   dcsim_generate_arrivals(&P, r, clocks, ring, (int)blockDim.x);
+}
+
+typedef void (*dcsim_advance_fn)(const dcsim_kparams_t, unsigned long long*);
+static dcsim_advance_fn dcsim_pick_kernel(bool cap, bool pre, bool staged) {
+  static const dcsim_advance_fn table[8] = {
+      dcsim_advance_kernel<false, false, false>, dcsim_advance_kernel<false, false, true>,
+      dcsim_advance_kernel<false, true, false>,  dcsim_advance_kernel<false, true, true>,
+      dcsim_advance_kernel<true, false, false>,  dcsim_advance_kernel<true, false, true>,
+      dcsim_advance_kernel<true, true, false>,   dcsim_advance_kernel<true, true, true>};
+  return table[(cap ? 4 : 0) + (pre ? 2 : 0) + (staged ? 1 : 0)];
 }
 
 /* Aggregates the summaries; every block reduces a slice, then one atomicAdd per component. */
@@ -244,22 +256,13 @@ int dcsim_create(const void* spec_blob, size_t spec_bytes, uint64_t n_replicas, 
   h->warps_per_cta = wpc;
   h->smem_bytes = h->staged ? wpc * h->L.total_bytes : 0;
   h->ctas = (int)((n_replicas + (uint64_t)wpc - 1) / (uint64_t)wpc);
-  const void* kern = h->L.cap_stale ? (h->prepass ? (const void*)dcsim_advance_kernel<true, true> : (const void*)dcsim_advance_kernel<true, false>)
-                                    : (h->prepass ? (const void*)dcsim_advance_kernel<false, true> : (const void*)dcsim_advance_kernel<false, false>);
+  const dcsim_advance_fn kern = dcsim_pick_kernel(h->L.cap_stale != 0, h->prepass != 0, h->staged != 0);
   CREATE_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
   cudaFuncAttributes fa;
   CREATE_TRY(cudaFuncGetAttributes(&fa, kern));
   h->regs = fa.numRegs;
   int blocks_per_sm = 0;
-  if (h->L.cap_stale && h->prepass) {
-    CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, dcsim_advance_kernel<true, true>, wpc * 32, h->smem_bytes));
-  } else if (h->L.cap_stale) {
-    CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, dcsim_advance_kernel<true, false>, wpc * 32, h->smem_bytes));
-  } else if (h->prepass) {
-    CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, dcsim_advance_kernel<false, true>, wpc * 32, h->smem_bytes));
-  } else {
-    CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, dcsim_advance_kernel<false, false>, wpc * 32, h->smem_bytes));
-  }
+  CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, wpc * 32, h->smem_bytes));
   h->resident_warps = blocks_per_sm * wpc;
 
   CREATE_TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
@@ -375,13 +378,7 @@ int dcsim_advance(dcsim_t* h, uint64_t max_events_per_replica, uint64_t* total_e
   dcsim_kparams_t P;
   fill_kparams(h, &P, max_events_per_replica);
   const dim3 grid(h->ctas), block(h->warps_per_cta * 32);
-  if (h->prepass) {
-    if (h->L.cap_stale) dcsim_advance_kernel<true, true><<<grid, block, h->smem_bytes, h->stream>>>(P, h->d_events);
-    else dcsim_advance_kernel<false, true><<<grid, block, h->smem_bytes, h->stream>>>(P, h->d_events);
-  } else {
-    if (h->L.cap_stale) dcsim_advance_kernel<true, false><<<grid, block, h->smem_bytes, h->stream>>>(P, h->d_events);
-    else dcsim_advance_kernel<false, false><<<grid, block, h->smem_bytes, h->stream>>>(P, h->d_events);
-  }
+  dcsim_pick_kernel(h->L.cap_stale != 0, h->prepass != 0, h->staged != 0)<<<grid, block, h->smem_bytes, h->stream>>>(P, h->d_events);
   CUDA_TRY(h, cudaGetLastError());
   h->launches++;
   if (total_events_out) {
