@@ -103,6 +103,7 @@ __global__ void dcsim_reduce_kernel(const double* __restrict__ summary, uint64_t
     acc[DCSIM_A_MEANLAT_SUM] += ml;
     acc[DCSIM_A_MEANLAT_SQ] += ml * ml;
     acc[DCSIM_A_RNG_WORDS] += s[DCSIM_S_RNG_WORDS];
+    acc[DCSIM_A_RUNNING] += (s[DCSIM_S_STATUS] == 0.0 && s[DCSIM_S_DONE] == 0.0) ? 1.0 : 0.0;
   }
 #pragma unroll
   for (int k = 0; k < DCSIM_AGG_K; ++k) {
@@ -410,7 +411,8 @@ int dcsim_summary_device_ptr(dcsim_t* h, void** dev_ptr_out) {
 
 int dcsim_all_done(dcsim_t* h, int* done_out) {
   if (!h || !done_out) return DCSIM_E_INVALID;
-  if (!h->launches) { *done_out = 0; return DCSIM_OK; }
+  *done_out = 0;
+  if (!h->launches) return DCSIM_OK;
   CUDA_TRY(h, cudaSetDevice(h->device));
   double* agg = NULL;
   CUDA_TRY(h, cudaMalloc(&agg, DCSIM_AGG_K * sizeof(double)));
@@ -423,24 +425,9 @@ int dcsim_all_done(dcsim_t* h, int* done_out) {
   }
   cudaFree(agg);
   if (rc != DCSIM_OK) return rc;
-  /* DCSIM_A_FAILED counts replicas that are not done OR stopped on a capacity overflow; the latter never
-   * finish, so report "done" once nothing is still running */
-  *done_out = 0;
-  {
-    /* not-done and status==0  <=> still running */
-    size_t need = (size_t)h->n_replicas * DCSIM_SUMMARY_K;
-    double* s = (double*)malloc(need * sizeof(double));
-    if (!s) return set_err(h, DCSIM_E_NOMEM, "all_done: host allocation failed%s%lld");
-    rc = dcsim_fetch_summary(h, s, need * sizeof(double));
-    if (rc == DCSIM_OK) {
-      int running = 0;
-      for (uint64_t r = 0; r < h->n_replicas && !running; ++r)
-        if (s[r * DCSIM_SUMMARY_K + DCSIM_S_DONE] == 0.0 && s[r * DCSIM_SUMMARY_K + DCSIM_S_STATUS] == 0.0) running = 1;
-      *done_out = !running;
-    }
-    free(s);
-  }
-  return rc;
+  /* a replica that stopped on a capacity overflow never finishes, so "done" = nothing is still running */
+  *done_out = host[DCSIM_A_RUNNING] == 0.0;
+  return DCSIM_OK;
 }
 
 int dcsim_reduce_summary(dcsim_t* h, double* dev_out) {

@@ -34,6 +34,7 @@ def aggregate_rows(summary: np.ndarray) -> np.ndarray:
     a[S.A_MEANLAT_SUM] = ml.sum()
     a[S.A_MEANLAT_SQ] = (ml * ml).sum()
     a[S.A_RNG_WORDS] = summary[:, S.S_RNG_WORDS].sum()
+    a[S.A_RUNNING] = np.count_nonzero((summary[:, S.S_STATUS] == 0) & (summary[:, S.S_DONE] == 0))
     return a
 
 

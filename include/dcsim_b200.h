@@ -181,7 +181,9 @@ enum { /* status bits: a replica that overflowed a capacity stops and says so â€
 enum {
   DCSIM_A_REPLICAS = 0, DCSIM_A_FAILED = 1, DCSIM_A_EVENTS = 2, DCSIM_A_JOBS = 3, DCSIM_A_ENERGY = 4,
   DCSIM_A_ENERGY_SQ = 5, DCSIM_A_LAT_SUM = 6, DCSIM_A_MEANLAT_SUM = 7, DCSIM_A_MEANLAT_SQ = 8,
-  DCSIM_A_RNG_WORDS = 9, DCSIM_A_FORKS = 10, DCSIM_AGG_K = 16
+  DCSIM_A_RNG_WORDS = 9, DCSIM_A_FORKS = 10,
+  DCSIM_A_RUNNING = 11, /* replicas neither finished nor stopped on a status bit: more dcsim_advance() calls needed */
+  DCSIM_AGG_K = 16
 };
 
 /* one trace record per processed event of the traced replica */
