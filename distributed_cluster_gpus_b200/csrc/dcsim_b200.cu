@@ -74,6 +74,13 @@ __global__ void __launch_bounds__(DCSIM_ARRIVALS_THREADS) dcsim_arrivals_kernel(
   dcsim_generate_arrivals(&P, r, clocks, ring, (int)blockDim.x);
 }
 
+/* Sums the per-replica latency histograms: thread b of every block owns bin b (coalesced 1 KB rows). */
+__global__ void dcsim_hist_reduce_kernel(const uint32_t* __restrict__ hist, uint64_t n, unsigned long long* __restrict__ out) {
+  unsigned long long acc = 0ull;
+  for (uint64_t r = blockIdx.x; r < n; r += gridDim.x) acc += hist[r * (2 * DCSIM_LAT_BINS) + threadIdx.x];
+  if (acc) atomicAdd(out + threadIdx.x, acc);
+}
+
 typedef void (*dcsim_advance_fn)(const dcsim_kparams_t, unsigned long long*);
 static dcsim_advance_fn dcsim_pick_kernel(bool cap, bool pre, bool staged) {
   static const dcsim_advance_fn table[8] = {
@@ -138,6 +145,7 @@ struct dcsim {
   double* d_arr_size;
   uint32_t* d_arr_meta;
   dcsim_arrhdr_t* d_arr_hdr;
+  uint32_t* d_hist;
   uint32_t cap_arr;
   unsigned long long events_seen;
   char err[512];
@@ -280,6 +288,8 @@ int dcsim_create(const void* spec_blob, size_t spec_bytes, uint64_t n_replicas, 
     CREATE_TRY(cudaMalloc(&h->d_arr_meta, ne * sizeof(uint32_t)));
     CREATE_TRY(cudaMalloc(&h->d_arr_hdr, (size_t)n_replicas * sizeof(dcsim_arrhdr_t)));
   }
+  CREATE_TRY(cudaMalloc(&h->d_hist, (size_t)n_replicas * 2 * DCSIM_LAT_BINS * sizeof(uint32_t)));
+  CREATE_TRY(cudaMemsetAsync(h->d_hist, 0, (size_t)n_replicas * 2 * DCSIM_LAT_BINS * sizeof(uint32_t), h->stream));
   CREATE_TRY(cudaMalloc(&h->d_events, sizeof(unsigned long long)));
   CREATE_TRY(cudaMalloc(&h->d_counts, 4 * sizeof(uint32_t)));
   CREATE_TRY(cudaMemsetAsync(h->d_state, 0, state_bytes, h->stream)); /* hdr.initialized == 0 => fresh replica */
@@ -298,6 +308,7 @@ int dcsim_reset(dcsim_t* h, uint64_t base_seed, uint64_t first_replica_id) {
   /* hdr.initialized == 0 marks a fresh replica; the FIFOs need no clearing (head == tail == 0) */
   CUDA_TRY(h, cudaMemsetAsync(h->d_state, 0, (size_t)h->n_replicas * (size_t)h->L.total_bytes, h->stream));
   CUDA_TRY(h, cudaMemsetAsync(h->d_counts, 0, 4 * sizeof(uint32_t), h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_hist, 0, (size_t)h->n_replicas * 2 * DCSIM_LAT_BINS * sizeof(uint32_t), h->stream));
   h->seed0 = base_seed + first_replica_id;
   h->arrivals_ready = 0;
   h->launches = 0; /* a reset batch is "fresh": recorders may be re-targeted before its first advance */
@@ -354,6 +365,7 @@ static void fill_kparams(const dcsim_t* h, dcsim_kparams_t* P, uint64_t max_even
   P->end_eps = h->spec.end_time + 1e-9; /* SIM:161 */
   P->arr_t = h->d_arr_t; P->arr_size = h->d_arr_size; P->arr_meta = h->d_arr_meta; P->arr_hdr = h->d_arr_hdr; P->cap_arr = h->cap_arr;
   P->staged = (uint32_t)h->staged;
+  P->lat_hist = h->d_hist;
 }
 
 int dcsim_prepare(dcsim_t* h) {
@@ -442,6 +454,28 @@ int dcsim_reduce_summary(dcsim_t* h, double* dev_out) {
   return DCSIM_OK;
 }
 
+int dcsim_fetch_latency_histogram(dcsim_t* h, uint64_t* out, size_t out_bytes) {
+  if (!h || !out) return DCSIM_E_INVALID;
+  const size_t need = 2 * DCSIM_LAT_BINS * sizeof(uint64_t);
+  if (out_bytes < need) return set_err(h, DCSIM_E_INVALID, "fetch_latency_histogram: buffer too small (need %s%lld bytes)", "", (long long)need);
+  if (!h->launches) return set_err(h, DCSIM_E_STATE, "fetch_latency_histogram before the first advance%s%lld");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  unsigned long long* d_out = NULL;
+  CUDA_TRY(h, cudaMalloc(&d_out, need));
+  cudaError_t e = cudaMemsetAsync(d_out, 0, need, h->stream);
+  if (e == cudaSuccess) {
+    int blocks = 8 * h->sm_count;
+    if ((uint64_t)blocks > h->n_replicas) blocks = (int)h->n_replicas;
+    dcsim_hist_reduce_kernel<<<blocks, 2 * DCSIM_LAT_BINS, 0, h->stream>>>(h->d_hist, h->n_replicas, d_out);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, need, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_out);
+  if (e != cudaSuccess) return set_err(h, DCSIM_E_CUDA, "CUDA error: %s%lld", cudaGetErrorString(e));
+  return DCSIM_OK;
+}
+
 static int fetch_records(dcsim_t* h, const void* dev, size_t rec_bytes, uint32_t dev_cap, int which, void* out,
                          uint32_t capacity, uint32_t* n_out) {
   if (!h || !n_out) return DCSIM_E_INVALID;
@@ -493,6 +527,7 @@ void dcsim_destroy(dcsim_t* h) {
   if (h->own_stream) { cudaStreamSynchronize(h->stream); }
   cudaFree(h->d_state); cudaFree(h->d_queues); cudaFree(h->d_summary); cudaFree(h->d_events); cudaFree(h->d_counts);
   cudaFree(h->d_trace); cudaFree(h->d_jobs); cudaFree(h->d_cluster);
+  cudaFree(h->d_hist);
   cudaFree(h->d_arr_t); cudaFree(h->d_arr_size); cudaFree(h->d_arr_meta); cudaFree(h->d_arr_hdr);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;

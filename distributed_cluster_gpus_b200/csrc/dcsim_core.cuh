@@ -73,6 +73,16 @@ DCSIM_DEV double dcsim_bcast_f64(double x, int src) {
 #endif
 }
 
+/* Histogram bin of a positive latency: 4 bins per octave from 2^-20 s, from the IEEE exponent and the top two
+ * mantissa bits — pure integer work, identical on host and device. */
+DCSIM_DEV int dcsim_lat_bin(double lat) {
+  const uint32_t hi = dcsim_hi(lat);
+  const int e = (int)((hi >> 20) & 0x7ffu) - (1023 - 20);
+  int idx = e * 4 + (int)((hi >> 18) & 3u);
+  idx = idx < 0 ? 0 : idx;
+  return idx > DCSIM_LAT_BINS - 1 ? DCSIM_LAT_BINS - 1 : idx;
+}
+
 /* ---- candidate slots (the event set, one slot per lane) -------------------------------------- */
 enum {
   CAND_DC0 = 0,      /* + d   : earliest job_finish among DC d's running jobs */
@@ -255,6 +265,7 @@ struct dcsim_kparams_t {
   double* arr_size;     /* job size (arrivals.py:5-11) */
   uint32_t* arr_meta;   /* stream (bits 0-3) | routed DC (4-6) | next arrival of the stream was schedulable (7) */
   struct dcsim_arrhdr_t* arr_hdr;
+  uint32_t* lat_hist;   /* [n_replicas][2][DCSIM_LAT_BINS] job-latency histograms, or NULL */
   uint32_t cap_arr;
   uint32_t staged;      /* 1: state blocks are staged in shared memory; 0: too large for that, run in place in HBM/L2 */
   double end_eps;       /* end_time + 1e-9, the _schedule cut-off (SIM:161) */
@@ -270,6 +281,7 @@ struct dcsim_ctx_t {
   char* q;               /* this replica's FIFOs (HBM) */
   dcsim_hdr_t* H;
   int lane;
+  uint32_t* hist;        /* this replica's [2][DCSIM_LAT_BINS] latency histogram in HBM, or NULL */
   bool is_traced, is_logged;
   /* Philox stream */
   uint32_t key0, key1;
@@ -1162,6 +1174,13 @@ DCSIM_DEV void dcsim_finish_account(dcsim_ctx_t& c, int d, int slot) {
   const double lat = now - dcsim_at<double>(c.blk, L.rn_start)[i]; /* SIM:820 */
   H->lat_sum += lat;
   if (jt == DCSIM_JT_INFERENCE) { H->lat_sum_inf += lat; H->n_fin_inf++; } else { H->lat_sum_trn += lat; H->n_fin_trn++; }
+  if (c.hist) { /* fire-and-forget: nothing waits for it */
+#ifdef DCSIM_HOST_EMU
+    c.hist[jt * DCSIM_LAT_BINS + dcsim_lat_bin(lat)] += 1u;
+#else
+    atomicAdd(c.hist + jt * DCSIM_LAT_BINS + dcsim_lat_bin(lat), 1u);
+#endif
+  }
   const double f_used = dcsim_at<double>(c.blk, L.rn_f)[i];
   if (c.is_logged && c.P->rec.jobs) { /* job_log.csv row, SIM:815-823 */
     const uint32_t r = c.P->rec.counts[1];
@@ -1605,6 +1624,7 @@ DCSIM_DEV uint32_t dcsim_replica_step(const dcsim_kparams_t* P, uint64_t r, char
   dcsim_ctx_t c;
   c.P = P; c.blk = blk; c.H = reinterpret_cast<dcsim_hdr_t*>(blk); c.lane = dcsim_lane();
   c.q = P->queues + r * P->L.queue_bytes;
+  c.hist = P->lat_hist ? P->lat_hist + r * (uint64_t)(2 * DCSIM_LAT_BINS) : nullptr;
   c.is_traced = ((int64_t)r == P->rec.trace_replica);
   c.is_logged = ((int64_t)r == P->rec.log_replica);
   const uint64_t key = P->seed0 + r;

@@ -18,6 +18,31 @@ assert TRACE_DTYPE.itemsize == C.sizeof(S.TraceRec) and JOB_DTYPE.itemsize == C.
 assert CLUSTER_DTYPE.itemsize == C.sizeof(S.ClusterRec)
 
 
+LAT_BINS = 128
+
+
+def latency_bin_edges() -> np.ndarray:
+    """Lower edges [s] of the LAT_BINS histogram bins (+ the upper edge of the last): 2^e * (1 + m/4), e from -20."""
+    k = np.arange(LAT_BINS + 1)
+    return np.ldexp(1.0 + (k % 4) / 4.0, k // 4 - 20)
+
+
+def latency_quantiles(hist_row, qs=(0.5, 0.9, 0.99)):
+    """Quantiles [s] of one histogram row, log-interpolated inside the bin that holds the quantile."""
+    h = np.asarray(hist_row, dtype=np.float64)
+    total = h.sum()
+    if total == 0:
+        return [float("nan")] * len(qs)
+    edges, cum, out = latency_bin_edges(), np.cumsum(h), []
+    for q in qs:
+        b = int(np.searchsorted(cum, q * total, side="left"))
+        b = min(b, LAT_BINS - 1)
+        below = cum[b - 1] if b else 0.0
+        frac = (q * total - below) / h[b] if h[b] else 0.0
+        out.append(float(edges[b] * (edges[b + 1] / edges[b]) ** frac))
+    return out
+
+
 class BatchedEngine:
     """R independent replicas of one scenario on one GPU.
 
@@ -93,6 +118,12 @@ class BatchedEngine:
     def reduce_into(self, device_ptr: int):
         """Writes the AGG_K-vector (spec.A_*) to device memory; the caller all-reduces it."""
         N.check(self._lib.dcsim_reduce_summary(self._h, C.c_void_p(device_ptr)), self._h)
+
+    def latency_histogram(self) -> np.ndarray:
+        """[2, LAT_BINS] uint64: job-latency counts of the whole batch ([0] inference, [1] training)."""
+        out = np.zeros((2, LAT_BINS), dtype=np.uint64)
+        N.check(self._lib.dcsim_fetch_latency_histogram(self._h, C.c_void_p(out.ctypes.data), out.nbytes), self._h)
+        return out
 
     # -- recorders -------------------------------------------------------------------------------
     def _fetch(self, fn, dtype, cap):

@@ -86,6 +86,10 @@ def main(argv=None):
     sim.run()
     s = sim.summary
     stats = batch_statistics(s)
+    from .engine import latency_quantiles
+    for jt, name in enumerate(("inference", "training")):        # job-level quantiles over the whole batch
+        p50, p90, p99 = latency_quantiles(sim.latency_histogram[jt])
+        stats[f"job_latency_s_{name}_p50_p90_p99"] = [p50, p90, p99]
     if args.summary_json:
         with open(args.summary_json, "w") as f:
             json.dump(stats, f, indent=1)

@@ -88,6 +88,7 @@ class MultiIngressPaperSimulator:
             self.job_log_path = os.path.join(log_path, "job_log.csv")
         self.now = 0.0
         self.summary: Optional[np.ndarray] = None
+        self.latency_histogram: Optional[np.ndarray] = None
         self.launch_info: Optional[dict] = None
         self._spec = self._flatten({})              # validates now, like the reference's constructor would fail now
 
@@ -115,6 +116,7 @@ class MultiIngressPaperSimulator:
                                       self.cuda_stream, configure=configure)
         try:
             self.summary = summ
+            self.latency_histogram = eng.latency_histogram()     # [2, 128] job-latency counts of the whole batch
             self.launch_info = eng.launch_info()
             self._store_replica0(summ[0])
             if self.write_logs:

@@ -269,6 +269,13 @@ int dcsim_summary_device_ptr(dcsim_t* h, void** dev_ptr_out);
  * all-reduces over NCCL at end of run; no other data crosses GPUs. */
 int dcsim_reduce_summary(dcsim_t* h, double* dev_out);
 
+/* Job-latency histogram of the whole batch (latency = finish - start, the job_log.csv latency_s column,
+ * simulator_paper_multi.py:820): DCSIM_LAT_BINS bins per job type, 4 per octave starting at 2^-20 s — bin index =
+ * 4 * (exponent + 20) + top two mantissa bits, clamped — summed over all replicas on the device.  `out` receives
+ * [2][DCSIM_LAT_BINS] counts ([0] = inference, [1] = training).  Quantiles (p50 / p99 ...) follow on the host. */
+#define DCSIM_LAT_BINS 128
+int dcsim_fetch_latency_histogram(dcsim_t* h, uint64_t* out, size_t out_bytes);
+
 int dcsim_fetch_trace(dcsim_t* h, dcsim_trace_rec_t* out, uint32_t capacity, uint32_t* n_out);
 int dcsim_fetch_job_log(dcsim_t* h, dcsim_job_rec_t* out, uint32_t capacity, uint32_t* n_out);
 int dcsim_fetch_cluster_log(dcsim_t* h, dcsim_cluster_rec_t* out, uint32_t capacity, uint32_t* n_out);

@@ -35,6 +35,9 @@ def lib():
         L.dcoracle_run_batch.restype = C.c_longlong
         L.dcoracle_run_batch.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int,
                                          C.c_void_p]
+        L.dcoracle_run_batch_hist.restype = C.c_longlong
+        L.dcoracle_run_batch_hist.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int,
+                                              C.c_void_p, C.c_void_p]
         L.dcoracle_open.restype = C.c_void_p
         L.dcoracle_open.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32]
         L.dcoracle_advance.restype = C.c_int
@@ -61,6 +64,18 @@ def run_batch(spec_bytes: bytes, n_replicas: int, base_seed: int, first_replica_
     if total < 0:
         raise ValueError("oracle rejected the spec blob")
     return out, int(total)
+
+
+def run_batch_hist(spec_bytes: bytes, n_replicas: int, base_seed: int, first_replica_id: int = 0, n_threads: int = 1):
+    """-> (summaries, per-replica latency histograms [n, 2, 128] uint32)."""
+    out = np.zeros((n_replicas, SUMMARY_K), dtype=np.float64)
+    hist = np.zeros((n_replicas, 2, 128), dtype=np.uint32)
+    buf = C.create_string_buffer(spec_bytes, len(spec_bytes))
+    total = lib().dcoracle_run_batch_hist(buf, len(spec_bytes), n_replicas, base_seed & (2**64 - 1), first_replica_id,
+                                          RNG_PHILOX, n_threads, out.ctypes.data, hist.ctypes.data)
+    if total < 0:
+        raise ValueError("oracle rejected the spec blob")
+    return out, hist
 
 
 class OracleSim:

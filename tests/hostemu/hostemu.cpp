@@ -21,7 +21,8 @@ size_t hostemu_sizeof_spec(void) { return sizeof(dcsim_spec_t); }
 long long hostemu_run_batch(const void* spec_blob, size_t spec_bytes, uint64_t n_replicas, uint64_t seed0,
                             uint64_t chunk_events, double* out_summaries, int64_t rec_replica,
                             dcsim_trace_rec_t* trace, uint32_t trace_cap, dcsim_job_rec_t* jobs, uint32_t jobs_cap,
-                            dcsim_cluster_rec_t* cluster, uint32_t cluster_cap, uint32_t* counts, int32_t* layout_out) {
+                            dcsim_cluster_rec_t* cluster, uint32_t cluster_cap, uint32_t* counts, int32_t* layout_out,
+                            uint32_t* lat_hist /* [n][2][DCSIM_LAT_BINS] or NULL */) {
   if (!spec_blob || spec_bytes != sizeof(dcsim_spec_t)) return -1;
   dcsim_kparams_t* P = (dcsim_kparams_t*)calloc(1, sizeof(dcsim_kparams_t));
   memcpy(&P->spec, spec_blob, sizeof(dcsim_spec_t));
@@ -42,6 +43,7 @@ long long hostemu_run_batch(const void* spec_blob, size_t spec_bytes, uint64_t n
   P->state = (char*)calloc(n_replicas, (size_t)P->L.total_bytes);
   P->queues = (char*)calloc(n_replicas, (size_t)P->L.queue_bytes + 16);
   P->summary = out_summaries;
+  P->lat_hist = lat_hist;
   if (prepass) { /* the arrival pre-pass, one replica after the other */
     P->arr_t = (double*)calloc(n_replicas * (size_t)P->cap_arr, sizeof(double));
     P->arr_size = (double*)calloc(n_replicas * (size_t)P->cap_arr, sizeof(double));

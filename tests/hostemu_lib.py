@@ -26,7 +26,7 @@ def lib():
         L.hostemu_run_batch.restype = C.c_longlong
         L.hostemu_run_batch.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p,
                                         C.c_int64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p,
-                                        C.c_uint32, C.c_void_p, C.c_void_p]
+                                        C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -40,15 +40,16 @@ def run_batch(spec_bytes, n_replicas, seed0, chunk_events=0, trace_cap=0, rec_re
     cluster = np.zeros(max(cluster_cap, 1), dtype=cluster_dtype) if cluster_dtype is not None else None
     counts = np.zeros(4, dtype=np.uint32)
     layout = np.zeros(8, dtype=np.int32)
+    hist = np.zeros((n_replicas, 2, 128), dtype=np.uint32)
     total = lib().hostemu_run_batch(buf, len(spec_bytes), n_replicas, seed0 & (2**64 - 1), chunk_events,
                                     out.ctypes.data, rec_replica,
                                     trace.ctypes.data if trace_cap else None, trace_cap,
                                     jobs.ctypes.data if jobs is not None and jobs_cap else None, jobs_cap,
                                     cluster.ctypes.data if cluster is not None and cluster_cap else None, cluster_cap,
-                                    counts.ctypes.data, layout.ctypes.data)
+                                    counts.ctypes.data, layout.ctypes.data, hist.ctypes.data)
     if total < 0:
         raise ValueError("hostemu rejected the spec blob")
-    res = {"summary": out, "events": int(total), "trace": trace[:min(int(counts[0]), trace_cap)],
+    res = {"summary": out, "events": int(total), "lat_hist": hist, "trace": trace[:min(int(counts[0]), trace_cap)],
            "layout": {"total_bytes": int(layout[0]), "cap_xfer": int(layout[1]), "cap_run": int(layout[2]),
                       "cap_q_inf": int(layout[3]), "cap_q_trn": int(layout[4])}}
     if jobs is not None:

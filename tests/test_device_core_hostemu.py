@@ -120,3 +120,26 @@ def test_in_loop_sampling_mode_equals_oracle(oracle, hostemu, monkeypatch, name)
     assert got["events"] == total and _same(got["summary"], want)
     parts = hostemu.run_batch(blob, 2, 31, chunk_events=997)
     assert np.array_equal(parts["summary"], got["summary"])
+
+
+def test_latency_histogram_equals_oracle(oracle, hostemu):
+    """Same integer binning on both sides (exponent + two mantissa bits) -> identical per-replica histograms."""
+    for name in ("cfg3_4x64_sinusoid_120s", "sweep_joint_nf", "trn_only_2x8"):
+        blob = SC.to_spec(SC.BY_NAME[name]).to_bytes()
+        want_s, want_h = oracle.run_batch_hist(blob, 3, 17)
+        got = hostemu.run_batch(blob, 3, 17)
+        assert np.array_equal(got["lat_hist"], want_h)
+        assert np.array_equal(want_h.sum(axis=2)[:, 0], want_s[:, S.S_FIN_INF])     # one count per finished job
+        assert np.array_equal(want_h.sum(axis=2)[:, 1], want_s[:, S.S_FIN_TRN])
+
+
+def test_latency_bins_and_quantiles():
+    from distributed_cluster_gpus_b200.engine import LAT_BINS, latency_bin_edges, latency_quantiles
+    e = latency_bin_edges()
+    assert len(e) == LAT_BINS + 1 and e[0] == 2.0 ** -20 and e[4] == 2.0 ** -19 and e[1] == 2.0 ** -20 * 1.25
+    assert np.all(np.diff(e) > 0)
+    h = np.zeros(LAT_BINS)
+    h[40] = 99
+    h[60] = 1
+    q50, q99, q100 = latency_quantiles(h, (0.5, 0.99, 1.0))
+    assert e[40] <= q50 <= e[41] and e[40] <= q99 <= e[41] and e[60] <= q100 <= e[61]

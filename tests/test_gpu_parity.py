@@ -278,3 +278,22 @@ def test_parked_engine_is_reseeded_correctly(tmp_path, oracle):
         assert E._CACHED["engine"] is not None                      # parked for the next run
     E.free_cached_engine()
     assert E._CACHED["engine"] is None
+
+
+def test_latency_histogram_on_device(oracle):
+    """Batch histogram = sum of the oracle's per-replica histograms, up to jobs whose latency sits within the
+    device's last-ulp difference of a bin edge (they may land one bin over); totals are exact."""
+    from distributed_cluster_gpus_b200.engine import latency_quantiles
+    sp = SC.to_spec(SC.BY_NAME["cfg3_4x64_sinusoid_600s"])
+    n = 32
+    with engine_cls()(sp, n, base_seed=4) as eng:
+        eng.advance(0)
+        got = eng.latency_histogram()
+        summ = eng.summary()
+    _, hist = oracle.run_batch_hist(sp.to_bytes(), n, 4, n_threads=os.cpu_count() or 1)
+    want = hist.astype(np.uint64).sum(axis=0)
+    assert got.sum(axis=1).tolist() == [summ[:, S.S_FIN_INF].sum(), summ[:, S.S_FIN_TRN].sum()] == want.sum(axis=1).tolist()
+    assert np.abs(got.astype(np.int64) - want.astype(np.int64)).sum() <= 4
+    for jt in (0, 1):
+        a, b = latency_quantiles(got[jt]), latency_quantiles(want[jt])
+        np.testing.assert_allclose(a, b, rtol=1e-3)

@@ -19,7 +19,7 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 from distributed_cluster_gpus_b200 import scenarios as SC, sharding, spec as S  # noqa: E402
-from distributed_cluster_gpus_b200.engine import BatchedEngine  # noqa: E402
+from distributed_cluster_gpus_b200.engine import BatchedEngine, latency_quantiles  # noqa: E402
 
 VARIANTS = [("default_policy", "energy_aware", {}), ("default_policy", "perf_first", {}), ("joint_nf", "energy_aware", {}),
             ("carbon_cost", "energy_aware", {}), ("eco_route", "energy_aware", {}), ("bandit", "energy_aware", {}),
@@ -42,6 +42,10 @@ for algo, policy, extra in VARIANTS:
     with BatchedEngine(SC.to_spec(sc), count, 123, first, torch.cuda.current_device()) as eng:
         eng.advance(0)
         summ = eng.summary()
+        hist = torch.from_numpy(eng.latency_histogram().astype(np.int64)).cuda()
+    if world > 1:
+        dist.all_reduce(hist)
+    hist = hist.cpu().numpy()
     vec = torch.from_numpy(sharding.aggregate_rows(summ)).cuda()
     sharding.allreduce_aggregate(vec)
     st = sharding.finalize(vec.cpu().numpy())
@@ -52,6 +56,8 @@ for algo, policy, extra in VARIANTS:
            "mean_job_latency_s_mean": st["mean_latency_s_mean"],
            "mean_job_latency_s_ci95": 1.96 * (st["mean_latency_s_var"] / n) ** 0.5,
            "jobs_finished_per_replica": st["jobs_finished"] / n,
+           "job_latency_s_inference_p50_p90_p99": latency_quantiles(hist[0]),
+           "job_latency_s_training_p50_p90_p99": latency_quantiles(hist[1]),
            "rank0_energy_MJ_p05_p50_p95": [float(q) / 1e6 for q in np.percentile(summ[:, S.S_TOTAL_ENERGY_J], [5, 50, 95])],
            "rank0_latency_s_p05_p50_p95": [float(q) for q in np.percentile(summ[:, S.S_LAT_SUM] / fin, [5, 50, 95])],
            "wall_s": time.perf_counter() - t0}
