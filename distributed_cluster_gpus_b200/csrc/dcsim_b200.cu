@@ -288,8 +288,6 @@ int dcsim_create(const void* spec_blob, size_t spec_bytes, uint64_t n_replicas, 
     CREATE_TRY(cudaMalloc(&h->d_arr_meta, ne * sizeof(uint32_t)));
     CREATE_TRY(cudaMalloc(&h->d_arr_hdr, (size_t)n_replicas * sizeof(dcsim_arrhdr_t)));
   }
-  CREATE_TRY(cudaMalloc(&h->d_hist, (size_t)n_replicas * 2 * DCSIM_LAT_BINS * sizeof(uint32_t)));
-  CREATE_TRY(cudaMemsetAsync(h->d_hist, 0, (size_t)n_replicas * 2 * DCSIM_LAT_BINS * sizeof(uint32_t), h->stream));
   CREATE_TRY(cudaMalloc(&h->d_events, sizeof(unsigned long long)));
   CREATE_TRY(cudaMalloc(&h->d_counts, 4 * sizeof(uint32_t)));
   CREATE_TRY(cudaMemsetAsync(h->d_state, 0, state_bytes, h->stream)); /* hdr.initialized == 0 => fresh replica */
@@ -308,7 +306,7 @@ int dcsim_reset(dcsim_t* h, uint64_t base_seed, uint64_t first_replica_id) {
   /* hdr.initialized == 0 marks a fresh replica; the FIFOs need no clearing (head == tail == 0) */
   CUDA_TRY(h, cudaMemsetAsync(h->d_state, 0, (size_t)h->n_replicas * (size_t)h->L.total_bytes, h->stream));
   CUDA_TRY(h, cudaMemsetAsync(h->d_counts, 0, 4 * sizeof(uint32_t), h->stream));
-  CUDA_TRY(h, cudaMemsetAsync(h->d_hist, 0, (size_t)h->n_replicas * 2 * DCSIM_LAT_BINS * sizeof(uint32_t), h->stream));
+  if (h->d_hist) CUDA_TRY(h, cudaMemsetAsync(h->d_hist, 0, (size_t)h->n_replicas * 2 * DCSIM_LAT_BINS * sizeof(uint32_t), h->stream));
   h->seed0 = base_seed + first_replica_id;
   h->arrivals_ready = 0;
   h->launches = 0; /* a reset batch is "fresh": recorders may be re-targeted before its first advance */
@@ -454,8 +452,20 @@ int dcsim_reduce_summary(dcsim_t* h, double* dev_out) {
   return DCSIM_OK;
 }
 
+int dcsim_enable_latency_histogram(dcsim_t* h) {
+  if (!h) return DCSIM_E_INVALID;
+  if (h->d_hist) return DCSIM_OK;
+  if (h->launches) return set_err(h, DCSIM_E_STATE, "enable_latency_histogram must precede the first advance%s%lld");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const size_t bytes = (size_t)h->n_replicas * 2 * DCSIM_LAT_BINS * sizeof(uint32_t);
+  CUDA_TRY(h, cudaMalloc(&h->d_hist, bytes));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_hist, 0, bytes, h->stream));
+  return DCSIM_OK;
+}
+
 int dcsim_fetch_latency_histogram(dcsim_t* h, uint64_t* out, size_t out_bytes) {
   if (!h || !out) return DCSIM_E_INVALID;
+  if (!h->d_hist) return set_err(h, DCSIM_E_STATE, "latency histogram not enabled (dcsim_enable_latency_histogram)%s%lld");
   const size_t need = 2 * DCSIM_LAT_BINS * sizeof(uint64_t);
   if (out_bytes < need) return set_err(h, DCSIM_E_INVALID, "fetch_latency_histogram: buffer too small (need %s%lld bytes)", "", (long long)need);
   if (!h->launches) return set_err(h, DCSIM_E_STATE, "fetch_latency_histogram before the first advance%s%lld");

@@ -281,7 +281,6 @@ struct dcsim_ctx_t {
   char* q;               /* this replica's FIFOs (HBM) */
   dcsim_hdr_t* H;
   int lane;
-  uint32_t* hist;        /* this replica's [2][DCSIM_LAT_BINS] latency histogram in HBM, or NULL */
   bool is_traced, is_logged;
   /* Philox stream */
   uint32_t key0, key1;
@@ -1160,7 +1159,7 @@ DCSIM_DEV void dcsim_handle_xfer(dcsim_ctx_t& c, int slot) {
 }
 
 /* SIM:701-927 minus RL/elastic branches (lane 0 part, after the record was read and before it is erased). */
-DCSIM_DEV void dcsim_finish_account(dcsim_ctx_t& c, int d, int slot) {
+DCSIM_DEV void dcsim_finish_account(dcsim_ctx_t& c, uint64_t r, int d, int slot) {
   const dcsim_spec_t& sp = c.P->spec;
   const dcsim_layout_t& L = c.P->L;
   dcsim_hdr_t* H = c.H;
@@ -1174,11 +1173,12 @@ DCSIM_DEV void dcsim_finish_account(dcsim_ctx_t& c, int d, int slot) {
   const double lat = now - dcsim_at<double>(c.blk, L.rn_start)[i]; /* SIM:820 */
   H->lat_sum += lat;
   if (jt == DCSIM_JT_INFERENCE) { H->lat_sum_inf += lat; H->n_fin_inf++; } else { H->lat_sum_trn += lat; H->n_fin_trn++; }
-  if (c.hist) { /* fire-and-forget: nothing waits for it */
+  if (c.P->lat_hist) { /* this replica's [2][DCSIM_LAT_BINS] histogram in HBM; fire-and-forget, nothing waits for it */
+    uint32_t* cell = c.P->lat_hist + r * (uint64_t)(2 * DCSIM_LAT_BINS) + (uint32_t)(jt * DCSIM_LAT_BINS + dcsim_lat_bin(lat));
 #ifdef DCSIM_HOST_EMU
-    c.hist[jt * DCSIM_LAT_BINS + dcsim_lat_bin(lat)] += 1u;
+    *cell += 1u;
 #else
-    atomicAdd(c.hist + jt * DCSIM_LAT_BINS + dcsim_lat_bin(lat), 1u);
+    atomicAdd(cell, 1u);
 #endif
   }
   const double f_used = dcsim_at<double>(c.blk, L.rn_f)[i];
@@ -1550,7 +1550,7 @@ DCSIM_DEV uint32_t dcsim_replica_run(dcsim_ctx_t& c, uint64_t r) {
     } else if (kind == KIND_FINISH) {
       const int d = win - CAND_DC0;
       const int slot = DCI(c, DI_FMIN_SLOT)[d];
-      if (c.lane == 0) { c.H->ev_fin++; dcsim_finish_account(c, d, slot); }
+      if (c.lane == 0) { c.H->ev_fin++; dcsim_finish_account(c, r, d, slot); }
       dcsim_running_erase<CAP>(c, d, slot); /* reads records the accounting did not touch; syncs before it returns */
       if (c.lane == 0) { dcsim_dequeue_loop<CAP>(c, d); dcsim_refresh_power(c, d); }
       dcsim_warp_sync();
@@ -1624,7 +1624,6 @@ DCSIM_DEV uint32_t dcsim_replica_step(const dcsim_kparams_t* P, uint64_t r, char
   dcsim_ctx_t c;
   c.P = P; c.blk = blk; c.H = reinterpret_cast<dcsim_hdr_t*>(blk); c.lane = dcsim_lane();
   c.q = P->queues + r * P->L.queue_bytes;
-  c.hist = P->lat_hist ? P->lat_hist + r * (uint64_t)(2 * DCSIM_LAT_BINS) : nullptr;
   c.is_traced = ((int64_t)r == P->rec.trace_replica);
   c.is_logged = ((int64_t)r == P->rec.log_replica);
   const uint64_t key = P->seed0 + r;

@@ -119,6 +119,10 @@ class BatchedEngine:
         """Writes the AGG_K-vector (spec.A_*) to device memory; the caller all-reduces it."""
         N.check(self._lib.dcsim_reduce_summary(self._h, C.c_void_p(device_ptr)), self._h)
 
+    def enable_latency_histogram(self):
+        """Opt-in, before the first advance of a batch: job-latency histogram of the whole batch (~1 % of kernel time)."""
+        N.check(self._lib.dcsim_enable_latency_histogram(self._h), self._h)
+
     def latency_histogram(self) -> np.ndarray:
         """[2, LAT_BINS] uint64: job-latency counts of the whole batch ([0] inference, [1] training)."""
         out = np.zeros((2, LAT_BINS), dtype=np.uint64)

@@ -109,6 +109,7 @@ class MultiIngressPaperSimulator:
         cluster_cap = n_ticks * len(self.dcs)
 
         def configure(eng):
+            eng.enable_latency_histogram()
             if self.write_logs:
                 eng.set_logging(0, job_cap, cluster_cap)
 

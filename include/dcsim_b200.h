@@ -274,6 +274,9 @@ int dcsim_reduce_summary(dcsim_t* h, double* dev_out);
  * 4 * (exponent + 20) + top two mantissa bits, clamped — summed over all replicas on the device.  `out` receives
  * [2][DCSIM_LAT_BINS] counts ([0] = inference, [1] = training).  Quantiles (p50 / p99 ...) follow on the host. */
 #define DCSIM_LAT_BINS 128
+/* Opt-in (before the first advance of a batch; stays on across dcsim_reset): allocates the per-replica histograms and
+ * makes the finish handler feed them (one fire-and-forget RED per finished job, ~1 % of kernel time). */
+int dcsim_enable_latency_histogram(dcsim_t* h);
 int dcsim_fetch_latency_histogram(dcsim_t* h, uint64_t* out, size_t out_bytes);
 
 int dcsim_fetch_trace(dcsim_t* h, dcsim_trace_rec_t* out, uint32_t capacity, uint32_t* n_out);

@@ -287,6 +287,7 @@ def test_latency_histogram_on_device(oracle):
     sp = SC.to_spec(SC.BY_NAME["cfg3_4x64_sinusoid_600s"])
     n = 32
     with engine_cls()(sp, n, base_seed=4) as eng:
+        eng.enable_latency_histogram()
         eng.advance(0)
         got = eng.latency_histogram()
         summ = eng.summary()

@@ -40,6 +40,7 @@ for algo, policy, extra in VARIANTS:
     sc = SC.scenario(f"sweep_{algo}_{policy}", 4, 64, SC.SIN10, SC.POI(1.0), args.duration, SC.FREQ3, algo=algo, policy=policy, **extra)
     t0 = time.perf_counter()
     with BatchedEngine(SC.to_spec(sc), count, 123, first, torch.cuda.current_device()) as eng:
+        eng.enable_latency_histogram()
         eng.advance(0)
         summ = eng.summary()
         hist = torch.from_numpy(eng.latency_histogram().astype(np.int64)).cuda()
