@@ -83,6 +83,22 @@ DCSIM_DEV int dcsim_lat_bin(double lat) {
   return idx > DCSIM_LAT_BINS - 1 ? DCSIM_LAT_BINS - 1 : idx;
 }
 
+/* One count into replica r's [2][DCSIM_LAT_BINS] histogram in HBM — fire-and-forget, nothing waits for it.
+ * Out of line so that the (opt-in) feature does not touch the event loop's register allocation. */
+#ifndef DCSIM_HOST_EMU
+__device__ __noinline__
+#else
+static
+#endif
+void dcsim_hist_add(uint32_t* hist, uint64_t r, int jt, double lat) {
+  uint32_t* cell = hist + r * (uint64_t)(2 * DCSIM_LAT_BINS) + (uint32_t)(jt * DCSIM_LAT_BINS + dcsim_lat_bin(lat));
+#ifdef DCSIM_HOST_EMU
+  *cell += 1u;
+#else
+  atomicAdd(cell, 1u);
+#endif
+}
+
 /* ---- candidate slots (the event set, one slot per lane) -------------------------------------- */
 enum {
   CAND_DC0 = 0,      /* + d   : earliest job_finish among DC d's running jobs */
@@ -1173,14 +1189,7 @@ DCSIM_DEV void dcsim_finish_account(dcsim_ctx_t& c, uint64_t r, int d, int slot)
   const double lat = now - dcsim_at<double>(c.blk, L.rn_start)[i]; /* SIM:820 */
   H->lat_sum += lat;
   if (jt == DCSIM_JT_INFERENCE) { H->lat_sum_inf += lat; H->n_fin_inf++; } else { H->lat_sum_trn += lat; H->n_fin_trn++; }
-  if (c.P->lat_hist) { /* this replica's [2][DCSIM_LAT_BINS] histogram in HBM; fire-and-forget, nothing waits for it */
-    uint32_t* cell = c.P->lat_hist + r * (uint64_t)(2 * DCSIM_LAT_BINS) + (uint32_t)(jt * DCSIM_LAT_BINS + dcsim_lat_bin(lat));
-#ifdef DCSIM_HOST_EMU
-    *cell += 1u;
-#else
-    atomicAdd(cell, 1u);
-#endif
-  }
+  if (c.P->lat_hist) dcsim_hist_add(c.P->lat_hist, r, jt, lat);
   const double f_used = dcsim_at<double>(c.blk, L.rn_f)[i];
   if (c.is_logged && c.P->rec.jobs) { /* job_log.csv row, SIM:815-823 */
     const uint32_t r = c.P->rec.counts[1];
