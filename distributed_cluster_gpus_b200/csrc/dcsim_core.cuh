@@ -83,14 +83,16 @@ DCSIM_DEV int dcsim_lat_bin(double lat) {
   return idx > DCSIM_LAT_BINS - 1 ? DCSIM_LAT_BINS - 1 : idx;
 }
 
-/* One count into replica r's [2][DCSIM_LAT_BINS] histogram in HBM — fire-and-forget, nothing waits for it.
- * Out of line so that the (opt-in) feature does not touch the event loop's register allocation. */
+/* Cold helpers are kept OUT OF LINE (by-value arguments only, so the context stays in registers): inlining them
+ * costs the event loop registers and instruction-cache footprint on paths most launches never take. */
 #ifndef DCSIM_HOST_EMU
-__device__ __noinline__
+#define DCSIM_COLD __device__ __noinline__
 #else
-static
+#define DCSIM_COLD static
 #endif
-void dcsim_hist_add(uint32_t* hist, uint64_t r, int jt, double lat) {
+
+/* One count into replica r's [2][DCSIM_LAT_BINS] histogram in HBM — fire-and-forget, nothing waits for it. */
+DCSIM_COLD void dcsim_hist_add(uint32_t* hist, uint64_t r, int jt, double lat) {
   uint32_t* cell = hist + r * (uint64_t)(2 * DCSIM_LAT_BINS) + (uint32_t)(jt * DCSIM_LAT_BINS + dcsim_lat_bin(lat));
 #ifdef DCSIM_HOST_EMU
   *cell += 1u;
@@ -871,21 +873,51 @@ DCSIM_DEV int dcsim_policy_select(dcsim_ctx_t& c, int d, int jt) {
 }
 
 /* learners.py:20-36 */
-DCSIM_DEV double dcsim_bandit_select(dcsim_ctx_t& c, int d, int jt) {
-  const dcsim_dc_t& cfg = c.P->spec.dc[d];
-  const uint32_t* N = dcsim_at<uint32_t>(c.blk, c.P->L.bandit_n) + (d * 2 + jt) * DCSIM_MAX_FREQ;
-  const double* S = dcsim_at<double>(c.blk, c.P->L.bandit_s) + (d * 2 + jt) * DCSIM_MAX_FREQ;
-  c.H->bandit_t += 1u;
+DCSIM_COLD double dcsim_bandit_select(const dcsim_kparams_t* P, char* blk, int d, int jt) {
+  const dcsim_dc_t& cfg = P->spec.dc[d];
+  dcsim_hdr_t* H = reinterpret_cast<dcsim_hdr_t*>(blk);
+  const uint32_t* N = dcsim_at<uint32_t>(blk, P->L.bandit_n) + (d * 2 + jt) * DCSIM_MAX_FREQ;
+  const double* S = dcsim_at<double>(blk, P->L.bandit_s) + (d * 2 + jt) * DCSIM_MAX_FREQ;
+  H->bandit_t += 1u;
+#pragma unroll 1
   for (int i = 0; i < cfg.n_freq; ++i)
     if (N[i] < 1u) return cfg.freq_levels[i];
   double best_ucb = -1e9, best_f = cfg.freq_levels[0];
-  const double two_log_t = 2.0 * log((double)c.H->bandit_t);
+  const double two_log_t = 2.0 * log((double)H->bandit_t);
+#pragma unroll 1
   for (int i = 0; i < cfg.n_freq; ++i) {
     const double n = (double)N[i];
     const double ucb = S[i] / n + sqrt(two_log_t / n);
     if (ucb > best_ucb) { best_ucb = ucb; best_f = cfg.freq_levels[i]; }
   }
   return best_f;
+}
+
+/* learners.py:38-42 with cost = E_pred = P_job * T(n, f) (SIM:716, 826-827) */
+DCSIM_COLD void dcsim_bandit_update(const dcsim_kparams_t* P, char* blk, int d, int jt, int g, double f_used, double p_job) {
+  const dcsim_dc_t& cfg = P->spec.dc[d];
+  const double E_pred = p_job * dcsim_step_time(g, f_used, cfg.coeffs[jt]);
+#pragma unroll 1
+  for (int q = 0; q < cfg.n_freq; ++q) {
+    if (cfg.freq_levels[q] == f_used) {
+      dcsim_at<uint32_t>(blk, P->L.bandit_n)[(d * 2 + jt) * DCSIM_MAX_FREQ + q] += 1u;
+      dcsim_at<double>(blk, P->L.bandit_s)[(d * 2 + jt) * DCSIM_MAX_FREQ + q] += -E_pred;
+      break;
+    }
+  }
+}
+
+/* job_log.csv row, SIM:815-823 (unrounded) */
+DCSIM_COLD void dcsim_joblog_write(const dcsim_kparams_t* P, uint32_t jid, uint32_t meta, int d, double size, double f_used,
+                                   double start_s, double finish_s) {
+  const uint32_t r = P->rec.counts[1];
+  if (r < P->rec.jobs_cap) {
+    dcsim_job_rec_t* o = P->rec.jobs + r;
+    o->jid = jid; o->ingress = (uint8_t)(meta >> 17); o->jtype = (uint8_t)((meta >> 16) & 1u);
+    o->dc = (uint8_t)d; o->n_gpus = (uint8_t)(meta & 0xffffu); o->size = size;
+    o->f_used = f_used; o->start_s = start_s; o->finish_s = finish_s;
+  }
+  P->rec.counts[1] = r + 1u;
 }
 
 /* SIM:680-699 (_start_job, use_dc_freq) and SIM:960-980 (_start_job_with_nf): allocate, stamp, push job_finish. */
@@ -926,7 +958,7 @@ DCSIM_DEV void dcsim_start_job(dcsim_ctx_t& c, int d, int jt, double size, uint3
 }
 
 /* SIM:982-984  int((now % 86400) // 3600), CPython float_rem / float_floor_div for positive operands */
-DCSIM_DEV int dcsim_current_hour(double now) {
+DCSIM_COLD int dcsim_current_hour(double now) {
   const double x = fmod(now, 86400.0);
   const double mod = fmod(x, 3600.0);
   const double div = (x - mod) / 3600.0;
@@ -947,7 +979,7 @@ DCSIM_DEV void dcsim_start_by_rule(dcsim_ctx_t& c, int rule, bool at_xfer, int d
     dcsim_start_job<CAP>(c, d, jt, size, jid, ing, n, nf.f);
   } else if (rule == DCSIM_START_BANDIT) {
     int n = free_g < sp.max_gpus_per_job ? free_g : sp.max_gpus_per_job;
-    const double f = dcsim_bandit_select(c, d, jt);
+    const double f = dcsim_bandit_select(c.P, c.blk, d, jt);
     n = n < free_g ? n : free_g;
     n = n > 1 ? n : 1;
     dcsim_start_job<CAP>(c, d, jt, size, jid, ing, n, f);
@@ -1191,27 +1223,11 @@ DCSIM_DEV void dcsim_finish_account(dcsim_ctx_t& c, uint64_t r, int d, int slot)
   if (jt == DCSIM_JT_INFERENCE) { H->lat_sum_inf += lat; H->n_fin_inf++; } else { H->lat_sum_trn += lat; H->n_fin_trn++; }
   if (c.P->lat_hist) dcsim_hist_add(c.P->lat_hist, r, jt, lat);
   const double f_used = dcsim_at<double>(c.blk, L.rn_f)[i];
-  if (c.is_logged && c.P->rec.jobs) { /* job_log.csv row, SIM:815-823 */
-    const uint32_t r = c.P->rec.counts[1];
-    if (r < c.P->rec.jobs_cap) {
-      dcsim_job_rec_t* o = c.P->rec.jobs + r;
-      o->jid = dcsim_at<uint32_t>(c.blk, L.rn_jid)[i]; o->ingress = (uint8_t)(meta >> 17); o->jtype = (uint8_t)jt;
-      o->dc = (uint8_t)d; o->n_gpus = (uint8_t)g; o->size = dcsim_at<double>(c.blk, L.rn_size)[i];
-      o->f_used = f_used; o->start_s = dcsim_at<double>(c.blk, L.rn_start)[i]; o->finish_s = now;
-    }
-    c.P->rec.counts[1] = r + 1u;
-  }
-  if (sp.deq_rule == DCSIM_START_BANDIT) { /* learners.py:38-42 with cost = E_pred (SIM:716, 826-827) */
-    const dcsim_dc_t& cfg = sp.dc[d];
-    const double E_pred = dcsim_at<double>(c.blk, L.rn_pw)[i] * dcsim_step_time(g, f_used, cfg.coeffs[jt]);
-    for (int q = 0; q < cfg.n_freq; ++q) {
-      if (cfg.freq_levels[q] == f_used) {
-        dcsim_at<uint32_t>(c.blk, L.bandit_n)[(d * 2 + jt) * DCSIM_MAX_FREQ + q] += 1u;
-        dcsim_at<double>(c.blk, L.bandit_s)[(d * 2 + jt) * DCSIM_MAX_FREQ + q] += -E_pred;
-        break;
-      }
-    }
-  }
+  if (c.is_logged && c.P->rec.jobs)
+    dcsim_joblog_write(c.P, dcsim_at<uint32_t>(c.blk, L.rn_jid)[i], meta, d, dcsim_at<double>(c.blk, L.rn_size)[i], f_used,
+                       dcsim_at<double>(c.blk, L.rn_start)[i], now);
+  if (sp.deq_rule == DCSIM_START_BANDIT)
+    dcsim_bandit_update(c.P, c.blk, d, jt, g, f_used, dcsim_at<double>(c.blk, L.rn_pw)[i]);
 }
 
 /* SIM:840-927: start queued jobs while GPUs are free, inference first when inf_priority. */
