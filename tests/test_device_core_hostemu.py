@@ -143,3 +143,14 @@ def test_latency_bins_and_quantiles():
     h[60] = 1
     q50, q99, q100 = latency_quantiles(h, (0.5, 0.99, 1.0))
     assert e[40] <= q50 <= e[41] and e[40] <= q99 <= e[41] and e[60] <= q100 <= e[61]
+
+
+@pytest.mark.parametrize("name", ["cfg3_4x64_sinusoid_120s", "sweep_eco_route", "cli_defaults_8dc_180s"])
+def test_wide_seed_against_reference_fixture(hostemu, name):
+    """Seed 2**40 + 7: the high Philox key word is non-zero.  Device core straight against the reference's numbers."""
+    from conftest import load_golden
+    from test_oracle_vs_reference import check_row_against_golden
+    doc = load_golden(name)
+    run = [r for r in doc["runs"] if r["rng"] == "philox" and r["seed"] == 2**40 + 7][0]
+    got = hostemu.run_batch(SC.to_spec(doc["scenario"]).to_bytes(), 1, 2**40 + 7)["summary"][0]
+    check_row_against_golden(got, run, doc["scenario"]["n_dc"], [])

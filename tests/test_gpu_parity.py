@@ -298,3 +298,18 @@ def test_latency_histogram_on_device(oracle):
     for jt in (0, 1):
         a, b = latency_quantiles(got[jt]), latency_quantiles(want[jt])
         np.testing.assert_allclose(a, b, rtol=1e-3)
+
+
+def test_wide_seed_on_device(oracle):
+    """base_seed 2**40 + 5 with replicas 0..3: seeds straddle the fixture's 2**40 + 7 (non-zero high key word)."""
+    doc = load_golden("cfg3_4x64_sinusoid_120s")
+    run = [r for r in doc["runs"] if r["rng"] == "philox" and r["seed"] == 2**40 + 7][0]
+    sp = SC.to_spec(doc["scenario"])
+    with engine_cls()(sp, 4, base_seed=2**40 + 5) as eng:
+        eng.advance(0)
+        got = eng.summary()
+    assert int(got[2, S.S_EVENTS]) == run["events"] and int(got[2, S.S_RNG_WORDS]) == run["rng_words"]
+    e_ref = float.fromhex(run["total_energy_j"])
+    assert abs(got[2, S.S_TOTAL_ENERGY_J] - e_ref) <= RTOL * e_ref
+    want, _ = oracle.run_batch(sp.to_bytes(), 4, 2**40 + 5)
+    assert_rows_match(got, want, 4)

@@ -130,3 +130,18 @@ def test_cli_parses_reference_flags():
                     "--log-path", "/tmp/x", "--progress", "", "--algo", "joint_nf", "--eco-objective", "carbon",
                     "--num_fixed_gpus", "2", "--upgr-device", "cpu", "--replicas", "128", "--n-dc", "4"])
     assert a.duration == 60 and a.algo == "joint_nf" and a.replicas == 128 and a.n_dc == 4
+
+
+def test_energy_price_map_forms():
+    """SIM:986-1005: a global {hour: price} map, a per-DC {dc: {hour: price}} map, or nothing."""
+    kw = SC.build_inputs(SC.BY_NAME["sweep_carbon_cost"])
+    args = (kw["ingresses"], kw["dcs"], kw["graph"], kw["arrival_inf"], kw["arrival_train"], kw["coeffs_map"], kw["policy"])
+    per_dc = {"us-west": {h: 0.5 for h in range(24)}, "us-east": {3: 0.25}}
+    sp = S.flatten(*args, carbon_intensity=kw["carbon_intensity"], energy_price=per_dc, algo="carbon_cost")
+    assert sp.dc[0].price_kwh[7] == 0.5 and sp.dc[1].price_kwh[3] == 0.25 and sp.dc[1].price_kwh[4] == 0.0
+    assert sp.dc[2].price_kwh[0] == 0.0                      # DC absent from the map
+    sp = S.flatten(*args, carbon_intensity=None, energy_price=None, algo="carbon_cost")
+    assert all(sp.dc[d].price_kwh[h] == 0.0 for d in range(4) for h in range(24))
+    assert sp.dc[0].carbon_intensity == 0.0
+    # price 0 everywhere -> the carbon objective with CI = 0: every score is 0, the first grid point wins (n=1, f=levels[0])
+    assert (sp.dc[0].nf_xfer[0][12].n, sp.dc[0].nf_xfer[0][12].f) == (1, 0.5)
