@@ -318,6 +318,10 @@ def run_b200(args, world, rank, local_rank):
                   "dcsim_fetch_summary -> DataCenter write-back + cluster_log.csv/job_log.csv of replica 0",
            "ms_per_step": 1000.0 * float(w.item()) / e2e_steps}
 
+    import shutil
+    from distributed_cluster_gpus_b200.engine import free_cached_engine
+    free_cached_engine()
+    shutil.rmtree(log_dir, ignore_errors=True)
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1000.0 * elapsed_s / args.steps, "higher_is_better": True, "scaling": "weak",
