@@ -2,9 +2,13 @@
  * dcsim_b200.cu — sm_100a kernels and the C-ABI of include/dcsim_b200.h.
  *
  * Kernels
- *   dcsim_advance_kernel   one warp per replica; stages the replica's state block HBM -> shared memory,
- *                          runs the event engine of dcsim_core.cuh, stages it back, writes the summary row.
- *   dcsim_reduce_kernel    [n_replicas][K] summaries -> DCSIM_AGG_K doubles (the only cross-GPU payload).
+ *   dcsim_arrivals_kernel     one thread per replica: the replica's arrival list (instants, sizes, routed DCs).
+ *   dcsim_advance_kernel      one warp per replica; stages the replica's state block HBM -> shared memory, runs the
+ *                             event loop of dcsim_core.cuh, stages it back, writes the summary row.  Instantiated
+ *                             over <CAP, PRE, STAGED> (power-cap controller compiled in / arrivals from the list /
+ *                             block staged in shared memory) and picked per handle.
+ *   dcsim_reduce_kernel       [n_replicas][K] summaries -> DCSIM_AGG_K doubles (the only cross-GPU payload).
+ *   dcsim_hist_reduce_kernel  per-replica job-latency histograms -> one [2][128] histogram (opt-in).
  *
  * Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false (see __graft_entry__.build()).
  * -fmad=false matters: the reference is CPython float arithmetic, one rounding per operation.

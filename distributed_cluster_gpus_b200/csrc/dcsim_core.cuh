@@ -1,26 +1,33 @@
 /*
- * dcsim_core.cuh — the per-replica event engine of the B200 batched simulator.
+ * dcsim_core.cuh — the device code of the B200 batched simulator (both kernels' bodies).
  *
- * One warp owns one Monte-Carlo replica of the reference's multi-DC event loop
- * (simcore/simulator_paper_multi.py:412-480 and the leaves it calls; citations are relative to the
- * reference tree).  The replica's whole working set — pending-event candidates, in-flight transfers,
- * running-job records, per-DC accumulators, a 128-word Philox window — is a "state block" that the warp
- * stages in shared memory for the duration of a launch; only the unbounded FIFO queues live in HBM.
+ * The reference's multi-DC event loop (simcore/simulator_paper_multi.py:412-480 and the leaves it calls; citations
+ * are relative to the reference tree) is split where its data dependencies split it:
  *
- * How the 32 lanes are used
- *   - pop-min: the pending events are kept as 32 *candidates* (one per DC = earliest job_finish of that DC,
- *     one per (ingress, job type) = its next arrival, one for the earliest in-flight transfer, one for the
- *     log tick); every lane loads one candidate and three REDUX.MIN (hi word, lo word, seq) find the winner;
- *   - the per-event sweep over all DCs (SIM:429-437) runs one DC per lane;
- *   - pool rescans, order-preserving compaction of the running set, Philox refill (one block per lane),
- *     state load/store run strided across the warp;
- *   - the handlers themselves are strictly sequential per replica (the RNG stream is consumed in order)
- *     and run on lane 0 out of shared memory.
+ *   arrival pre-pass  (dcsim_generate_arrivals, one THREAD per replica)
+ *       Only arrival handlers draw random numbers and routing never looks at DC state, so a replica's whole arrival
+ *       sequence — instants, job sizes, routed DCs, which pushes were schedulable — is drawn ahead, in the reference's
+ *       draw order, with all 32 lanes of a warp running the samplers (pow / log / sin, rejection loops).
  *
- * All arithmetic that defines results is FP64 and is written so that, compiled with -fmad=false, every
- * + - * / happens in the reference's order with one rounding each.  log/exp/pow/sin come from CUDA's
- * libdevice (<= 2 ulp from glibc's), which is why parity with the reference is asserted at 1e-9 relative
- * and exact event/job/RNG-word counts rather than bit-for-bit.
+ *   event loop        (dcsim_replica_run, one WARP per replica)
+ *       The replica's working set — pending-event candidates, in-flight transfers, running-job records, per-DC
+ *       accumulators, a window of its arrival list — is a "state block" staged in shared memory for the launch; only
+ *       the unbounded FIFO queues (and the arrival lists) live in HBM.  How the 32 lanes are used:
+ *         - pop-min: the pending events are kept as 32 *candidates* (one per DC = earliest job_finish of that DC, the
+ *           next arrival, the earliest in-flight transfer, the log tick, ...); every lane loads one candidate and
+ *           three REDUX.MIN (hi word, lo word, seq) find the winner;
+ *         - the per-event sweep over all DCs (SIM:429-437) runs one DC per lane;
+ *         - pool rescans, order-preserving compaction of the running set, staging of the arrival window and the state
+ *           block run strided across the warp;
+ *         - the handlers themselves are strictly sequential per replica and run on lane 0 out of shared memory.
+ *       With DCSIM_PREPASS=0 the samplers stay in this loop instead (Philox window filled by all lanes, rejection
+ *       loops evaluated speculatively one candidate per lane): the earlier single-kernel design, kept as a
+ *       cross-check — both must give the same bits.
+ *
+ * All arithmetic that defines results is FP64 and is written so that, compiled with -fmad=false, every + - * /
+ * happens in the reference's order with one rounding each.  log/exp/pow/sin come from CUDA's libdevice (<= 2 ulp
+ * from glibc's), which is why parity with the reference is asserted at 1e-9 relative and exact event/job/RNG-word
+ * counts rather than bit-for-bit.
  *
  * The file compiles two ways:
  *   - nvcc, sm_100a: DCSIM_LANES = 32, warp collectives are real (csrc/dcsim_b200.cu);
