@@ -204,6 +204,58 @@ static int validate_spec(const dcsim_spec_t* sp) {
   return DCSIM_OK;
 }
 
+/* Launch geometry for the handle's current state-block layout: warps per CTA, shared memory, staged / in place. */
+static cudaError_t size_launch(dcsim_t* h) {
+  cudaError_t e;
+  int smem_optin = 0, smem_sm = 0;
+  if ((e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device)) != cudaSuccess) return e;
+  if ((e = cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, h->device)) != cudaSuccess) return e;
+  /* warps per CTA: whichever of 4 / 2 / 1 keeps the most warps resident (each CTA also reserves 1 KB of shared
+   * memory and an SM holds at most 32 CTAs); small state blocks end up at 4 x 8 CTAs, large ones at 1 or 2 */
+  int wpc = 0, best_warps = 0;
+  for (int cand = DCSIM_MAX_WARPS_PER_CTA; cand >= 1; cand >>= 1) {
+    const long long per_cta = (long long)cand * h->L.total_bytes;
+    if (per_cta > smem_optin) continue;
+    int ctas = (int)(smem_sm / (per_cta + 1024));
+    if (ctas > 32) ctas = 32;
+    int warps = ctas * cand;
+    if (warps > DCSIM_MIN_CTAS_PER_SM * DCSIM_MAX_WARPS_PER_CTA) warps = DCSIM_MIN_CTAS_PER_SM * DCSIM_MAX_WARPS_PER_CTA; /* register bound */
+    if (warps > best_warps) { best_warps = warps; wpc = cand; }
+  }
+  h->staged = 1;
+  if (wpc < 1) { /* the block does not fit a CTA's shared memory: run in place out of HBM/L2 */
+    h->staged = 0;
+    wpc = DCSIM_MAX_WARPS_PER_CTA;
+  }
+  h->warps_per_cta = wpc;
+  h->smem_bytes = h->staged ? wpc * h->L.total_bytes : 0;
+  h->ctas = (int)((h->n_replicas + (uint64_t)wpc - 1) / (uint64_t)wpc);
+  const dcsim_advance_fn kern = dcsim_pick_kernel(h->L.cap_stale != 0, h->prepass != 0, h->staged != 0);
+  if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin)) != cudaSuccess) return e;
+  cudaFuncAttributes fa;
+  if ((e = cudaFuncGetAttributes(&fa, kern)) != cudaSuccess) return e;
+  h->regs = fa.numRegs;
+  int blocks_per_sm = 0;
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, wpc * 32, h->smem_bytes)) != cudaSuccess) return e;
+  h->resident_warps = blocks_per_sm * wpc;
+  return cudaSuccess;
+}
+
+/* job_log.csv needs size / f / jid in the running records; switching it on or off re-lays the state block out. */
+static int relayout(dcsim_t* h, int job_log) {
+  dcsim_layout_t L;
+  dcsim_make_layout(&h->spec, &L, h->prepass, job_log);
+  if (L.lean == h->L.lean) return DCSIM_OK;
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  h->L = L;
+  CUDA_TRY(h, size_launch(h));
+  if (h->d_state) { cudaFree(h->d_state); h->d_state = NULL; }
+  const size_t state_bytes = (size_t)h->n_replicas * (size_t)h->L.total_bytes;
+  CUDA_TRY(h, cudaMalloc(&h->d_state, state_bytes));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_state, 0, state_bytes, h->stream));
+  return DCSIM_OK;
+}
+
 int dcsim_create(const void* spec_blob, size_t spec_bytes, uint64_t n_replicas, uint64_t base_seed,
                  uint64_t first_replica_id, int device, dcsim_t** out) {
   if (!out) return set_err(NULL, DCSIM_E_INVALID, "create: out is NULL%s%lld");
@@ -224,7 +276,7 @@ int dcsim_create(const void* spec_blob, size_t spec_bytes, uint64_t n_replicas, 
     const char* e = getenv("DCSIM_PREPASS");
     h->prepass = !(e && e[0] == '0');
   }
-  dcsim_make_layout(&h->spec, &h->L, h->prepass);
+  dcsim_make_layout(&h->spec, &h->L, h->prepass, /*job_log=*/0);
   h->cap_arr = (uint32_t)(h->spec.cap_arrivals > 0 ? h->spec.cap_arrivals : 16384);
   h->n_replicas = n_replicas;
   h->seed0 = base_seed + first_replica_id;
@@ -244,40 +296,8 @@ int dcsim_create(const void* spec_blob, size_t spec_bytes, uint64_t n_replicas, 
   } while (0)
 
   CREATE_TRY(cudaSetDevice(device));
-  int smem_optin = 0;
   CREATE_TRY(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
-  CREATE_TRY(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-  /* warps per CTA: whichever of 4 / 2 / 1 keeps the most warps resident (each CTA also reserves 1 KB of shared
-   * memory and an SM holds at most 32 CTAs); small state blocks end up at 4 x 8 CTAs, large ones at 1 or 2 */
-  int smem_sm = 0;
-  CREATE_TRY(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device));
-  int wpc = 0, best_warps = 0;
-  for (int cand = DCSIM_MAX_WARPS_PER_CTA; cand >= 1; cand >>= 1) {
-    const long long per_cta = (long long)cand * h->L.total_bytes;
-    if (per_cta > smem_optin) continue;
-    int ctas = (int)(smem_sm / (per_cta + 1024));
-    if (ctas > 32) ctas = 32;
-    int warps = ctas * cand;
-    if (warps > DCSIM_MIN_CTAS_PER_SM * DCSIM_MAX_WARPS_PER_CTA) warps = DCSIM_MIN_CTAS_PER_SM * DCSIM_MAX_WARPS_PER_CTA; /* register bound */
-    if (warps > best_warps) { best_warps = warps; wpc = cand; }
-  }
-  h->staged = 1;
-  if (wpc < 1) { /* the block does not fit a CTA's shared memory: run in place out of HBM/L2 */
-    h->staged = 0;
-    wpc = DCSIM_MAX_WARPS_PER_CTA;
-  }
-  h->warps_per_cta = wpc;
-  h->smem_bytes = h->staged ? wpc * h->L.total_bytes : 0;
-  h->ctas = (int)((n_replicas + (uint64_t)wpc - 1) / (uint64_t)wpc);
-  const dcsim_advance_fn kern = dcsim_pick_kernel(h->L.cap_stale != 0, h->prepass != 0, h->staged != 0);
-  CREATE_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
-  cudaFuncAttributes fa;
-  CREATE_TRY(cudaFuncGetAttributes(&fa, kern));
-  h->regs = fa.numRegs;
-  int blocks_per_sm = 0;
-  CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, wpc * 32, h->smem_bytes));
-  h->resident_warps = blocks_per_sm * wpc;
-
+  CREATE_TRY(size_launch(h));
   CREATE_TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   h->stream = h->own_stream;
   const size_t state_bytes = (size_t)n_replicas * (size_t)h->L.total_bytes;
@@ -345,8 +365,10 @@ int dcsim_set_logging(dcsim_t* h, uint64_t replica, uint32_t job_capacity, uint3
   if (h->d_jobs) { cudaFree(h->d_jobs); h->d_jobs = NULL; }
   if (h->d_cluster) { cudaFree(h->d_cluster); h->d_cluster = NULL; }
   h->jobs_cap = h->cluster_cap = 0; h->log_replica = -1;
+  if (replica >= h->n_replicas && (job_capacity || cluster_capacity))
+    return set_err(h, DCSIM_E_INVALID, "set_logging: replica out of range%s%lld");
+  { const int rc = relayout(h, job_capacity != 0); if (rc != DCSIM_OK) return rc; }
   if (job_capacity == 0 && cluster_capacity == 0) return DCSIM_OK;
-  if (replica >= h->n_replicas) return set_err(h, DCSIM_E_INVALID, "set_logging: replica out of range%s%lld");
   if (job_capacity) CUDA_TRY(h, cudaMalloc(&h->d_jobs, (size_t)job_capacity * sizeof(dcsim_job_rec_t)));
   if (cluster_capacity) CUDA_TRY(h, cudaMalloc(&h->d_cluster, (size_t)cluster_capacity * sizeof(dcsim_cluster_rec_t)));
   h->jobs_cap = job_capacity; h->cluster_cap = cluster_capacity; h->log_replica = (int64_t)replica;

@@ -176,16 +176,21 @@ struct dcsim_layout_t {
   int32_t total_bytes;
   int32_t cap_xfer, cap_run;
   int32_t cap_q[2];        /* FIFO entries per DC: [0]=inference [1]=training */
-  int32_t _pad;
+  int32_t lean;            /* 1: running records carry no size / f / jid (nobody reads them: no job log, bandit or cap) */
   uint64_t queue_bytes;    /* HBM bytes of one replica's FIFOs */
 };
 
 static inline int32_t dcsim_align16(int32_t x) { return (x + 15) & ~15; }
 
 /* Host-side: sizes the state block from the spec's capacities. */
-static inline void dcsim_make_layout(const dcsim_spec_t* sp, dcsim_layout_t* L, int prepass) {
+static inline void dcsim_make_layout(const dcsim_spec_t* sp, dcsim_layout_t* L, int prepass, int job_log) {
   memset(L, 0, sizeof(*L));
   L->prepass = prepass ? 1 : 0;
+  const bool bandit = sp->xfer_rule == DCSIM_START_BANDIT || sp->deq_rule == DCSIM_START_BANDIT;
+  const bool cap = sp->algo == DCSIM_ALGO_CAP_GREEDY && sp->power_cap > 0.0;
+  /* size (job_log.csv, cap re-timing), f (job_log.csv, bandit reward, cap) and jid (job_log.csv) of a running job
+     are dead weight in the state block unless one of those readers exists: 60 -> 40 bytes per record. */
+  L->lean = (job_log || bandit || cap) ? 0 : 1;
   const int D = DCSIM_MAX_DC;
   int32_t cx = sp->cap_xfer > 0 ? sp->cap_xfer : 64;
   int32_t cr = sp->cap_run > 0 ? sp->cap_run : 16;
@@ -210,11 +215,11 @@ static inline void dcsim_make_layout(const dcsim_spec_t* sp, dcsim_layout_t* L, 
   L->rn_pw = o; o += nr * 8;
   L->rn_tpt = o; o += nr * 8;
   L->rn_start = o; o += nr * 8;
-  L->rn_size = o; o += nr * 8;
-  L->rn_f = o; o += nr * 8;
+  if (!L->lean) { L->rn_size = o; o += nr * 8; L->rn_f = o; o += nr * 8; }
   L->rn_seq = o; o += nr * 4;
   L->rn_meta = o; o += nr * 4;
-  L->rn_jid = o; o = dcsim_align16(o + nr * 4);
+  if (!L->lean) { L->rn_jid = o; o += nr * 4; }
+  o = dcsim_align16(o);
   if (prepass) { /* no in-kernel sampling: the Philox window gives way to the arrival-list window */
     L->aw_t = o; o += (int32_t)DCSIM_ARR_WINDOW * 8;
     L->aw_size = o; o += (int32_t)DCSIM_ARR_WINDOW * 8;
@@ -223,11 +228,11 @@ static inline void dcsim_make_layout(const dcsim_spec_t* sp, dcsim_layout_t* L, 
   } else {
     L->rng_buf = o; o += (int32_t)DCSIM_RNG_WINDOW * 4;
   }
-  if (sp->xfer_rule == DCSIM_START_BANDIT || sp->deq_rule == DCSIM_START_BANDIT) {
+  if (bandit) {
     L->bandit_s = o; o += sp->n_dc * 2 * DCSIM_MAX_FREQ * 8;
     L->bandit_n = o; o += sp->n_dc * 2 * DCSIM_MAX_FREQ * 4;
   }
-  if (sp->algo == DCSIM_ALGO_CAP_GREEDY && sp->power_cap > 0.0) {
+  if (cap) {
     L->cap_stale = sp->cap_stale > 0 ? ((sp->cap_stale + 3) & ~3) : 64;
     L->cap_atoms = nr * (DCSIM_MAX_FREQ - 1);
     int max_levels = 1;
@@ -791,25 +796,30 @@ DCSIM_DEV void dcsim_running_erase(dcsim_ctx_t& c, int d, int k) {
   const dcsim_layout_t& L = c.P->L;
   const int n = DCI(c, DI_NRUN)[d];
   const int off = d * L.cap_run;
-  double* f64s[6] = {dcsim_at<double>(c.blk, L.rn_t) + off, dcsim_at<double>(c.blk, L.rn_pw) + off,
-                     dcsim_at<double>(c.blk, L.rn_tpt) + off, dcsim_at<double>(c.blk, L.rn_start) + off,
-                     dcsim_at<double>(c.blk, L.rn_size) + off, dcsim_at<double>(c.blk, L.rn_f) + off};
-  uint32_t* u32s[3] = {dcsim_at<uint32_t>(c.blk, L.rn_seq) + off, dcsim_at<uint32_t>(c.blk, L.rn_meta) + off,
-                       dcsim_at<uint32_t>(c.blk, L.rn_jid) + off};
+  double* f64s[4] = {dcsim_at<double>(c.blk, L.rn_t) + off, dcsim_at<double>(c.blk, L.rn_pw) + off,
+                     dcsim_at<double>(c.blk, L.rn_tpt) + off, dcsim_at<double>(c.blk, L.rn_start) + off};
+  uint32_t* u32s[2] = {dcsim_at<uint32_t>(c.blk, L.rn_seq) + off, dcsim_at<uint32_t>(c.blk, L.rn_meta) + off};
+  const bool full = L.lean == 0;
+  double* sz = dcsim_at<double>(c.blk, L.rn_size) + off;
+  double* fq = dcsim_at<double>(c.blk, L.rn_f) + off;
+  uint32_t* ji = dcsim_at<uint32_t>(c.blk, L.rn_jid) + off;
   for (int j0 = k; j0 < n - 1; j0 += DCSIM_LANES) {
     const int j = j0 + c.lane;
     const bool act = j < n - 1;
-    double a[6]; uint32_t b[3];
+    double a[4]; uint32_t b[2];
+    double c0 = 0.0, c1 = 0.0; uint32_t c2 = 0u;
 #pragma unroll
-    for (int q = 0; q < 6; ++q) a[q] = act ? f64s[q][j + 1] : 0.0;
+    for (int q = 0; q < 4; ++q) a[q] = act ? f64s[q][j + 1] : 0.0;
 #pragma unroll
-    for (int q = 0; q < 3; ++q) b[q] = act ? u32s[q][j + 1] : 0u;
+    for (int q = 0; q < 2; ++q) b[q] = act ? u32s[q][j + 1] : 0u;
+    if (full && act) { c0 = sz[j + 1]; c1 = fq[j + 1]; c2 = ji[j + 1]; }
     dcsim_warp_sync();
     if (act) {
 #pragma unroll
-      for (int q = 0; q < 6; ++q) f64s[q][j] = a[q];
+      for (int q = 0; q < 4; ++q) f64s[q][j] = a[q];
 #pragma unroll
-      for (int q = 0; q < 3; ++q) u32s[q][j] = b[q];
+      for (int q = 0; q < 2; ++q) u32s[q][j] = b[q];
+      if (full) { sz[j] = c0; fq[j] = c1; ji[j] = c2; }
     }
     if (j0 + DCSIM_LANES < n - 1) dcsim_warp_sync(); /* next chunk reads what this one did not write; keep order */
   }
@@ -946,10 +956,12 @@ DCSIM_DEV void dcsim_start_job(dcsim_ctx_t& c, int d, int jt, double size, uint3
   dcsim_at<double>(c.blk, L.rn_pw)[i] = dcsim_task_power(n, f, k);
   dcsim_at<double>(c.blk, L.rn_tpt)[i] = 1.0 / T_unit; /* SIM:956 */
   dcsim_at<double>(c.blk, L.rn_start)[i] = c.now;
-  dcsim_at<double>(c.blk, L.rn_size)[i] = size;
-  dcsim_at<double>(c.blk, L.rn_f)[i] = f;
   dcsim_at<uint32_t>(c.blk, L.rn_meta)[i] = (uint32_t)n | ((uint32_t)jt << 16) | (ing << 17);
-  dcsim_at<uint32_t>(c.blk, L.rn_jid)[i] = jid;
+  if (CAP || L.lean == 0) {
+    dcsim_at<double>(c.blk, L.rn_size)[i] = size;
+    dcsim_at<double>(c.blk, L.rn_f)[i] = f;
+    dcsim_at<uint32_t>(c.blk, L.rn_jid)[i] = jid;
+  }
   if constexpr (CAP) { /* SIM:690-692: units_done = 0, last_update = now */
     dcsim_at<double>(c.blk, L.rn_done)[i] = 0.0;
     dcsim_at<double>(c.blk, L.rn_upd)[i] = c.now;
@@ -1229,12 +1241,14 @@ DCSIM_DEV void dcsim_finish_account(dcsim_ctx_t& c, uint64_t r, int d, int slot)
   H->lat_sum += lat;
   if (jt == DCSIM_JT_INFERENCE) { H->lat_sum_inf += lat; H->n_fin_inf++; } else { H->lat_sum_trn += lat; H->n_fin_trn++; }
   if (c.P->lat_hist) dcsim_hist_add(c.P->lat_hist, r, jt, lat);
-  const double f_used = dcsim_at<double>(c.blk, L.rn_f)[i];
-  if (c.is_logged && c.P->rec.jobs)
-    dcsim_joblog_write(c.P, dcsim_at<uint32_t>(c.blk, L.rn_jid)[i], meta, d, dcsim_at<double>(c.blk, L.rn_size)[i], f_used,
-                       dcsim_at<double>(c.blk, L.rn_start)[i], now);
-  if (sp.deq_rule == DCSIM_START_BANDIT)
-    dcsim_bandit_update(c.P, c.blk, d, jt, g, f_used, dcsim_at<double>(c.blk, L.rn_pw)[i]);
+  if (L.lean == 0) { /* the readers of a finished job's size / f / jid: job_log.csv and the bandit's reward */
+    const double f_used = dcsim_at<double>(c.blk, L.rn_f)[i];
+    if (c.is_logged && c.P->rec.jobs)
+      dcsim_joblog_write(c.P, dcsim_at<uint32_t>(c.blk, L.rn_jid)[i], meta, d, dcsim_at<double>(c.blk, L.rn_size)[i], f_used,
+                         dcsim_at<double>(c.blk, L.rn_start)[i], now);
+    if (sp.deq_rule == DCSIM_START_BANDIT)
+      dcsim_bandit_update(c.P, c.blk, d, jt, g, f_used, dcsim_at<double>(c.blk, L.rn_pw)[i]);
+  }
 }
 
 /* SIM:840-927: start queued jobs while GPUs are free, inference first when inf_priority. */

@@ -29,7 +29,7 @@ long long hostemu_run_batch(const void* spec_blob, size_t spec_bytes, uint64_t n
   if (P->spec.magic != DCSIM_SPEC_MAGIC) { free(P); return -1; }
   const char* pe = getenv("DCSIM_PREPASS");
   const int prepass = !(pe && pe[0] == '0');
-  dcsim_make_layout(&P->spec, &P->L, prepass);
+  dcsim_make_layout(&P->spec, &P->L, prepass, /*job_log=*/jobs != NULL);
   P->cap_arr = (uint32_t)(P->spec.cap_arrivals > 0 ? P->spec.cap_arrivals : 16384);
   if (layout_out) { layout_out[0] = P->L.total_bytes; layout_out[1] = P->L.cap_xfer; layout_out[2] = P->L.cap_run;
                     layout_out[3] = P->L.cap_q[0]; layout_out[4] = P->L.cap_q[1]; }
