@@ -154,3 +154,23 @@ def test_wide_seed_against_reference_fixture(hostemu, name):
     run = [r for r in doc["runs"] if r["rng"] == "philox" and r["seed"] == 2**40 + 7][0]
     got = hostemu.run_batch(SC.to_spec(doc["scenario"]).to_bytes(), 1, 2**40 + 7)["summary"][0]
     check_row_against_golden(got, run, doc["scenario"]["n_dc"], [])
+
+
+def test_random_scenarios_equal_oracle(oracle, hostemu, monkeypatch):
+    """Differential fuzz (tools/fuzz_core.py, fixed generator seed): random algo / policy / DC shapes / frequency
+    ladders / caps / arrival processes — summaries, traces and both logs bit-identical to the oracle, in the
+    pre-pass and the in-loop sampling mode, with lean and with full running-job records."""
+    import os
+    import random as pyrandom
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import fuzz_core
+    monkeypatch.setenv("DCSIM_PREPASS", "1")  # check() rewrites it; monkeypatch restores the original at teardown
+    rnd = pyrandom.Random(20260922)
+    for case in range(60):
+        sc = fuzz_core.random_scenario(rnd, case)
+        seed = rnd.randrange(1, 2 ** 40)
+        for prepass in (True, False):
+            for with_logs in (False, True):
+                res = fuzz_core.check(sc, seed, prepass, with_logs)
+                assert res == "ok" or res.startswith("overflow"), (case, prepass, with_logs, res, sc, seed)

@@ -313,3 +313,33 @@ def test_wide_seed_on_device(oracle):
     assert abs(got[2, S.S_TOTAL_ENERGY_J] - e_ref) <= RTOL * e_ref
     want, _ = oracle.run_batch(sp.to_bytes(), 4, 2**40 + 5)
     assert_rows_match(got, want, 4)
+
+
+def test_random_scenarios_match_oracle(oracle):
+    """Differential fuzz on the device (generator of tools/fuzz_core.py, fixed seed): plain runs (lean records),
+    logged + traced runs (full records) and chunked stepping, counts exact and floats within 1e-9."""
+    import random as pyrandom
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import fuzz_core
+    rnd = pyrandom.Random(20260923)
+    worst = 0.0
+    for case in range(90):
+        sc = fuzz_core.random_scenario(rnd, case)
+        seed = rnd.randrange(1, 2 ** 40)
+        sp = SC.to_spec(sc)
+        want, want_total = oracle.run_batch(sp.to_bytes(), 4, seed, 0, n_threads=4)
+        with engine_cls()(sp, 4, base_seed=seed) as eng:
+            if case % 3 == 1:
+                eng.set_logging(1, 60000, 4000)
+                eng.set_trace(1, 4000)
+            if case % 3 == 2:
+                total = 0
+                while not eng.all_done():
+                    total += eng.advance(997)
+            else:
+                total = eng.advance(0)
+            got = eng.summary()
+        assert total == want_total, (case, sc, seed)
+        worst = max(worst, assert_rows_match(got, want, sc["n_dc"]))
+    print(f"90 random scenarios, worst float rel err {worst:.2e}")
