@@ -31,7 +31,13 @@ def pytest_configure(config):
 
 
 def golden_names():
-    return sorted(f[:-5] for f in os.listdir(GOLDEN_DIR) if f.endswith(".json") and f != "kat.json")
+    return sorted(f[:-5] for f in os.listdir(GOLDEN_DIR) if f.endswith(".json") and f not in ("kat.json", "fuzz_reference.json"))
+
+
+def load_fuzz_reference():
+    """Random scenarios run through the unmodified reference (tests/golden/make_golden_fuzz.py)."""
+    with open(os.path.join(GOLDEN_DIR, "fuzz_reference.json")) as f:
+        return json.load(f)["cases"]
 
 
 def load_golden(name):

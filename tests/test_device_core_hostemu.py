@@ -174,3 +174,15 @@ def test_random_scenarios_equal_oracle(oracle, hostemu, monkeypatch):
             for with_logs in (False, True):
                 res = fuzz_core.check(sc, seed, prepass, with_logs)
                 assert res == "ok" or res.startswith("overflow"), (case, prepass, with_logs, res, sc, seed)
+
+
+def test_device_core_against_reference_on_random_scenarios(hostemu):
+    """The device core (host build) straight against the reference's numbers on the random-scenario fixture."""
+    from conftest import load_fuzz_reference
+    from test_oracle_vs_reference import check_row_against_golden
+    notes = []
+    for c in load_fuzz_reference():
+        sc, run = c["scenario"], c["run"]
+        got = hostemu.run_batch(SC.to_spec(sc).to_bytes(), 1, run["seed"])
+        assert got["events"] == run["events"], sc
+        check_row_against_golden(got["summary"][0], run, sc["n_dc"], notes)

@@ -343,3 +343,30 @@ def test_random_scenarios_match_oracle(oracle):
         assert total == want_total, (case, sc, seed)
         worst = max(worst, assert_rows_match(got, want, sc["n_dc"]))
     print(f"90 random scenarios, worst float rel err {worst:.2e}")
+
+
+def test_kernel_matches_reference_on_random_scenarios():
+    """The kernels straight against the reference's numbers on the random-scenario fixture
+    (tests/golden/fuzz_reference.json: 160 scenarios nobody picked by hand): counts exact, floats within 1e-9."""
+    from conftest import load_fuzz_reference
+    worst = 0.0
+    for c in load_fuzz_reference():
+        sc, run = c["scenario"], c["run"]
+        with engine_cls()(SC.to_spec(sc), 1, base_seed=run["seed"]) as eng:
+            eng.advance(0)
+            row = eng.summary()[0]
+        assert int(row[S.S_STATUS]) == 0 and int(row[S.S_EVENTS]) == run["events"], sc
+        assert int(row[S.S_JOBS_FINISHED]) == run["jobs_finished"] and int(row[S.S_JOBS_CREATED]) == run["jobs_created"], sc
+        assert int(row[S.S_RNG_WORDS]) == run["rng_words"] and int(row[S.S_SEQ]) == run["seq_pushed"], sc
+        pairs = [(row[S.S_TOTAL_ENERGY_J], run["total_energy_j"]), (row[S.S_LAT_SUM], run["latency_sum_s"])]
+        for d in range(sc["n_dc"]):
+            b = S.S_DC0 + d * S.S_DC_STRIDE
+            pairs += [(row[b + S.SD_ENERGY_J], run["dc"][d]["energy_j"]), (row[b + S.SD_UTIL_GPU_TIME], run["dc"][d]["util_gpu_time"]),
+                      (row[b + S.SD_ACC_JOB_UNIT], run["dc"][d]["acc_job_unit"])]
+            assert int(row[b + S.SD_BUSY]) == run["dc"][d]["busy"] and int(row[b + S.SD_RUNNING]) == run["dc"][d]["running"], sc
+        for got, want_hex in pairs:
+            want = float.fromhex(want_hex)
+            rel = 0.0 if got == want else abs(got - want) / max(abs(want), 1e-300)
+            assert rel <= RTOL, (sc, got, want)
+            worst = max(worst, rel)
+    print(f"160 random scenarios vs the reference, worst float rel err {worst:.2e}")
