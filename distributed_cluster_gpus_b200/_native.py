@@ -19,7 +19,7 @@ EXPORTS = (
     "dcsim_sizeof_spec", "dcsim_abi_version", "dcsim_summary_k", "dcsim_create", "dcsim_reset", "dcsim_set_stream",
     "dcsim_set_trace", "dcsim_set_logging", "dcsim_prepare", "dcsim_advance", "dcsim_all_done", "dcsim_fetch_summary",
     "dcsim_summary_device_ptr", "dcsim_reduce_summary", "dcsim_enable_latency_histogram", "dcsim_fetch_latency_histogram", "dcsim_fetch_trace", "dcsim_fetch_job_log",
-    "dcsim_fetch_cluster_log", "dcsim_launch_info", "dcsim_last_error", "dcsim_destroy",
+    "dcsim_fetch_cluster_log", "dcsim_launch_info", "dcsim_last_error", "dcsim_destroy", "dcsim_set_rng",
 )
 
 _lib = None
@@ -71,6 +71,8 @@ def load():
     L.dcsim_summary_device_ptr.argtypes = [vp, C.POINTER(vp)]
     L.dcsim_reduce_summary.restype = i32
     L.dcsim_reduce_summary.argtypes = [vp, vp]
+    L.dcsim_set_rng.restype = i32
+    L.dcsim_set_rng.argtypes = [vp, C.c_int]
     L.dcsim_enable_latency_histogram.restype = i32
     L.dcsim_enable_latency_histogram.argtypes = [vp]
     L.dcsim_fetch_latency_histogram.restype = i32

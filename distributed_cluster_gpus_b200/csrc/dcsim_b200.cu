@@ -70,12 +70,13 @@ dcsim_advance_kernel(const __grid_constant__ dcsim_kparams_t P, unsigned long lo
  * samplers (pow / log / sin / rejection loops) that the event loop would otherwise run on one lane. */
 #define DCSIM_ARRIVALS_THREADS 128
 extern __shared__ __align__(16) double dcsim_arr_scratch[];
+template <bool MT>
 __global__ void __launch_bounds__(DCSIM_ARRIVALS_THREADS) dcsim_arrivals_kernel(const __grid_constant__ dcsim_kparams_t P) {
   const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= P.n_replicas) return;
   double* clocks = dcsim_arr_scratch + threadIdx.x;                                     /* [stream][thread] */
   uint32_t* ring = reinterpret_cast<uint32_t*>(dcsim_arr_scratch + 2 * DCSIM_MAX_ING * blockDim.x) + threadIdx.x; /* [word][thread] */
-  dcsim_generate_arrivals(&P, r, clocks, ring, (int)blockDim.x);
+  dcsim_generate_arrivals<MT>(&P, r, clocks, ring, (int)blockDim.x);
 }
 
 /* Sums the per-replica latency histograms: thread b of every block owns bin b (coalesced 1 KB rows). */
@@ -150,6 +151,8 @@ struct dcsim {
   uint32_t* d_arr_meta;
   dcsim_arrhdr_t* d_arr_hdr;
   uint32_t* d_hist;
+  uint32_t* d_mt; /* [624][n_replicas] Mersenne Twister states, rng_kind == DCSIM_RNG_MT19937 only */
+  int rng_kind;
   uint32_t cap_arr;
   unsigned long long events_seen;
   char err[512];
@@ -390,6 +393,7 @@ static void fill_kparams(const dcsim_t* h, dcsim_kparams_t* P, uint64_t max_even
   P->arr_t = h->d_arr_t; P->arr_size = h->d_arr_size; P->arr_meta = h->d_arr_meta; P->arr_hdr = h->d_arr_hdr; P->cap_arr = h->cap_arr;
   P->staged = (uint32_t)h->staged;
   P->lat_hist = h->d_hist;
+  P->mt_state = h->d_mt;
 }
 
 int dcsim_prepare(dcsim_t* h) {
@@ -400,7 +404,8 @@ int dcsim_prepare(dcsim_t* h) {
   fill_kparams(h, &P, 0);
   const int nb = (int)((h->n_replicas + DCSIM_ARRIVALS_THREADS - 1) / DCSIM_ARRIVALS_THREADS);
   const size_t scratch = (size_t)DCSIM_ARRIVALS_THREADS * (2 * DCSIM_MAX_ING * sizeof(double) + DCSIM_TRNG_RING * sizeof(uint32_t));
-  dcsim_arrivals_kernel<<<nb, DCSIM_ARRIVALS_THREADS, scratch, h->stream>>>(P);
+  if (h->rng_kind == DCSIM_RNG_MT19937) dcsim_arrivals_kernel<true><<<nb, DCSIM_ARRIVALS_THREADS, scratch, h->stream>>>(P);
+  else dcsim_arrivals_kernel<false><<<nb, DCSIM_ARRIVALS_THREADS, scratch, h->stream>>>(P);
   CUDA_TRY(h, cudaGetLastError());
   h->arrivals_ready = 1;
   h->launches++;
@@ -475,6 +480,19 @@ int dcsim_reduce_summary(dcsim_t* h, double* dev_out) {
   if (blocks > 4 * h->sm_count) blocks = 4 * h->sm_count;
   dcsim_reduce_kernel<<<blocks, 256, 0, h->stream>>>(h->d_summary, h->n_replicas, dev_out);
   CUDA_TRY(h, cudaGetLastError());
+  return DCSIM_OK;
+}
+
+int dcsim_set_rng(dcsim_t* h, int rng_kind) {
+  if (!h) return DCSIM_E_INVALID;
+  if (rng_kind != DCSIM_RNG_PHILOX && rng_kind != DCSIM_RNG_MT19937) return set_err(h, DCSIM_E_INVALID, "set_rng: unknown rng kind %s%lld", "", (long long)rng_kind);
+  if (h->launches) return set_err(h, DCSIM_E_STATE, "set_rng must precede the first advance%s%lld");
+  if (rng_kind == DCSIM_RNG_MT19937 && !h->prepass)
+    return set_err(h, DCSIM_E_UNSUPPORTED, "set_rng: MT19937 needs the arrival pre-pass (unset DCSIM_PREPASS=0)%s%lld");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  if (rng_kind == DCSIM_RNG_MT19937 && !h->d_mt)
+    CUDA_TRY(h, cudaMalloc(&h->d_mt, (size_t)h->n_replicas * DCSIM_MT_N * sizeof(uint32_t)));
+  h->rng_kind = rng_kind;
   return DCSIM_OK;
 }
 
@@ -564,6 +582,7 @@ void dcsim_destroy(dcsim_t* h) {
   cudaFree(h->d_state); cudaFree(h->d_queues); cudaFree(h->d_summary); cudaFree(h->d_events); cudaFree(h->d_counts);
   cudaFree(h->d_trace); cudaFree(h->d_jobs); cudaFree(h->d_cluster);
   cudaFree(h->d_hist);
+  cudaFree(h->d_mt);
   cudaFree(h->d_arr_t); cudaFree(h->d_arr_size); cudaFree(h->d_arr_meta); cudaFree(h->d_arr_hdr);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;

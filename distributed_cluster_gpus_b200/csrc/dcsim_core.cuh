@@ -296,6 +296,7 @@ struct dcsim_kparams_t {
   uint32_t* arr_meta;   /* stream (bits 0-3) | routed DC (4-6) | next arrival of the stream was schedulable (7) */
   struct dcsim_arrhdr_t* arr_hdr;
   uint32_t* lat_hist;   /* [n_replicas][2][DCSIM_LAT_BINS] job-latency histograms, or NULL */
+  uint32_t* mt_state;   /* [624][n_replicas] Mersenne Twister states (rng = MT19937 only), else NULL */
   uint32_t cap_arr;
   uint32_t staged;      /* 1: state blocks are staged in shared memory; 0: too large for that, run in place in HBM/L2 */
   double end_eps;       /* end_time + 1e-9, the _schedule cut-off (SIM:161) */
@@ -510,30 +511,90 @@ DCSIM_DEV double dcsim_next_interarrival(dcsim_ctx_t& c, int jt, double t) {
  * inside the samplers instead makes 32 out-of-phase lanes drag the warp through the block function at almost every
  * draw (measured: 43 % of the pre-pass). */
 #define DCSIM_TRNG_RING 32u
-struct dcsim_trng_t { uint32_t k0, k1, pos, filled; uint32_t* buf; int stride; };
+/* Word source = CPython's own Mersenne Twister instead of Philox (dcsim_set_rng(h, DCSIM_RNG_MT19937)): the replica
+ * then IS the stock reference at random.seed(seed0 + r) (SIM:71).  State: 624 words in HBM, element i at
+ * mt[i * mt_stride] ([word][replica], coalesced across the warp's replicas). */
+struct dcsim_mt_t { uint32_t* mt; uint64_t mt_stride; uint32_t mti; };
+/* The stream is a template over the word source so that the Philox instantiation carries no trace of the other one
+ * (a run-time switch cost the pre-pass 3 %: different register allocation, more local-memory traffic). */
+template <bool MT> struct dcsim_trng_t { uint32_t k0, k1, pos, filled; uint32_t* buf; int stride; };
+template <> struct dcsim_trng_t<true> { uint32_t k0, k1, pos, filled; uint32_t* buf; int stride; dcsim_mt_t mt; };
 
-DCSIM_DEV void dcsim_trng_block(dcsim_trng_t& g) { /* appends block filled/4 */
+/* MT19937 (Matsumoto & Nishimura) as CPython drives it: Modules/_randommodule.c init_by_array / genrand_uint32. */
+#define DCSIM_MT_N 624u
+#define DCSIM_MT_M 397u
+#define DCSIM_MT_AT(g, i) ((g).mt[(uint64_t)(i) * (g).mt_stride])
+DCSIM_DEV void dcsim_mt_seed(dcsim_mt_t& g, uint64_t seed) { /* random.seed(int): key = 32-bit digits of |seed| */
+  const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+  const uint32_t len = key[1] ? 2u : 1u;
+  uint32_t prev = 19650218u;
+  DCSIM_MT_AT(g, 0) = prev;
+  for (uint32_t i = 1; i < DCSIM_MT_N; ++i) { prev = 1812433253u * (prev ^ (prev >> 30)) + i; DCSIM_MT_AT(g, i) = prev; }
+  uint32_t i = 1, j = 0;
+  prev = DCSIM_MT_AT(g, 0);
+  for (uint32_t k = DCSIM_MT_N; k; --k) {
+    prev = (DCSIM_MT_AT(g, i) ^ ((prev ^ (prev >> 30)) * 1664525u)) + key[j] + j;
+    DCSIM_MT_AT(g, i) = prev;
+    if (++i >= DCSIM_MT_N) { DCSIM_MT_AT(g, 0) = prev; i = 1; }
+    if (++j >= len) j = 0;
+  }
+  for (uint32_t k = DCSIM_MT_N - 1u; k; --k) {
+    prev = (DCSIM_MT_AT(g, i) ^ ((prev ^ (prev >> 30)) * 1566083941u)) - i;
+    DCSIM_MT_AT(g, i) = prev;
+    if (++i >= DCSIM_MT_N) { DCSIM_MT_AT(g, 0) = prev; i = 1; }
+  }
+  DCSIM_MT_AT(g, 0) = 0x80000000u;
+  g.mti = DCSIM_MT_N;
+}
+DCSIM_DEV uint32_t dcsim_mt_next(dcsim_mt_t& g) {
+  if (g.mti >= DCSIM_MT_N) { /* regenerate the 624 words in place */
+    /* word kk needs the OLD words kk, kk+1 and word kk+M (old while kk+M < N, already NEW once it wraps); the last
+     * word pairs with the NEW word 0 — reading the array in place gives exactly that */
+    for (uint32_t kk = 0; kk < DCSIM_MT_N; ++kk) {
+      const uint32_t a = DCSIM_MT_AT(g, kk);
+      const uint32_t b = DCSIM_MT_AT(g, kk + 1u < DCSIM_MT_N ? kk + 1u : 0u);
+      const uint32_t m = DCSIM_MT_AT(g, kk + DCSIM_MT_M < DCSIM_MT_N ? kk + DCSIM_MT_M : kk + DCSIM_MT_M - DCSIM_MT_N);
+      const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+      DCSIM_MT_AT(g, kk) = m ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    }
+    g.mti = 0u;
+  }
+  uint32_t y = DCSIM_MT_AT(g, g.mti++);
+  y ^= y >> 11;
+  y ^= (y << 7) & 0x9d2c5680u;
+  y ^= (y << 15) & 0xefc60000u;
+  y ^= y >> 18;
+  return y;
+}
+
+template <bool MT>
+DCSIM_DEV void dcsim_trng_block(dcsim_trng_t<MT>& g) { /* appends block filled/4 */
   uint32_t w[4];
-  dcsim_philox_block(g.k0, g.k1, g.filled >> 2, w);
+  if constexpr (MT) { w[0] = dcsim_mt_next(g.mt); w[1] = dcsim_mt_next(g.mt); w[2] = dcsim_mt_next(g.mt); w[3] = dcsim_mt_next(g.mt); }
+  else dcsim_philox_block(g.k0, g.k1, g.filled >> 2, w);
   const uint32_t i = g.filled & (DCSIM_TRNG_RING - 1u);
   g.buf[(i + 0u) * g.stride] = w[0]; g.buf[(i + 1u) * g.stride] = w[1];
   g.buf[(i + 2u) * g.stride] = w[2]; g.buf[(i + 3u) * g.stride] = w[3];
   g.filled += 4u;
 }
-DCSIM_DEV void dcsim_trng_topup(dcsim_trng_t& g) {
+template <bool MT>
+DCSIM_DEV void dcsim_trng_topup(dcsim_trng_t<MT>& g) {
   while (g.filled - g.pos <= DCSIM_TRNG_RING - 4u) dcsim_trng_block(g);
 }
+template <bool MT>
 #ifndef DCSIM_HOST_EMU
 __device__ __noinline__
 #else
 static
 #endif
-void dcsim_trng_dry(dcsim_trng_t* g) { dcsim_trng_block(*g); } /* a sampler out-ran the ring (long rejection run) */
-DCSIM_DEV uint32_t dcsim_trng_word(dcsim_trng_t& g) {
+void dcsim_trng_dry(dcsim_trng_t<MT>* g) { dcsim_trng_block(*g); } /* a sampler out-ran the ring (long rejection run) */
+template <bool MT>
+DCSIM_DEV uint32_t dcsim_trng_word(dcsim_trng_t<MT>& g) {
   if (g.pos == g.filled) dcsim_trng_dry(&g);
   return g.buf[(g.pos++ & (DCSIM_TRNG_RING - 1u)) * g.stride];
 }
-DCSIM_DEV double dcsim_trng_random(dcsim_trng_t& g) {
+template <bool MT>
+DCSIM_DEV double dcsim_trng_random(dcsim_trng_t<MT>& g) {
   const uint32_t a = dcsim_trng_word(g), b = dcsim_trng_word(g);
   return dcsim_u53(a, b);
 }
@@ -565,7 +626,8 @@ DCSIM_DEV dcsim_squeeze_t dcsim_squeeze_setup(const dcsim_arrival_t& a, double t
  * a very long gap) evaluate the reference's expression.  Same words consumed, same decisions, same w — but a thread
  * spends ~20 instructions instead of ~500 on a rejected candidate, which matters because a warp's lanes all wait
  * for the lane with the longest rejection run. */
-DCSIM_DEV double dcsim_t_gap(dcsim_trng_t& g, const dcsim_spec_t& sp, const dcsim_squeeze_t& q, int jt, double t, uint32_t* status) {
+template <bool MT>
+DCSIM_DEV double dcsim_t_gap(dcsim_trng_t<MT>& g, const dcsim_spec_t& sp, const dcsim_squeeze_t& q, int jt, double t, uint32_t* status) {
   const dcsim_arrival_t& a = sp.arr[jt];
   if (a.mode == DCSIM_ARR_POISSON) return a.rate <= 0.0 ? DCSIM_INF : -log(1.0 - dcsim_trng_random(g)) / a.rate;
   if (a.mode == DCSIM_ARR_SINUSOID) {
@@ -591,7 +653,8 @@ DCSIM_DEV double dcsim_t_gap(dcsim_trng_t& g, const dcsim_spec_t& sp, const dcsi
 }
 
 /* arrivals.py:5-11 with random.py:541-549, 597 */
-DCSIM_DEV double dcsim_t_size(dcsim_trng_t& g, const dcsim_spec_t& sp, int jt, uint32_t* status) {
+template <bool MT>
+DCSIM_DEV double dcsim_t_size(dcsim_trng_t<MT>& g, const dcsim_spec_t& sp, int jt, uint32_t* status) {
   if (jt == DCSIM_JT_INFERENCE) {
     const double x = 1.0 - dcsim_trng_random(g);
     const double u = x > sp.uniform_floor ? x : sp.uniform_floor;
@@ -612,12 +675,14 @@ DCSIM_DEV double dcsim_t_size(dcsim_trng_t& g, const dcsim_spec_t& sp, int jt, u
 
 /* One replica's arrival list.  `next_t` is scratch for the 2*n_ing stream clocks (element s at next_t[s * stride]),
  * `ring` for the DCSIM_TRNG_RING staged Philox words (element i at ring[i * stride]). */
+template <bool MT>
 DCSIM_DEV void dcsim_generate_arrivals(const dcsim_kparams_t* P, uint64_t r, double* next_t, uint32_t* ring, int stride) {
   const dcsim_spec_t& sp = P->spec;
   const int n_streams = 2 * sp.n_ing;
-  dcsim_trng_t g;
+  dcsim_trng_t<MT> g;
   const uint64_t key = P->seed0 + r;
   g.k0 = (uint32_t)key; g.k1 = (uint32_t)(key >> 32); g.pos = 0u; g.filled = 0u; g.buf = ring; g.stride = stride;
+  if constexpr (MT) { g.mt.mt = P->mt_state + r; g.mt.mt_stride = P->n_replicas; dcsim_mt_seed(g.mt, key); }
   uint32_t status = 0u, first_mask = 0u, count = 0u;
   const double end_eps = P->end_eps;
   dcsim_squeeze_t sq[2];

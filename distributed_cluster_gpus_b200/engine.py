@@ -43,6 +43,9 @@ def latency_quantiles(hist_row, qs=(0.5, 0.9, 0.99)):
     return out
 
 
+RNG_KINDS = {"philox": 0, "mt19937": 1}
+
+
 class BatchedEngine:
     """R independent replicas of one scenario on one GPU.
 
@@ -71,6 +74,13 @@ class BatchedEngine:
     def reset(self, base_seed: int, first_replica_id: int = 0):
         """All replicas back to t = 0 with new keys; allocations are kept."""
         N.check(self._lib.dcsim_reset(self._h, base_seed & (2**64 - 1), first_replica_id), self._h)
+
+    def set_rng(self, kind: str = "philox"):
+        """Word source of the replicas' random streams: "philox" (default; key = seed) or "mt19937" (CPython's own
+        generator seeded like ``random.seed(seed)``: replica r is then the STOCK reference run at rng_seed + r)."""
+        if kind not in RNG_KINDS:
+            raise ValueError(f"unknown rng {kind!r}; expected one of {sorted(RNG_KINDS)}")
+        N.check(self._lib.dcsim_set_rng(self._h, RNG_KINDS[kind]), self._h)
 
     def set_trace(self, replica: int, capacity: int):
         N.check(self._lib.dcsim_set_trace(self._h, replica, capacity), self._h)
@@ -195,6 +205,7 @@ def acquire_engine(sp, n_replicas, base_seed, first_replica_id=0, device=0, cuda
         eng.reset(base_seed, first_replica_id)   # fresh batch: recorders may be re-targeted again
         eng.set_trace(0, 0)
         eng.set_logging(0, 0, 0)
+        eng.set_rng("philox")
         return eng
     free_cached_engine()
     return BatchedEngine(sp, n_replicas, base_seed, first_replica_id, device, cuda_stream)

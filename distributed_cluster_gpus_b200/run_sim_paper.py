@@ -52,6 +52,8 @@ def parse_args(argv=None):
     # --- batched engine ---
     p.add_argument("--replicas", type=int, default=1, help="independent Monte-Carlo replicas (seed, seed+1, ...)")
     p.add_argument("--device", type=int, default=0, help="CUDA device ordinal")
+    p.add_argument("--rng", choices=["philox", "mt19937"], default="philox",
+                   help="mt19937 = CPython's own generator: replica r reproduces the stock reference at --seed + r")
     p.add_argument("--n-dc", type=int, default=8, help="keep the first N data centres of build_dcs()")
     p.add_argument("--gpus-per-dc", type=int, default=None, help="override total_gpus of every kept DC")
     p.add_argument("--freq-levels", type=str, default=None, help="comma-separated DVFS levels, e.g. 0.5,0.8,1.0")
@@ -82,7 +84,7 @@ def main(argv=None):
         control_interval=args.control_interval, show_progress=args.progress,
         energy_budget_j=args.energy_budget_j, sla_p99_ms=args.sla_p99_ms, upgr_batch=args.upgr_batch,
         upgr_warmup=args.upgr_warmup, upgr_buffer=args.upgr_buffer, num_fixed_gpus=args.num_fixed_gpus,
-        fixed_freq=args.fixed_freq, logger=get_logger(log_dir=out_dir), replicas=args.replicas, device=args.device)
+        fixed_freq=args.fixed_freq, logger=get_logger(log_dir=out_dir), replicas=args.replicas, device=args.device, rng=args.rng)
     sim.run()
     s = sim.summary
     stats = batch_statistics(s)

@@ -17,7 +17,7 @@ from typing import Dict, Optional, Tuple, Union
 import numpy as np
 
 from .. import spec as S
-from ..engine import release_engine, run_to_completion
+from ..engine import RNG_KINDS, release_engine, run_to_completion
 from .arrivals import ArrivalConfig
 from .models import DataCenter
 from .network import Graph, Ingress
@@ -59,7 +59,7 @@ class MultiIngressPaperSimulator:
                  num_fixed_gpus=1, fixed_freq=None,
                  # --- batched-engine additions (keyword only in spirit; defaults reproduce one trajectory) ---
                  replicas: int = 1, device: int = 0, first_replica_id: int = 0, write_logs: bool = True,
-                 cuda_stream: int = 0, keep_engine: bool = True):
+                 cuda_stream: int = 0, keep_engine: bool = True, rng: str = "philox"):
         self.ingresses, self.dcs, self.graph = ingresses, dcs, graph
         self.arr_inf, self.arr_trn = arrival_inf, arrival_train
         self.router_policy = router_policy          # stored, never consulted — as in the reference (SIM:65)
@@ -79,6 +79,9 @@ class MultiIngressPaperSimulator:
         self.replicas, self.device, self.first_replica_id = int(replicas), int(device), int(first_replica_id)
         self.write_logs, self.cuda_stream = bool(write_logs), int(cuda_stream)
         self.keep_engine = bool(keep_engine)   # park the device allocations for the next run of the same shape
+        if rng not in RNG_KINDS:
+            raise ValueError(f"unknown rng {rng!r}; expected one of {sorted(RNG_KINDS)}")
+        self.rng = rng                         # "mt19937": the stock reference's own generator (random.seed, SIM:71)
         if algo == "chsac_af" or elastic_scaling and algo == "chsac_af":
             raise NotImplementedError("algo=chsac_af is outside the batched path (SIM:555-573)")
         self.cluster_log_path, self.job_log_path = "cluster_log.csv", "job_log.csv"
@@ -109,6 +112,7 @@ class MultiIngressPaperSimulator:
         cluster_cap = n_ticks * len(self.dcs)
 
         def configure(eng):
+            eng.set_rng(self.rng)
             eng.enable_latency_histogram()
             if self.write_logs:
                 eng.set_logging(0, job_cap, cluster_cap)

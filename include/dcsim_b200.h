@@ -279,6 +279,17 @@ int dcsim_reduce_summary(dcsim_t* h, double* dev_out);
 int dcsim_enable_latency_histogram(dcsim_t* h);
 int dcsim_fetch_latency_histogram(dcsim_t* h, uint64_t* out, size_t out_bytes);
 
+/* Word source of the replicas' random streams (before the first advance of a batch; stays across dcsim_reset).
+ *   DCSIM_RNG_PHILOX   (default) Philox4x32-10, key = base_seed + replica id: counter-based, no state.
+ *   DCSIM_RNG_MT19937  CPython's own Mersenne Twister seeded like random.seed(base_seed + replica id)
+ *                      (simulator_paper_multi.py:71): replica r then reproduces the STOCK reference run with
+ *                      rng_seed = base_seed + first_replica_id + r — no re-binding of `random` on the reference side.
+ *                      Costs 2.5 kB of HBM per replica and a slower pre-pass; needs the arrival pre-pass
+ *                      (DCSIM_E_UNSUPPORTED under DCSIM_PREPASS=0). */
+#define DCSIM_RNG_PHILOX 0
+#define DCSIM_RNG_MT19937 1
+int dcsim_set_rng(dcsim_t* h, int rng_kind);
+
 int dcsim_fetch_trace(dcsim_t* h, dcsim_trace_rec_t* out, uint32_t capacity, uint32_t* n_out);
 int dcsim_fetch_job_log(dcsim_t* h, dcsim_job_rec_t* out, uint32_t capacity, uint32_t* n_out);
 int dcsim_fetch_cluster_log(dcsim_t* h, dcsim_cluster_rec_t* out, uint32_t capacity, uint32_t* n_out);

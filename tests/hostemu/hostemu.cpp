@@ -22,7 +22,7 @@ long long hostemu_run_batch(const void* spec_blob, size_t spec_bytes, uint64_t n
                             uint64_t chunk_events, double* out_summaries, int64_t rec_replica,
                             dcsim_trace_rec_t* trace, uint32_t trace_cap, dcsim_job_rec_t* jobs, uint32_t jobs_cap,
                             dcsim_cluster_rec_t* cluster, uint32_t cluster_cap, uint32_t* counts, int32_t* layout_out,
-                            uint32_t* lat_hist /* [n][2][DCSIM_LAT_BINS] or NULL */) {
+                            uint32_t* lat_hist /* [n][2][DCSIM_LAT_BINS] or NULL */, int rng_kind /* 0 Philox, 1 MT19937 */) {
   if (!spec_blob || spec_bytes != sizeof(dcsim_spec_t)) return -1;
   dcsim_kparams_t* P = (dcsim_kparams_t*)calloc(1, sizeof(dcsim_kparams_t));
   memcpy(&P->spec, spec_blob, sizeof(dcsim_spec_t));
@@ -51,7 +51,10 @@ long long hostemu_run_batch(const void* spec_blob, size_t spec_bytes, uint64_t n
     P->arr_hdr = (dcsim_arrhdr_t*)calloc(n_replicas, sizeof(dcsim_arrhdr_t));
     double clocks[2 * DCSIM_MAX_ING];
     uint32_t ring[DCSIM_TRNG_RING];
-    for (uint64_t r = 0; r < n_replicas; ++r) dcsim_generate_arrivals(P, r, clocks, ring, 1);
+    if (rng_kind == 1) P->mt_state = (uint32_t*)calloc(n_replicas * (size_t)DCSIM_MT_N, sizeof(uint32_t));
+    for (uint64_t r = 0; r < n_replicas; ++r) {
+      if (rng_kind == 1) dcsim_generate_arrivals<true>(P, r, clocks, ring, 1); else dcsim_generate_arrivals<false>(P, r, clocks, ring, 1);
+    }
   }
   char* work = (char*)malloc((size_t)P->L.total_bytes);
   long long total = 0;
@@ -67,7 +70,7 @@ long long hostemu_run_batch(const void* spec_blob, size_t spec_bytes, uint64_t n
       if (H->done || H->status || chunk_events == 0) break;
     }
   }
-  free(work); free(P->state); free(P->queues); free(P->arr_t); free(P->arr_size); free(P->arr_meta); free(P->arr_hdr); free(P);
+  free(work); free(P->state); free(P->queues); free(P->arr_t); free(P->arr_size); free(P->arr_meta); free(P->arr_hdr); free(P->mt_state); free(P);
   return total;
 }
 

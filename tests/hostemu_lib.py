@@ -26,13 +26,13 @@ def lib():
         L.hostemu_run_batch.restype = C.c_longlong
         L.hostemu_run_batch.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p,
                                         C.c_int64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p,
-                                        C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+                                        C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         _lib = L
     return _lib
 
 
 def run_batch(spec_bytes, n_replicas, seed0, chunk_events=0, trace_cap=0, rec_replica=-1, job_dtype=None,
-              jobs_cap=0, cluster_dtype=None, cluster_cap=0):
+              jobs_cap=0, cluster_dtype=None, cluster_cap=0, rng_kind=0):
     out = np.zeros((n_replicas, SUMMARY_K))
     buf = C.create_string_buffer(spec_bytes, len(spec_bytes))
     trace = np.zeros(max(trace_cap, 1), dtype=TRACE_DTYPE)
@@ -46,7 +46,7 @@ def run_batch(spec_bytes, n_replicas, seed0, chunk_events=0, trace_cap=0, rec_re
                                     trace.ctypes.data if trace_cap else None, trace_cap,
                                     jobs.ctypes.data if jobs is not None and jobs_cap else None, jobs_cap,
                                     cluster.ctypes.data if cluster is not None and cluster_cap else None, cluster_cap,
-                                    counts.ctypes.data, layout.ctypes.data, hist.ctypes.data)
+                                    counts.ctypes.data, layout.ctypes.data, hist.ctypes.data, rng_kind)
     if total < 0:
         raise ValueError("hostemu rejected the spec blob")
     res = {"summary": out, "events": int(total), "lat_hist": hist, "trace": trace[:min(int(counts[0]), trace_cap)],

@@ -186,3 +186,25 @@ def test_device_core_against_reference_on_random_scenarios(hostemu):
         got = hostemu.run_batch(SC.to_spec(sc).to_bytes(), 1, run["seed"])
         assert got["events"] == run["events"], sc
         check_row_against_golden(got["summary"][0], run, sc["n_dc"], notes)
+
+
+@pytest.mark.parametrize("name", DEVICE_SUPPORTED)
+def test_mersenne_twister_mode_is_the_stock_reference(hostemu, name):
+    """rng = MT19937: the device core draws from CPython's own generator seeded like random.seed(seed) — the fixture's
+    "mt" run is the reference EXACTLY as shipped (no Philox re-binding), and the device core must reproduce it."""
+    from conftest import load_golden
+    from test_oracle_vs_reference import check_row_against_golden
+    doc = load_golden(name)
+    run = [r for r in doc["runs"] if r["rng"] == "mt"][0]
+    got = hostemu.run_batch(SC.to_spec(doc["scenario"]).to_bytes(), 1, run["seed"], rng_kind=1)
+    assert got["events"] == run["events"]
+    check_row_against_golden(got["summary"][0], run, doc["scenario"]["n_dc"], [])
+
+
+def test_mersenne_twister_mode_equals_oracle_on_wide_seeds(oracle, hostemu):
+    """Seeds >= 2**32 take a two-word init_by_array key (CPython: 32-bit digits of |seed|)."""
+    blob = SC.to_spec(dict(SC.CFG3, duration=40.0)).to_bytes()
+    for seed in (0, 1, 2**32 - 1, 2**32, 2**40 + 7, 2**63 + 5):
+        want, total = oracle.run_batch(blob, 2, seed, 0, oracle.RNG_MT19937)
+        got = hostemu.run_batch(blob, 2, seed, rng_kind=1)
+        assert got["events"] == total and _same(got["summary"], want), seed

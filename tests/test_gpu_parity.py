@@ -370,3 +370,58 @@ def test_kernel_matches_reference_on_random_scenarios():
             assert rel <= RTOL, (sc, got, want)
             worst = max(worst, rel)
     print(f"160 random scenarios vs the reference, worst float rel err {worst:.2e}")
+
+
+@pytest.mark.parametrize("name", DEVICE_SUPPORTED)
+def test_mersenne_twister_mode_reproduces_the_stock_reference(name):
+    """rng = "mt19937": the kernels against the fixture's "mt" run — the reference exactly as shipped, its own
+    process-global Mersenne Twister at random.seed(123) (SIM:71), nothing re-bound."""
+    doc = load_golden(name)
+    sc = doc["scenario"]
+    run = [r for r in doc["runs"] if r["rng"] == "mt"][0]
+    with engine_cls()(SC.to_spec(sc), 3, base_seed=run["seed"]) as eng:
+        eng.set_rng("mt19937")
+        eng.advance(0)
+        row = eng.summary()[0]
+    assert int(row[S.S_STATUS]) == 0 and int(row[S.S_EVENTS]) == run["events"]
+    assert int(row[S.S_JOBS_FINISHED]) == run["jobs_finished"] and int(row[S.S_SEQ]) == run["seq_pushed"]
+    for got, want_hex in [(row[S.S_TOTAL_ENERGY_J], run["total_energy_j"]), (row[S.S_LAT_SUM], run["latency_sum_s"])] + \
+            [(row[S.S_DC0 + d * S.S_DC_STRIDE + S.SD_ENERGY_J], run["dc"][d]["energy_j"]) for d in range(sc["n_dc"])]:
+        want = float.fromhex(want_hex)
+        assert got == want or abs(got - want) <= RTOL * abs(want), (got, want)
+
+
+def test_survey_known_answers_on_device(tmp_path):
+    """SURVEY.md App. C through the drop-in simulator: `rng="mt19937", rng_seed=123` gives the event counts and total
+    energies the survey recorded from the unmodified reference."""
+    import json
+    import logging
+    from conftest import GOLDEN_DIR
+    from distributed_cluster_gpus_b200.configs import paper_config as pc
+    from distributed_cluster_gpus_b200.simcore.simulator_paper_multi import MultiIngressPaperSimulator
+    with open(os.path.join(GOLDEN_DIR, "kat.json")) as f:
+        kat = json.load(f)["survey_known_answers"]
+    for name, k in kat.items():
+        sc = SC.BY_NAME[name]
+        kw = SC.build_inputs(sc)
+        sim = MultiIngressPaperSimulator(router_policy=pc.build_router_policy(), logger=logging.getLogger("t"),
+                                         sim_duration=sc["duration"], log_interval=sc["log_interval"], log_path=str(tmp_path),
+                                         rng_seed=123, algo=sc["algo"], show_progress=False, replicas=2, write_logs=False,
+                                         rng="mt19937", **kw).run()
+        assert int(sim.summary[0, S.S_EVENTS]) == k["expected"]["events"], name
+        if "jobs" in k["expected"]:
+            assert int(sim.summary[0, S.S_JOBS_FINISHED]) == k["expected"]["jobs"], name
+        total = sum(dc.energy_joules for dc in kw["dcs"].values())      # what the survey printed (builtin sum)
+        want = float(k["expected"]["total_energy_repr"])
+        assert abs(total - want) <= RTOL * want, (name, total, want)
+
+
+def test_set_rng_rejects_bad_use():
+    from distributed_cluster_gpus_b200 import _native as N
+    with engine_cls()(SC.to_spec(dict(SC.CFG3, duration=5.0)), 2, base_seed=1) as eng:
+        with pytest.raises(ValueError):
+            eng.set_rng("xorshift")
+        eng.set_rng("mt19937")
+        eng.advance(10)
+        with pytest.raises(N.DcsimError):
+            eng.set_rng("philox")      # the batch has started
