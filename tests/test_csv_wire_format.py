@@ -16,6 +16,7 @@ from distributed_cluster_gpus_b200 import scenarios as SC
 from distributed_cluster_gpus_b200.simcore.simulator_paper_multi import write_csv_logs
 
 CASES = [("ragged_3dc_12_5_40", 123), ("csv_joint_nf_4x64_20s", 7), ("csv_carbon_cost_2x16", 11)]
+STOCK_CASES = [("ragged_3dc_12_5_40", 123), ("csv_carbon_cost_2x16", 42)]   # the reference exactly as shipped (its own MT19937)
 
 
 def golden(name, seed, which):
@@ -35,6 +36,22 @@ def test_writer_reproduces_reference_files_byte_for_byte(oracle, tmp_path, name,
     assert filecmp.cmp(cl, golden(name, seed, "cluster"), shallow=False)
 
 
+@pytest.mark.parametrize("name,seed", STOCK_CASES)
+def test_device_core_in_mt_mode_reproduces_stock_reference_files(hostemu, tmp_path, name, seed):
+    """No Philox anywhere: the device core (host build) drawing from CPython's Mersenne Twister + the product's CSV
+    writer == the files `python run_sim_paper.py` of the untouched reference writes at the same seed."""
+    from distributed_cluster_gpus_b200.engine import CLUSTER_DTYPE, JOB_DTYPE
+    sc = SC.CSV_SCENARIOS[name]
+    kw = SC.build_inputs(sc)
+    sp = SC.to_spec(sc)
+    got = hostemu.run_batch(sp.to_bytes(), 1, seed, rec_replica=0, job_dtype=JOB_DTYPE, jobs_cap=100000,
+                            cluster_dtype=CLUSTER_DTYPE, cluster_cap=10000, rng_kind=1)
+    cl, jl = str(tmp_path / "cluster_log.csv"), str(tmp_path / "job_log.csv")
+    write_csv_logs(got["jobs"], got["cluster"], kw["dcs"], list(kw["ingresses"]), kw["coeffs_map"], sp.net_lat_s, cl, jl)
+    assert filecmp.cmp(jl, golden(name, f"{seed}_mt", "job"), shallow=False)
+    assert filecmp.cmp(cl, golden(name, f"{seed}_mt", "cluster"), shallow=False)
+
+
 def _rows(path):
     with open(path) as f:
         return list(csv.reader(f))
@@ -42,16 +59,18 @@ def _rows(path):
 
 @pytest.mark.gpu
 @pytest.mark.skipif(not has_cuda(), reason="needs a CUDA device")
-@pytest.mark.parametrize("name,seed", CASES)
+@pytest.mark.parametrize("name,seed", CASES + [(n, f"{s}_mt") for n, s in STOCK_CASES])
 def test_drop_in_csvs_match_reference_files(tmp_path, name, seed):
     from distributed_cluster_gpus_b200.configs import paper_config as pc
     from distributed_cluster_gpus_b200.simcore.simulator_paper_multi import MultiIngressPaperSimulator
     sc = SC.CSV_SCENARIOS[name]
     kw = SC.build_inputs(sc)
+    stock = isinstance(seed, str)          # "<seed>_mt": files of the reference as shipped -> rng="mt19937"
     MultiIngressPaperSimulator(router_policy=pc.build_router_policy(), logger=logging.getLogger("t"),
                                sim_duration=sc["duration"], log_interval=sc["log_interval"], log_path=str(tmp_path),
-                               rng_seed=seed, algo=sc["algo"], power_cap=sc["power_cap"], show_progress=False,
-                               num_fixed_gpus=sc["num_fixed_gpus"], fixed_freq=sc["fixed_freq"], replicas=4, **kw).run()
+                               rng_seed=int(seed.split("_")[0]) if stock else seed, algo=sc["algo"], power_cap=sc["power_cap"],
+                               show_progress=False, num_fixed_gpus=sc["num_fixed_gpus"], fixed_freq=sc["fixed_freq"],
+                               replicas=4, rng="mt19937" if stock else "philox", **kw).run()
     for which, textual in (("job", {1, 2, 4}), ("cluster", {1})):
         got, want = _rows(tmp_path / f"{which}_log.csv"), _rows(golden(name, seed, which))
         assert got[0] == want[0] and len(got) == len(want)
