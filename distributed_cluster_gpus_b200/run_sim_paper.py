@@ -61,8 +61,8 @@ def parse_args(argv=None):
     return p.parse_args(argv)
 
 
-def main(argv=None):
-    args = parse_args(argv)
+def build_simulator(args):
+    """argparse namespace -> configured (not yet run) simulator: run_sim_paper.py:115-159 of the reference."""
     levels = [float(x) for x in args.freq_levels.split(",")] if args.freq_levels else None
     ingresses, dcs, graph, coeffs = build_scenario(args.n_dc, args.gpus_per_dc, levels)
     for m in validate_gpus((dc.gpu_type for dc in dcs.values()), strict=False):
@@ -85,6 +85,12 @@ def main(argv=None):
         energy_budget_j=args.energy_budget_j, sla_p99_ms=args.sla_p99_ms, upgr_batch=args.upgr_batch,
         upgr_warmup=args.upgr_warmup, upgr_buffer=args.upgr_buffer, num_fixed_gpus=args.num_fixed_gpus,
         fixed_freq=args.fixed_freq, logger=get_logger(log_dir=out_dir), replicas=args.replicas, device=args.device, rng=args.rng)
+    return sim
+
+
+def main(argv=None):
+    args = parse_args(argv)
+    sim = build_simulator(args)
     sim.run()
     s = sim.summary
     stats = batch_statistics(s)

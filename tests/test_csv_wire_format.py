@@ -85,3 +85,50 @@ def test_drop_in_csvs_match_reference_files(tmp_path, name, seed):
                     decimals = len(b.split(".")[1]) if "." in b else 0
                     assert abs(float(a) - float(b)) <= 1.01 * 10 ** (-decimals), (which, k, a, b)
         assert exact >= 0.999 * sum(len(r) for r in want[1:])
+
+
+def _cli_cases():
+    import json
+    with open(os.path.join(GOLDEN_DIR, "cli", "cases.json")) as f:
+        return sorted(json.load(f).items())
+
+
+@pytest.mark.parametrize("name,flags", _cli_cases())
+def test_cli_configuration_reproduces_the_reference_command_line(hostemu, tmp_path, name, flags):
+    """`python run_sim_paper.py <flags>` of the untouched reference wrote tests/golden/cli/*.  The product's CLI builds
+    its simulator from the same flags; its spec through the device core (host build, rng = MT19937) and its CSV
+    writer must give the same bytes — scenario defaults, builders, flattening and writer all in one comparison."""
+    from distributed_cluster_gpus_b200 import run_sim_paper as cli
+    from distributed_cluster_gpus_b200.engine import CLUSTER_DTYPE, JOB_DTYPE
+    args = cli.parse_args(flags + ["--log-path", str(tmp_path / "logs" / "x"), "--rng", "mt19937"])
+    sim = cli.build_simulator(args)
+    got = hostemu.run_batch(sim._spec.to_bytes(), 1, args.seed, rec_replica=0, job_dtype=JOB_DTYPE, jobs_cap=200000,
+                            cluster_dtype=CLUSTER_DTYPE, cluster_cap=20000, rng_kind=1)
+    assert int(got["summary"][0, 0]) == 0
+    sim._write_csvs(got["jobs"], got["cluster"])
+    for f in ("cluster_log.csv", "job_log.csv"):
+        assert filecmp.cmp(str(tmp_path / "logs" / "x" / f), os.path.join(GOLDEN_DIR, "cli", f"{name}_{f}"), shallow=False), f
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not has_cuda(), reason="needs a CUDA device")
+@pytest.mark.parametrize("name,flags", _cli_cases())
+def test_cli_on_device_matches_the_reference_command_line(tmp_path, name, flags):
+    """The product's command line, end to end on the GPU, against the files the reference's command line wrote."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    logs = tmp_path / "logs" / "x"
+    subprocess.run([sys.executable, "-m", "distributed_cluster_gpus_b200.run_sim_paper", "--log-path", str(logs), "--rng", "mt19937",
+                    "--replicas", "3"] + flags, cwd=root, check=True, capture_output=True, timeout=600)
+    for which, textual in (("job", {1, 2, 4}), ("cluster", {1})):
+        got, want = _rows(logs / f"{which}_log.csv"), _rows(os.path.join(GOLDEN_DIR, "cli", f"{name}_{which}_log.csv"))
+        assert got[0] == want[0] and len(got) == len(want)
+        for g, w in zip(got[1:], want[1:]):
+            assert len(g) == len(w)
+            for k, (a, b) in enumerate(zip(g, w)):
+                if k in textual or a == b:
+                    assert a == b
+                else:
+                    decimals = len(b.split(".")[1]) if "." in b else 0
+                    assert abs(float(a) - float(b)) <= 1.01 * 10 ** (-decimals), (which, k, a, b)
