@@ -143,6 +143,8 @@ struct dcsim {
   dcsim_job_rec_t* d_jobs;
   dcsim_cluster_rec_t* d_cluster;
   uint32_t trace_cap, jobs_cap, cluster_cap;
+  uint32_t jobs_alloc, cluster_alloc; /* rows the log buffers can hold (kept across set_logging calls) */
+  int want_job_log;                   /* layout the NEXT batch needs; applied lazily by ensure_layout() */
   int64_t trace_replica, log_replica;
   int launches;
   int prepass, arrivals_ready, staged;
@@ -365,16 +367,24 @@ int dcsim_set_logging(dcsim_t* h, uint64_t replica, uint32_t job_capacity, uint3
   if (!h) return DCSIM_E_INVALID;
   if (h->launches) return set_err(h, DCSIM_E_STATE, "set_logging must precede the first advance%s%lld");
   CUDA_TRY(h, cudaSetDevice(h->device));
-  if (h->d_jobs) { cudaFree(h->d_jobs); h->d_jobs = NULL; }
-  if (h->d_cluster) { cudaFree(h->d_cluster); h->d_cluster = NULL; }
   h->jobs_cap = h->cluster_cap = 0; h->log_replica = -1;
+  h->want_job_log = 0; /* the state block is re-laid out (if at all) by the batch's first launch: a caller that
+                          switches logging off and on again between batches pays for neither */
   if (replica >= h->n_replicas && (job_capacity || cluster_capacity))
     return set_err(h, DCSIM_E_INVALID, "set_logging: replica out of range%s%lld");
-  { const int rc = relayout(h, job_capacity != 0); if (rc != DCSIM_OK) return rc; }
   if (job_capacity == 0 && cluster_capacity == 0) return DCSIM_OK;
-  if (job_capacity) CUDA_TRY(h, cudaMalloc(&h->d_jobs, (size_t)job_capacity * sizeof(dcsim_job_rec_t)));
-  if (cluster_capacity) CUDA_TRY(h, cudaMalloc(&h->d_cluster, (size_t)cluster_capacity * sizeof(dcsim_cluster_rec_t)));
+  if (job_capacity > h->jobs_alloc) { /* buffers only ever grow; a smaller request reuses them */
+    if (h->d_jobs) { cudaFree(h->d_jobs); h->d_jobs = NULL; h->jobs_alloc = 0; }
+    CUDA_TRY(h, cudaMalloc(&h->d_jobs, (size_t)job_capacity * sizeof(dcsim_job_rec_t)));
+    h->jobs_alloc = job_capacity;
+  }
+  if (cluster_capacity > h->cluster_alloc) {
+    if (h->d_cluster) { cudaFree(h->d_cluster); h->d_cluster = NULL; h->cluster_alloc = 0; }
+    CUDA_TRY(h, cudaMalloc(&h->d_cluster, (size_t)cluster_capacity * sizeof(dcsim_cluster_rec_t)));
+    h->cluster_alloc = cluster_capacity;
+  }
   h->jobs_cap = job_capacity; h->cluster_cap = cluster_capacity; h->log_replica = (int64_t)replica;
+  h->want_job_log = job_capacity != 0;
   return DCSIM_OK;
 }
 
@@ -382,7 +392,7 @@ static void fill_kparams(const dcsim_t* h, dcsim_kparams_t* P, uint64_t max_even
   memset(P, 0, sizeof(*P));
   P->spec = h->spec;
   P->L = h->L;
-  P->rec.trace = h->d_trace; P->rec.jobs = h->d_jobs; P->rec.cluster = h->d_cluster; P->rec.counts = h->d_counts;
+  P->rec.trace = h->d_trace; P->rec.jobs = h->jobs_cap ? h->d_jobs : NULL; P->rec.cluster = h->cluster_cap ? h->d_cluster : NULL; P->rec.counts = h->d_counts;
   P->rec.trace_cap = h->trace_cap; P->rec.jobs_cap = h->jobs_cap; P->rec.cluster_cap = h->cluster_cap;
   P->rec.trace_replica = h->trace_replica; P->rec.log_replica = h->log_replica;
   P->n_replicas = h->n_replicas;
@@ -398,8 +408,9 @@ static void fill_kparams(const dcsim_t* h, dcsim_kparams_t* P, uint64_t max_even
 
 int dcsim_prepare(dcsim_t* h) {
   if (!h) return DCSIM_E_INVALID;
-  if (!h->prepass || h->arrivals_ready) return DCSIM_OK;
   CUDA_TRY(h, cudaSetDevice(h->device));
+  if (h->launches == 0) { const int rc0 = relayout(h, h->want_job_log); if (rc0 != DCSIM_OK) return rc0; }
+  if (!h->prepass || h->arrivals_ready) return DCSIM_OK;
   dcsim_kparams_t P;
   fill_kparams(h, &P, 0);
   const int nb = (int)((h->n_replicas + DCSIM_ARRIVALS_THREADS - 1) / DCSIM_ARRIVALS_THREADS);
@@ -415,6 +426,7 @@ int dcsim_prepare(dcsim_t* h) {
 int dcsim_advance(dcsim_t* h, uint64_t max_events_per_replica, uint64_t* total_events_out) {
   if (!h) return DCSIM_E_INVALID;
   CUDA_TRY(h, cudaSetDevice(h->device));
+  if (h->launches == 0) { const int rc0 = relayout(h, h->want_job_log); if (rc0 != DCSIM_OK) return rc0; }
   int rc = dcsim_prepare(h); /* once per (re)seeded batch: the arrival lists of all replicas */
   if (rc != DCSIM_OK) return rc;
   dcsim_kparams_t P;
@@ -553,10 +565,10 @@ int dcsim_fetch_trace(dcsim_t* h, dcsim_trace_rec_t* out, uint32_t capacity, uin
   return fetch_records(h, h ? h->d_trace : NULL, sizeof(dcsim_trace_rec_t), h ? h->trace_cap : 0, 0, out, capacity, n_out);
 }
 int dcsim_fetch_job_log(dcsim_t* h, dcsim_job_rec_t* out, uint32_t capacity, uint32_t* n_out) {
-  return fetch_records(h, h ? h->d_jobs : NULL, sizeof(dcsim_job_rec_t), h ? h->jobs_cap : 0, 1, out, capacity, n_out);
+  return fetch_records(h, h && h->jobs_cap ? h->d_jobs : NULL, sizeof(dcsim_job_rec_t), h ? h->jobs_cap : 0, 1, out, capacity, n_out);
 }
 int dcsim_fetch_cluster_log(dcsim_t* h, dcsim_cluster_rec_t* out, uint32_t capacity, uint32_t* n_out) {
-  return fetch_records(h, h ? h->d_cluster : NULL, sizeof(dcsim_cluster_rec_t), h ? h->cluster_cap : 0, 2, out, capacity, n_out);
+  return fetch_records(h, h && h->cluster_cap ? h->d_cluster : NULL, sizeof(dcsim_cluster_rec_t), h ? h->cluster_cap : 0, 2, out, capacity, n_out);
 }
 
 int dcsim_launch_info(dcsim_t* h, dcsim_launch_info_t* out) {

@@ -5,3 +5,6 @@ cd "$(dirname "$0")"
 mkdir -p _build
 g++ -O2 -fPIC -shared -std=gnu++17 -ffp-contract=off -fno-fast-math -Wall -Wno-unused-function -Wno-unknown-pragmas \
     -o _build/libdcsim_hostemu.so hostemu.cpp -lm
+# conditioning probe: the same build with every 5th pow() result moved by one ulp (see hostemu.cpp)
+g++ -O2 -fPIC -shared -std=gnu++17 -ffp-contract=off -fno-fast-math -Wall -Wno-unused-function -Wno-unknown-pragmas \
+    -DDCSIM_HOSTEMU_PERTURB -o _build/libdcsim_hostemu_perturbed.so hostemu.cpp -lm

@@ -7,6 +7,20 @@
  * `-m gpu` parity tests are for.
  */
 #define DCSIM_HOST_EMU 1
+#ifdef DCSIM_HOSTEMU_PERTURB
+/* Conditioning probe (second build, libdcsim_hostemu_perturbed.so): every 5th pow() result is moved by ONE ulp — the
+ * kind of difference two correct libm implementations (glibc here, CUDA's on the device) have.  How far a scenario's
+ * results move under it is that scenario's sensitivity to last-bit differences: ~1e-15 for ordinary scenarios, orders
+ * of magnitude more where the power-cap controller keeps re-timing back-to-back jobs (each re-timing multiplies a
+ * start-time error by rate_old/rate_new).  tools/fuzz_gpu.py uses it to tell ill-conditioned scenarios from bugs. */
+#include <math.h>
+static inline double dcsim_hostemu_perturbed_pow(double a, double b) {
+  static unsigned long calls = 0;
+  const double r = pow(a, b);
+  return (++calls % 5ul == 0ul) ? nextafter(r, INFINITY) : r;
+}
+#define pow dcsim_hostemu_perturbed_pow
+#endif
 #include "../../distributed_cluster_gpus_b200/csrc/dcsim_core.cuh"
 
 #include <stdlib.h>

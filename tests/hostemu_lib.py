@@ -12,27 +12,40 @@ _CORE = os.path.join(_HERE, "..", "distributed_cluster_gpus_b200", "csrc", "dcsi
 _HDR = os.path.join(_HERE, "..", "include", "dcsim_b200.h")
 SUMMARY_K = 24 + 8 * 8
 TRACE_DTYPE = np.dtype([("t", "<f8"), ("seq", "<u4"), ("kind", "<u4")])
+_SO_PERTURBED = os.path.join(_DIR, "_build", "libdcsim_hostemu_perturbed.so")
 _lib = None
+_lib_perturbed = None
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        srcs = (os.path.join(_DIR, "hostemu.cpp"), _CORE, _HDR)
-        if not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
+def _bind(path):
+    L = C.CDLL(path)
+    L.hostemu_sizeof_spec.restype = C.c_size_t
+    L.hostemu_run_batch.restype = C.c_longlong
+    L.hostemu_run_batch.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p,
+                                    C.c_int64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p,
+                                    C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    return L
+
+
+def _ensure_built():
+    srcs = (os.path.join(_DIR, "hostemu.cpp"), os.path.join(_DIR, "build.sh"), _CORE, _HDR)
+    for so in (_SO, _SO_PERTURBED):
+        if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
             subprocess.run([os.path.join(_DIR, "build.sh")], check=True, capture_output=True)
-        L = C.CDLL(_SO)
-        L.hostemu_sizeof_spec.restype = C.c_size_t
-        L.hostemu_run_batch.restype = C.c_longlong
-        L.hostemu_run_batch.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p,
-                                        C.c_int64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p,
-                                        C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
-        _lib = L
-    return _lib
+            return
+
+
+def lib(perturbed=False):
+    """perturbed=True: the conditioning probe (every 5th pow() result moved by one ulp, see hostemu.cpp)."""
+    global _lib, _lib_perturbed
+    if _lib is None:
+        _ensure_built()
+        _lib, _lib_perturbed = _bind(_SO), _bind(_SO_PERTURBED)
+    return _lib_perturbed if perturbed else _lib
 
 
 def run_batch(spec_bytes, n_replicas, seed0, chunk_events=0, trace_cap=0, rec_replica=-1, job_dtype=None,
-              jobs_cap=0, cluster_dtype=None, cluster_cap=0, rng_kind=0):
+              jobs_cap=0, cluster_dtype=None, cluster_cap=0, rng_kind=0, perturbed=False):
     out = np.zeros((n_replicas, SUMMARY_K))
     buf = C.create_string_buffer(spec_bytes, len(spec_bytes))
     trace = np.zeros(max(trace_cap, 1), dtype=TRACE_DTYPE)
@@ -41,7 +54,7 @@ def run_batch(spec_bytes, n_replicas, seed0, chunk_events=0, trace_cap=0, rec_re
     counts = np.zeros(4, dtype=np.uint32)
     layout = np.zeros(8, dtype=np.int32)
     hist = np.zeros((n_replicas, 2, 128), dtype=np.uint32)
-    total = lib().hostemu_run_batch(buf, len(spec_bytes), n_replicas, seed0 & (2**64 - 1), chunk_events,
+    total = lib(perturbed).hostemu_run_batch(buf, len(spec_bytes), n_replicas, seed0 & (2**64 - 1), chunk_events,
                                     out.ctypes.data, rec_replica,
                                     trace.ctypes.data if trace_cap else None, trace_cap,
                                     jobs.ctypes.data if jobs is not None and jobs_cap else None, jobs_cap,

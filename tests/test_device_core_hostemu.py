@@ -2,6 +2,8 @@
 the oracle.  On the same libm the two must agree bit for bit on the whole 88-double summary — this pins the
 handler logic, the state-block layout, the Philox window / slow path, the FIFO rings and the resume path
 before any GPU time is spent.  Lane mapping and warp collectives are covered by the -m gpu tests."""
+import os
+
 import numpy as np
 import pytest
 
@@ -208,3 +210,27 @@ def test_mersenne_twister_mode_equals_oracle_on_wide_seeds(oracle, hostemu):
         want, total = oracle.run_batch(blob, 2, seed, 0, oracle.RNG_MT19937)
         got = hostemu.run_batch(blob, 2, seed, rng_kind=1)
         assert got["events"] == total and _same(got["summary"], want), seed
+
+
+def test_conditioning_probe_separates_chaotic_scenarios(oracle, hostemu):
+    """libdcsim_hostemu_perturbed.so moves every 5th pow() result by ONE ulp (what two correct libm's may differ by).
+    Ordinary scenarios do not care (<= 1e-13); a power-cap controller re-timing back-to-back jobs on a 2-GPU DC
+    amplifies it a billion-fold (each re-timing multiplies a start-time error by rate_old/rate_new) with every count
+    still exact — that scenario's 1e-9 parity with ANY other libm is not attainable, the reference's own included."""
+    import json
+    from conftest import GOLDEN_DIR
+
+    def moved(sc, seed):
+        blob = SC.to_spec(sc).to_bytes()
+        want, _ = oracle.run_batch(blob, 6, seed, 0)
+        got = hostemu.run_batch(blob, 6, seed, perturbed=True)["summary"]
+        for col in (S.S_EVENTS, S.S_JOBS_FINISHED, S.S_SEQ, S.S_RNG_WORDS):
+            assert np.array_equal(got[:, col], want[:, col])
+        cols = (S.S_TOTAL_ENERGY_J, S.S_LAT_SUM)
+        return max(float(np.max(np.abs(got[:, c] - want[:, c]) / np.abs(want[:, c]))) for c in cols)
+
+    for name in ("cfg3_4x64_sinusoid_120s", "sweep_joint_nf", "cap_greedy_4x64", "sweep_bandit", "ragged_3dc_12_5_40"):
+        assert moved(SC.BY_NAME[name], 123) <= 1e-13, name
+    with open(os.path.join(GOLDEN_DIR, "ill_conditioned_cap_greedy_case.json")) as f:
+        case = json.load(f)
+    assert moved(case["scenario"], case["seed"]) >= 1e-7
