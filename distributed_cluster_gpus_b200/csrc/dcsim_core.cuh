@@ -182,6 +182,22 @@ struct dcsim_layout_t {
 
 static inline int32_t dcsim_align16(int32_t x) { return (x + 15) & ~15; }
 
+/* The head of a state block has a FIXED layout — header, event set, per-DC arrays, arrival-list window, the base of
+ * the transfer pool — so the event loop addresses it with immediate offsets (LDS [blk + imm]) instead of adding a
+ * layout field from the constant bank in front of every access; only the capacity-dependent arrays behind it go
+ * through dcsim_layout_t. */
+enum : int32_t {
+  DCSIM_OFF_CAND_T = ((int32_t)sizeof(dcsim_hdr_t) + 15) & ~15,
+  DCSIM_OFF_CAND_SEQ = DCSIM_OFF_CAND_T + CAND_N * 8,
+  DCSIM_OFF_DC_F64 = DCSIM_OFF_CAND_SEQ + CAND_N * 4,
+  DCSIM_OFF_DC_I32 = DCSIM_OFF_DC_F64 + DF_N * DCSIM_MAX_DC * 8,
+  DCSIM_OFF_AW_T = (DCSIM_OFF_DC_I32 + DI_N * DCSIM_MAX_DC * 4 + 15) & ~15,
+  DCSIM_OFF_AW_SIZE = DCSIM_OFF_AW_T + (int32_t)DCSIM_ARR_WINDOW * 8,
+  DCSIM_OFF_AW_META = DCSIM_OFF_AW_SIZE + (int32_t)DCSIM_ARR_WINDOW * 8,
+  DCSIM_OFF_PEND_SEQ = DCSIM_OFF_AW_META + (int32_t)DCSIM_ARR_WINDOW * 4,
+  DCSIM_OFF_XF_T = (DCSIM_OFF_PEND_SEQ + 2 * DCSIM_MAX_ING * 4 + 15) & ~15
+};
+
 /* Host-side: sizes the state block from the spec's capacities. */
 static inline void dcsim_make_layout(const dcsim_spec_t* sp, dcsim_layout_t* L, int prepass, int job_log) {
   memset(L, 0, sizeof(*L));
@@ -200,11 +216,11 @@ static inline void dcsim_make_layout(const dcsim_spec_t* sp, dcsim_layout_t* L, 
   L->cap_run = cr;
   L->cap_q[0] = sp->cap_q_inf > 0 ? sp->cap_q_inf : 4096;
   L->cap_q[1] = sp->cap_q_trn > 0 ? sp->cap_q_trn : 512;
-  int32_t o = dcsim_align16((int32_t)sizeof(dcsim_hdr_t));
-  L->cand_t = o; o += CAND_N * 8;
-  L->cand_seq = o; o += CAND_N * 4;
-  L->dc_f64 = o; o += DF_N * D * 8;
-  L->dc_i32 = o; o = dcsim_align16(o + DI_N * D * 4);
+  L->cand_t = DCSIM_OFF_CAND_T; L->cand_seq = DCSIM_OFF_CAND_SEQ;
+  L->dc_f64 = DCSIM_OFF_DC_F64; L->dc_i32 = DCSIM_OFF_DC_I32;
+  L->aw_t = DCSIM_OFF_AW_T; L->aw_size = DCSIM_OFF_AW_SIZE; L->aw_meta = DCSIM_OFF_AW_META; L->pend_seq = DCSIM_OFF_PEND_SEQ;
+  (void)D;
+  int32_t o = DCSIM_OFF_XF_T;
   L->xf_t = o; o += cx * 8;
   L->xf_size = o; o += cx * 8;
   L->xf_seq = o; o += cx * 4;
@@ -220,12 +236,7 @@ static inline void dcsim_make_layout(const dcsim_spec_t* sp, dcsim_layout_t* L, 
   L->rn_meta = o; o += nr * 4;
   if (!L->lean) { L->rn_jid = o; o += nr * 4; }
   o = dcsim_align16(o);
-  if (prepass) { /* no in-kernel sampling: the Philox window gives way to the arrival-list window */
-    L->aw_t = o; o += (int32_t)DCSIM_ARR_WINDOW * 8;
-    L->aw_size = o; o += (int32_t)DCSIM_ARR_WINDOW * 8;
-    L->aw_meta = o; o += (int32_t)DCSIM_ARR_WINDOW * 4;
-    L->pend_seq = o; o += 2 * DCSIM_MAX_ING * 4;
-  } else {
+  if (!prepass) { /* in-kernel sampling (legacy mode): the Philox window; the arrival-list window of the fixed head idles */
     L->rng_buf = o; o += (int32_t)DCSIM_RNG_WINDOW * 4;
   }
   if (bandit) {
@@ -323,10 +334,10 @@ struct dcsim_ctx_t {
   double now;            /* warp-uniform */
 };
 
-#define DCF(c, which) (dcsim_at<double>((c).blk, (c).P->L.dc_f64) + (which) * DCSIM_MAX_DC)
-#define DCI(c, which) (dcsim_at<int32_t>((c).blk, (c).P->L.dc_i32) + (which) * DCSIM_MAX_DC)
-#define CAND_T(c) (dcsim_at<double>((c).blk, (c).P->L.cand_t))
-#define CAND_SEQ(c) (dcsim_at<uint32_t>((c).blk, (c).P->L.cand_seq))
+#define DCF(c, which) (dcsim_at<double>((c).blk, DCSIM_OFF_DC_F64 + (which) * DCSIM_MAX_DC * 8))
+#define DCI(c, which) (dcsim_at<int32_t>((c).blk, DCSIM_OFF_DC_I32 + (which) * DCSIM_MAX_DC * 4))
+#define CAND_T(c) (dcsim_at<double>((c).blk, DCSIM_OFF_CAND_T))
+#define CAND_SEQ(c) (dcsim_at<uint32_t>((c).blk, DCSIM_OFF_CAND_SEQ))
 #define RNG_BUF(c) (dcsim_at<uint32_t>((c).blk, (c).P->L.rng_buf))
 
 /* ================================================================================================
@@ -845,7 +856,7 @@ DCSIM_DEV void dcsim_rescan_dc(dcsim_ctx_t& c, int d) {
 /* Warp.  Earliest in-flight transfer -> candidate slot CAND_XFER. */
 DCSIM_DEV void dcsim_rescan_xfer(dcsim_ctx_t& c) {
   double t; uint32_t s;
-  const int k = dcsim_argmin_ts(dcsim_at<double>(c.blk, c.P->L.xf_t), dcsim_at<uint32_t>(c.blk, c.P->L.xf_seq),
+  const int k = dcsim_argmin_ts(dcsim_at<double>(c.blk, DCSIM_OFF_XF_T), dcsim_at<uint32_t>(c.blk, c.P->L.xf_seq),
                                 (int)c.H->n_xfer, c.lane, &t, &s);
   if (c.lane == 0) {
     CAND_T(c)[CAND_XFER] = k >= 0 ? t : DCSIM_INF;
@@ -1128,7 +1139,7 @@ DCSIM_DEV void dcsim_handle_arrival(dcsim_ctx_t& c, int stream) {
         H->status |= DCSIM_ST_XFER_OVERFLOW;
       } else {
         const uint32_t seq = c.seq++;
-        dcsim_at<double>(c.blk, L.xf_t)[slot] = t_x;
+        dcsim_at<double>(c.blk, DCSIM_OFF_XF_T)[slot] = t_x;
         dcsim_at<double>(c.blk, L.xf_size)[slot] = size;
         dcsim_at<uint32_t>(c.blk, L.xf_seq)[slot] = seq;
         dcsim_at<uint32_t>(c.blk, L.xf_meta)[slot] = (uint32_t)dc_sel | ((uint32_t)jt << 3) | ((uint32_t)ing << 4);
@@ -1192,14 +1203,13 @@ DCSIM_DEV void dcsim_handle_arrival(dcsim_ctx_t& c, int stream) {
 
 /* Warp.  Stages entries [base, base+DCSIM_ARR_WINDOW) of the replica's arrival list into shared memory (coalesced). */
 DCSIM_DEV void dcsim_arrivals_stage(dcsim_ctx_t& c, uint64_t r, uint32_t base) {
-  const dcsim_layout_t& L = c.P->L;
   const uint64_t off = r * (uint64_t)c.P->cap_arr + base;
   const uint32_t count = c.H->arr_count;
   for (uint32_t i = (uint32_t)c.lane; i < DCSIM_ARR_WINDOW; i += DCSIM_LANES) {
     const bool in = base + i < count;
-    dcsim_at<double>(c.blk, L.aw_t)[i] = in ? c.P->arr_t[off + i] : DCSIM_INF;
-    dcsim_at<double>(c.blk, L.aw_size)[i] = in ? c.P->arr_size[off + i] : 0.0;
-    dcsim_at<uint32_t>(c.blk, L.aw_meta)[i] = in ? c.P->arr_meta[off + i] : 0u;
+    dcsim_at<double>(c.blk, DCSIM_OFF_AW_T)[i] = in ? c.P->arr_t[off + i] : DCSIM_INF;
+    dcsim_at<double>(c.blk, DCSIM_OFF_AW_SIZE)[i] = in ? c.P->arr_size[off + i] : 0.0;
+    dcsim_at<uint32_t>(c.blk, DCSIM_OFF_AW_META)[i] = in ? c.P->arr_meta[off + i] : 0u;
   }
   if (c.lane == 0) c.H->aw_base = base;
   dcsim_warp_sync();
@@ -1208,12 +1218,11 @@ DCSIM_DEV void dcsim_arrivals_stage(dcsim_ctx_t& c, uint64_t r, uint32_t base) {
 /* Lane 0.  Publishes list entry `k` as the (single) arrival candidate; its seq is the one its stream was given
  * when the stream's previous arrival (or the constructor) pushed it. */
 DCSIM_DEV void dcsim_arrival_candidate(dcsim_ctx_t& c, uint32_t k) {
-  const dcsim_layout_t& L = c.P->L;
   if (k < c.H->arr_count) {
     const uint32_t i = k - c.H->aw_base;
-    const uint32_t stream = dcsim_at<uint32_t>(c.blk, L.aw_meta)[i] & 15u;
-    CAND_T(c)[CAND_STREAM0] = dcsim_at<double>(c.blk, L.aw_t)[i];
-    CAND_SEQ(c)[CAND_STREAM0] = dcsim_at<uint32_t>(c.blk, L.pend_seq)[stream];
+    const uint32_t stream = dcsim_at<uint32_t>(c.blk, DCSIM_OFF_AW_META)[i] & 15u;
+    CAND_T(c)[CAND_STREAM0] = dcsim_at<double>(c.blk, DCSIM_OFF_AW_T)[i];
+    CAND_SEQ(c)[CAND_STREAM0] = dcsim_at<uint32_t>(c.blk, DCSIM_OFF_PEND_SEQ)[stream];
   } else {
     CAND_T(c)[CAND_STREAM0] = DCSIM_INF;
     CAND_SEQ(c)[CAND_STREAM0] = 0xffffffffu;
@@ -1231,8 +1240,8 @@ DCSIM_DEV void dcsim_handle_arrival_listed(dcsim_ctx_t& c, uint64_t r) {
   const uint32_t wbase = dcsim_bcast_u32(c.lane == 0 ? H->aw_base : 0u, 0);
   if (c.lane == 0) {
     const uint32_t i = k - wbase;
-    const double size = dcsim_at<double>(c.blk, L.aw_size)[i];
-    const uint32_t meta = dcsim_at<uint32_t>(c.blk, L.aw_meta)[i];
+    const double size = dcsim_at<double>(c.blk, DCSIM_OFF_AW_SIZE)[i];
+    const uint32_t meta = dcsim_at<uint32_t>(c.blk, DCSIM_OFF_AW_META)[i];
     const uint32_t stream = meta & 15u;
     const int jt = (int)(stream & 1u), ing = (int)(stream >> 1), dc_sel = (int)((meta >> 4) & 7u);
     const uint32_t jid = k + 1u; /* SIM:539: jids count arrivals */
@@ -1245,7 +1254,7 @@ DCSIM_DEV void dcsim_handle_arrival_listed(dcsim_ctx_t& c, uint64_t r) {
         H->status |= DCSIM_ST_XFER_OVERFLOW;
       } else {
         const uint32_t seq = c.seq++;
-        dcsim_at<double>(c.blk, L.xf_t)[slot] = t_x;
+        dcsim_at<double>(c.blk, DCSIM_OFF_XF_T)[slot] = t_x;
         dcsim_at<double>(c.blk, L.xf_size)[slot] = size;
         dcsim_at<uint32_t>(c.blk, L.xf_seq)[slot] = seq;
         dcsim_at<uint32_t>(c.blk, L.xf_meta)[slot] = (uint32_t)dc_sel | ((uint32_t)jt << 3) | ((uint32_t)ing << 4);
@@ -1258,7 +1267,7 @@ DCSIM_DEV void dcsim_handle_arrival_listed(dcsim_ctx_t& c, uint64_t r) {
         }
       }
     }
-    if (meta & 0x80u) dcsim_at<uint32_t>(c.blk, L.pend_seq)[stream] = c.seq++; /* SIM:591-592 push of the next arrival */
+    if (meta & 0x80u) dcsim_at<uint32_t>(c.blk, DCSIM_OFF_PEND_SEQ)[stream] = c.seq++; /* SIM:591-592 push of the next arrival */
     H->arr_cursor = k + 1u;
   }
   dcsim_warp_sync();
@@ -1272,7 +1281,7 @@ DCSIM_DEV void dcsim_handle_xfer(dcsim_ctx_t& c, int slot) {
   const dcsim_spec_t& sp = c.P->spec;
   const dcsim_layout_t& L = c.P->L;
   dcsim_hdr_t* H = c.H;
-  double* xt = dcsim_at<double>(c.blk, L.xf_t); double* xs = dcsim_at<double>(c.blk, L.xf_size);
+  double* xt = dcsim_at<double>(c.blk, DCSIM_OFF_XF_T); double* xs = dcsim_at<double>(c.blk, L.xf_size);
   uint32_t* xq = dcsim_at<uint32_t>(c.blk, L.xf_seq); uint32_t* xm = dcsim_at<uint32_t>(c.blk, L.xf_meta);
   uint32_t* xj = dcsim_at<uint32_t>(c.blk, L.xf_jid);
   const double size = xs[slot];
@@ -1544,7 +1553,7 @@ DCSIM_DEV void dcsim_replica_init(dcsim_ctx_t& c, uint64_t r) {
       c.H->arr_count = ah.count; c.H->arr_cursor = 0u; c.H->status |= ah.status;
       c.rng_pos = ah.rng_words;
       for (int s = 0; s < 2 * sp.n_ing; ++s)
-        if ((ah.first_mask >> s) & 1u) dcsim_at<uint32_t>(c.blk, L.pend_seq)[s] = c.seq++;
+        if ((ah.first_mask >> s) & 1u) dcsim_at<uint32_t>(c.blk, DCSIM_OFF_PEND_SEQ)[s] = c.seq++;
       const double t = 0.0 + sp.log_interval;
       if (dcsim_schedulable(c, t)) { CAND_T(c)[CAND_LOG] = t; CAND_SEQ(c)[CAND_LOG] = c.seq++; }
       c.H->xmin_slot = 0xffffffffu;
@@ -1636,7 +1645,7 @@ DCSIM_DEV uint32_t dcsim_replica_run(dcsim_ctx_t& c, uint64_t r) {
     int kind = win < CAND_STREAM0 ? KIND_FINISH
                : (win < CAND_XFER ? (win & 1) : (win == CAND_XFER ? KIND_XFER : (win == CAND_LOG ? KIND_LOG : KIND_STALE)));
     if constexpr (PRE) { /* one arrival candidate for all streams: the job type is in the list entry */
-      if (win == CAND_STREAM0) kind = (int)(dcsim_at<uint32_t>(c.blk, c.P->L.aw_meta)[c.H->arr_cursor - c.H->aw_base] & 1u);
+      if (win == CAND_STREAM0) kind = (int)(dcsim_at<uint32_t>(c.blk, DCSIM_OFF_AW_META)[c.H->arr_cursor - c.H->aw_base] & 1u);
     }
     if (tracing && c.lane == 0) {
       {
