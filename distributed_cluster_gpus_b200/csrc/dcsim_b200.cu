@@ -398,6 +398,7 @@ static void fill_kparams(const dcsim_t* h, dcsim_kparams_t* P, uint64_t max_even
   P->n_replicas = h->n_replicas;
   P->seed0 = h->seed0;
   P->max_events = max_events;
+  P->budget32 = (max_events == 0ull || max_events > 0xfffffffeull) ? 0xffffffffu : (uint32_t)max_events;
   P->state = h->d_state; P->queues = h->d_queues; P->summary = h->d_summary;
   P->end_eps = h->spec.end_time + 1e-9; /* SIM:161 */
   P->arr_t = h->d_arr_t; P->arr_size = h->d_arr_size; P->arr_meta = h->d_arr_meta; P->arr_hdr = h->d_arr_hdr; P->cap_arr = h->cap_arr;

@@ -298,6 +298,8 @@ struct dcsim_kparams_t {
   uint64_t n_replicas;
   uint64_t seed0;       /* Philox key of local replica 0 (base_seed + first_replica_id) */
   uint64_t max_events;  /* per replica per launch; 0 = run to the end */
+  uint32_t budget32;    /* the same as one 32-bit compare: 0 (unlimited) and anything >= 2^32 become 0xffffffff (host-computed) */
+  uint32_t _pad32;
   char* state;          /* [n_replicas][L.total_bytes] */
   char* queues;         /* [n_replicas][L.queue_bytes] */
   double* summary;      /* [n_replicas][DCSIM_SUMMARY_K] */
@@ -1613,16 +1615,17 @@ DCSIM_DEV void dcsim_replica_tail(dcsim_ctx_t& c) {
 template <bool CAP, bool PRE>
 DCSIM_DEV uint32_t dcsim_replica_run(dcsim_ctx_t& c, uint64_t r) {
   const dcsim_spec_t& sp = c.P->spec;
-  /* per-launch event budget as one 32-bit compare: 0 (unlimited) and anything >= 2^32 never trips */
-  const uint32_t budget = (c.P->max_events == 0ull || c.P->max_events > 0xfffffffeull) ? 0xffffffffu : (uint32_t)c.P->max_events;
+  const uint32_t budget = c.P->budget32; /* per-launch event budget; 0xffffffff = unlimited */
   const bool tracing = c.is_traced && c.P->rec.trace != nullptr;
   uint32_t done_here = 0u;
   bool finished = false;
   for (;;) {
-    if (done_here >= budget) break;
     /* a capacity overflowed (or a sampler ran away): stop and report, never guess.  Polled every 16 events — every
      * capacity check refuses the write on its own, so a replica that overflowed stays memory-safe until it is seen */
-    if ((done_here & 15u) == 0u && c.H->status != 0u) break;
+    if (done_here >= budget || c.H->status != 0u) break;
+    uint32_t chunk = budget - done_here; chunk = chunk < 16u ? chunk : 16u;
+    uint32_t k = 0u;
+    for (; k < chunk; ++k) {
     double t; uint32_t seq;
     const int win = dcsim_argmin_cand(c, &t, &seq);
     if (win < 0) { finished = true; break; }         /* `while self.event_q` */
@@ -1640,22 +1643,21 @@ DCSIM_DEV uint32_t dcsim_replica_run(dcsim_ctx_t& c, uint64_t r) {
       DCF(c, DF_LAST_T)[d] = t;
     }
     dcsim_warp_sync(); /* every lane has read its candidate / busy / power before lane 0's handler rewrites them */
-    ++done_here;
     c.now = t;
-    int kind = win < CAND_STREAM0 ? KIND_FINISH
-               : (win < CAND_XFER ? (win & 1) : (win == CAND_XFER ? KIND_XFER : (win == CAND_LOG ? KIND_LOG : KIND_STALE)));
-    if constexpr (PRE) { /* one arrival candidate for all streams: the job type is in the list entry */
-      if (win == CAND_STREAM0) kind = (int)(dcsim_at<uint32_t>(c.blk, DCSIM_OFF_AW_META)[c.H->arr_cursor - c.H->aw_base] & 1u);
-    }
+    /* dispatch on the winning slot itself; the event kind is only spelled out for the (cold) trace */
+    const bool is_arrival = PRE ? (win == CAND_STREAM0) : (win >= CAND_STREAM0 && win < CAND_XFER);
     if (tracing && c.lane == 0) {
-      {
-        const uint32_t r = c.P->rec.counts[0];
-        if (r < c.P->rec.trace_cap) { c.P->rec.trace[r].t = t; c.P->rec.trace[r].seq = seq; c.P->rec.trace[r].kind = (uint32_t)(kind == KIND_STALE ? KIND_FINISH : kind); }
-        c.P->rec.counts[0] = r + 1u;
+      int kind = win < CAND_STREAM0 ? KIND_FINISH
+                 : (win < CAND_XFER ? (win & 1) : (win == CAND_XFER ? KIND_XFER : (win == CAND_LOG ? KIND_LOG : KIND_FINISH)));
+      if constexpr (PRE) { /* one arrival candidate for all streams: the job type is in the list entry */
+        if (win == CAND_STREAM0) kind = (int)(dcsim_at<uint32_t>(c.blk, DCSIM_OFF_AW_META)[c.H->arr_cursor - c.H->aw_base] & 1u);
       }
+      const uint32_t row = c.P->rec.counts[0];
+      if (row < c.P->rec.trace_cap) { c.P->rec.trace[row].t = t; c.P->rec.trace[row].seq = seq; c.P->rec.trace[row].kind = (uint32_t)kind; }
+      c.P->rec.counts[0] = row + 1u;
     }
 
-    if (kind == KIND_ARR_INF || kind == KIND_ARR_TRN) {
+    if (is_arrival) {
       if constexpr (PRE) {
         dcsim_handle_arrival_listed(c, r);
       } else {
@@ -1663,11 +1665,11 @@ DCSIM_DEV uint32_t dcsim_replica_run(dcsim_ctx_t& c, uint64_t r) {
         dcsim_handle_arrival(c, win - CAND_STREAM0);
       }
       dcsim_warp_sync();
-    } else if (kind == KIND_XFER) {
+    } else if (win == CAND_XFER) {
       if (c.lane == 0) { c.H->ev_xfer++; dcsim_handle_xfer<CAP>(c, (int)c.H->xmin_slot); }
       dcsim_warp_sync();
       dcsim_rescan_xfer(c);
-    } else if (kind == KIND_FINISH) {
+    } else if (win < CAND_STREAM0) {
       const int d = win - CAND_DC0;
       const int slot = DCI(c, DI_FMIN_SLOT)[d];
       if (c.lane == 0) { c.H->ev_fin++; dcsim_finish_account(c, r, d, slot); }
@@ -1675,20 +1677,23 @@ DCSIM_DEV uint32_t dcsim_replica_run(dcsim_ctx_t& c, uint64_t r) {
       if (c.lane == 0) { dcsim_dequeue_loop<CAP>(c, d); dcsim_refresh_power(c, d); }
       dcsim_warp_sync();
       dcsim_rescan_dc(c, d);
-    } else if (kind == KIND_LOG) {
+    } else if (win == CAND_LOG) {
       if (c.lane == 0) c.H->ev_log++;
       dcsim_handle_log<CAP>(c);
     } else if constexpr (CAP) { /* a superseded job_finish: it advanced the clock and accrued energy, nothing else (SIM:456-461) */
       if (c.lane == 0) {
         c.H->ev_fin++;
-        const uint32_t k = c.H->smin_slot, last = c.H->n_stale - 1u;
-        dcsim_at<double>(c.blk, c.P->L.st_t)[k] = dcsim_at<double>(c.blk, c.P->L.st_t)[last];
-        dcsim_at<uint32_t>(c.blk, c.P->L.st_seq)[k] = dcsim_at<uint32_t>(c.blk, c.P->L.st_seq)[last];
+        const uint32_t ks = c.H->smin_slot, last = c.H->n_stale - 1u;
+        dcsim_at<double>(c.blk, c.P->L.st_t)[ks] = dcsim_at<double>(c.blk, c.P->L.st_t)[last];
+        dcsim_at<uint32_t>(c.blk, c.P->L.st_seq)[ks] = dcsim_at<uint32_t>(c.blk, c.P->L.st_seq)[last];
         c.H->n_stale = last;
       }
       dcsim_warp_sync();
       dcsim_rescan_stale(c);
     }
+    } /* 16-event chunk */
+    done_here += k;
+    if (finished) break;
   }
   if (finished && c.H->done == 0u) {
     dcsim_replica_tail(c);

@@ -53,6 +53,7 @@ long long hostemu_run_batch(const void* spec_blob, size_t spec_bytes, uint64_t n
   P->rec.trace_replica = trace ? rec_replica : -1; P->rec.log_replica = (jobs || cluster) ? rec_replica : -1;
   if (counts) counts[0] = counts[1] = counts[2] = 0;
   P->n_replicas = n_replicas; P->seed0 = seed0; P->max_events = chunk_events;
+  P->budget32 = (chunk_events == 0ull || chunk_events > 0xfffffffeull) ? 0xffffffffu : (uint32_t)chunk_events;
   P->end_eps = P->spec.end_time + 1e-9;
   P->state = (char*)calloc(n_replicas, (size_t)P->L.total_bytes);
   P->queues = (char*)calloc(n_replicas, (size_t)P->L.queue_bytes + 16);
