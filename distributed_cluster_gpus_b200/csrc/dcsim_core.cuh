@@ -164,6 +164,7 @@ struct dcsim_layout_t {
   int32_t xf_t, xf_size, xf_seq, xf_meta, xf_jid;
   int32_t rn_t, rn_pw, rn_tpt, rn_start, rn_size, rn_f, rn_seq, rn_meta, rn_jid;
   int32_t rng_buf;
+  int32_t memo_f64, memo_n; /* per (DC, jtype): the last (n, f) a job started with and its T(n,f), n*P_gpu(f), 1/T */
   int32_t bandit_n, bandit_s;
   /* power-cap controller (algo = cap_greedy with power_cap > 0 only) */
   int32_t rn_done, rn_upd;           /* per running record: units_done, last_update (models.py:20-21) */
@@ -236,6 +237,8 @@ static inline void dcsim_make_layout(const dcsim_spec_t* sp, dcsim_layout_t* L, 
   L->rn_meta = o; o += nr * 4;
   if (!L->lean) { L->rn_jid = o; o += nr * 4; }
   o = dcsim_align16(o);
+  L->memo_f64 = o; o += sp->n_dc * 2 * 4 * 8;
+  L->memo_n = o; o = dcsim_align16(o + sp->n_dc * 2 * 4);
   if (!prepass) { /* in-kernel sampling (legacy mode): the Philox window; the arrival-list window of the fixed head idles */
     L->rng_buf = o; o += (int32_t)DCSIM_RNG_WINDOW * 4;
   }
@@ -1024,15 +1027,30 @@ DCSIM_DEV void dcsim_start_job(dcsim_ctx_t& c, int d, int jt, double size, uint3
   const int slot = *nrun;
   if (slot >= L.cap_run) { c.H->status |= DCSIM_ST_RUN_OVERFLOW; return; }
   DCI(c, DI_BUSY)[d] += n;
-  const double T_unit = dcsim_step_time(n, f, k);
+  /* T(n,f), n*P_gpu(f) and 1/T cost three FP64 divisions and a cube per start (~85 instructions); jobs of one type at
+   * one DC mostly start with the (n, f) of the previous one, so the last result is kept per (DC, jtype).  Same
+   * operations on the same inputs: the cached values are bit-identical to recomputing. */
+  double T_unit, pw_job, tpt_job;
+  {
+    double* mf = dcsim_at<double>(c.blk, L.memo_f64) + (d * 2 + jt) * 4; /* f, T, n*P, 1/T */
+    int32_t* mn = dcsim_at<int32_t>(c.blk, L.memo_n) + (d * 2 + jt);
+    if (*mn == n && mf[0] == f) {
+      T_unit = mf[1]; pw_job = mf[2]; tpt_job = mf[3];
+    } else {
+      T_unit = dcsim_step_time(n, f, k);
+      pw_job = dcsim_task_power(n, f, k);
+      tpt_job = 1.0 / T_unit; /* SIM:956 */
+      *mn = n; mf[0] = f; mf[1] = T_unit; mf[2] = pw_job; mf[3] = tpt_job;
+    }
+  }
   const double t_fin = c.now + size * T_unit;
   const int i = d * L.cap_run + slot;
   const bool ok = dcsim_schedulable(c, t_fin);
   const uint32_t seq = ok ? c.seq++ : 0xffffffffu;
   dcsim_at<double>(c.blk, L.rn_t)[i] = ok ? t_fin : DCSIM_INF; /* a dropped finish holds its GPUs for ever */
   dcsim_at<uint32_t>(c.blk, L.rn_seq)[i] = seq;
-  dcsim_at<double>(c.blk, L.rn_pw)[i] = dcsim_task_power(n, f, k);
-  dcsim_at<double>(c.blk, L.rn_tpt)[i] = 1.0 / T_unit; /* SIM:956 */
+  dcsim_at<double>(c.blk, L.rn_pw)[i] = pw_job;
+  dcsim_at<double>(c.blk, L.rn_tpt)[i] = tpt_job;
   dcsim_at<double>(c.blk, L.rn_start)[i] = c.now;
   dcsim_at<uint32_t>(c.blk, L.rn_meta)[i] = (uint32_t)n | ((uint32_t)jt << 16) | (ing << 17);
   if (CAP || L.lean == 0) {
@@ -1246,9 +1264,7 @@ DCSIM_DEV void dcsim_handle_arrival_listed(dcsim_ctx_t& c, uint64_t r) {
     const uint32_t meta = dcsim_at<uint32_t>(c.blk, DCSIM_OFF_AW_META)[i];
     const uint32_t stream = meta & 15u;
     const int jt = (int)(stream & 1u), ing = (int)(stream >> 1), dc_sel = (int)((meta >> 4) & 7u);
-    const uint32_t jid = k + 1u; /* SIM:539: jids count arrivals */
-    H->jid = jid;
-    H->ev_arr++;
+    const uint32_t jid = k + 1u; /* SIM:539: jids count arrivals (H->jid and H->ev_arr follow from the cursor at stage-out) */
     const double t_x = c.now + sp.transfer_s[ing][dc_sel][jt];
     if (dcsim_schedulable(c, t_x)) { /* SIM:580-588 */
       const uint32_t slot = H->n_xfer;
@@ -1763,6 +1779,7 @@ DCSIM_DEV uint32_t dcsim_replica_step(const dcsim_kparams_t* P, uint64_t r, char
   if (c.H->done == 0u) n = dcsim_replica_run<CAP, PRE>(c, r);
   dcsim_warp_sync();
   if (c.lane == 0) {
+    if constexpr (PRE) { c.H->ev_arr = c.H->arr_cursor; c.H->jid = c.H->arr_cursor; } /* one list entry = one arrival = one jid */
     c.H->n_events = c.H->ev_arr + c.H->ev_xfer + c.H->ev_fin + c.H->ev_log; /* every processed event is one of these */
     c.H->rng_pos = c.rng_pos; c.H->seq = c.seq; c.H->now = c.now; c.H->last_t = c.H->n_events ? c.now : 0.0;
   }

@@ -1,9 +1,7 @@
 #!/bin/sh
-# GPU tests + same-box A/B of variants/libdcsim_base.so against the in-tree build (and the in-tree build with 4-warp CTAs)
+# GPU tests + same-box A/B of variants/libdcsim_base.so against the in-tree build
 {
 (timeout 600 python -m pytest tests -m gpu -x -q) 2>&1 | tail -1
 sh tools/ab_bench.sh variants/libdcsim_base.so distributed_cluster_gpus_b200/csrc/libdcsim_b200.so
-echo "--- in-tree build, CTA width pinned to 4 warps (DCSIM_WPC=4)"
-DCSIM_WPC=4 sh tools/ab_bench.sh distributed_cluster_gpus_b200/csrc/libdcsim_b200.so
 } > gpurun_out/ab_round.log 2>&1
 cat gpurun_out/ab_round.log
