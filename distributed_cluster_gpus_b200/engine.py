@@ -192,6 +192,7 @@ def describe_status(bits: int) -> str:
 # spec blob, replica count, device, stream) re-seeds the existing device allocations (dcsim_reset) instead of
 # freeing and re-allocating tens of GB.  free_cached_engine() drops it.
 _CACHED = {"key": None, "engine": None}
+_CACHED_LOGGED = {"key": None, "engine": None}   # the one-replica companion engine of LoggedReplica
 
 
 def _cache_key(sp, n_replicas, device, cuda_stream):
@@ -218,9 +219,47 @@ def release_engine(eng, sp, device=0, cuda_stream=0):
 
 
 def free_cached_engine():
-    if _CACHED["engine"] is not None:
-        _CACHED["engine"].close()
-    _CACHED["engine"], _CACHED["key"] = None, None
+    for slot in (_CACHED, _CACHED_LOGGED):
+        if slot["engine"] is not None:
+            slot["engine"].close()
+        slot["engine"], slot["key"] = None, None
+
+
+class LoggedReplica:
+    """The cluster_log.csv / job_log.csv rows of ONE replica of a batch, produced by a one-replica companion engine
+    that runs the same trajectory (same spec, same key) on its own stream WHILE the batch runs.
+
+    Switching the recorders on inside the batch makes every replica carry the job log's fields in its running-job
+    records (60 instead of 40 bytes; fewer resident warps: +9 % on the 65 536-replica bench batch); a single warp
+    next to the batch's grid costs nothing — it is launched first, is resident before the grid fills the GPU, and
+    finishes long before it.  Results are identical by construction (one replica = one deterministic trajectory)."""
+
+    def __init__(self, sp, seed, replica_id, device, job_rows, cluster_rows, rng="philox"):
+        key = (sp.to_bytes(), int(device), os.environ.get("DCSIM_PREPASS", ""))
+        if _CACHED_LOGGED["engine"] is not None and _CACHED_LOGGED["key"] == key:
+            self.eng, _CACHED_LOGGED["engine"], _CACHED_LOGGED["key"] = _CACHED_LOGGED["engine"], None, None
+            self.eng.reset(seed, replica_id)
+        else:
+            if _CACHED_LOGGED["engine"] is not None:
+                _CACHED_LOGGED["engine"].close()
+                _CACHED_LOGGED["engine"], _CACHED_LOGGED["key"] = None, None
+            self.eng = BatchedEngine(sp, 1, seed, replica_id, device)    # its own (non-blocking) stream
+        self._key = key
+        self.eng.set_rng(rng)
+        self.eng.set_logging(0, job_rows, cluster_rows)
+        self.eng.advance(0, sync=False)                                 # in flight; the caller launches the batch now
+
+    def collect(self):
+        """(status bits, job rows, cluster rows); synchronises with the companion's stream."""
+        bits = int(self.eng.summary()[0, S.S_STATUS])
+        return bits, self.eng.job_log(), self.eng.cluster_log()
+
+    def release(self, keep=True):
+        if keep:
+            _CACHED_LOGGED["engine"], _CACHED_LOGGED["key"] = self.eng, self._key
+        else:
+            self.eng.close()
+        self.eng = None
 
 
 def run_to_completion(spec_factory, n_replicas, base_seed, first_replica_id=0, device=0, cuda_stream=0,

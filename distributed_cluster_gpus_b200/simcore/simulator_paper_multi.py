@@ -17,7 +17,7 @@ from typing import Dict, Optional, Tuple, Union
 import numpy as np
 
 from .. import spec as S
-from ..engine import RNG_KINDS, release_engine, run_to_completion
+from ..engine import RNG_KINDS, LoggedReplica, release_engine, run_to_completion
 from .arrivals import ArrivalConfig
 from .models import DataCenter
 from .network import Graph, Ingress
@@ -111,24 +111,55 @@ class MultiIngressPaperSimulator:
         job_cap = int(expected_jobs * 1.2 + 10 * expected_jobs ** 0.5 + 64)
         cluster_cap = n_ticks * len(self.dcs)
 
+        # The CSV rows of replica 0 come from a one-replica companion engine running beside the batch (LoggedReplica):
+        # recorders inside a big batch cost every replica occupancy.  A batch of one simply logs itself.
+        companion = None
+        in_batch_log = self.write_logs and self.replicas == 1
+        if self.write_logs and not in_batch_log:
+            companion = LoggedReplica(self._spec, self.rng_seed, self.first_replica_id, self.device, job_cap, cluster_cap, self.rng)
+
         def configure(eng):
             eng.set_rng(self.rng)
             eng.enable_latency_histogram()
-            if self.write_logs:
+            if in_batch_log:
                 eng.set_logging(0, job_cap, cluster_cap)
 
-        eng, summ = run_to_completion(self._flatten, self.replicas, self.rng_seed, self.first_replica_id, self.device,
-                                      self.cuda_stream, configure=configure)
+        try:
+            eng, summ = run_to_completion(self._flatten, self.replicas, self.rng_seed, self.first_replica_id, self.device,
+                                          self.cuda_stream, configure=configure)
+        except BaseException:
+            if companion is not None:
+                companion.release(keep=False)
+            raise
         try:
             self.summary = summ
             self.latency_histogram = eng.latency_histogram()     # [2, 128] job-latency counts of the whole batch
             self.launch_info = eng.launch_info()
             self._store_replica0(summ[0])
-            if self.write_logs:
+            if in_batch_log:
                 self._write_csvs(eng.job_log(), eng.cluster_log())
+            elif companion is not None:
+                bits, jobs, cluster = companion.collect()
+                if bits or eng.spec.to_bytes() != self._spec.to_bytes():
+                    # the batch (or the companion) needed larger capacities: log replica 0 again under the final spec
+                    companion.release(keep=False)
+                    companion = None
+
+                    def configure_one(e):
+                        e.set_rng(self.rng)
+                        e.set_logging(0, job_cap, cluster_cap)
+                    one, _ = run_to_completion(lambda caps: eng.spec, 1, self.rng_seed, self.first_replica_id, self.device,
+                                               0, configure=configure_one)
+                    jobs, cluster = one.job_log(), one.cluster_log()
+                    one.close()
+                self._write_csvs(jobs, cluster)
         except BaseException:
             eng.close()
+            if companion is not None:
+                companion.release(keep=False)
             raise
+        if companion is not None:
+            companion.release(keep=self.keep_engine)
         if self.keep_engine:
             release_engine(eng, eng.spec, self.device, self.cuda_stream)   # next run of this shape re-seeds it
         else:

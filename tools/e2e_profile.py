@@ -21,3 +21,17 @@ for rep in range(2):
     sim._write_csvs(j, c); t0 = T("write csvs", t0)
     eng.close(); t0 = T("engine close (free)", t0)
     t0 = time.perf_counter(); sim.run(); T("sim.run() total", t0)
+
+# steady state of the drop-in call (parked engine reused): where the host time goes
+import cProfile, pstats, io
+for rep in range(2):
+    sim = MultiIngressPaperSimulator(router_policy=pc.build_router_policy(), logger=logging.getLogger("x"), sim_duration=sc["duration"], log_interval=sc["log_interval"], log_path="/dev/shm/e2e", rng_seed=7 + rep, algo=sc["algo"], show_progress=False, replicas=R, **SC.build_inputs(sc))
+    sim.run()
+pr = cProfile.Profile()
+t0 = time.perf_counter()
+pr.enable()
+sim = MultiIngressPaperSimulator(router_policy=pc.build_router_policy(), logger=logging.getLogger("x"), sim_duration=sc["duration"], log_interval=sc["log_interval"], log_path="/dev/shm/e2e", rng_seed=11, algo=sc["algo"], show_progress=False, replicas=R, **SC.build_inputs(sc))
+sim.run()
+pr.disable()
+print("steady-state ctor+run(): %.1f ms" % (1000 * (time.perf_counter() - t0)))
+out = io.StringIO(); pstats.Stats(pr, stream=out).sort_stats("cumulative").print_stats(22); print(out.getvalue()[:5000])
