@@ -263,18 +263,25 @@ class LoggedReplica:
 
 
 def run_to_completion(spec_factory, n_replicas, base_seed, first_replica_id=0, device=0, cuda_stream=0,
-                      max_retries=3, configure=None):
+                      max_retries=3, configure=None, while_running=None):
     """Runs all replicas to end_time.  A replica that overflowed a capacity is never trusted: the whole batch
     is re-run with that capacity raised (``spec_factory(caps)`` rebuilds the blob).  Returns (engine, summary);
-    hand the engine back with release_engine() (reuse) or close()."""
+    hand the engine back with release_engine() (reuse) or close().  ``while_running()`` is called once, after the
+    kernels of the first attempt were launched and before the host waits for them (host work that can overlap)."""
     caps = {}
     for attempt in range(max_retries + 1):
         sp = spec_factory(dict(caps))
         eng = acquire_engine(sp, n_replicas, base_seed, first_replica_id, device, cuda_stream)
         if configure:
             configure(eng)
-        eng.advance(0)
-        summ = eng.summary()
+        eng.advance(0, sync=False)
+        if while_running is not None and attempt == 0:
+            try:
+                while_running()
+            except BaseException:
+                eng.close()
+                raise
+        summ = eng.summary()                     # synchronises with the batch's stream
         bits = int(np.bitwise_or.reduce(summ[:, S.S_STATUS].astype(np.int64)))
         if bits == 0:
             return eng, summ

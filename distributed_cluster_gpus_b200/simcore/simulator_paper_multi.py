@@ -124,9 +124,21 @@ class MultiIngressPaperSimulator:
             if in_batch_log:
                 eng.set_logging(0, job_cap, cluster_cap)
 
+        early = {}
+
+        def while_running():
+            # the companion's single replica is done long before the batch: fetch its rows and write the CSV files
+            # while the GPU is still busy with the batch
+            if companion is not None:
+                bits, jobs, cluster = companion.collect()
+                early["bits"] = bits
+                if bits == 0:
+                    self._write_csvs(jobs, cluster)
+                    early["written"] = True
+
         try:
             eng, summ = run_to_completion(self._flatten, self.replicas, self.rng_seed, self.first_replica_id, self.device,
-                                          self.cuda_stream, configure=configure)
+                                          self.cuda_stream, configure=configure, while_running=while_running)
         except BaseException:
             if companion is not None:
                 companion.release(keep=False)
@@ -139,8 +151,7 @@ class MultiIngressPaperSimulator:
             if in_batch_log:
                 self._write_csvs(eng.job_log(), eng.cluster_log())
             elif companion is not None:
-                bits, jobs, cluster = companion.collect()
-                if bits or eng.spec.to_bytes() != self._spec.to_bytes():
+                if not early.get("written") or eng.spec.to_bytes() != self._spec.to_bytes():
                     # the batch (or the companion) needed larger capacities: log replica 0 again under the final spec
                     companion.release(keep=False)
                     companion = None
@@ -150,9 +161,8 @@ class MultiIngressPaperSimulator:
                         e.set_logging(0, job_cap, cluster_cap)
                     one, _ = run_to_completion(lambda caps: eng.spec, 1, self.rng_seed, self.first_replica_id, self.device,
                                                0, configure=configure_one)
-                    jobs, cluster = one.job_log(), one.cluster_log()
+                    self._write_csvs(one.job_log(), one.cluster_log())
                     one.close()
-                self._write_csvs(jobs, cluster)
         except BaseException:
             eng.close()
             if companion is not None:
