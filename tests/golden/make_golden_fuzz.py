@@ -1,5 +1,6 @@
 """Regenerates tests/golden/fuzz_reference.json: RANDOM scenarios (generator of tools/fuzz_core.py, fixed seed) run
-through the UNMODIFIED reference with the Philox stream injected (oracle/ref_harness.py) — only possible where
+through the UNMODIFIED reference — once with the Philox stream injected (oracle/ref_harness.py) and once exactly as
+shipped, on its own Mersenne Twister ("run_mt") — only possible where
 /root/reference is mounted.  The fixture pins the oracle (tests/test_oracle_vs_reference.py) and, through it, the
 device path on parameter combinations nobody picked by hand.  Usage: python tests/golden/make_golden_fuzz.py [cases]
 """
@@ -53,6 +54,7 @@ def main():
         signal.alarm(40)
         try:
             run = run_reference(sc, seed, rng="philox")
+            run_mt = run_reference(sc, seed, rng="mt")      # the reference exactly as shipped (its own MT19937)
         except _Timeout:
             skipped += 1
             print("case", case, "skipped: reference did not finish in 40 s", sc, flush=True)
@@ -60,7 +62,8 @@ def main():
         finally:
             signal.alarm(0)
         run.pop("ref_wall_s", None)
-        cases.append({"scenario": sc, "run": run})
+        run_mt.pop("ref_wall_s", None)
+        cases.append({"scenario": sc, "run": run, "run_mt": run_mt})
         if case % 20 == 0:
             print(case, sc["algo"], run["events"], "events", "%.0f s" % (time.time() - t0), flush=True)
     doc = {"meta": {"generated_by": "tests/golden/make_golden_fuzz.py", "reference": "filrg/distributed_cluster_GPUs @ 9e78013",

@@ -234,3 +234,14 @@ def test_conditioning_probe_separates_chaotic_scenarios(oracle, hostemu):
     with open(os.path.join(GOLDEN_DIR, "ill_conditioned_cap_greedy_case.json")) as f:
         case = json.load(f)
     assert moved(case["scenario"], case["seed"]) >= 1e-7
+
+
+def test_device_core_mt_mode_against_stock_reference_on_random_scenarios(hostemu):
+    """rng = MT19937 of the device core (host build) against the reference as shipped on the 160 random scenarios."""
+    from conftest import load_fuzz_reference
+    from test_oracle_vs_reference import check_row_against_golden
+    for c in load_fuzz_reference():
+        sc, run = c["scenario"], c["run_mt"]
+        got = hostemu.run_batch(SC.to_spec(sc).to_bytes(), 1, run["seed"], rng_kind=1)
+        assert got["events"] == run["events"], sc
+        check_row_against_golden(got["summary"][0], run, sc["n_dc"], [])
