@@ -138,6 +138,32 @@ def oracle_rate(sc, n_replicas, threads, seed=123):
     return events, dt
 
 
+def host_cpu_info(sc):
+    """What the host really offers the CPU arm: logical CPUs, this process's affinity, a cgroup CPU quota if one is
+    set, and the port's single-thread rate (so that the many-thread figure can be read as a scaling factor)."""
+    info = {"logical_cpus": os.cpu_count() or 1, "affinity_cpus": None, "cgroup_quota_cpus": None}
+    try:
+        info["affinity_cpus"] = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        pass
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:                       # cgroup v2: "<quota|max> <period>"
+            quota, period = f.read().split()[:2]
+            if quota != "max":
+                info["cgroup_quota_cpus"] = round(int(quota) / int(period), 2)
+    except (OSError, ValueError):
+        try:
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as f, open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as g:
+                quota, period = int(f.read()), int(g.read())            # cgroup v1: -1 = no quota
+                if quota > 0:
+                    info["cgroup_quota_cpus"] = round(quota / period, 2)
+        except (OSError, ValueError):
+            pass
+    ev, dt = oracle_rate(sc, 4, 1, seed=77)
+    info["single_thread_events_per_s"] = ev / dt
+    return info
+
+
 def cpu_baseline(sc, target_s=12.0):
     cores = os.cpu_count() or 1
     oracle_rate(sc, cores, cores)                            # load + page in
@@ -145,7 +171,7 @@ def cpu_baseline(sc, target_s=12.0):
     n = int(max(cores, min(16384, cores * max(1.0, target_s / max(dt, 1e-3)))))
     n -= n % cores
     ev, dt = oracle_rate(sc, n, cores, seed=1000)
-    return {"value": ev / dt, "unit": UNIT, "cores": cores, "kind": "port",
+    return {"value": ev / dt, "unit": UNIT, "cores": cores, "kind": "port", "host": host_cpu_info(sc),
             "sample": f"{n} replicas of the same workload ({ev} events) in {dt:.1f} s on {cores} threads; "
                       "oracle/dcsim_oracle.c = C restatement of the reference's Python loop (the Python original "
                       "measured 7-20 k events/s/core on this scenario, tests/golden/*.json ref_wall_s)"}
@@ -174,7 +200,8 @@ def run_reference_arm(args, world, rank):
             "warmup": args.warmup, "ms_per_step": 1000.0 * total / max(args.steps, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(sc, args, world, {"sample_replicas_per_step": n}),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "host": host_cpu_info(sc)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
