@@ -34,30 +34,36 @@ extern __shared__ __align__(16) char dcsim_smem[];
  * separate instantiation because merely inlining that cold code costs the common path 17 % (measured,
  * profiles/r01_variants_ab.md). */
 /* PRE = arrivals come from the list written by dcsim_arrivals_kernel (no sampling in this kernel). */
-/* STAGED = the replica's state block is staged in shared memory for the launch (the normal case).  When it is
- * too large for that (e.g. one running-job record per GPU of a 512-GPU DC), the !STAGED instantiation works on it in
- * place in HBM/L2 — same core, the block is just a pointer — slower but not refused.  A compile-time switch: a
- * run-time select would turn every state access into a generic load/store (measured -15 %). */
-template <bool CAP, bool PRE, bool STAGED>
+/* MODE = where the replica's state block lives during the launch (a compile-time switch: a run-time select would turn
+ * every state access into a generic load/store, measured -15 %):
+ *   DCSIM_MODE_STAGED  the whole block is staged in shared memory (small blocks: 4 DC x 64 is 5.6 kB, 32 warps/SM);
+ *   DCSIM_MODE_HEAD    only the head [0, L.rec_off) — header, event set, per-DC arrays, arrival window, transfer pool —
+ *                      is staged; the running-job records stay at the block's home in HBM/L2 and are touched once per
+ *                      job_finish (dcsim_handle_finish) and written once per start.  Picked when the whole block would
+ *                      leave the SM below its 32 warps (8 DC x 256: 17.5 kB -> 12 warps/SM; head 4.7 kB -> 32);
+ *   DCSIM_MODE_INPLACE nothing is staged (even the head exceeds a CTA's shared memory): same core on the HBM copy. */
+enum { DCSIM_MODE_INPLACE = 0, DCSIM_MODE_STAGED = 1, DCSIM_MODE_HEAD = 2 };
+template <bool CAP, bool PRE, int MODE>
 __global__ void __launch_bounds__(DCSIM_MAX_WARPS_PER_CTA * 32, DCSIM_MIN_CTAS_PER_SM)
 dcsim_advance_kernel(const __grid_constant__ dcsim_kparams_t P, unsigned long long* __restrict__ events_total) {
   const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31u);
   const int wpc = (int)(blockDim.x >> 5);
   const uint64_t r = (uint64_t)blockIdx.x * (uint64_t)wpc + (uint64_t)warp;
   if (r >= P.n_replicas) return; /* whole warps leave together */
-  const int bytes = P.L.total_bytes;
-  char* home = P.state + r * (uint64_t)bytes;
-  char* blk = STAGED ? dcsim_smem + (size_t)warp * (size_t)bytes : home;
+  const int bytes = MODE == DCSIM_MODE_HEAD ? P.L.rec_off : P.L.total_bytes; /* what is staged */
+  char* home = P.state + r * (uint64_t)P.L.total_bytes;
+  char* blk = MODE != DCSIM_MODE_INPLACE ? dcsim_smem + (size_t)warp * (size_t)bytes : home;
+  char* rec = MODE == DCSIM_MODE_STAGED ? blk : home;
   const bool fresh = reinterpret_cast<const dcsim_hdr_t*>(home)->initialized == 0u;
-  if (STAGED && !fresh) { /* resume: coalesced 16-byte loads of the replica's block */
+  if (MODE != DCSIM_MODE_INPLACE && !fresh) { /* resume: coalesced 16-byte loads of the replica's block */
     const uint4* src = reinterpret_cast<const uint4*>(home);
     uint4* dst = reinterpret_cast<uint4*>(blk);
     for (int i = lane; i < bytes / 16; i += 32) dst[i] = src[i];
   }
   __syncwarp();
-  const uint32_t n = dcsim_replica_step<CAP, PRE>(&P, r, blk, fresh);
+  const uint32_t n = dcsim_replica_step<CAP, PRE>(&P, r, blk, rec, fresh);
   __syncwarp();
-  if (STAGED) {
+  if (MODE != DCSIM_MODE_INPLACE) {
     const uint4* src = reinterpret_cast<const uint4*>(blk);
     uint4* dst = reinterpret_cast<uint4*>(home);
     for (int i = lane; i < bytes / 16; i += 32) dst[i] = src[i];
@@ -87,13 +93,13 @@ __global__ void dcsim_hist_reduce_kernel(const uint32_t* __restrict__ hist, uint
 }
 
 typedef void (*dcsim_advance_fn)(const dcsim_kparams_t, unsigned long long*);
-static dcsim_advance_fn dcsim_pick_kernel(bool cap, bool pre, bool staged) {
-  static const dcsim_advance_fn table[8] = {
-      dcsim_advance_kernel<false, false, false>, dcsim_advance_kernel<false, false, true>,
-      dcsim_advance_kernel<false, true, false>,  dcsim_advance_kernel<false, true, true>,
-      dcsim_advance_kernel<true, false, false>,  dcsim_advance_kernel<true, false, true>,
-      dcsim_advance_kernel<true, true, false>,   dcsim_advance_kernel<true, true, true>};
-  return table[(cap ? 4 : 0) + (pre ? 2 : 0) + (staged ? 1 : 0)];
+static dcsim_advance_fn dcsim_pick_kernel(bool cap, bool pre, int mode) {
+  static const dcsim_advance_fn table[12] = {
+      dcsim_advance_kernel<false, false, 0>, dcsim_advance_kernel<false, false, 1>, dcsim_advance_kernel<false, false, 2>,
+      dcsim_advance_kernel<false, true, 0>,  dcsim_advance_kernel<false, true, 1>,  dcsim_advance_kernel<false, true, 2>,
+      dcsim_advance_kernel<true, false, 0>,  dcsim_advance_kernel<true, false, 1>,  dcsim_advance_kernel<true, false, 2>,
+      dcsim_advance_kernel<true, true, 0>,   dcsim_advance_kernel<true, true, 1>,   dcsim_advance_kernel<true, true, 2>};
+  return table[(cap ? 6 : 0) + (pre ? 3 : 0) + mode];
 }
 
 /* Aggregates the summaries; every block reduces a slice, then one atomicAdd per component. */
@@ -147,7 +153,7 @@ struct dcsim {
   int want_job_log;                   /* layout the NEXT batch needs; applied lazily by ensure_layout() */
   int64_t trace_replica, log_replica;
   int launches;
-  int prepass, arrivals_ready, staged;
+  int prepass, arrivals_ready, mode; /* mode: DCSIM_MODE_* of the advance kernel for this handle's layout */
   double* d_arr_t;
   double* d_arr_size;
   uint32_t* d_arr_meta;
@@ -203,23 +209,22 @@ static int validate_spec(const dcsim_spec_t* sp) {
     const dcsim_dc_t* c = &sp->dc[d];
     if (c->total_gpus < 0 || c->n_freq < 1 || c->n_freq > DCSIM_MAX_FREQ)
       return set_err(NULL, DCSIM_E_INVALID, "spec: DC %s%lld has bad total_gpus / n_freq", "", d);
+    if (c->total_gpus > 65535) /* a running record packs the job's GPU count into 16 bits */
+      return set_err(NULL, DCSIM_E_INVALID, "spec: DC %s%lld has more than 65535 GPUs", "", d);
   }
   if (sp->algo < DCSIM_ALGO_DEFAULT || sp->algo > DCSIM_ALGO_CAP_GREEDY)
     return set_err(NULL, DCSIM_E_UNSUPPORTED, "spec: unknown algo id %s%lld", "", sp->algo);
   return DCSIM_OK;
 }
 
-/* Launch geometry for the handle's current state-block layout: warps per CTA, shared memory, staged / in place. */
-static cudaError_t size_launch(dcsim_t* h) {
-  cudaError_t e;
-  int smem_optin = 0, smem_sm = 0;
-  if ((e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device)) != cudaSuccess) return e;
-  if ((e = cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, h->device)) != cudaSuccess) return e;
+/* Launch geometry for the handle's current state-block layout: what is staged (whole block / head only / nothing),
+ * warps per CTA, shared memory.  DCSIM_RECORDS=shared|global forces the whole-block / head-only mode (A/B runs). */
+static int resident_warps_for(int bytes_per_warp, int smem_optin, int smem_sm, int* wpc_out) {
   /* warps per CTA: whichever of 4 / 2 / 1 keeps the most warps resident (each CTA also reserves 1 KB of shared
    * memory and an SM holds at most 32 CTAs); small state blocks end up at 4 x 8 CTAs, large ones at 1 or 2 */
   int wpc = 0, best_warps = 0;
   for (int cand = DCSIM_MAX_WARPS_PER_CTA; cand >= 1; cand >>= 1) {
-    const long long per_cta = (long long)cand * h->L.total_bytes;
+    const long long per_cta = (long long)cand * bytes_per_warp;
     if (per_cta > smem_optin) continue;
     int ctas = (int)(smem_sm / (per_cta + 1024));
     if (ctas > 32) ctas = 32;
@@ -227,15 +232,32 @@ static cudaError_t size_launch(dcsim_t* h) {
     if (warps > DCSIM_MIN_CTAS_PER_SM * DCSIM_MAX_WARPS_PER_CTA) warps = DCSIM_MIN_CTAS_PER_SM * DCSIM_MAX_WARPS_PER_CTA; /* register bound */
     if (warps > best_warps) { best_warps = warps; wpc = cand; }
   }
-  h->staged = 1;
-  if (wpc < 1) { /* the block does not fit a CTA's shared memory: run in place out of HBM/L2 */
-    h->staged = 0;
-    wpc = DCSIM_MAX_WARPS_PER_CTA;
+  *wpc_out = wpc;
+  return best_warps;
+}
+
+static cudaError_t size_launch(dcsim_t* h) {
+  cudaError_t e;
+  int smem_optin = 0, smem_sm = 0;
+  if ((e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device)) != cudaSuccess) return e;
+  if ((e = cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, h->device)) != cudaSuccess) return e;
+  int wpc_full = 0, wpc_head = 0;
+  const int warps_full = resident_warps_for(h->L.total_bytes, smem_optin, smem_sm, &wpc_full);
+  const int warps_head = resident_warps_for(h->L.rec_off, smem_optin, smem_sm, &wpc_head);
+  const char* force = getenv("DCSIM_RECORDS");
+  int mode, wpc, bytes;
+  if (wpc_full >= 1 && (warps_full >= warps_head || (force && force[0] == 's')) && !(force && force[0] == 'g' && wpc_head >= 1)) {
+    mode = DCSIM_MODE_STAGED; wpc = wpc_full; bytes = h->L.total_bytes;   /* records staged with the rest */
+  } else if (wpc_head >= 1) {
+    mode = DCSIM_MODE_HEAD; wpc = wpc_head; bytes = h->L.rec_off;          /* records stay in HBM/L2 */
+  } else { /* not even the head fits a CTA's shared memory: run in place out of HBM/L2 */
+    mode = DCSIM_MODE_INPLACE; wpc = DCSIM_MAX_WARPS_PER_CTA; bytes = 0;
   }
+  h->mode = mode;
   h->warps_per_cta = wpc;
-  h->smem_bytes = h->staged ? wpc * h->L.total_bytes : 0;
+  h->smem_bytes = wpc * bytes;
   h->ctas = (int)((h->n_replicas + (uint64_t)wpc - 1) / (uint64_t)wpc);
-  const dcsim_advance_fn kern = dcsim_pick_kernel(h->L.cap_stale != 0, h->prepass != 0, h->staged != 0);
+  const dcsim_advance_fn kern = dcsim_pick_kernel(h->L.cap_stale != 0, h->prepass != 0, h->mode);
   if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin)) != cudaSuccess) return e;
   cudaFuncAttributes fa;
   if ((e = cudaFuncGetAttributes(&fa, kern)) != cudaSuccess) return e;
@@ -402,7 +424,7 @@ static void fill_kparams(const dcsim_t* h, dcsim_kparams_t* P, uint64_t max_even
   P->state = h->d_state; P->queues = h->d_queues; P->summary = h->d_summary;
   P->end_eps = h->spec.end_time + 1e-9; /* SIM:161 */
   P->arr_t = h->d_arr_t; P->arr_size = h->d_arr_size; P->arr_meta = h->d_arr_meta; P->arr_hdr = h->d_arr_hdr; P->cap_arr = h->cap_arr;
-  P->staged = (uint32_t)h->staged;
+  P->staged = (uint32_t)h->mode;
   P->lat_hist = h->d_hist;
   P->mt_state = h->d_mt;
 }
@@ -433,7 +455,7 @@ int dcsim_advance(dcsim_t* h, uint64_t max_events_per_replica, uint64_t* total_e
   dcsim_kparams_t P;
   fill_kparams(h, &P, max_events_per_replica);
   const dim3 grid(h->ctas), block(h->warps_per_cta * 32);
-  dcsim_pick_kernel(h->L.cap_stale != 0, h->prepass != 0, h->staged != 0)<<<grid, block, h->smem_bytes, h->stream>>>(P, h->d_events);
+  dcsim_pick_kernel(h->L.cap_stale != 0, h->prepass != 0, h->mode)<<<grid, block, h->smem_bytes, h->stream>>>(P, h->d_events);
   CUDA_TRY(h, cudaGetLastError());
   h->launches++;
   if (total_events_out) {
@@ -583,6 +605,9 @@ int dcsim_launch_info(dcsim_t* h, dcsim_launch_info_t* out) {
   out->hbm_bytes_queues = (uint64_t)h->n_replicas * h->L.queue_bytes;
   out->arrivals_prepass = h->prepass;
   out->hbm_bytes_arrivals = h->prepass ? (uint64_t)h->n_replicas * ((uint64_t)h->cap_arr * 20ull + sizeof(dcsim_arrhdr_t)) : 0ull;
+  out->staging_mode = h->mode; out->state_block_bytes = h->L.total_bytes;
+  out->staged_bytes_per_replica = h->warps_per_cta ? h->smem_bytes / h->warps_per_cta : 0;
+  out->cap_stale = h->L.cap_stale;
   return DCSIM_OK;
 }
 

@@ -72,6 +72,14 @@ DCSIM_DEV int dcsim_bit_length(uint32_t n) { return 32 - __clz((int)n); }
 #define DCSIM_INF (__longlong_as_double(0x7ff0000000000000LL))
 #endif
 
+DCSIM_DEV double dcsim_hilo_f64(uint32_t hi, uint32_t lo) {
+#ifdef DCSIM_HOST_EMU
+  const uint64_t u = ((uint64_t)hi << 32) | (uint64_t)lo; double x; memcpy(&x, &u, 8); return x;
+#else
+  return __hiloint2double((int)hi, (int)lo);
+#endif
+}
+
 DCSIM_DEV double dcsim_bcast_f64(double x, int src) {
 #ifdef DCSIM_HOST_EMU
   (void)src; return x;
@@ -123,7 +131,10 @@ enum { /* per-DC f64 arrays inside the state block, each DCSIM_MAX_DC long */
   DF_ENERGY = 0,
   DF_LAST_T,     /* util_last_ts (SIM:430-436) AND last_energy_time (models.py:100-106): both are 0.0 until the
                     first event and are set to t on every event, so one slot carries both */
-  DF_UTIL_TIME, DF_UTIL_BEGIN, DF_ACC_UNIT, DF_CUR_FREQ, DF_POWER, DF_N
+  DF_UTIL_TIME, DF_UTIL_BEGIN, DF_ACC_UNIT, DF_CUR_FREQ, DF_POWER,
+  DF_PSUM,       /* sum of the running jobs' n*P_gpu(f) in dict (= start) order from 0.0 (SIM:168-179): extended by one
+                    addition when a job starts (the same additions a re-sum would do), re-summed when one leaves */
+  DF_N
 };
 enum { /* per-DC i32 arrays; FIFO rings are (head index, length) so no modulo is needed */
   DI_BUSY = 0, DI_NRUN, DI_QH_INF, DI_QN_INF, DI_QH_TRN, DI_QN_TRN, DI_FMIN_SLOT, DI_N
@@ -175,6 +186,8 @@ struct dcsim_layout_t {
   int32_t aw_t, aw_size, aw_meta, pend_seq;
   int32_t prepass;
   int32_t total_bytes;
+  int32_t rec_off;         /* the running-job records occupy [rec_off, total_bytes): the part of the block that may stay
+                              in HBM/L2 while [0, rec_off) is staged in shared memory ("head staged" launch mode) */
   int32_t cap_xfer, cap_run;
   int32_t cap_q[2];        /* FIFO entries per DC: [0]=inference [1]=training */
   int32_t lean;            /* 1: running records carry no size / f / jid (nobody reads them: no job log, bandit or cap) */
@@ -228,15 +241,6 @@ static inline void dcsim_make_layout(const dcsim_spec_t* sp, dcsim_layout_t* L, 
   L->xf_meta = o; o += cx * 4;
   L->xf_jid = o; o = dcsim_align16(o + cx * 4);
   const int32_t nr = sp->n_dc * cr;
-  L->rn_t = o; o += nr * 8;
-  L->rn_pw = o; o += nr * 8;
-  L->rn_tpt = o; o += nr * 8;
-  L->rn_start = o; o += nr * 8;
-  if (!L->lean) { L->rn_size = o; o += nr * 8; L->rn_f = o; o += nr * 8; }
-  L->rn_seq = o; o += nr * 4;
-  L->rn_meta = o; o += nr * 4;
-  if (!L->lean) { L->rn_jid = o; o += nr * 4; }
-  o = dcsim_align16(o);
   L->memo_f64 = o; o += sp->n_dc * 2 * 4 * 8;
   L->memo_n = o; o = dcsim_align16(o + sp->n_dc * 2 * 4);
   if (!prepass) { /* in-kernel sampling (legacy mode): the Philox window; the arrival-list window of the fixed head idles */
@@ -248,13 +252,10 @@ static inline void dcsim_make_layout(const dcsim_spec_t* sp, dcsim_layout_t* L, 
   }
   if (cap) {
     L->cap_stale = sp->cap_stale > 0 ? ((sp->cap_stale + 3) & ~3) : 64;
-    L->cap_atoms = nr * (DCSIM_MAX_FREQ - 1);
     int max_levels = 1;
     for (int d = 0; d < sp->n_dc; ++d) max_levels = sp->dc[d].n_freq > max_levels ? sp->dc[d].n_freq : max_levels;
     L->cap_atoms = (nr * (max_levels - 1) + 3) & ~3;
     if (L->cap_atoms < 4) L->cap_atoms = 4;
-    L->rn_done = o; o += nr * 8;
-    L->rn_upd = o; o += nr * 8;
     L->st_t = o; o += L->cap_stale * 8;
     L->at_rho = o; o += L->cap_atoms * 8;
     L->at_fto = o; o += L->cap_atoms * 8;
@@ -262,6 +263,18 @@ static inline void dcsim_make_layout(const dcsim_spec_t* sp, dcsim_layout_t* L, 
     L->at_ref = o; o += L->cap_atoms * 4;
     L->at_idx = o; o = dcsim_align16(o + L->cap_atoms * 4);
   }
+  /* the running-job records come last: everything in front of rec_off is the "head" (always staged) */
+  o = dcsim_align16(o);
+  L->rec_off = o;
+  L->rn_t = o; o += nr * 8;
+  L->rn_pw = o; o += nr * 8;
+  L->rn_tpt = o; o += nr * 8;
+  L->rn_start = o; o += nr * 8;
+  if (!L->lean) { L->rn_size = o; o += nr * 8; L->rn_f = o; o += nr * 8; }
+  if (cap) { L->rn_done = o; o += nr * 8; L->rn_upd = o; o += nr * 8; }
+  L->rn_seq = o; o += nr * 4;
+  L->rn_meta = o; o += nr * 4;
+  if (!L->lean) { L->rn_jid = o; o += nr * 4; }
   L->total_bytes = dcsim_align16(o);
   L->queue_bytes = (uint64_t)sp->n_dc * ((uint64_t)L->cap_q[0] + (uint64_t)L->cap_q[1]) * 16ull;
 }
@@ -325,6 +338,8 @@ DCSIM_DEV T* dcsim_at(char* blk, int32_t off) { return reinterpret_cast<T*>(blk 
 struct dcsim_ctx_t {
   const dcsim_kparams_t* P;
   char* blk;             /* this replica's state block (shared memory on the GPU) */
+  char* rec;             /* base the running-job record offsets (L.rn_*) apply to: blk when the records are staged with
+                            the rest of the block, the block's home in HBM/L2 when only the head is staged */
   char* q;               /* this replica's FIFOs (HBM) */
   dcsim_hdr_t* H;
   int lane;
@@ -830,17 +845,22 @@ DCSIM_DEV int dcsim_argmin_cand(dcsim_ctx_t& c, double* t_out, uint32_t* seq_out
 /* SIM:160-163: an event later than end_time + 1e-9 (or at +inf) is never scheduled and takes no seq. */
 DCSIM_DEV bool dcsim_schedulable(const dcsim_ctx_t& c, double t) { return !(t == DCSIM_INF) && !(t > c.P->end_eps); }
 
-/* Lane 0.  Re-derives DC d's estimated power exactly as SIM:168-179 does on every event:
- * running jobs summed in dict (= start) order from 0.0, then the idle term. */
+/* Lane 0.  DC d's estimated power as SIM:168-179 computes it on every event: the running jobs' powers summed in
+ * dict (= start) order from 0.0 — kept in DF_PSUM, see there — then the idle term. */
 DCSIM_DEV void dcsim_refresh_power(dcsim_ctx_t& c, int d) {
   const dcsim_dc_t& cfg = c.P->spec.dc[d];
-  const int n = DCI(c, DI_NRUN)[d];
-  const double* pw = dcsim_at<double>(c.blk, c.P->L.rn_pw) + d * c.P->L.cap_run;
-  double p_active = 0.0;
-  for (int i = 0; i < n; ++i) p_active += pw[i];
   const int idle = cfg.total_gpus - DCI(c, DI_BUSY)[d];
   const double p_idle = (double)idle * (cfg.power_gating ? cfg.p_sleep : cfg.p_idle);
-  DCF(c, DF_POWER)[d] = p_active + p_idle;
+  DCF(c, DF_POWER)[d] = DCF(c, DF_PSUM)[d] + p_idle;
+}
+
+/* Lane 0, cold (power-cap controller only: it changes a record's power in place).  DF_PSUM of DC d from scratch. */
+DCSIM_DEV void dcsim_resum_power(dcsim_ctx_t& c, int d) {
+  const int n = DCI(c, DI_NRUN)[d];
+  const double* pw = dcsim_at<double>(c.rec, c.P->L.rn_pw) + d * c.P->L.cap_run;
+  double p_active = 0.0;
+  for (int i = 0; i < n; ++i) p_active += pw[i];
+  DCF(c, DF_PSUM)[d] = p_active;
 }
 
 /* Warp.  Earliest job_finish among DC d's running records -> candidate slot d. */
@@ -848,7 +868,7 @@ DCSIM_DEV void dcsim_rescan_dc(dcsim_ctx_t& c, int d) {
   const int n = DCI(c, DI_NRUN)[d];
   const int off = d * c.P->L.cap_run;
   double t; uint32_t s;
-  const int k = dcsim_argmin_ts(dcsim_at<double>(c.blk, c.P->L.rn_t) + off, dcsim_at<uint32_t>(c.blk, c.P->L.rn_seq) + off,
+  const int k = dcsim_argmin_ts(dcsim_at<double>(c.rec, c.P->L.rn_t) + off, dcsim_at<uint32_t>(c.rec, c.P->L.rn_seq) + off,
                                 n, c.lane, &t, &s);
   if (c.lane == 0) {
     CAND_T(c)[CAND_DC0 + d] = k >= 0 ? t : DCSIM_INF;
@@ -868,55 +888,6 @@ DCSIM_DEV void dcsim_rescan_xfer(dcsim_ctx_t& c) {
     CAND_SEQ(c)[CAND_XFER] = k >= 0 ? s : 0xffffffffu;
     c.H->xmin_slot = (uint32_t)k;
   }
-  dcsim_warp_sync();
-}
-
-/* Warp.  Removes running record `k` of DC d keeping the others in start order (dict semantics, models.py:60). */
-template <bool CAP>
-DCSIM_DEV void dcsim_running_erase(dcsim_ctx_t& c, int d, int k) {
-  const dcsim_layout_t& L = c.P->L;
-  const int n = DCI(c, DI_NRUN)[d];
-  const int off = d * L.cap_run;
-  double* f64s[4] = {dcsim_at<double>(c.blk, L.rn_t) + off, dcsim_at<double>(c.blk, L.rn_pw) + off,
-                     dcsim_at<double>(c.blk, L.rn_tpt) + off, dcsim_at<double>(c.blk, L.rn_start) + off};
-  uint32_t* u32s[2] = {dcsim_at<uint32_t>(c.blk, L.rn_seq) + off, dcsim_at<uint32_t>(c.blk, L.rn_meta) + off};
-  const bool full = L.lean == 0;
-  double* sz = dcsim_at<double>(c.blk, L.rn_size) + off;
-  double* fq = dcsim_at<double>(c.blk, L.rn_f) + off;
-  uint32_t* ji = dcsim_at<uint32_t>(c.blk, L.rn_jid) + off;
-  for (int j0 = k; j0 < n - 1; j0 += DCSIM_LANES) {
-    const int j = j0 + c.lane;
-    const bool act = j < n - 1;
-    double a[4]; uint32_t b[2];
-    double c0 = 0.0, c1 = 0.0; uint32_t c2 = 0u;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) a[q] = act ? f64s[q][j + 1] : 0.0;
-#pragma unroll
-    for (int q = 0; q < 2; ++q) b[q] = act ? u32s[q][j + 1] : 0u;
-    if (full && act) { c0 = sz[j + 1]; c1 = fq[j + 1]; c2 = ji[j + 1]; }
-    dcsim_warp_sync();
-    if (act) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) f64s[q][j] = a[q];
-#pragma unroll
-      for (int q = 0; q < 2; ++q) u32s[q][j] = b[q];
-      if (full) { sz[j] = c0; fq[j] = c1; ji[j] = c2; }
-    }
-    if (j0 + DCSIM_LANES < n - 1) dcsim_warp_sync(); /* next chunk reads what this one did not write; keep order */
-  }
-  if constexpr (CAP) { /* the controller's per-record progress fields travel with the record (cold path) */
-    double* ex[2] = {dcsim_at<double>(c.blk, L.rn_done) + off, dcsim_at<double>(c.blk, L.rn_upd) + off};
-    for (int j0 = k; j0 < n - 1; j0 += DCSIM_LANES) {
-      const int j = j0 + c.lane;
-      const bool act = j < n - 1;
-      const double a0 = act ? ex[0][j + 1] : 0.0, a1 = act ? ex[1][j + 1] : 0.0;
-      dcsim_warp_sync();
-      if (act) { ex[0][j] = a0; ex[1][j] = a1; }
-      dcsim_warp_sync();
-    }
-  }
-  dcsim_warp_sync(); /* every lane has read n (and finished its copies) before the count changes */
-  if (c.lane == 0) DCI(c, DI_NRUN)[d] = n - 1;
   dcsim_warp_sync();
 }
 
@@ -1012,7 +983,7 @@ DCSIM_COLD void dcsim_joblog_write(const dcsim_kparams_t* P, uint32_t jid, uint3
   if (r < P->rec.jobs_cap) {
     dcsim_job_rec_t* o = P->rec.jobs + r;
     o->jid = jid; o->ingress = (uint8_t)(meta >> 17); o->jtype = (uint8_t)((meta >> 16) & 1u);
-    o->dc = (uint8_t)d; o->n_gpus = (uint8_t)(meta & 0xffffu); o->size = size;
+    o->dc = (uint8_t)d; o->_pad0 = 0; o->_pad1 = 0u; o->n_gpus = meta & 0xffffu; o->size = size;
     o->f_used = f_used; o->start_s = start_s; o->finish_s = finish_s;
   }
   P->rec.counts[1] = r + 1u;
@@ -1047,22 +1018,23 @@ DCSIM_DEV void dcsim_start_job(dcsim_ctx_t& c, int d, int jt, double size, uint3
   const int i = d * L.cap_run + slot;
   const bool ok = dcsim_schedulable(c, t_fin);
   const uint32_t seq = ok ? c.seq++ : 0xffffffffu;
-  dcsim_at<double>(c.blk, L.rn_t)[i] = ok ? t_fin : DCSIM_INF; /* a dropped finish holds its GPUs for ever */
-  dcsim_at<uint32_t>(c.blk, L.rn_seq)[i] = seq;
-  dcsim_at<double>(c.blk, L.rn_pw)[i] = pw_job;
-  dcsim_at<double>(c.blk, L.rn_tpt)[i] = tpt_job;
-  dcsim_at<double>(c.blk, L.rn_start)[i] = c.now;
-  dcsim_at<uint32_t>(c.blk, L.rn_meta)[i] = (uint32_t)n | ((uint32_t)jt << 16) | (ing << 17);
+  dcsim_at<double>(c.rec, L.rn_t)[i] = ok ? t_fin : DCSIM_INF; /* a dropped finish holds its GPUs for ever */
+  dcsim_at<uint32_t>(c.rec, L.rn_seq)[i] = seq;
+  dcsim_at<double>(c.rec, L.rn_pw)[i] = pw_job;
+  dcsim_at<double>(c.rec, L.rn_tpt)[i] = tpt_job;
+  dcsim_at<double>(c.rec, L.rn_start)[i] = c.now;
+  dcsim_at<uint32_t>(c.rec, L.rn_meta)[i] = (uint32_t)n | ((uint32_t)jt << 16) | (ing << 17);
   if (CAP || L.lean == 0) {
-    dcsim_at<double>(c.blk, L.rn_size)[i] = size;
-    dcsim_at<double>(c.blk, L.rn_f)[i] = f;
-    dcsim_at<uint32_t>(c.blk, L.rn_jid)[i] = jid;
+    dcsim_at<double>(c.rec, L.rn_size)[i] = size;
+    dcsim_at<double>(c.rec, L.rn_f)[i] = f;
+    dcsim_at<uint32_t>(c.rec, L.rn_jid)[i] = jid;
   }
   if constexpr (CAP) { /* SIM:690-692: units_done = 0, last_update = now */
-    dcsim_at<double>(c.blk, L.rn_done)[i] = 0.0;
-    dcsim_at<double>(c.blk, L.rn_upd)[i] = c.now;
+    dcsim_at<double>(c.rec, L.rn_done)[i] = 0.0;
+    dcsim_at<double>(c.rec, L.rn_upd)[i] = c.now;
   }
   *nrun = slot + 1;
+  DCF(c, DF_PSUM)[d] += pw_job; /* the addition a re-sum in dict order would end with */
   if ((uint32_t)(slot + 1) > c.H->max_run) c.H->max_run = (uint32_t)(slot + 1);
   if (ok) { /* incremental update of DC d's earliest finish */
     const double ct = CAND_T(c)[CAND_DC0 + d];
@@ -1323,23 +1295,23 @@ DCSIM_DEV void dcsim_finish_account(dcsim_ctx_t& c, uint64_t r, int d, int slot)
   const dcsim_layout_t& L = c.P->L;
   dcsim_hdr_t* H = c.H;
   const int i = d * L.cap_run + slot;
-  const uint32_t meta = dcsim_at<uint32_t>(c.blk, L.rn_meta)[i];
+  const uint32_t meta = dcsim_at<uint32_t>(c.rec, L.rn_meta)[i];
   const int g = (int)(meta & 0xffffu), jt = (int)((meta >> 16) & 1u);
   int32_t* busy = DCI(c, DI_BUSY) + d;
   *busy = *busy - g > 0 ? *busy - g : 0; /* SIM:707 */
   const double now = c.now;
-  DCF(c, DF_ACC_UNIT)[d] += dcsim_at<double>(c.blk, L.rn_tpt)[i] * dcsim_mod_pos(now, sp.log_interval); /* SIM:711 */
-  const double lat = now - dcsim_at<double>(c.blk, L.rn_start)[i]; /* SIM:820 */
+  DCF(c, DF_ACC_UNIT)[d] += dcsim_at<double>(c.rec, L.rn_tpt)[i] * dcsim_mod_pos(now, sp.log_interval); /* SIM:711 */
+  const double lat = now - dcsim_at<double>(c.rec, L.rn_start)[i]; /* SIM:820 */
   H->lat_sum += lat;
   if (jt == DCSIM_JT_INFERENCE) { H->lat_sum_inf += lat; H->n_fin_inf++; } else { H->lat_sum_trn += lat; H->n_fin_trn++; }
   if (c.P->lat_hist) dcsim_hist_add(c.P->lat_hist, r, jt, lat);
   if (L.lean == 0) { /* the readers of a finished job's size / f / jid: job_log.csv and the bandit's reward */
-    const double f_used = dcsim_at<double>(c.blk, L.rn_f)[i];
+    const double f_used = dcsim_at<double>(c.rec, L.rn_f)[i];
     if (c.is_logged && c.P->rec.jobs)
-      dcsim_joblog_write(c.P, dcsim_at<uint32_t>(c.blk, L.rn_jid)[i], meta, d, dcsim_at<double>(c.blk, L.rn_size)[i], f_used,
-                         dcsim_at<double>(c.blk, L.rn_start)[i], now);
+      dcsim_joblog_write(c.P, dcsim_at<uint32_t>(c.rec, L.rn_jid)[i], meta, d, dcsim_at<double>(c.rec, L.rn_size)[i], f_used,
+                         dcsim_at<double>(c.rec, L.rn_start)[i], now);
     if (sp.deq_rule == DCSIM_START_BANDIT)
-      dcsim_bandit_update(c.P, c.blk, d, jt, g, f_used, dcsim_at<double>(c.blk, L.rn_pw)[i]);
+      dcsim_bandit_update(c.P, c.blk, d, jt, g, f_used, dcsim_at<double>(c.rec, L.rn_pw)[i]);
   }
 }
 
@@ -1355,6 +1327,80 @@ DCSIM_DEV void dcsim_dequeue_loop(dcsim_ctx_t& c, int d) {
     const dcsim_qent_t e = dcsim_dequeue(c, d, jt);
     dcsim_start_by_rule<CAP>(c, sp.deq_rule, false, d, jt, e.size, e.jid, e.ing);
   }
+}
+
+/* SIM:701-927, whole warp: the job_finish of DC d's earliest-finishing record (slot DI_FMIN_SLOT).
+ *
+ * One pass over the DC's records does everything the reference's `del dc.running_jobs[jid]` + next `_estimate_dc_power`
+ * + next heap pop imply: lane j loads record j of the set WITHOUT the finished one (slot j, or j + 1 behind the hole),
+ * lanes behind the hole store it one slot down (dict order is start order, models.py:60), the earliest remaining
+ * finish is an arg-min over the registers, and the active power is re-summed in dict order from the registers by
+ * shuffles.  The records are touched once — which is what lets them live in HBM/L2 instead of shared memory
+ * (c.rec) when the block is large: one load round trip per job_finish, stores fire-and-forget. */
+template <bool CAP>
+DCSIM_DEV void dcsim_handle_finish(dcsim_ctx_t& c, uint64_t r, int d) {
+  const dcsim_layout_t& L = c.P->L;
+  const int off = d * L.cap_run;
+  const int n = DCI(c, DI_NRUN)[d];
+  const int k = DCI(c, DI_FMIN_SLOT)[d];
+  if (c.lane == 0) { c.H->ev_fin++; dcsim_finish_account(c, r, d, k); } /* reads record k; writes no record */
+  double* rt = dcsim_at<double>(c.rec, L.rn_t) + off; double* rp = dcsim_at<double>(c.rec, L.rn_pw) + off;
+  double* rv = dcsim_at<double>(c.rec, L.rn_tpt) + off; double* ra = dcsim_at<double>(c.rec, L.rn_start) + off;
+  uint32_t* rq = dcsim_at<uint32_t>(c.rec, L.rn_seq) + off; uint32_t* rm = dcsim_at<uint32_t>(c.rec, L.rn_meta) + off;
+  const bool full = L.lean == 0;
+  const int n1 = n - 1;
+  uint32_t bh = 0x7ff00000u, bl = 0u, bs = 0xffffffffu;
+  int bi = -1;
+  double psum = 0.0;
+  dcsim_warp_sync(); /* lane 0's reads of record k are done before anybody overwrites slot k */
+  for (int base = 0; base < n1; base += DCSIM_LANES) {
+    const int j = base + c.lane;
+    const bool act = j < n1, moved = act && j >= k;
+    const int src = moved ? j + 1 : j;
+    double a_t = DCSIM_INF, a_pw = 0.0, a_tpt = 0.0, a_start = 0.0, a_size = 0.0, a_f = 0.0, a_done = 0.0, a_upd = 0.0;
+    uint32_t a_seq = 0xffffffffu, a_meta = 0u, a_jid = 0u;
+    if (act) { a_t = rt[src]; a_seq = rq[src]; a_pw = rp[src]; }
+    if (moved) {
+      a_tpt = rv[src]; a_start = ra[src]; a_meta = rm[src];
+      if (full) { a_size = dcsim_at<double>(c.rec, L.rn_size)[off + src]; a_f = dcsim_at<double>(c.rec, L.rn_f)[off + src];
+                  a_jid = dcsim_at<uint32_t>(c.rec, L.rn_jid)[off + src]; }
+      if constexpr (CAP) { a_done = dcsim_at<double>(c.rec, L.rn_done)[off + src]; a_upd = dcsim_at<double>(c.rec, L.rn_upd)[off + src]; }
+    }
+    const int cnt = n1 - base < DCSIM_LANES ? n1 - base : DCSIM_LANES;
+    for (int i = 0; i < cnt; ++i) psum += dcsim_bcast_f64(a_pw, i); /* SIM:168-179: dict order, from 0.0 */
+    {
+      const uint32_t h = dcsim_hi(a_t), l = dcsim_lo(a_t);
+      if (act && (h < bh || (h == bh && (l < bl || (l == bl && a_seq < bs))))) { bh = h; bl = l; bs = a_seq; bi = j; }
+    }
+    dcsim_warp_sync(); /* every lane holds its record before the slot it came from is overwritten */
+    if (moved) {
+      rt[j] = a_t; rq[j] = a_seq; rp[j] = a_pw; rv[j] = a_tpt; ra[j] = a_start; rm[j] = a_meta;
+      if (full) { dcsim_at<double>(c.rec, L.rn_size)[off + j] = a_size; dcsim_at<double>(c.rec, L.rn_f)[off + j] = a_f;
+                  dcsim_at<uint32_t>(c.rec, L.rn_jid)[off + j] = a_jid; }
+      if constexpr (CAP) { dcsim_at<double>(c.rec, L.rn_done)[off + j] = a_done; dcsim_at<double>(c.rec, L.rn_upd)[off + j] = a_upd; }
+    }
+  }
+  /* earliest remaining finish of DC d, in (t, seq) order */
+  const uint32_t mh = dcsim_warp_min_u32(bh);
+  int win = -1;
+  double wt = DCSIM_INF;
+  uint32_t ws = 0xffffffffu;
+  if (mh < 0x7ff00000u) {
+    const uint32_t ml = dcsim_warp_min_u32(bh == mh ? bl : 0xffffffffu);
+    const bool m = (bh == mh) && (bl == ml);
+    ws = dcsim_warp_min_u32(m ? bs : 0xffffffffu);
+    const uint32_t votes = dcsim_warp_ballot(m && bs == ws && bi >= 0);
+    win = (int)dcsim_bcast_u32((uint32_t)bi, dcsim_ffs(votes) - 1);
+    wt = dcsim_hilo_f64(mh, ml);
+  }
+  if (c.lane == 0) {
+    CAND_T(c)[CAND_DC0 + d] = wt; CAND_SEQ(c)[CAND_DC0 + d] = ws; DCI(c, DI_FMIN_SLOT)[d] = win;
+    DCI(c, DI_NRUN)[d] = n1;
+    DCF(c, DF_PSUM)[d] = psum;
+  }
+  dcsim_warp_sync(); /* the compacted records and the new count are visible before the dequeue loop appends */
+  if (c.lane == 0) { dcsim_dequeue_loop<CAP>(c, d); dcsim_refresh_power(c, d); }
+  dcsim_warp_sync();
 }
 
 /* Warp.  Earliest superseded job_finish -> candidate slot CAND_STALE. */
@@ -1375,40 +1421,40 @@ DCSIM_DEV void dcsim_rescan_stale(dcsim_ctx_t& c) {
 DCSIM_DEV void dcsim_reschedule_job(dcsim_ctx_t& c, int d, int slot, double new_f) {
   const dcsim_layout_t& L = c.P->L;
   const int i = d * L.cap_run + slot;
-  const uint32_t meta = dcsim_at<uint32_t>(c.blk, L.rn_meta)[i];
+  const uint32_t meta = dcsim_at<uint32_t>(c.rec, L.rn_meta)[i];
   const int g = (int)(meta & 0xffffu), jt = (int)((meta >> 16) & 1u);
   const dcsim_coeffs_t& k = c.P->spec.dc[d].coeffs[jt];
-  const double f_old = dcsim_at<double>(c.blk, L.rn_f)[i];
+  const double f_old = dcsim_at<double>(c.rec, L.rn_f)[i];
   const double f_cur = f_old != 0.0 ? f_old : DCF(c, DF_CUR_FREQ)[d];
-  const double total = dcsim_at<double>(c.blk, L.rn_size)[i];
+  const double total = dcsim_at<double>(c.rec, L.rn_size)[i];
   const double T0 = dcsim_step_time(g, f_cur, k);
   const double rate = 1.0 / (T0 > 1e-9 ? T0 : 1e-9);
-  double dt = c.now - dcsim_at<double>(c.blk, L.rn_upd)[i]; dt = dt > 0.0 ? dt : 0.0;
-  const double ud = dcsim_at<double>(c.blk, L.rn_done)[i] + rate * dt;
+  double dt = c.now - dcsim_at<double>(c.rec, L.rn_upd)[i]; dt = dt > 0.0 ? dt : 0.0;
+  const double ud = dcsim_at<double>(c.rec, L.rn_done)[i] + rate * dt;
   const double done = total < ud ? total : ud;
-  dcsim_at<double>(c.blk, L.rn_done)[i] = done;
-  dcsim_at<double>(c.blk, L.rn_upd)[i] = c.now;
-  dcsim_at<double>(c.blk, L.rn_f)[i] = new_f;
+  dcsim_at<double>(c.rec, L.rn_done)[i] = done;
+  dcsim_at<double>(c.rec, L.rn_upd)[i] = c.now;
+  dcsim_at<double>(c.rec, L.rn_f)[i] = new_f;
   double left = total - done; left = left > 0.0 ? left : 0.0;
   const double T1 = dcsim_step_time(g, new_f, k);
   const double rate_new = 1.0 / (T1 > 1e-9 ? T1 : 1e-9);
   const double finish_in = left / (rate_new > 1e-9 ? rate_new : 1e-9);
-  const double t_old = dcsim_at<double>(c.blk, L.rn_t)[i];
+  const double t_old = dcsim_at<double>(c.rec, L.rn_t)[i];
   if (!(t_old == DCSIM_INF)) { /* the superseded event stays in the event set */
     const uint32_t ns = c.H->n_stale;
     if ((int)ns >= L.cap_stale) { c.H->status |= DCSIM_ST_STALE_OVERFLOW; }
     else {
       dcsim_at<double>(c.blk, L.st_t)[ns] = t_old;
-      dcsim_at<uint32_t>(c.blk, L.st_seq)[ns] = dcsim_at<uint32_t>(c.blk, L.rn_seq)[i];
+      dcsim_at<uint32_t>(c.blk, L.st_seq)[ns] = dcsim_at<uint32_t>(c.rec, L.rn_seq)[i];
       c.H->n_stale = ns + 1u;
     }
   }
   const double t_new = c.now + finish_in;
   const bool ok = dcsim_schedulable(c, t_new);
-  dcsim_at<double>(c.blk, L.rn_t)[i] = ok ? t_new : DCSIM_INF;
-  dcsim_at<uint32_t>(c.blk, L.rn_seq)[i] = ok ? c.seq++ : 0xffffffffu;
-  dcsim_at<double>(c.blk, L.rn_pw)[i] = dcsim_task_power(g, new_f, k);
-  dcsim_at<double>(c.blk, L.rn_tpt)[i] = 1.0 / T1;
+  dcsim_at<double>(c.rec, L.rn_t)[i] = ok ? t_new : DCSIM_INF;
+  dcsim_at<uint32_t>(c.rec, L.rn_seq)[i] = ok ? c.seq++ : 0xffffffffu;
+  dcsim_at<double>(c.rec, L.rn_pw)[i] = dcsim_task_power(g, new_f, k);
+  dcsim_at<double>(c.rec, L.rn_tpt)[i] = 1.0 / T1;
 }
 
 /* Lane 0.  SIM:207-315 for algo = cap_greedy (cap_uniform never changes state: SIM:197-203 compares two identical
@@ -1442,10 +1488,10 @@ DCSIM_DEV void dcsim_control_cap_greedy(dcsim_ctx_t& c) {
 #pragma unroll 1
       for (int slot = 0; slot < n; ++slot) {
         const int i = d * L.cap_run + slot;
-        const uint32_t meta = dcsim_at<uint32_t>(c.blk, L.rn_meta)[i];
+        const uint32_t meta = dcsim_at<uint32_t>(c.rec, L.rn_meta)[i];
         const int g = (int)(meta & 0xffffu), jt = (int)((meta >> 16) & 1u);
         const dcsim_coeffs_t& k = cfg.coeffs[jt];
-        const double f_job = dcsim_at<double>(c.blk, L.rn_f)[i];
+        const double f_job = dcsim_at<double>(c.rec, L.rn_f)[i];
         const double cur_f = f_job != 0.0 ? f_job : DCF(c, DF_CUR_FREQ)[d];
         if (cur_f <= f_min + 1e-12) continue;
         ++n_tasks;
@@ -1483,10 +1529,11 @@ DCSIM_DEV void dcsim_control_cap_greedy(dcsim_ctx_t& c) {
       if (deficit <= 1e-6) break;
       const uint32_t id = at_idx[a];
       const int d = (int)(at_ref[id] >> 16), slot = (int)(at_ref[id] & 0xffffu);
-      const double cur_f = dcsim_at<double>(c.blk, L.rn_f)[d * L.cap_run + slot];
+      const double cur_f = dcsim_at<double>(c.rec, L.rn_f)[d * L.cap_run + slot];
       if (at_fto[id] >= cur_f - 1e-12) continue; /* SIM:296 */
       dcsim_reschedule_job(c, d, slot, at_fto[id]);
       applied = true;
+      dcsim_resum_power(c, d);
       dcsim_refresh_power(c, d);
       totalP = 0.0;
       for (int e = 0; e < sp.n_dc; ++e) totalP += DCF(c, DF_POWER)[e];
@@ -1518,14 +1565,14 @@ DCSIM_DEV void dcsim_handle_log(dcsim_ctx_t& c) {
       DCF(c, DF_CUR_FREQ)[d] = m;
     }
     const int n = DCI(c, DI_NRUN)[d];
-    const double* tpt = dcsim_at<double>(c.blk, L.rn_tpt) + d * L.cap_run;
+    const double* tpt = dcsim_at<double>(c.rec, L.rn_tpt) + d * L.cap_run;
     double acc = DCF(c, DF_ACC_UNIT)[d];
     for (int i = 0; i < n; ++i) acc += tpt[i] * interval; /* SIM:941-942, running jobs in dict order */
     DCF(c, DF_ACC_UNIT)[d] = acc;
     if (rec) { /* cluster_log.csv row, SIM:944-948; the rows of one tick are DC-ordered */
       const uint32_t r = c.P->rec.counts[2] + (uint32_t)d;
       if (r < c.P->rec.cluster_cap) {
-        const uint32_t* meta = dcsim_at<uint32_t>(c.blk, L.rn_meta) + d * L.cap_run;
+        const uint32_t* meta = dcsim_at<uint32_t>(c.rec, L.rn_meta) + d * L.cap_run;
         int run_inf = 0;
         for (int i = 0; i < n; ++i) run_inf += ((meta[i] >> 16) & 1u) ? 0 : 1;
         dcsim_cluster_rec_t* o = c.P->rec.cluster + r;
@@ -1555,7 +1602,8 @@ template <bool PRE>
 DCSIM_DEV void dcsim_replica_init(dcsim_ctx_t& c, uint64_t r) {
   const dcsim_spec_t& sp = c.P->spec;
   const dcsim_layout_t& L = c.P->L;
-  for (int i = c.lane; i < L.total_bytes / 4; i += DCSIM_LANES) dcsim_at<uint32_t>(c.blk, 0)[i] = 0u;
+  /* the head only: with every DI_NRUN at 0 no record is ever read before it was written */
+  for (int i = c.lane; i < L.rec_off / 4; i += DCSIM_LANES) dcsim_at<uint32_t>(c.blk, 0)[i] = 0u;
   dcsim_warp_sync();
   for (int i = c.lane; i < CAND_N; i += DCSIM_LANES) { CAND_T(c)[i] = DCSIM_INF; CAND_SEQ(c)[i] = 0xffffffffu; }
   DCSIM_FOR_EACH_DC(d, c, sp.n_dc) {
@@ -1686,13 +1734,7 @@ DCSIM_DEV uint32_t dcsim_replica_run(dcsim_ctx_t& c, uint64_t r) {
       dcsim_warp_sync();
       dcsim_rescan_xfer(c);
     } else if (win < CAND_STREAM0) {
-      const int d = win - CAND_DC0;
-      const int slot = DCI(c, DI_FMIN_SLOT)[d];
-      if (c.lane == 0) { c.H->ev_fin++; dcsim_finish_account(c, r, d, slot); }
-      dcsim_running_erase<CAP>(c, d, slot); /* reads records the accounting did not touch; syncs before it returns */
-      if (c.lane == 0) { dcsim_dequeue_loop<CAP>(c, d); dcsim_refresh_power(c, d); }
-      dcsim_warp_sync();
-      dcsim_rescan_dc(c, d);
+      dcsim_handle_finish<CAP>(c, r, win - CAND_DC0);
     } else if (win == CAND_LOG) {
       if (c.lane == 0) c.H->ev_log++;
       dcsim_handle_log<CAP>(c);
@@ -1759,11 +1801,12 @@ DCSIM_DEV void dcsim_write_summary(dcsim_ctx_t& c, double* out) {
 }
 
 /* One replica, one launch: (init |) resume -> run -> summary.  `blk` is the working copy of the state
- * block (shared memory on the GPU), already loaded unless `fresh`. */
+ * block (shared memory on the GPU), already loaded unless `fresh`; `rec` is the base the running-job record offsets
+ * apply to (== blk when the records were staged with it, the block's home in HBM when only the head was). */
 template <bool CAP, bool PRE>
-DCSIM_DEV uint32_t dcsim_replica_step(const dcsim_kparams_t* P, uint64_t r, char* blk, bool fresh) {
+DCSIM_DEV uint32_t dcsim_replica_step(const dcsim_kparams_t* P, uint64_t r, char* blk, char* rec, bool fresh) {
   dcsim_ctx_t c;
-  c.P = P; c.blk = blk; c.H = reinterpret_cast<dcsim_hdr_t*>(blk); c.lane = dcsim_lane();
+  c.P = P; c.blk = blk; c.rec = rec; c.H = reinterpret_cast<dcsim_hdr_t*>(blk); c.lane = dcsim_lane();
   c.q = P->queues + r * P->L.queue_bytes;
   c.is_traced = ((int64_t)r == P->rec.trace_replica);
   c.is_logged = ((int64_t)r == P->rec.log_replica);

@@ -17,7 +17,7 @@ from .simcore.policy_paper import best_energy_freq, best_nf_grid
 
 MAX_DC, MAX_ING, MAX_FREQ, HOURS = 8, 8, 16, 24
 SPEC_MAGIC = 0x3130304244435344
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 JT_NAMES = ("inference", "training")
 ARR_MODES = {"off": 0, "poisson": 1, "sinusoid": 2}
@@ -92,9 +92,9 @@ class TraceRec(C.Structure):
 
 
 class JobRec(C.Structure):
-    _fields_ = [("jid", C.c_uint32), ("ingress", C.c_uint8), ("jtype", C.c_uint8), ("dc", C.c_uint8),
-                ("n_gpus", C.c_uint8), ("size", C.c_double), ("f_used", C.c_double), ("start_s", C.c_double),
-                ("finish_s", C.c_double)]
+    _fields_ = [("jid", C.c_uint32), ("n_gpus", C.c_uint32), ("ingress", C.c_uint8), ("jtype", C.c_uint8),
+                ("dc", C.c_uint8), ("_pad0", C.c_uint8), ("_pad1", C.c_uint32), ("size", C.c_double),
+                ("f_used", C.c_double), ("start_s", C.c_double), ("finish_s", C.c_double)]
 
 
 class ClusterRec(C.Structure):
@@ -109,7 +109,9 @@ class LaunchInfo(C.Structure):
                 ("regs_per_thread", C.c_int32), ("resident_warps_per_sm", C.c_int32), ("sm_count", C.c_int32),
                 ("cap_xfer", C.c_int32), ("cap_run", C.c_int32), ("cap_q_inf", C.c_int32), ("cap_q_trn", C.c_int32),
                 ("kernel_launches", C.c_int32), ("arrivals_prepass", C.c_int32),
-                ("hbm_bytes_state", C.c_uint64), ("hbm_bytes_queues", C.c_uint64), ("hbm_bytes_arrivals", C.c_uint64)]
+                ("hbm_bytes_state", C.c_uint64), ("hbm_bytes_queues", C.c_uint64), ("hbm_bytes_arrivals", C.c_uint64),
+                ("staging_mode", C.c_int32), ("state_block_bytes", C.c_int32), ("staged_bytes_per_replica", C.c_int32),
+                ("cap_stale", C.c_int32)]
 
 
 def _price_for(energy_price, dc_name: str, hour: int) -> float:
@@ -210,6 +212,8 @@ def flatten(ingresses, dcs, graph, arrival_inf, arrival_train, coeffs_map, polic
             raise ValueError(f"DC {name}: 1..{MAX_FREQ} freq_levels supported")
         if dc.default_freq not in levels:
             raise AssertionError("default_freq must be one of freq_levels")  # models.py:75
+        if int(dc.total_gpus) > 65535:
+            raise ValueError(f"DC {name}: at most 65535 GPUs per data centre (a running record packs the job's GPU count into 16 bits)")
         o = sp.dc[d]
         o.total_gpus, o.power_gating, o.n_freq = int(dc.total_gpus), int(bool(dc.power_gating)), len(levels)
         gt = dc.gpu_type

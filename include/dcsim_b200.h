@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define DCSIM_ABI_VERSION 1u
+#define DCSIM_ABI_VERSION 2u
 #define DCSIM_SPEC_MAGIC 0x3130304244435344ull /* "DSCDB001" */
 
 #define DCSIM_MAX_DC 8    /* reference ships 8 DCs: configs/paper_config.py:39-64 */
@@ -196,7 +196,9 @@ typedef struct dcsim_trace_rec {
 /* one row of job_log.csv (simulator_paper_multi.py:420-421, 815-823), unrounded */
 typedef struct dcsim_job_rec {
   uint32_t jid;
-  uint8_t ingress, jtype, dc, n_gpus;
+  uint32_t n_gpus;                 /* up to the DC's total_gpus (<= 65535, checked by dcsim_create) */
+  uint8_t ingress, jtype, dc, _pad0;
+  uint32_t _pad1;
   double size, f_used, start_s, finish_s;
 } dcsim_job_rec_t;
 
@@ -300,6 +302,11 @@ typedef struct dcsim_launch_info {
   int32_t resident_warps_per_sm, sm_count, cap_xfer, cap_run;
   int32_t cap_q_inf, cap_q_trn, kernel_launches, arrivals_prepass;
   uint64_t hbm_bytes_state, hbm_bytes_queues, hbm_bytes_arrivals;
+  int32_t staging_mode;            /* 1 whole state block in shared memory, 2 head only (running-job records stay in
+                                      HBM/L2), 0 nothing (in place) */
+  int32_t state_block_bytes;       /* one replica's state block */
+  int32_t staged_bytes_per_replica;/* the part of it that is staged in shared memory during a launch */
+  int32_t cap_stale;
 } dcsim_launch_info_t;
 int dcsim_launch_info(dcsim_t* h, dcsim_launch_info_t* out);
 

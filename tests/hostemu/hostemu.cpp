@@ -72,15 +72,21 @@ long long hostemu_run_batch(const void* spec_blob, size_t spec_bytes, uint64_t n
     }
   }
   char* work = (char*)malloc((size_t)P->L.total_bytes);
+  /* DCSIM_RECORDS=global: the kernel's "head staged" mode — only [0, rec_off) round-trips through the working copy,
+   * the running-job records are used where they live (the block's home) */
+  const char* rm = getenv("DCSIM_RECORDS");
+  const bool head_only = rm && rm[0] == 'g';
+  const size_t staged = head_only ? (size_t)P->L.rec_off : (size_t)P->L.total_bytes;
   long long total = 0;
   for (uint64_t r = 0; r < n_replicas; ++r) {
     char* home = P->state + r * (uint64_t)P->L.total_bytes;
+    char* rec = head_only ? home : work;
     for (int guard = 0; guard < 100000000; ++guard) {
       const bool fresh = ((dcsim_hdr_t*)home)->initialized == 0u;
-      if (!fresh) memcpy(work, home, (size_t)P->L.total_bytes); /* stage in */
-      total += P->L.cap_stale ? (prepass ? dcsim_replica_step<true, true>(P, r, work, fresh) : dcsim_replica_step<true, false>(P, r, work, fresh))
-                               : (prepass ? dcsim_replica_step<false, true>(P, r, work, fresh) : dcsim_replica_step<false, false>(P, r, work, fresh));
-      memcpy(home, work, (size_t)P->L.total_bytes);             /* stage out */
+      if (!fresh) memcpy(work, home, staged); /* stage in */
+      total += P->L.cap_stale ? (prepass ? dcsim_replica_step<true, true>(P, r, work, rec, fresh) : dcsim_replica_step<true, false>(P, r, work, rec, fresh))
+                               : (prepass ? dcsim_replica_step<false, true>(P, r, work, rec, fresh) : dcsim_replica_step<false, false>(P, r, work, rec, fresh));
+      memcpy(home, work, staged);             /* stage out */
       const dcsim_hdr_t* H = (const dcsim_hdr_t*)home;
       if (H->done || H->status || chunk_events == 0) break;
     }

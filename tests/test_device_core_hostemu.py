@@ -34,6 +34,23 @@ def test_device_core_equals_oracle(oracle, hostemu, name):
     assert _same(got["summary"], want), np.argwhere(got["summary"] != want)[:10]
 
 
+@pytest.mark.parametrize("name", ["cfg5_8x256_sinusoid_60s", "sweep_joint_nf", "cap_greedy_4x64", "sweep_bandit",
+                                  "ragged_3dc_12_5_40", "cli_defaults_8dc_joint_nf_60s"])
+def test_head_staged_mode_equals_oracle(oracle, hostemu, monkeypatch, name):
+    """DCSIM_RECORDS=global: only the head of the state block goes through the working copy, the running-job records
+    are read and written at the block's home (the kernel's mode for blocks too large for 32 warps/SM) — one-shot
+    and in chunks (resume path)."""
+    monkeypatch.setenv("DCSIM_RECORDS", "global")
+    sc = SC.BY_NAME[name]
+    if sc["duration"] > 100 and sc["n_dc"] >= 4:
+        sc = dict(sc, duration=100.0)
+    blob = SC.to_spec(sc).to_bytes()
+    want, total = oracle.run_batch(blob, 2, 55, 3)
+    for chunk in (0, 977):
+        got = hostemu.run_batch(blob, 2, 55 + 3, chunk_events=chunk)
+        assert got["events"] == total and _same(got["summary"], want), (name, chunk)
+
+
 @pytest.mark.parametrize("chunk", [1, 7, 1000])
 def test_resume_is_invariant(oracle, hostemu, chunk):
     """advance() in chunks (state block staged out and in between launches) == one advance to the end."""
