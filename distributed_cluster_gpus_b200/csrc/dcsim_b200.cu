@@ -2,11 +2,12 @@
  * dcsim_b200.cu — sm_100a kernels and the C-ABI of include/dcsim_b200.h.
  *
  * Kernels
- *   dcsim_arrivals_kernel     one thread per replica: the replica's arrival list (instants, sizes, routed DCs).
+ *   dcsim_arrivals_kernel     one thread per replica: the replica's arrival sequence (instants, routed DCs, size deviates).
+ *   dcsim_merge_kernel        one warp per replica: job sizes, xfer_done instants and the merged, time-ordered
+ *                             {arrival, xfer_done} list the event loop consumes.
  *   dcsim_advance_kernel      one warp per replica; stages the replica's state block HBM -> shared memory, runs the
  *                             event loop of dcsim_core.cuh, stages it back, writes the summary row.  Instantiated
- *                             over <CAP, PRE, STAGED> (power-cap controller compiled in / arrivals from the list /
- *                             block staged in shared memory) and picked per handle.
+ *                             over <CAP, MODE> (power-cap controller compiled in / what is staged) and picked per handle.
  *   dcsim_reduce_kernel       [n_replicas][K] summaries -> DCSIM_AGG_K doubles (the only cross-GPU payload).
  *   dcsim_hist_reduce_kernel  per-replica job-latency histograms -> one [2][128] histogram (opt-in).
  *
@@ -33,17 +34,16 @@ extern __shared__ __align__(16) char dcsim_smem[];
 /* CAP = the power-cap controller (algo = cap_greedy with power_cap > 0: SIM:207-338) is compiled in.  It is a
  * separate instantiation because merely inlining that cold code costs the common path 17 % (measured,
  * profiles/r01_variants_ab.md). */
-/* PRE = arrivals come from the list written by dcsim_arrivals_kernel (no sampling in this kernel). */
 /* MODE = where the replica's state block lives during the launch (a compile-time switch: a run-time select would turn
  * every state access into a generic load/store, measured -15 %):
- *   DCSIM_MODE_STAGED  the whole block is staged in shared memory (small blocks: 4 DC x 64 is 5.6 kB, 32 warps/SM);
- *   DCSIM_MODE_HEAD    only the head [0, L.rec_off) — header, event set, per-DC arrays, arrival window, transfer pool —
+ *   DCSIM_MODE_STAGED  the whole block is staged in shared memory (small blocks: 4 DC x 64 is ~5 kB, 32 warps/SM);
+ *   DCSIM_MODE_HEAD    only the head [0, L.rec_off) — header, event set, per-DC arrays, list window, seq ring —
  *                      is staged; the running-job records stay at the block's home in HBM/L2 and are touched once per
  *                      job_finish (dcsim_handle_finish) and written once per start.  Picked when the whole block would
- *                      leave the SM below its 32 warps (8 DC x 256: 17.5 kB -> 12 warps/SM; head 4.7 kB -> 32);
+ *                      leave the SM below its 32 warps (8 DC x 256: 17 kB -> 12 warps/SM; head ~4 kB -> 32);
  *   DCSIM_MODE_INPLACE nothing is staged (even the head exceeds a CTA's shared memory): same core on the HBM copy. */
 enum { DCSIM_MODE_INPLACE = 0, DCSIM_MODE_STAGED = 1, DCSIM_MODE_HEAD = 2 };
-template <bool CAP, bool PRE, int MODE>
+template <bool CAP, int MODE>
 __global__ void __launch_bounds__(DCSIM_MAX_WARPS_PER_CTA * 32, DCSIM_MIN_CTAS_PER_SM)
 dcsim_advance_kernel(const __grid_constant__ dcsim_kparams_t P, unsigned long long* __restrict__ events_total) {
   const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31u);
@@ -61,7 +61,7 @@ dcsim_advance_kernel(const __grid_constant__ dcsim_kparams_t P, unsigned long lo
     for (int i = lane; i < bytes / 16; i += 32) dst[i] = src[i];
   }
   __syncwarp();
-  const uint32_t n = dcsim_replica_step<CAP, PRE>(&P, r, blk, rec, fresh);
+  const uint32_t n = dcsim_replica_step<CAP, MODE != DCSIM_MODE_STAGED>(&P, r, blk, rec, fresh);
   __syncwarp();
   if (MODE != DCSIM_MODE_INPLACE) {
     const uint4* src = reinterpret_cast<const uint4*>(blk);
@@ -71,18 +71,29 @@ dcsim_advance_kernel(const __grid_constant__ dcsim_kparams_t P, unsigned long lo
   if (lane == 0 && n) atomicAdd(events_total, (unsigned long long)n);
 }
 
-/* Arrival pre-pass: one THREAD per replica generates that replica's whole arrival list (instants, sizes, routed
- * DCs) in the reference's draw order; consecutive threads = consecutive replicas, so all 32 lanes of a warp run the
- * samplers (pow / log / sin / rejection loops) that the event loop would otherwise run on one lane. */
+/* Arrival pre-pass: one THREAD per replica draws that replica's whole arrival sequence in the reference's draw order;
+ * consecutive threads = consecutive replicas, so all 32 lanes of a warp run the samplers that the event loop would
+ * otherwise run on one lane.  Per-thread scratch in shared memory, [slot][thread]: 2*MAX_ING stream clocks (f64),
+ * 2*MAX_ING "latest arrival of the stream" indices (u32), DCSIM_TRNG_RING staged random words (u32). */
 #define DCSIM_ARRIVALS_THREADS 128
+#define DCSIM_ARRIVALS_SCRATCH_PER_THREAD (2 * DCSIM_MAX_ING * (sizeof(double) + sizeof(uint32_t)) + DCSIM_TRNG_RING * sizeof(uint32_t))
 extern __shared__ __align__(16) double dcsim_arr_scratch[];
 template <bool MT>
 __global__ void __launch_bounds__(DCSIM_ARRIVALS_THREADS) dcsim_arrivals_kernel(const __grid_constant__ dcsim_kparams_t P) {
   const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= P.n_replicas) return;
-  double* clocks = dcsim_arr_scratch + threadIdx.x;                                     /* [stream][thread] */
-  uint32_t* ring = reinterpret_cast<uint32_t*>(dcsim_arr_scratch + 2 * DCSIM_MAX_ING * blockDim.x) + threadIdx.x; /* [word][thread] */
-  dcsim_generate_arrivals<MT>(&P, r, clocks, ring, (int)blockDim.x);
+  double* clocks = dcsim_arr_scratch + threadIdx.x;                                                   /* [stream][thread] */
+  uint32_t* last = reinterpret_cast<uint32_t*>(dcsim_arr_scratch + 2 * DCSIM_MAX_ING * blockDim.x) + threadIdx.x; /* [stream][thread] */
+  uint32_t* ring = last + 2 * DCSIM_MAX_ING * blockDim.x;                                             /* [word][thread] */
+  dcsim_generate_arrivals<MT>(&P, r, clocks, last, ring, (int)blockDim.x);
+}
+
+/* List merge: one WARP per replica (lane-parallel over the replica's arrivals). */
+#define DCSIM_MERGE_THREADS 128
+__global__ void __launch_bounds__(DCSIM_MERGE_THREADS) dcsim_merge_kernel(const __grid_constant__ dcsim_kparams_t P) {
+  const uint64_t r = (uint64_t)blockIdx.x * (DCSIM_MERGE_THREADS / 32) + (threadIdx.x >> 5);
+  if (r >= P.n_replicas) return;
+  dcsim_merge_arrivals(&P, r, (int)(threadIdx.x & 31u));
 }
 
 /* Sums the per-replica latency histograms: thread b of every block owns bin b (coalesced 1 KB rows). */
@@ -93,13 +104,11 @@ __global__ void dcsim_hist_reduce_kernel(const uint32_t* __restrict__ hist, uint
 }
 
 typedef void (*dcsim_advance_fn)(const dcsim_kparams_t, unsigned long long*);
-static dcsim_advance_fn dcsim_pick_kernel(bool cap, bool pre, int mode) {
-  static const dcsim_advance_fn table[12] = {
-      dcsim_advance_kernel<false, false, 0>, dcsim_advance_kernel<false, false, 1>, dcsim_advance_kernel<false, false, 2>,
-      dcsim_advance_kernel<false, true, 0>,  dcsim_advance_kernel<false, true, 1>,  dcsim_advance_kernel<false, true, 2>,
-      dcsim_advance_kernel<true, false, 0>,  dcsim_advance_kernel<true, false, 1>,  dcsim_advance_kernel<true, false, 2>,
-      dcsim_advance_kernel<true, true, 0>,   dcsim_advance_kernel<true, true, 1>,   dcsim_advance_kernel<true, true, 2>};
-  return table[(cap ? 6 : 0) + (pre ? 3 : 0) + mode];
+static dcsim_advance_fn dcsim_pick_kernel(bool cap, int mode) {
+  static const dcsim_advance_fn table[6] = {
+      dcsim_advance_kernel<false, 0>, dcsim_advance_kernel<false, 1>, dcsim_advance_kernel<false, 2>,
+      dcsim_advance_kernel<true, 0>,  dcsim_advance_kernel<true, 1>,  dcsim_advance_kernel<true, 2>};
+  return table[(cap ? 3 : 0) + mode];
 }
 
 /* Aggregates the summaries; every block reduces a slice, then one atomicAdd per component. */
@@ -153,11 +162,18 @@ struct dcsim {
   int want_job_log;                   /* layout the NEXT batch needs; applied lazily by ensure_layout() */
   int64_t trace_replica, log_replica;
   int launches;
-  int prepass, arrivals_ready, mode; /* mode: DCSIM_MODE_* of the advance kernel for this handle's layout */
+  int arrivals_ready, mode; /* mode: DCSIM_MODE_* of the advance kernel for this handle's layout */
   double* d_arr_t;
-  double* d_arr_size;
+  double* d_arr_raw;
   uint32_t* d_arr_meta;
+  uint32_t* d_arr_pred;
+  double* d_arr_tx;
+  uint32_t* d_arr_fin;
+  double* d_ml_t;
+  double* d_ml_aux;
+  uint32_t* d_ml_meta;
   dcsim_arrhdr_t* d_arr_hdr;
+  double max_transfer;
   uint32_t* d_hist;
   uint32_t* d_mt; /* [624][n_replicas] Mersenne Twister states, rng_kind == DCSIM_RNG_MT19937 only */
   int rng_kind;
@@ -212,6 +228,8 @@ static int validate_spec(const dcsim_spec_t* sp) {
     if (c->total_gpus > 65535) /* a running record packs the job's GPU count into 16 bits */
       return set_err(NULL, DCSIM_E_INVALID, "spec: DC %s%lld has more than 65535 GPUs", "", d);
   }
+  if (sp->cap_arrivals < 0 || (uint32_t)sp->cap_arrivals >= DCSIM_MAX_ARRIVALS)
+    return set_err(NULL, DCSIM_E_INVALID, "spec: cap_arrivals must be below 2^24 (%s%lld given)", "", sp->cap_arrivals);
   if (sp->algo < DCSIM_ALGO_DEFAULT || sp->algo > DCSIM_ALGO_CAP_GREEDY)
     return set_err(NULL, DCSIM_E_UNSUPPORTED, "spec: unknown algo id %s%lld", "", sp->algo);
   return DCSIM_OK;
@@ -257,7 +275,7 @@ static cudaError_t size_launch(dcsim_t* h) {
   h->warps_per_cta = wpc;
   h->smem_bytes = wpc * bytes;
   h->ctas = (int)((h->n_replicas + (uint64_t)wpc - 1) / (uint64_t)wpc);
-  const dcsim_advance_fn kern = dcsim_pick_kernel(h->L.cap_stale != 0, h->prepass != 0, h->mode);
+  const dcsim_advance_fn kern = dcsim_pick_kernel(h->L.cap_stale != 0, h->mode);
   if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin)) != cudaSuccess) return e;
   cudaFuncAttributes fa;
   if ((e = cudaFuncGetAttributes(&fa, kern)) != cudaSuccess) return e;
@@ -271,7 +289,7 @@ static cudaError_t size_launch(dcsim_t* h) {
 /* job_log.csv needs size / f / jid in the running records; switching it on or off re-lays the state block out. */
 static int relayout(dcsim_t* h, int job_log) {
   dcsim_layout_t L;
-  dcsim_make_layout(&h->spec, &L, h->prepass, job_log);
+  dcsim_make_layout(&h->spec, &L, job_log);
   if (L.lean == h->L.lean) return DCSIM_OK;
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   h->L = L;
@@ -299,12 +317,14 @@ int dcsim_create(const void* spec_blob, size_t spec_bytes, uint64_t n_replicas, 
   if (!h) return set_err(NULL, DCSIM_E_NOMEM, "create: host allocation failed%s%lld");
   memset(h, 0, sizeof(*h));
   h->spec = sp;
-  { /* DCSIM_PREPASS=0 keeps the samplers inside the event loop (the round-1 v3 kernel); default: pre-pass */
-    const char* e = getenv("DCSIM_PREPASS");
-    h->prepass = !(e && e[0] == '0');
-  }
-  dcsim_make_layout(&h->spec, &h->L, h->prepass, /*job_log=*/0);
+  dcsim_make_layout(&h->spec, &h->L, /*job_log=*/0);
   h->cap_arr = (uint32_t)(h->spec.cap_arrivals > 0 ? h->spec.cap_arrivals : 16384);
+  for (int i = 0; i < h->spec.n_ing; ++i)
+    for (int d = 0; d < h->spec.n_dc; ++d)
+      for (int jt = 0; jt < 2; ++jt) {
+        const double v = h->spec.transfer_s[i][d][jt];
+        if (v == v && v < 1e300 && v > h->max_transfer) h->max_transfer = v; /* finite ones only */
+      }
   h->n_replicas = n_replicas;
   h->seed0 = base_seed + first_replica_id;
   h->device = device;
@@ -332,11 +352,17 @@ int dcsim_create(const void* spec_blob, size_t spec_bytes, uint64_t n_replicas, 
   CREATE_TRY(cudaMalloc(&h->d_state, state_bytes));
   CREATE_TRY(cudaMalloc(&h->d_queues, queue_bytes ? queue_bytes : 16));
   CREATE_TRY(cudaMalloc(&h->d_summary, (size_t)n_replicas * DCSIM_SUMMARY_K * sizeof(double)));
-  if (h->prepass) {
+  {
     const size_t ne = (size_t)n_replicas * (size_t)h->cap_arr;
     CREATE_TRY(cudaMalloc(&h->d_arr_t, ne * sizeof(double)));
-    CREATE_TRY(cudaMalloc(&h->d_arr_size, ne * sizeof(double)));
+    CREATE_TRY(cudaMalloc(&h->d_arr_raw, ne * sizeof(double)));
     CREATE_TRY(cudaMalloc(&h->d_arr_meta, ne * sizeof(uint32_t)));
+    CREATE_TRY(cudaMalloc(&h->d_arr_pred, ne * sizeof(uint32_t)));
+    CREATE_TRY(cudaMalloc(&h->d_arr_tx, ne * sizeof(double)));
+    CREATE_TRY(cudaMalloc(&h->d_arr_fin, ne * sizeof(uint32_t)));
+    CREATE_TRY(cudaMalloc(&h->d_ml_t, 2 * ne * sizeof(double)));
+    CREATE_TRY(cudaMalloc(&h->d_ml_aux, 2 * ne * sizeof(double)));
+    CREATE_TRY(cudaMalloc(&h->d_ml_meta, 2 * ne * sizeof(uint32_t)));
     CREATE_TRY(cudaMalloc(&h->d_arr_hdr, (size_t)n_replicas * sizeof(dcsim_arrhdr_t)));
   }
   CREATE_TRY(cudaMalloc(&h->d_events, sizeof(unsigned long long)));
@@ -423,8 +449,11 @@ static void fill_kparams(const dcsim_t* h, dcsim_kparams_t* P, uint64_t max_even
   P->budget32 = (max_events == 0ull || max_events > 0xfffffffeull) ? 0xffffffffu : (uint32_t)max_events;
   P->state = h->d_state; P->queues = h->d_queues; P->summary = h->d_summary;
   P->end_eps = h->spec.end_time + 1e-9; /* SIM:161 */
-  P->arr_t = h->d_arr_t; P->arr_size = h->d_arr_size; P->arr_meta = h->d_arr_meta; P->arr_hdr = h->d_arr_hdr; P->cap_arr = h->cap_arr;
-  P->staged = (uint32_t)h->mode;
+  P->arr_t = h->d_arr_t; P->arr_raw = h->d_arr_raw; P->arr_meta = h->d_arr_meta; P->arr_pred = h->d_arr_pred;
+  P->arr_tx = h->d_arr_tx; P->arr_fin = h->d_arr_fin;
+  P->ml_t = h->d_ml_t; P->ml_aux = h->d_ml_aux; P->ml_meta = h->d_ml_meta;
+  P->arr_hdr = h->d_arr_hdr; P->cap_arr = h->cap_arr;
+  P->max_transfer = h->max_transfer;
   P->lat_hist = h->d_hist;
   P->mt_state = h->d_mt;
 }
@@ -433,16 +462,19 @@ int dcsim_prepare(dcsim_t* h) {
   if (!h) return DCSIM_E_INVALID;
   CUDA_TRY(h, cudaSetDevice(h->device));
   if (h->launches == 0) { const int rc0 = relayout(h, h->want_job_log); if (rc0 != DCSIM_OK) return rc0; }
-  if (!h->prepass || h->arrivals_ready) return DCSIM_OK;
+  if (h->arrivals_ready) return DCSIM_OK;
   dcsim_kparams_t P;
   fill_kparams(h, &P, 0);
   const int nb = (int)((h->n_replicas + DCSIM_ARRIVALS_THREADS - 1) / DCSIM_ARRIVALS_THREADS);
-  const size_t scratch = (size_t)DCSIM_ARRIVALS_THREADS * (2 * DCSIM_MAX_ING * sizeof(double) + DCSIM_TRNG_RING * sizeof(uint32_t));
+  const size_t scratch = (size_t)DCSIM_ARRIVALS_THREADS * DCSIM_ARRIVALS_SCRATCH_PER_THREAD;
   if (h->rng_kind == DCSIM_RNG_MT19937) dcsim_arrivals_kernel<true><<<nb, DCSIM_ARRIVALS_THREADS, scratch, h->stream>>>(P);
   else dcsim_arrivals_kernel<false><<<nb, DCSIM_ARRIVALS_THREADS, scratch, h->stream>>>(P);
   CUDA_TRY(h, cudaGetLastError());
+  const int wpb = DCSIM_MERGE_THREADS / 32;
+  dcsim_merge_kernel<<<(int)((h->n_replicas + wpb - 1) / wpb), DCSIM_MERGE_THREADS, 0, h->stream>>>(P);
+  CUDA_TRY(h, cudaGetLastError());
   h->arrivals_ready = 1;
-  h->launches++;
+  h->launches += 2;
   return DCSIM_OK;
 }
 
@@ -455,7 +487,7 @@ int dcsim_advance(dcsim_t* h, uint64_t max_events_per_replica, uint64_t* total_e
   dcsim_kparams_t P;
   fill_kparams(h, &P, max_events_per_replica);
   const dim3 grid(h->ctas), block(h->warps_per_cta * 32);
-  dcsim_pick_kernel(h->L.cap_stale != 0, h->prepass != 0, h->mode)<<<grid, block, h->smem_bytes, h->stream>>>(P, h->d_events);
+  dcsim_pick_kernel(h->L.cap_stale != 0, h->mode)<<<grid, block, h->smem_bytes, h->stream>>>(P, h->d_events);
   CUDA_TRY(h, cudaGetLastError());
   h->launches++;
   if (total_events_out) {
@@ -522,8 +554,6 @@ int dcsim_set_rng(dcsim_t* h, int rng_kind) {
   if (!h) return DCSIM_E_INVALID;
   if (rng_kind != DCSIM_RNG_PHILOX && rng_kind != DCSIM_RNG_MT19937) return set_err(h, DCSIM_E_INVALID, "set_rng: unknown rng kind %s%lld", "", (long long)rng_kind);
   if (h->launches) return set_err(h, DCSIM_E_STATE, "set_rng must precede the first advance%s%lld");
-  if (rng_kind == DCSIM_RNG_MT19937 && !h->prepass)
-    return set_err(h, DCSIM_E_UNSUPPORTED, "set_rng: MT19937 needs the arrival pre-pass (unset DCSIM_PREPASS=0)%s%lld");
   CUDA_TRY(h, cudaSetDevice(h->device));
   if (rng_kind == DCSIM_RNG_MT19937 && !h->d_mt)
     CUDA_TRY(h, cudaMalloc(&h->d_mt, (size_t)h->n_replicas * DCSIM_MT_N * sizeof(uint32_t)));
@@ -599,12 +629,13 @@ int dcsim_launch_info(dcsim_t* h, dcsim_launch_info_t* out) {
   memset(out, 0, sizeof(*out));
   out->warps_per_cta = h->warps_per_cta; out->ctas = h->ctas; out->smem_bytes_per_cta = h->smem_bytes;
   out->regs_per_thread = h->regs; out->resident_warps_per_sm = h->resident_warps; out->sm_count = h->sm_count;
-  out->cap_xfer = h->L.cap_xfer; out->cap_run = h->L.cap_run; out->cap_q_inf = h->L.cap_q[0]; out->cap_q_trn = h->L.cap_q[1];
+  out->cap_xfer = (h->L.xring_mask + 1) / 2; out->cap_run = h->L.cap_run; out->cap_q_inf = h->L.cap_q[0]; out->cap_q_trn = h->L.cap_q[1];
   out->kernel_launches = h->launches;
   out->hbm_bytes_state = (uint64_t)h->n_replicas * (uint64_t)h->L.total_bytes;
   out->hbm_bytes_queues = (uint64_t)h->n_replicas * h->L.queue_bytes;
-  out->arrivals_prepass = h->prepass;
-  out->hbm_bytes_arrivals = h->prepass ? (uint64_t)h->n_replicas * ((uint64_t)h->cap_arr * 20ull + sizeof(dcsim_arrhdr_t)) : 0ull;
+  out->arrivals_prepass = 1;
+  /* per arrival: pre-pass output 24 B + merge scratch 12 B + two list entries of 20 B */
+  out->hbm_bytes_arrivals = (uint64_t)h->n_replicas * ((uint64_t)h->cap_arr * 76ull + sizeof(dcsim_arrhdr_t));
   out->staging_mode = h->mode; out->state_block_bytes = h->L.total_bytes;
   out->staged_bytes_per_replica = h->warps_per_cta ? h->smem_bytes / h->warps_per_cta : 0;
   out->cap_stale = h->L.cap_stale;
@@ -621,7 +652,8 @@ void dcsim_destroy(dcsim_t* h) {
   cudaFree(h->d_trace); cudaFree(h->d_jobs); cudaFree(h->d_cluster);
   cudaFree(h->d_hist);
   cudaFree(h->d_mt);
-  cudaFree(h->d_arr_t); cudaFree(h->d_arr_size); cudaFree(h->d_arr_meta); cudaFree(h->d_arr_hdr);
+  cudaFree(h->d_arr_t); cudaFree(h->d_arr_raw); cudaFree(h->d_arr_meta); cudaFree(h->d_arr_pred); cudaFree(h->d_arr_tx);
+  cudaFree(h->d_arr_fin); cudaFree(h->d_ml_t); cudaFree(h->d_ml_aux); cudaFree(h->d_ml_meta); cudaFree(h->d_arr_hdr);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
 }

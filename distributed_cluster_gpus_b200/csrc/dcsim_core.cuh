@@ -1,28 +1,33 @@
 /*
- * dcsim_core.cuh — the device code of the B200 batched simulator (both kernels' bodies).
+ * dcsim_core.cuh — the device code of the B200 batched simulator (all kernels' bodies).
  *
  * The reference's multi-DC event loop (simcore/simulator_paper_multi.py:412-480 and the leaves it calls; citations
  * are relative to the reference tree) is split where its data dependencies split it:
  *
  *   arrival pre-pass  (dcsim_generate_arrivals, one THREAD per replica)
  *       Only arrival handlers draw random numbers and routing never looks at DC state, so a replica's whole arrival
- *       sequence — instants, job sizes, routed DCs, which pushes were schedulable — is drawn ahead, in the reference's
- *       draw order, with all 32 lanes of a warp running the samplers (pow / log / sin, rejection loops).
+ *       sequence — instants, routed DCs, which pushes were schedulable, and the uniform / normal deviate its job size
+ *       is a function of — is drawn ahead, in the reference's draw order, with all 32 lanes of a warp running the
+ *       samplers.  Only what the NEXT draw depends on stays in this sequential chain (stream position, stream clocks).
+ *
+ *   list merge        (dcsim_merge_arrivals, one WARP per replica, lane-parallel over arrivals)
+ *       Everything that hangs off an arrival without feeding back into the draws: the job size (pow / exp), the
+ *       xfer_done instant t + transfer_s[ingress][dc][jtype] (SIM:580-588), and the position both events take in the
+ *       replica's time-ordered list of {arrival, xfer_done} events — ties broken exactly as the heap would, by push
+ *       order (SIM:163).
  *
  *   event loop        (dcsim_replica_run, one WARP per replica)
- *       The replica's working set — pending-event candidates, in-flight transfers, running-job records, per-DC
- *       accumulators, a window of its arrival list — is a "state block" staged in shared memory for the launch; only
- *       the unbounded FIFO queues (and the arrival lists) live in HBM.  How the 32 lanes are used:
- *         - pop-min: the pending events are kept as 32 *candidates* (one per DC = earliest job_finish of that DC, the
- *           next arrival, the earliest in-flight transfer, the log tick, ...); every lane loads one candidate and
- *           three REDUX.MIN (hi word, lo word, seq) find the winner;
+ *       The replica's working set — pending-event candidates, per-DC accumulators, a window of its event list, (small
+ *       blocks:) its running-job records — is a "state block" staged in shared memory for the launch; the unbounded
+ *       FIFO queues, the event lists and (large blocks) the running-job records live in HBM/L2.  How the 32 lanes are
+ *       used:
+ *         - pop-min: the pending events are kept as *candidates* (one per DC = earliest job_finish of that DC, the next
+ *           list entry, the log tick, ...); every lane loads one candidate and three REDUX.MIN (hi word, lo word, seq)
+ *           find the winner;
  *         - the per-event sweep over all DCs (SIM:429-437) runs one DC per lane;
- *         - pool rescans, order-preserving compaction of the running set, staging of the arrival window and the state
- *           block run strided across the warp;
+ *         - a job_finish is one lane-parallel pass over the DC's records (compaction, next finish, power re-sum);
+ *         - staging of the list window and the state block run strided across the warp;
  *         - the handlers themselves are strictly sequential per replica and run on lane 0 out of shared memory.
- *       With DCSIM_PREPASS=0 the samplers stay in this loop instead (Philox window filled by all lanes, rejection
- *       loops evaluated speculatively one candidate per lane): the earlier single-kernel design, kept as a
- *       cross-check — both must give the same bits.
  *
  * All arithmetic that defines results is FP64 and is written so that, compiled with -fmad=false, every + - * /
  * happens in the reference's order with one rounding each.  log/exp/pow/sin come from CUDA's libdevice (<= 2 ulp
@@ -55,6 +60,10 @@ static inline uint32_t dcsim_hi(double x) { uint64_t u; memcpy(&u, &x, 8); retur
 static inline uint32_t dcsim_lo(double x) { uint64_t u; memcpy(&u, &x, 8); return (uint32_t)u; }
 static inline uint32_t dcsim_mulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 static inline int dcsim_bit_length(uint32_t n) { return 32 - __builtin_clz(n); }
+static inline uint32_t dcsim_popc(uint32_t x) { return (uint32_t)__builtin_popcount(x); }
+static inline uint32_t dcsim_lanemask_lt(int) { return 0u; }
+static inline uint32_t dcsim_warp_add_u32(uint32_t x) { return x; }
+static inline uint32_t dcsim_warp_max_u32(uint32_t x) { return x; }
 #define DCSIM_INF (__builtin_inf())
 #else
 #define DCSIM_DEV __device__ __forceinline__
@@ -69,6 +78,10 @@ DCSIM_DEV uint32_t dcsim_hi(double x) { return (uint32_t)__double2hiint(x); }
 DCSIM_DEV uint32_t dcsim_lo(double x) { return (uint32_t)__double2loint(x); }
 DCSIM_DEV uint32_t dcsim_mulhi(uint32_t a, uint32_t b) { return __umulhi(a, b); }
 DCSIM_DEV int dcsim_bit_length(uint32_t n) { return 32 - __clz((int)n); }
+DCSIM_DEV uint32_t dcsim_popc(uint32_t x) { return (uint32_t)__popc(x); }
+DCSIM_DEV uint32_t dcsim_lanemask_lt(int lane) { return (1u << lane) - 1u; }
+DCSIM_DEV uint32_t dcsim_warp_add_u32(uint32_t x) { return __reduce_add_sync(0xffffffffu, x); }
+DCSIM_DEV uint32_t dcsim_warp_max_u32(uint32_t x) { return __reduce_max_sync(0xffffffffu, x); }
 #define DCSIM_INF (__longlong_as_double(0x7ff0000000000000LL))
 #endif
 
@@ -119,13 +132,24 @@ DCSIM_COLD void dcsim_hist_add(uint32_t* hist, uint64_t r, int jt, double lat) {
 /* ---- candidate slots (the event set, one slot per lane) -------------------------------------- */
 enum {
   CAND_DC0 = 0,      /* + d   : earliest job_finish among DC d's running jobs */
-  CAND_STREAM0 = 8,  /* + 2*ingress + jtype : next arrival of that stream */
-  CAND_XFER = 24,    /* earliest in-flight xfer_done */
-  CAND_LOG = 25,     /* the log tick */
-  CAND_STALE = 26,   /* earliest superseded job_finish (cap_greedy re-scheduling leaves the old event in the heap, SIM:330-338) */
+  CAND_LIST = 8,     /* the next entry of the replica's {arrival, xfer_done} list */
+  CAND_LOG = 9,      /* the log tick */
+  CAND_STALE = 10,   /* earliest superseded job_finish (cap_greedy re-scheduling leaves the old event in the heap, SIM:330-338) */
   CAND_N = 32
 };
 enum { KIND_ARR_INF = 0, KIND_ARR_TRN = 1, KIND_XFER = 2, KIND_FINISH = 3, KIND_LOG = 4, KIND_STALE = 5 };
+
+/* ---- one entry of a replica's event list (SoA: t f64, aux f64, meta u32) ----------------------
+ * arrival : t = arrival instant; aux (low 32 bits) = list position of its xfer_done entry (ML_A_XIN);
+ *           meta = 0 | stream << 1 | ML_A_NEXT | ML_A_XSCHED | ML_A_XIN
+ * xfer    : t = xfer_done instant; aux = job size; meta = 1 | dc << 1 | jtype << 4 | ingress << 5 | arrival index << 8 */
+enum : uint32_t {
+  ML_XFER = 1u,
+  ML_A_NEXT = 1u << 5,   /* the stream's next arrival was schedulable: its push takes a seq (SIM:591-592) */
+  ML_A_XSCHED = 1u << 6, /* the xfer_done push was schedulable: it takes a seq (SIM:580-588) */
+  ML_A_XIN = 1u << 7     /* ... and falls at or before end_time, i.e. it is in the list (aux holds its position) */
+};
+#define DCSIM_MAX_ARRIVALS (1u << 24) /* arrival index field of an xfer entry */
 
 enum { /* per-DC f64 arrays inside the state block, each DCSIM_MAX_DC long */
   DF_ENERGY = 0,
@@ -147,12 +171,7 @@ enum { /* per-DC i32 arrays; FIFO rings are (head index, length) so no modulo is
 #define DCSIM_FOR_EACH_DC(d, c, n) for (int d = 0; d < (n); ++d)
 #endif
 
-#define DCSIM_RNG_WINDOW 128u /* Philox words staged per refill: one block per lane */
-#define DCSIM_RNG_MARGIN 64u  /* refill when fewer than this many staged words remain at an arrival: covers one
-                                 arrival's speculative look-ahead (2 size + 16 route + 8x4 thinning words) */
-#define DCSIM_ARR_WINDOW 16u   /* arrival-list entries staged in shared memory at a time (pre-pass mode) */
-#define DCSIM_SPEC_ROUTE (DCSIM_LANES < 16 ? DCSIM_LANES : 16) /* lanes trying random.choice draws at once */
-#define DCSIM_SPEC_THIN (DCSIM_LANES < 8 ? DCSIM_LANES : 8)    /* lanes trying thinning candidates at once */
+#define DCSIM_LIST_WINDOW 32u   /* event-list entries staged in shared memory at a time: one per lane */
 /* A rejection loop that has not accepted after this many draws stops the replica with DCSIM_ST_RNG_RUNAWAY
  * instead of spinning (the reference would spin: e.g. arrivals.py:41-45 under a clipped lambda). */
 #define DCSIM_REJECTION_LIMIT (1 << 24)
@@ -161,20 +180,20 @@ enum { /* per-DC i32 arrays; FIFO rings are (head index, length) so no modulo is
 struct dcsim_hdr_t {
   double now, lat_sum, lat_sum_inf, lat_sum_trn, last_t;
   uint32_t n_events, seq, jid, rng_pos;
-  uint32_t n_xfer, status, done, initialized;
+  uint32_t _r0, status, done, initialized;
   uint32_t n_fin_inf, n_fin_trn, ev_arr, ev_xfer;
-  uint32_t ev_fin, ev_log, max_xfer, max_run;
-  uint32_t max_q, xmin_slot, bandit_t, n_stale;
-  uint32_t smin_slot, arr_cursor, arr_count, aw_base; /* arrival-list cursor / length / first staged entry */
+  uint32_t ev_fin, ev_log, _r1, max_run;
+  uint32_t max_q, _r2, bandit_t, n_stale;
+  uint32_t smin_slot, ml_cursor, ml_count, lw_base; /* event-list cursor / length / first staged entry */
 };
 
 /* Byte offsets of the arrays inside a state block; computed once per handle on the host. */
 struct dcsim_layout_t {
   int32_t cand_t, cand_seq;
   int32_t dc_f64, dc_i32;
-  int32_t xf_t, xf_size, xf_seq, xf_meta, xf_jid;
+  int32_t lw_t, lw_aux, lw_meta, pend_seq, xring; /* list window, pending seq per stream, seq ring of in-flight transfers */
+  int32_t xring_mask;                              /* ring entries - 1 (a power of two) */
   int32_t rn_t, rn_pw, rn_tpt, rn_start, rn_size, rn_f, rn_seq, rn_meta, rn_jid;
-  int32_t rng_buf;
   int32_t memo_f64, memo_n; /* per (DC, jtype): the last (n, f) a job started with and its T(n,f), n*P_gpu(f), 1/T */
   int32_t bandit_n, bandit_s;
   /* power-cap controller (algo = cap_greedy with power_cap > 0 only) */
@@ -182,13 +201,10 @@ struct dcsim_layout_t {
   int32_t st_t, st_seq;              /* stale job_finish pool */
   int32_t at_rho, at_fto, at_ref, at_idx; /* DVFS atoms scratch (freq_load_agg.py) */
   int32_t cap_stale, cap_atoms;
-  /* arrival pre-pass mode: a staging window of the replica's arrival list + per-stream pending seq */
-  int32_t aw_t, aw_size, aw_meta, pend_seq;
-  int32_t prepass;
   int32_t total_bytes;
   int32_t rec_off;         /* the running-job records occupy [rec_off, total_bytes): the part of the block that may stay
                               in HBM/L2 while [0, rec_off) is staged in shared memory ("head staged" launch mode) */
-  int32_t cap_xfer, cap_run;
+  int32_t cap_run;
   int32_t cap_q[2];        /* FIFO entries per DC: [0]=inference [1]=training */
   int32_t lean;            /* 1: running records carry no size / f / jid (nobody reads them: no job log, bandit or cap) */
   uint64_t queue_bytes;    /* HBM bytes of one replica's FIFOs */
@@ -196,56 +212,51 @@ struct dcsim_layout_t {
 
 static inline int32_t dcsim_align16(int32_t x) { return (x + 15) & ~15; }
 
-/* The head of a state block has a FIXED layout — header, event set, per-DC arrays, arrival-list window, the base of
- * the transfer pool — so the event loop addresses it with immediate offsets (LDS [blk + imm]) instead of adding a
- * layout field from the constant bank in front of every access; only the capacity-dependent arrays behind it go
- * through dcsim_layout_t. */
+/* The head of a state block has a FIXED layout — header, event set, per-DC arrays, list window, pending seqs, the
+ * base of the transfer-seq ring — so the event loop addresses it with immediate offsets (LDS [blk + imm]) instead of
+ * adding a layout field from the constant bank in front of every access; only the capacity-dependent arrays behind it
+ * go through dcsim_layout_t. */
 enum : int32_t {
   DCSIM_OFF_CAND_T = ((int32_t)sizeof(dcsim_hdr_t) + 15) & ~15,
   DCSIM_OFF_CAND_SEQ = DCSIM_OFF_CAND_T + CAND_N * 8,
   DCSIM_OFF_DC_F64 = DCSIM_OFF_CAND_SEQ + CAND_N * 4,
   DCSIM_OFF_DC_I32 = DCSIM_OFF_DC_F64 + DF_N * DCSIM_MAX_DC * 8,
-  DCSIM_OFF_AW_T = (DCSIM_OFF_DC_I32 + DI_N * DCSIM_MAX_DC * 4 + 15) & ~15,
-  DCSIM_OFF_AW_SIZE = DCSIM_OFF_AW_T + (int32_t)DCSIM_ARR_WINDOW * 8,
-  DCSIM_OFF_AW_META = DCSIM_OFF_AW_SIZE + (int32_t)DCSIM_ARR_WINDOW * 8,
-  DCSIM_OFF_PEND_SEQ = DCSIM_OFF_AW_META + (int32_t)DCSIM_ARR_WINDOW * 4,
-  DCSIM_OFF_XF_T = (DCSIM_OFF_PEND_SEQ + 2 * DCSIM_MAX_ING * 4 + 15) & ~15
+  DCSIM_OFF_LW_T = (DCSIM_OFF_DC_I32 + DI_N * DCSIM_MAX_DC * 4 + 15) & ~15,
+  DCSIM_OFF_LW_AUX = DCSIM_OFF_LW_T + (int32_t)DCSIM_LIST_WINDOW * 8,
+  DCSIM_OFF_LW_META = DCSIM_OFF_LW_AUX + (int32_t)DCSIM_LIST_WINDOW * 8,
+  DCSIM_OFF_PEND_SEQ = DCSIM_OFF_LW_META + (int32_t)DCSIM_LIST_WINDOW * 4,
+  DCSIM_OFF_XRING = (DCSIM_OFF_PEND_SEQ + 2 * DCSIM_MAX_ING * 4 + 15) & ~15
 };
 
 /* Host-side: sizes the state block from the spec's capacities. */
-static inline void dcsim_make_layout(const dcsim_spec_t* sp, dcsim_layout_t* L, int prepass, int job_log) {
+static inline void dcsim_make_layout(const dcsim_spec_t* sp, dcsim_layout_t* L, int job_log) {
   memset(L, 0, sizeof(*L));
-  L->prepass = prepass ? 1 : 0;
   const bool bandit = sp->xfer_rule == DCSIM_START_BANDIT || sp->deq_rule == DCSIM_START_BANDIT;
   const bool cap = sp->algo == DCSIM_ALGO_CAP_GREEDY && sp->power_cap > 0.0;
   /* size (job_log.csv, cap re-timing), f (job_log.csv, bandit reward, cap) and jid (job_log.csv) of a running job
      are dead weight in the state block unless one of those readers exists: 60 -> 40 bytes per record. */
   L->lean = (job_log || bandit || cap) ? 0 : 1;
-  const int D = DCSIM_MAX_DC;
   int32_t cx = sp->cap_xfer > 0 ? sp->cap_xfer : 64;
   int32_t cr = sp->cap_run > 0 ? sp->cap_run : 16;
-  cx = (cx + 3) & ~3;
   cr = (cr + 3) & ~3;
-  L->cap_xfer = cx;
   L->cap_run = cr;
   L->cap_q[0] = sp->cap_q_inf > 0 ? sp->cap_q_inf : 4096;
   L->cap_q[1] = sp->cap_q_trn > 0 ? sp->cap_q_trn : 512;
   L->cand_t = DCSIM_OFF_CAND_T; L->cand_seq = DCSIM_OFF_CAND_SEQ;
   L->dc_f64 = DCSIM_OFF_DC_F64; L->dc_i32 = DCSIM_OFF_DC_I32;
-  L->aw_t = DCSIM_OFF_AW_T; L->aw_size = DCSIM_OFF_AW_SIZE; L->aw_meta = DCSIM_OFF_AW_META; L->pend_seq = DCSIM_OFF_PEND_SEQ;
-  (void)D;
-  int32_t o = DCSIM_OFF_XF_T;
-  L->xf_t = o; o += cx * 8;
-  L->xf_size = o; o += cx * 8;
-  L->xf_seq = o; o += cx * 4;
-  L->xf_meta = o; o += cx * 4;
-  L->xf_jid = o; o = dcsim_align16(o + cx * 4);
+  L->lw_t = DCSIM_OFF_LW_T; L->lw_aux = DCSIM_OFF_LW_AUX; L->lw_meta = DCSIM_OFF_LW_META; L->pend_seq = DCSIM_OFF_PEND_SEQ;
+  /* seq of an in-flight xfer_done, indexed by its list position: an arrival writes it, the entry reads it when the
+   * cursor gets there.  cap_xfer bounds the transfers in flight; an xfer entry lies at most (arrivals + transfers in
+   * between) ahead of its arrival — the merge kernel measures that distance and flags DCSIM_ST_XFER_OVERFLOW when the
+   * ring is too small for it, so the bound is checked, not assumed. */
+  int32_t ring = 8;
+  while (ring < 2 * cx) ring <<= 1;
+  L->xring = DCSIM_OFF_XRING;
+  L->xring_mask = ring - 1;
+  int32_t o = dcsim_align16(DCSIM_OFF_XRING + ring * 4);
   const int32_t nr = sp->n_dc * cr;
   L->memo_f64 = o; o += sp->n_dc * 2 * 4 * 8;
   L->memo_n = o; o = dcsim_align16(o + sp->n_dc * 2 * 4);
-  if (!prepass) { /* in-kernel sampling (legacy mode): the Philox window; the arrival-list window of the fixed head idles */
-    L->rng_buf = o; o += (int32_t)DCSIM_RNG_WINDOW * 4;
-  }
   if (bandit) {
     L->bandit_s = o; o += sp->n_dc * 2 * DCSIM_MAX_FREQ * 8;
     L->bandit_n = o; o += sp->n_dc * 2 * DCSIM_MAX_FREQ * 4;
@@ -297,12 +308,15 @@ struct dcsim_recorders_t {
   int64_t log_replica;
 };
 
-/* Per-replica result of the arrival pre-pass. */
+/* Per-replica result of the two pre-pass kernels. */
 struct dcsim_arrhdr_t {
   uint32_t count;      /* arrivals with t <= end_time, i.e. arrival events the loop will process */
   uint32_t first_mask; /* bit s: stream s's first arrival was schedulable (took a seq at construction, SIM:154-156) */
   uint32_t rng_words;  /* words the whole run consumes */
-  uint32_t status;     /* DCSIM_ST_* raised while generating */
+  uint32_t status;     /* DCSIM_ST_* raised while generating / merging */
+  uint32_t ml_count;   /* entries of the merged {arrival, xfer_done} list */
+  uint32_t max_ahead;  /* largest distance (in list entries) between an arrival and its xfer_done entry */
+  uint32_t _pad[2];
 };
 
 /* Everything a launch needs.  Passed as ONE __grid_constant__ kernel parameter, so the scenario is read
@@ -319,16 +333,26 @@ struct dcsim_kparams_t {
   char* state;          /* [n_replicas][L.total_bytes] */
   char* queues;         /* [n_replicas][L.queue_bytes] */
   double* summary;      /* [n_replicas][DCSIM_SUMMARY_K] */
-  /* arrival lists (pre-pass mode), replica-major SoA: entry k of replica r at [r * cap_arr + k] */
+  /* arrival pre-pass output, replica-major SoA: arrival k of replica r at [r * cap_arr + k] */
   double* arr_t;        /* arrival instant */
-  double* arr_size;     /* job size (arrivals.py:5-11) */
-  uint32_t* arr_meta;   /* stream (bits 0-3) | routed DC (4-6) | next arrival of the stream was schedulable (7) */
+  double* arr_raw;      /* what the job size is a function of: the clamped uniform (inference, arrivals.py:8), the normal
+                           deviate z (training, arrivals.py:10-11) — or the size itself under eco_route, which routes by it */
+  uint32_t* arr_meta;   /* stream (bits 0-3) | routed DC (4-6) | next arrival of the stream was schedulable (7) | raw is the size (8) */
+  uint32_t* arr_pred;   /* index of the stream's previous arrival (whose processing pushed this one), 0xffffffff = the constructor */
+  /* merge scratch, same indexing */
+  double* arr_tx;       /* xfer_done instant of arrival k (+inf: not schedulable / unreachable) */
+  uint32_t* arr_fin;    /* number of arrivals j < k whose xfer_done instant is finite */
+  /* merged event list, replica-major SoA: entry p of replica r at [r * 2 * cap_arr + p] (see ML_*) */
+  double* ml_t;
+  double* ml_aux;
+  uint32_t* ml_meta;
   struct dcsim_arrhdr_t* arr_hdr;
   uint32_t* lat_hist;   /* [n_replicas][2][DCSIM_LAT_BINS] job-latency histograms, or NULL */
   uint32_t* mt_state;   /* [624][n_replicas] Mersenne Twister states (rng = MT19937 only), else NULL */
   uint32_t cap_arr;
-  uint32_t staged;      /* 1: state blocks are staged in shared memory; 0: too large for that, run in place in HBM/L2 */
+  uint32_t _pad33;
   double end_eps;       /* end_time + 1e-9, the _schedule cut-off (SIM:161) */
+  double max_transfer;  /* largest finite transfer_s[ingress][dc][jtype] of the scenario */
 };
 
 /* ---- small typed views ------------------------------------------------------------------------ */
@@ -344,21 +368,23 @@ struct dcsim_ctx_t {
   dcsim_hdr_t* H;
   int lane;
   bool is_traced, is_logged;
-  /* Philox stream */
-  uint32_t key0, key1;
-  uint32_t rng_base;     /* warp-uniform: stream index of rng_buf[0] (multiple of 4); rng_pos + 1 = nothing staged */
-  /* Hot scalars kept in registers; lane 0's copy is authoritative (only lane 0 runs handlers) and is written
-   * back to the header when the launch ends. */
-  uint32_t rng_pos;      /* words consumed */
+  /* Hot scalars kept in registers and written back to the header when the launch ends.  seq: lane 0's copy is
+   * authoritative (only lane 0 runs handlers); the others are warp-uniform. */
   uint32_t seq;          /* successful pushes (SIM:163) */
-  double now;            /* warp-uniform */
+  uint32_t cursor;       /* next entry of the event list */
+  uint32_t lw_base;      /* list position of the window's first entry */
+  double now;
 };
 
 #define DCF(c, which) (dcsim_at<double>((c).blk, DCSIM_OFF_DC_F64 + (which) * DCSIM_MAX_DC * 8))
 #define DCI(c, which) (dcsim_at<int32_t>((c).blk, DCSIM_OFF_DC_I32 + (which) * DCSIM_MAX_DC * 4))
 #define CAND_T(c) (dcsim_at<double>((c).blk, DCSIM_OFF_CAND_T))
 #define CAND_SEQ(c) (dcsim_at<uint32_t>((c).blk, DCSIM_OFF_CAND_SEQ))
-#define RNG_BUF(c) (dcsim_at<uint32_t>((c).blk, (c).P->L.rng_buf))
+#define LW_T(c) (dcsim_at<double>((c).blk, DCSIM_OFF_LW_T))
+#define LW_AUX(c) (dcsim_at<double>((c).blk, DCSIM_OFF_LW_AUX))
+#define LW_META(c) (dcsim_at<uint32_t>((c).blk, DCSIM_OFF_LW_META))
+#define PEND_SEQ(c) (dcsim_at<uint32_t>((c).blk, DCSIM_OFF_PEND_SEQ))
+#define XRING(c) (dcsim_at<uint32_t>((c).blk, DCSIM_OFF_XRING))
 
 /* ================================================================================================
  * Philox4x32-10 stream; definition shared with oracle/philox_random.py
@@ -377,85 +403,8 @@ DCSIM_DEV void dcsim_philox_block(uint32_t k0, uint32_t k1, uint32_t b, uint32_t
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-/* Warp-uniform.  Makes sure at least DCSIM_RNG_MARGIN staged words are ahead of `pos`: every lane
- * computes one block of the window [pos & ~3, +128).  Ends with a warp sync when it refilled. */
-DCSIM_DEV void dcsim_rng_ensure(dcsim_ctx_t& c, uint32_t pos) {
-  if (pos - c.rng_base <= DCSIM_RNG_WINDOW - DCSIM_RNG_MARGIN) return; /* unsigned: also false when nothing is staged */
-  const uint32_t base = pos & ~3u;
-  uint32_t* buf = RNG_BUF(c);
-  for (uint32_t b = (uint32_t)c.lane; b < DCSIM_RNG_WINDOW / 4u; b += DCSIM_LANES) {
-    uint32_t w[4];
-    dcsim_philox_block(c.key0, c.key1, (base >> 2) + b, w);
-    buf[4 * b + 0] = w[0]; buf[4 * b + 1] = w[1]; buf[4 * b + 2] = w[2]; buf[4 * b + 3] = w[3];
-  }
-  c.rng_base = base;
-  dcsim_warp_sync();
-}
-
-/* Rare: a handler out-ran the staged window (a long rejection run); lane 0 computes the block alone. */
-#ifndef DCSIM_HOST_EMU
-__device__ __noinline__
-#else
-static
-#endif
-uint32_t dcsim_rng_word_slow(uint32_t k0, uint32_t k1, uint32_t pos) {
-  uint32_t w[4];
-  dcsim_philox_block(k0, k1, pos >> 2, w);
-  const uint32_t j = pos & 3u;
-  return j == 0u ? w[0] : (j == 1u ? w[1] : (j == 2u ? w[2] : w[3]));
-}
-
-/* Lane 0 only.  Next word of the stream. */
-DCSIM_DEV uint32_t dcsim_rng_word(dcsim_ctx_t& c) {
-  const uint32_t pos = c.rng_pos++;
-  const uint32_t idx = pos - c.rng_base;
-  if (idx < DCSIM_RNG_WINDOW) return RNG_BUF(c)[idx];
-  return dcsim_rng_word_slow(c.key0, c.key1, pos);
-}
-
-/* Any lane.  Word at absolute stream position `pos` without consuming it (speculative look-ahead). */
-DCSIM_DEV uint32_t dcsim_rng_peek(const dcsim_ctx_t& c, uint32_t pos) {
-  const uint32_t idx = pos - c.rng_base;
-  if (idx < DCSIM_RNG_WINDOW) return RNG_BUF(c)[idx];
-  return dcsim_rng_word_slow(c.key0, c.key1, pos);
-}
 DCSIM_DEV double dcsim_u53(uint32_t w0, uint32_t w1) { /* genrand_res53 on two given words */
   return ((double)(w0 >> 5) * 67108864.0 + (double)(w1 >> 6)) * (1.0 / 9007199254740992.0);
-}
-
-/* CPython genrand_res53 (Modules/_randommodule.c): 53-bit uniform on [0,1) from two words */
-DCSIM_DEV double dcsim_rng_random(dcsim_ctx_t& c) {
-  const uint32_t a = dcsim_rng_word(c) >> 5, b = dcsim_rng_word(c) >> 6;
-  return ((double)a * 67108864.0 + (double)b) * (1.0 / 9007199254740992.0);
-}
-
-/* random.py:242-250 via random.choice (SIM:576): k = n.bit_length(); redraw until < n */
-DCSIM_DEV int dcsim_rng_randbelow(dcsim_ctx_t& c, int n) {
-  const int k = dcsim_bit_length((uint32_t)n);
-  uint32_t v = dcsim_rng_word(c) >> (32 - k);
-  for (int it = 0; v >= (uint32_t)n; ++it) {
-    if (it >= DCSIM_REJECTION_LIMIT) { c.H->status |= DCSIM_ST_RNG_RUNAWAY; return 0; }
-    v = dcsim_rng_word(c) >> (32 - k);
-  }
-  return (int)v;
-}
-
-/* random.py:617 */
-DCSIM_DEV double dcsim_expovariate(dcsim_ctx_t& c, double lambd) { return -log(1.0 - dcsim_rng_random(c)) / lambd; }
-
-/* random.py:541-549 (Kinderman-Monahan) */
-DCSIM_DEV double dcsim_normalvariate(dcsim_ctx_t& c, double mu, double sigma) {
-  const double NV = c.P->spec.nv_magicconst;
-  double z = 0.0;
-  for (int it = 0;; ++it) {
-    if (it >= DCSIM_REJECTION_LIMIT) { c.H->status |= DCSIM_ST_RNG_RUNAWAY; break; }
-    const double u1 = dcsim_rng_random(c);
-    const double u2 = 1.0 - dcsim_rng_random(c);
-    z = NV * (u1 - 0.5) / u2;
-    const double zz = z * z / 4.0;
-    if (zz <= -log(u2)) break;
-  }
-  return mu + z * sigma;
 }
 
 /* ================================================================================================
@@ -496,51 +445,27 @@ DCSIM_DEV double dcsim_mod_pos(double x, double y) {
   return r;
 }
 
-/* arrivals.py:5-11 */
-DCSIM_DEV double dcsim_sample_size(dcsim_ctx_t& c, int jt) {
-  const dcsim_spec_t& sp = c.P->spec;
-  if (jt == DCSIM_JT_INFERENCE) {
-    const double x = 1.0 - dcsim_rng_random(c);
-    const double u = x > sp.uniform_floor ? x : sp.uniform_floor;
-    return sp.pareto_xm / pow(u, sp.pareto_inv_alpha);
-  }
-  const double v = exp(dcsim_normalvariate(c, sp.lognorm_mu, sp.lognorm_sigma));
-  return v > sp.lognorm_floor ? v : sp.lognorm_floor;
-}
-
-/* arrivals.py:25-48.  Returns the inter-arrival gap, +inf for a dead stream. */
-DCSIM_DEV double dcsim_next_interarrival(dcsim_ctx_t& c, int jt, double t) {
-  const dcsim_arrival_t& a = c.P->spec.arr[jt];
-  if (a.mode == DCSIM_ARR_POISSON) return a.rate <= 0.0 ? DCSIM_INF : dcsim_expovariate(c, a.rate);
-  if (a.mode == DCSIM_ARR_SINUSOID) {
-    const double abs_amp = a.amp < 0.0 ? -a.amp : a.amp;
-    const double max_rate = a.rate * (1.0 + abs_amp);
-    for (int it = 0;; ++it) {
-      if (it >= DCSIM_REJECTION_LIMIT) { c.H->status |= DCSIM_ST_RNG_RUNAWAY; return DCSIM_INF; }
-      const double w = dcsim_expovariate(c, max_rate);
-      const double tc = t + w;
-      double lam = a.rate * (1.0 + a.amp * sin(c.P->spec.two_pi * dcsim_mod_pos(tc, a.period) / a.period));
-      lam = lam > 0.0 ? lam : 0.0;
-      if (dcsim_rng_random(c) <= lam / max_rate) return w;
-    }
-  }
-  return DCSIM_INF;
-}
-
 /* ================================================================================================
  * Arrival pre-pass (one THREAD per replica)
  *
  * In every algo on this path the arrival process does not depend on data-centre state: only arrival handlers
  * draw random numbers (arrivals.py:8,11,15,44; SIM:576) and routing is random.choice or eco_route's static
- * E_unit * size score (SIM:544-553, 575-577).  So the replica's whole arrival sequence — instants, sizes, routed
- * DCs, and which pushes were schedulable — can be generated ahead of the event loop, in the reference's draw order
- * (arrival events in time order; inside one: size -> route -> next gap), by one thread per replica with all 32
- * lanes of a warp busy, instead of on one lane of the replica's warp.  The event loop then consumes the list.
+ * E_unit * size score (SIM:544-553, 575-577).  So the replica's whole arrival sequence — instants, routed DCs, which
+ * pushes were schedulable — can be generated ahead of the event loop, in the reference's draw order (arrival events in
+ * time order; inside one: size -> route -> next gap), by one thread per replica with all 32 lanes of a warp busy,
+ * instead of on one lane of the replica's warp.
+ *
+ * The chain is kept as short as the draw order allows: what decides the NEXT draw is only the stream position (how
+ * many words each sampler consumed) and the stream clocks.  A job size never feeds back (except under eco_route), so
+ * the pre-pass stores the deviate it is a function of and the merge kernel evaluates pow / exp lane-parallel; the
+ * rejection samplers decide through squeeze tests, and every lane of the warp ends an arrival with ONE converged
+ * log() for its next gap.
  * ============================================================================================== */
-/* Thread-level Philox stream with a 32-word ring (element i at buf[i * stride]: [word][thread] in shared memory on
- * the GPU).  The ring is topped up ONCE per arrival, by all lanes of the warp at the same program point; refilling
- * inside the samplers instead makes 32 out-of-phase lanes drag the warp through the block function at almost every
- * draw (measured: 43 % of the pre-pass). */
+/* Thread-level Philox stream with a 32-word ring (element i at ring[i * stride]: [word][thread] in shared memory on
+ * the GPU; the pointer is passed alongside the stream, not inside it, so that the accesses compile to LDS/STS).  The
+ * ring is topped up ONCE per arrival, by all lanes of the warp at the same program point; refilling inside the
+ * samplers instead makes 32 out-of-phase lanes drag the warp through the block function at almost every draw
+ * (measured: 43 % of the pre-pass). */
 #define DCSIM_TRNG_RING 32u
 /* Word source = CPython's own Mersenne Twister instead of Philox (dcsim_set_rng(h, DCSIM_RNG_MT19937)): the replica
  * then IS the stock reference at random.seed(seed0 + r) (SIM:71).  State: 624 words in HBM, element i at
@@ -548,8 +473,8 @@ DCSIM_DEV double dcsim_next_interarrival(dcsim_ctx_t& c, int jt, double t) {
 struct dcsim_mt_t { uint32_t* mt; uint64_t mt_stride; uint32_t mti; };
 /* The stream is a template over the word source so that the Philox instantiation carries no trace of the other one
  * (a run-time switch cost the pre-pass 3 %: different register allocation, more local-memory traffic). */
-template <bool MT> struct dcsim_trng_t { uint32_t k0, k1, pos, filled; uint32_t* buf; int stride; };
-template <> struct dcsim_trng_t<true> { uint32_t k0, k1, pos, filled; uint32_t* buf; int stride; dcsim_mt_t mt; };
+template <bool MT> struct dcsim_trng_t { uint32_t k0, k1, pos, filled; };
+template <> struct dcsim_trng_t<true> { uint32_t k0, k1, pos, filled; dcsim_mt_t mt; };
 
 /* MT19937 (Matsumoto & Nishimura) as CPython drives it: Modules/_randommodule.c init_by_array / genrand_uint32. */
 #define DCSIM_MT_N 624u
@@ -599,18 +524,18 @@ DCSIM_DEV uint32_t dcsim_mt_next(dcsim_mt_t& g) {
 }
 
 template <bool MT>
-DCSIM_DEV void dcsim_trng_block(dcsim_trng_t<MT>& g) { /* appends block filled/4 */
+DCSIM_DEV void dcsim_trng_block(dcsim_trng_t<MT>& g, uint32_t* ring, int stride) { /* appends block filled/4 */
   uint32_t w[4];
   if constexpr (MT) { w[0] = dcsim_mt_next(g.mt); w[1] = dcsim_mt_next(g.mt); w[2] = dcsim_mt_next(g.mt); w[3] = dcsim_mt_next(g.mt); }
   else dcsim_philox_block(g.k0, g.k1, g.filled >> 2, w);
   const uint32_t i = g.filled & (DCSIM_TRNG_RING - 1u);
-  g.buf[(i + 0u) * g.stride] = w[0]; g.buf[(i + 1u) * g.stride] = w[1];
-  g.buf[(i + 2u) * g.stride] = w[2]; g.buf[(i + 3u) * g.stride] = w[3];
+  ring[(i + 0u) * stride] = w[0]; ring[(i + 1u) * stride] = w[1];
+  ring[(i + 2u) * stride] = w[2]; ring[(i + 3u) * stride] = w[3];
   g.filled += 4u;
 }
 template <bool MT>
-DCSIM_DEV void dcsim_trng_topup(dcsim_trng_t<MT>& g) {
-  while (g.filled - g.pos <= DCSIM_TRNG_RING - 4u) dcsim_trng_block(g);
+DCSIM_DEV void dcsim_trng_topup(dcsim_trng_t<MT>& g, uint32_t* ring, int stride) {
+  while (g.filled - g.pos <= DCSIM_TRNG_RING - 4u) dcsim_trng_block(g, ring, stride);
 }
 template <bool MT>
 #ifndef DCSIM_HOST_EMU
@@ -618,23 +543,24 @@ __device__ __noinline__
 #else
 static
 #endif
-void dcsim_trng_dry(dcsim_trng_t<MT>* g) { dcsim_trng_block(*g); } /* a sampler out-ran the ring (long rejection run) */
+void dcsim_trng_dry(dcsim_trng_t<MT>* g, uint32_t* ring, int stride) { dcsim_trng_block(*g, ring, stride); } /* a sampler out-ran the ring (long rejection run) */
 template <bool MT>
-DCSIM_DEV uint32_t dcsim_trng_word(dcsim_trng_t<MT>& g) {
-  if (g.pos == g.filled) dcsim_trng_dry(&g);
-  return g.buf[(g.pos++ & (DCSIM_TRNG_RING - 1u)) * g.stride];
+DCSIM_DEV uint32_t dcsim_trng_word(dcsim_trng_t<MT>& g, uint32_t* ring, int stride) {
+  if (g.pos == g.filled) dcsim_trng_dry(&g, ring, stride);
+  return ring[(g.pos++ & (DCSIM_TRNG_RING - 1u)) * stride];
 }
 template <bool MT>
-DCSIM_DEV double dcsim_trng_random(dcsim_trng_t<MT>& g) {
-  const uint32_t a = dcsim_trng_word(g), b = dcsim_trng_word(g);
+DCSIM_DEV double dcsim_trng_random(dcsim_trng_t<MT>& g, uint32_t* ring, int stride) {
+  const uint32_t a = dcsim_trng_word(g, ring, stride), b = dcsim_trng_word(g, ring, stride);
   return dcsim_u53(a, b);
 }
 
 /* Constants of the thinning squeeze for one arrival stream (computed once per replica). */
 struct dcsim_squeeze_t {
-  double max_rate; /* rate * (1 + |amp|), arrivals.py:40 */
-  double x1_min;   /* 1-U1 >= x1_min guarantees the candidate gap w = -log(1-U1)/max_rate <= w_max */
-  double eps;      /* |lambda(t+w) - lambda(t)| / max_rate <= eps for 0 <= w <= w_max (+ a generous rounding slop) */
+  double max_rate;   /* rate * (1 + |amp|), arrivals.py:40 */
+  double x1_min;     /* 1-U1 >= x1_min guarantees the candidate gap w = -log(1-U1)/max_rate <= w_max */
+  double eps;        /* |lambda(t+w) - lambda(t)| / max_rate <= eps for 0 <= w <= w_max (+ the slop of the cheap lambda(t)) */
+  double inv_period; /* 1 / period, for the cheap phase of lambda(t) */
 };
 DCSIM_DEV dcsim_squeeze_t dcsim_squeeze_setup(const dcsim_arrival_t& a, double two_pi) {
   dcsim_squeeze_t q;
@@ -643,76 +569,131 @@ DCSIM_DEV dcsim_squeeze_t dcsim_squeeze_setup(const dcsim_arrival_t& a, double t
   double w_max = 8.0 / q.max_rate;                 /* covers all but e^-8 of the candidate gaps ... */
   if (w_max > 0.002 * a.period) w_max = 0.002 * a.period; /* ... unless the rate varies too fast for that */
   q.x1_min = exp(-q.max_rate * w_max * 0.999);     /* 0.999: errs towards the exact path */
-  /* lambda is rate*(1+amp*sin(2 pi t/period)) clipped at 0: Lipschitz constant rate*|amp|*2 pi/period */
-  q.eps = a.rate * abs_amp * two_pi * w_max / a.period / q.max_rate + 1e-9;
+  /* lambda is rate*(1+amp*sin(2 pi t/period)) clipped at 0: Lipschitz constant rate*|amp|*2 pi/period.  The band's
+   * centre lambda(t) itself is evaluated in single precision (absolute error of the sine < 1e-6, i.e. < 1e-6 of
+   * max_rate in lambda/max_rate): 4e-6 of extra half-width covers it with room to spare. */
+  q.eps = a.rate * abs_amp * two_pi * w_max / a.period / q.max_rate + 4e-6 + 1e-9;
+  q.inv_period = a.period > 0.0 ? 1.0 / a.period : 0.0;
   return q;
+}
+
+/* sin(2 pi * frac(t / period)) good to ~1e-6 absolute: only ever used to CENTRE the squeeze band, never to decide. */
+DCSIM_DEV double dcsim_sin_phase_approx(double t, double inv_period, double two_pi) {
+  const double tp = t * inv_period;
+  const double ph = (tp - floor(tp)) * two_pi; /* [0, 2 pi) */
+#ifdef DCSIM_HOST_EMU
+  return sin(ph);
+#else
+  float x = (float)ph;
+  x = x > 3.14159274f ? x - 6.28318548f : x;   /* MUFU.SIN is accurate to 2^-21.4 on [-pi, pi] */
+  return (double)__sinf(x);
+#endif
 }
 
 /* arrivals.py:35-48 with random.py:617; returns the gap (+inf for a dead stream).
  *
  * Sinusoid "thinning" (arrivals.py:41-45) redraws (w, U2) until U2 <= lambda(t+w)/max_rate, keeping only the last w.
  * The decision of a candidate is taken WITHOUT log and sin whenever it is not close: w <= w_max is implied by
- * 1-U1 >= x1_min, and then lambda(t+w)/max_rate lies within eps of p0 = lambda(t)/max_rate, so U2 <= p0 - eps
+ * 1-U1 >= x1_min, and then lambda(t+w)/max_rate lies within eps of p0 ~ lambda(t)/max_rate, so U2 <= p0 - eps
  * accepts and U2 > p0 + eps rejects exactly as the full formula would; only candidates inside the +-eps band (or with
  * a very long gap) evaluate the reference's expression.  Same words consumed, same decisions, same w — but a thread
  * spends ~20 instructions instead of ~500 on a rejected candidate, which matters because a warp's lanes all wait
- * for the lane with the longest rejection run. */
+ * for the lane with the longest rejection run.  The accepted candidate's gap -log(1-U1)/max_rate is evaluated AFTER the
+ * loop, at the same program point as a Poisson stream's -log(1-U)/rate: one converged log() per arrival and warp. */
 template <bool MT>
-DCSIM_DEV double dcsim_t_gap(dcsim_trng_t<MT>& g, const dcsim_spec_t& sp, const dcsim_squeeze_t& q, int jt, double t, uint32_t* status) {
+DCSIM_DEV double dcsim_t_gap(dcsim_trng_t<MT>& g, uint32_t* ring, int stride, const dcsim_spec_t& sp, const dcsim_squeeze_t& q, int jt,
+                             double t, uint32_t* status) {
   const dcsim_arrival_t& a = sp.arr[jt];
-  if (a.mode == DCSIM_ARR_POISSON) return a.rate <= 0.0 ? DCSIM_INF : -log(1.0 - dcsim_trng_random(g)) / a.rate;
-  if (a.mode == DCSIM_ARR_SINUSOID) {
+  double x, rate;
+  if (a.mode == DCSIM_ARR_POISSON) {
+    if (a.rate <= 0.0) return DCSIM_INF;
+    x = 1.0 - dcsim_trng_random(g, ring, stride);
+    rate = a.rate;
+  } else if (a.mode == DCSIM_ARR_SINUSOID) {
     const double max_rate = q.max_rate;
-    double lam0 = a.rate * (1.0 + a.amp * sin(sp.two_pi * dcsim_mod_pos(t, a.period) / a.period));
+    double lam0 = a.rate * (1.0 + a.amp * dcsim_sin_phase_approx(t, q.inv_period, sp.two_pi));
     lam0 = lam0 > 0.0 ? lam0 : 0.0;
     const double p0 = lam0 / max_rate, p_lo = p0 - q.eps, p_hi = p0 + q.eps;
     for (int it = 0;; ++it) {
       if (it >= DCSIM_REJECTION_LIMIT) { *status |= DCSIM_ST_RNG_RUNAWAY; return DCSIM_INF; }
-      const double x1 = 1.0 - dcsim_trng_random(g);
-      const double u2 = dcsim_trng_random(g);
-      const bool near_t = x1 >= q.x1_min;
-      if (near_t && u2 > p_hi) continue;                  /* certainly rejected */
-      const double w = -log(x1) / max_rate;
-      if (near_t && u2 <= p_lo) return w;                 /* certainly accepted */
-      const double tc = t + w;                            /* in the band: the reference's expression */
+      const double x1 = 1.0 - dcsim_trng_random(g, ring, stride);
+      const double u2 = dcsim_trng_random(g, ring, stride);
+      if (x1 >= q.x1_min) {
+        if (u2 > p_hi) continue;                          /* certainly rejected */
+        if (u2 <= p_lo) { x = x1; break; }                /* certainly accepted */
+      }
+      const double w = -log(x1) / max_rate;               /* in the band: the reference's expression */
+      const double tc = t + w;
       double lam = a.rate * (1.0 + a.amp * sin(sp.two_pi * dcsim_mod_pos(tc, a.period) / a.period));
       lam = lam > 0.0 ? lam : 0.0;
       if (u2 <= lam / max_rate) return w;
     }
+    rate = max_rate;
+  } else {
+    return DCSIM_INF;
   }
-  return DCSIM_INF;
+  return -log(x) / rate;
 }
 
-/* arrivals.py:5-11 with random.py:541-549, 597 */
+/* arrivals.py:5-11 with random.py:541-549, 597: draws what the job size is a function of — the clamped uniform of the
+ * Pareto branch, the Kinderman-Monahan normal deviate of the log-normal branch — consuming exactly the reference's words.
+ * The K-M acceptance zz <= -log(u2) is decided by the bounds 1-u <= -log(u) <= (1-u)/u (1-u2 is exact: u2 is a
+ * multiple of 2^-53) whenever they settle it with a 1e-6 relative margin — far more than any libm's log is off — and
+ * by the reference's expression otherwise.  dcsim_size_from_raw() finishes the job. */
 template <bool MT>
-DCSIM_DEV double dcsim_t_size(dcsim_trng_t<MT>& g, const dcsim_spec_t& sp, int jt, uint32_t* status) {
+DCSIM_DEV double dcsim_t_size_raw(dcsim_trng_t<MT>& g, uint32_t* ring, int stride, const dcsim_spec_t& sp, int jt, uint32_t* status) {
   if (jt == DCSIM_JT_INFERENCE) {
-    const double x = 1.0 - dcsim_trng_random(g);
-    const double u = x > sp.uniform_floor ? x : sp.uniform_floor;
-    return sp.pareto_xm / pow(u, sp.pareto_inv_alpha);
+    const double x = 1.0 - dcsim_trng_random(g, ring, stride);
+    return x > sp.uniform_floor ? x : sp.uniform_floor;
   }
   double z = 0.0;
   for (int it = 0;; ++it) {
     if (it >= DCSIM_REJECTION_LIMIT) { *status |= DCSIM_ST_RNG_RUNAWAY; break; }
-    const double u1 = dcsim_trng_random(g);
-    const double u2 = 1.0 - dcsim_trng_random(g);
+    const double u1 = dcsim_trng_random(g, ring, stride);
+    const double u2 = 1.0 - dcsim_trng_random(g, ring, stride);
     z = sp.nv_magicconst * (u1 - 0.5) / u2;
     const double zz = z * z / 4.0;
+    const double om = 1.0 - u2;
+    if (zz <= om * 0.999999) break;        /* zz < 1-u2 <= -log(u2) */
+    if (zz * u2 > om * 1.000001) continue; /* zz > (1-u2)/u2 >= -log(u2) */
     if (zz <= -log(u2)) break;
   }
-  const double v = exp(sp.lognorm_mu + z * sp.lognorm_sigma);
+  return z;
+}
+
+/* arrivals.py:7-8 / 10-11 from the stored deviate. */
+DCSIM_DEV double dcsim_size_from_raw(const dcsim_spec_t& sp, double raw, int jt) {
+  if (jt == DCSIM_JT_INFERENCE) return sp.pareto_xm / pow(raw, sp.pareto_inv_alpha);
+  const double v = exp(sp.lognorm_mu + raw * sp.lognorm_sigma);
   return v > sp.lognorm_floor ? v : sp.lognorm_floor;
 }
 
-/* One replica's arrival list.  `next_t` is scratch for the 2*n_ing stream clocks (element s at next_t[s * stride]),
- * `ring` for the DCSIM_TRNG_RING staged Philox words (element i at ring[i * stride]). */
+/* TEST HOOK, host build only (see oracle/dcsim_oracle.c g_test_time_quantum): rounds arrival and xfer_done instants up
+ * to a multiple of a quantum so that same-instant events become common and the tie-breaking below is exercised. */
+#ifdef DCSIM_HOST_EMU
+static double dcsim_test_time_quantum = 0.0;
+static inline double dcsim_test_quantize(double t) {
+  return (dcsim_test_time_quantum > 0.0 && !(t == DCSIM_INF)) ? ceil(t / dcsim_test_time_quantum) * dcsim_test_time_quantum : t;
+}
+#else
+#define dcsim_test_quantize(t) (t)
+#endif
+
+#define DCSIM_NO_PRED 0xffffffffu
+/* Push rank of stream q's pending arrival: the constructor pushed the first arrivals in stream order (SIM:154-156),
+ * every later one was pushed while its predecessor — list entry `last` — was being processed (SIM:591-592). */
+DCSIM_DEV uint32_t dcsim_stream_rank(uint32_t last, int q) { return last == DCSIM_NO_PRED ? (uint32_t)q : 16u + last; }
+
+/* One replica's arrival list.  Per-thread scratch, element s of each array at [s * stride] ([slot][thread] in shared
+ * memory): `next_t` the 2*n_ing stream clocks, `last_idx` the list index of each stream's latest arrival, `ring` the
+ * DCSIM_TRNG_RING staged words of the stream. */
 template <bool MT>
-DCSIM_DEV void dcsim_generate_arrivals(const dcsim_kparams_t* P, uint64_t r, double* next_t, uint32_t* ring, int stride) {
+DCSIM_DEV void dcsim_generate_arrivals(const dcsim_kparams_t* P, uint64_t r, double* next_t, uint32_t* last_idx, uint32_t* ring, int stride) {
   const dcsim_spec_t& sp = P->spec;
   const int n_streams = 2 * sp.n_ing;
   dcsim_trng_t<MT> g;
   const uint64_t key = P->seed0 + r;
-  g.k0 = (uint32_t)key; g.k1 = (uint32_t)(key >> 32); g.pos = 0u; g.filled = 0u; g.buf = ring; g.stride = stride;
+  g.k0 = (uint32_t)key; g.k1 = (uint32_t)(key >> 32); g.pos = 0u; g.filled = 0u;
   if constexpr (MT) { g.mt.mt = P->mt_state + r; g.mt.mt_stride = P->n_replicas; dcsim_mt_seed(g.mt, key); }
   uint32_t status = 0u, first_mask = 0u, count = 0u;
   const double end_eps = P->end_eps;
@@ -720,57 +701,172 @@ DCSIM_DEV void dcsim_generate_arrivals(const dcsim_kparams_t* P, uint64_t r, dou
   sq[0] = dcsim_squeeze_setup(sp.arr[0], sp.two_pi);
   sq[1] = dcsim_squeeze_setup(sp.arr[1], sp.two_pi);
   for (int s = 0; s < n_streams; ++s) { /* SIM:154-156 */
-    dcsim_trng_topup(g);
-    const double t = 0.0 + dcsim_t_gap(g, sp, sq[s & 1], s & 1, 0.0, &status);
+    dcsim_trng_topup(g, ring, stride);
+    const double t = dcsim_test_quantize(0.0 + dcsim_t_gap(g, ring, stride, sp, sq[s & 1], s & 1, 0.0, &status));
     const bool ok = !(t == DCSIM_INF) && !(t > end_eps);
     next_t[s * stride] = ok ? t : DCSIM_INF;
+    last_idx[s * stride] = DCSIM_NO_PRED;
     if (ok) first_mask |= 1u << s;
   }
   double* out_t = P->arr_t + r * (uint64_t)P->cap_arr;
-  double* out_size = P->arr_size + r * (uint64_t)P->cap_arr;
+  double* out_raw = P->arr_raw + r * (uint64_t)P->cap_arr;
   uint32_t* out_meta = P->arr_meta + r * (uint64_t)P->cap_arr;
+  uint32_t* out_pred = P->arr_pred + r * (uint64_t)P->cap_arr;
   const int k_bits = dcsim_bit_length((uint32_t)sp.n_dc);
   for (;;) {
     int s = -1;
     double t = DCSIM_INF;
-    bool tie = false;
-    for (int q = 0; q < n_streams; ++q) {
+    for (int q = 0; q < n_streams; ++q) { /* heap order (t, seq): two pending arrivals at the same instant pop in push order */
       const double tq = next_t[q * stride];
-      if (tq < t) { t = tq; s = q; tie = false; } else if (tq == t && s >= 0 && !(tq == DCSIM_INF)) tie = true;
+      if (tq < t) { t = tq; s = q; }
+      else if (tq == t && s >= 0 && !(tq == DCSIM_INF) &&
+               dcsim_stream_rank(last_idx[q * stride], q) < dcsim_stream_rank(last_idx[s * stride], s)) s = q;
     }
     if (s < 0 || t > sp.end_time) break; /* heap empty / SIM:427 */
-    if (tie) { status |= DCSIM_ST_ARRIVAL_TIE; break; }
     if (status) break;
-    dcsim_trng_topup(g); /* all lanes refill here, together */
+    dcsim_trng_topup(g, ring, stride); /* all lanes refill here, together */
     const int jt = s & 1;
-    const double size = dcsim_t_size(g, sp, jt, &status); /* draw order: size -> route -> next gap (SIM:540,576,591) */
+    double raw = dcsim_t_size_raw(g, ring, stride, sp, jt, &status); /* draw order: size -> route -> next gap (SIM:540,576,591) */
     int dc_sel = 0;
-    if (sp.route_rule == DCSIM_ROUTE_ECO) { /* SIM:544-553 */
+    uint32_t raw_is_size = 0u;
+    if (sp.route_rule == DCSIM_ROUTE_ECO) { /* SIM:544-553: routes by E_unit * size, so the size is needed here */
+      const double size = dcsim_size_from_raw(sp, raw, jt);
       double best = sp.dc[0].eco_e_unit[jt] * size;
       for (int d = 1; d < sp.n_dc; ++d) {
         const double score = sp.dc[d].eco_e_unit[jt] * size;
         if (score < best) { best = score; dc_sel = d; }
       }
+      raw = size; raw_is_size = 0x100u;
     } else { /* random.choice: random.py:242-250 */
-      uint32_t v = dcsim_trng_word(g) >> (32 - k_bits);
+      uint32_t v = dcsim_trng_word(g, ring, stride) >> (32 - k_bits);
       for (int it = 0; v >= (uint32_t)sp.n_dc; ++it) {
         if (it >= DCSIM_REJECTION_LIMIT) { status |= DCSIM_ST_RNG_RUNAWAY; v = 0u; break; }
-        v = dcsim_trng_word(g) >> (32 - k_bits);
+        v = dcsim_trng_word(g, ring, stride) >> (32 - k_bits);
       }
       dc_sel = (int)v;
     }
-    const double tn = t + dcsim_t_gap(g, sp, jt ? sq[1] : sq[0], jt, t, &status);
+    const double tn = dcsim_test_quantize(t + dcsim_t_gap(g, ring, stride, sp, jt ? sq[1] : sq[0], jt, t, &status));
     const bool has_next = !(tn == DCSIM_INF) && !(tn > end_eps);
     next_t[s * stride] = has_next ? tn : DCSIM_INF;
     if (count >= P->cap_arr) { status |= DCSIM_ST_ARRIVALS_OVERFLOW; break; }
     out_t[count] = t;
-    out_size[count] = size;
-    out_meta[count] = (uint32_t)s | ((uint32_t)dc_sel << 4) | (has_next ? 0x80u : 0u);
+    out_raw[count] = raw;
+    out_meta[count] = (uint32_t)s | ((uint32_t)dc_sel << 4) | (has_next ? 0x80u : 0u) | raw_is_size;
+    out_pred[count] = last_idx[s * stride];
+    last_idx[s * stride] = count;
     ++count;
   }
   dcsim_arrhdr_t h;
   h.count = count; h.first_mask = first_mask; h.rng_words = g.pos; h.status = status;
+  h.ml_count = 0u; h.max_ahead = 0u; h._pad[0] = h._pad[1] = 0u;
   P->arr_hdr[r] = h;
+}
+
+/* ================================================================================================
+ * List merge (one WARP per replica, lane-parallel over its arrivals)
+ *
+ * An arrival at t is followed by its xfer_done at t + transfer_s[ingress][dc][jtype] (SIM:580-588) — a constant per
+ * (ingress, DC, job type), known as soon as the arrival is.  So both kinds of event go into ONE time-ordered list and
+ * the event loop needs no pool of in-flight transfers (no push, no removal, no min-rescan per transfer).  Order is the
+ * heap's (t, seq): between two list events seq order is push order, and every push in the list happens while an
+ * arrival is processed (the xfer_done first, then the stream's next arrival, SIM:580-592; the constructor's pushes
+ * before all, in stream order) — so ties are resolved exactly from list indices alone:
+ *     arrival k   pushed while arrival pred(k) was processed, after pred(k)'s own xfer_done;
+ *     xfer_done j pushed while arrival j was processed.
+ * The position of an event is the number of events before it; with the arrivals already in order only the transfers
+ * within max_transfer of it need to be looked at.  The same pass evaluates the job sizes (pow / exp), all 32 lanes
+ * on different arrivals.
+ * ============================================================================================== */
+DCSIM_DEV bool dcsim_finite(double x) { return !(x == DCSIM_INF); }
+
+DCSIM_DEV void dcsim_merge_arrivals(const dcsim_kparams_t* P, uint64_t r, int lane) {
+  const dcsim_spec_t& sp = P->spec;
+  dcsim_arrhdr_t* hdr = P->arr_hdr + r;
+  const uint32_t n = hdr->count;
+  const uint64_t ab = r * (uint64_t)P->cap_arr;
+  const double* at = P->arr_t + ab;
+  double* raw = P->arr_raw + ab;
+  const uint32_t* am = P->arr_meta + ab;
+  const uint32_t* pred = P->arr_pred + ab;
+  double* tx = P->arr_tx + ab;
+  uint32_t* fin = P->arr_fin + ab;
+  double* mt = P->ml_t + 2ull * ab;
+  double* ma = P->ml_aux + 2ull * ab;
+  uint32_t* mm = P->ml_meta + 2ull * ab;
+  const double end = sp.end_time, end_eps = P->end_eps, tmax = P->max_transfer;
+
+  /* sweep 1: sizes, xfer_done instants, running count of the finite ones */
+  uint32_t fin_base = 0u;
+  for (uint32_t k0 = 0u; k0 < n; k0 += DCSIM_LANES) {
+    const uint32_t k = k0 + (uint32_t)lane;
+    bool f = false;
+    if (k < n) {
+      const uint32_t meta = am[k];
+      const int stream = (int)(meta & 15u), jt = stream & 1, ing = stream >> 1, dc = (int)((meta >> 4) & 7u);
+      if (!(meta & 0x100u)) raw[k] = dcsim_size_from_raw(sp, raw[k], jt); /* from here on raw[] holds the sizes */
+      const double v = dcsim_test_quantize(at[k] + sp.transfer_s[ing][dc][jt]); /* SIM:580: now + transfer_s, now == the arrival instant */
+      f = dcsim_finite(v);
+      tx[k] = v;
+    }
+    const uint32_t votes = dcsim_warp_ballot(f);
+    if (k < n) fin[k] = fin_base + dcsim_popc(votes & dcsim_lanemask_lt(lane));
+    fin_base += dcsim_popc(votes);
+  }
+  dcsim_warp_sync(); /* tx[] / fin[] / raw[] written by other lanes are read below */
+
+  /* sweep 2: list positions, emission */
+  uint32_t n_x = 0u, ahead = 0u;
+  for (uint32_t k0 = 0u; k0 < n; k0 += DCSIM_LANES) {
+    const uint32_t k = k0 + (uint32_t)lane;
+    if (k >= n) continue;
+    const double tk = at[k], txk = tx[k];
+    const uint32_t meta = am[k], pk = pred[k];
+    /* arrival k: the k earlier arrivals + the transfers that come before it */
+    uint32_t cnt = 0u;
+    for (uint32_t j = k; j > 0u;) {
+      --j;
+      if (at[j] + tmax < tk) { cnt += fin[j] + (dcsim_finite(tx[j]) ? 1u : 0u); break; } /* every finite one up to j is earlier */
+      const double txj = tx[j];
+      if (txj < tk || (txj == tk && pk != DCSIM_NO_PRED && j <= pk)) ++cnt;
+    }
+    const uint32_t pos_a = k + cnt;
+    const bool xs = dcsim_finite(txk) && !(txk > end_eps); /* SIM:160-163 */
+    const bool xin = xs && !(txk > end);                    /* SIM:427: later events are never processed */
+    uint32_t pos_x = 0xffffffffu;
+    if (xin) {
+      uint32_t ca = k + 1u, cx = 0u; /* arrivals 0..k come first (their pushes precede arrival k's processing) */
+      for (uint32_t j = k; j > 0u;) {
+        --j;
+        if (at[j] + tmax < txk) { cx += fin[j] + (dcsim_finite(tx[j]) ? 1u : 0u); break; }
+        if (tx[j] <= txk) ++cx; /* tie: pushed earlier */
+      }
+      for (uint32_t i = k + 1u; i < n; ++i) {
+        const double ti = at[i];
+        if (ti > txk) break;
+        if (ti < txk || pred[i] == DCSIM_NO_PRED || pred[i] < k) ++ca; /* tie: arrival i was pushed before arrival k ran */
+        if (tx[i] < txk) ++cx;                                          /* tie: pushed later */
+      }
+      pos_x = ca + cx;
+      ++n_x;
+      ahead = pos_x - pos_a > ahead ? pos_x - pos_a : ahead;
+    }
+    const uint32_t stream = meta & 15u;
+    mt[pos_a] = tk;
+    ma[pos_a] = dcsim_hilo_f64(0u, pos_x);
+    mm[pos_a] = (stream << 1) | ((meta & 0x80u) ? ML_A_NEXT : 0u) | (xs ? ML_A_XSCHED : 0u) | (xin ? ML_A_XIN : 0u);
+    if (xin) {
+      mt[pos_x] = txk;
+      ma[pos_x] = raw[k];
+      mm[pos_x] = ML_XFER | (((meta >> 4) & 7u) << 1) | ((stream & 1u) << 4) | ((stream >> 1) << 5) | (k << 8);
+    }
+  }
+  n_x = dcsim_warp_add_u32(n_x);
+  ahead = dcsim_warp_max_u32(ahead);
+  if (lane == 0) {
+    hdr->ml_count = n + n_x;
+    hdr->max_ahead = ahead;
+    if (ahead > (uint32_t)P->L.xring_mask) hdr->status |= DCSIM_ST_XFER_OVERFLOW; /* the seq ring would wrap onto a pending entry */
+  }
 }
 
 /* ================================================================================================
@@ -874,19 +970,6 @@ DCSIM_DEV void dcsim_rescan_dc(dcsim_ctx_t& c, int d) {
     CAND_T(c)[CAND_DC0 + d] = k >= 0 ? t : DCSIM_INF;
     CAND_SEQ(c)[CAND_DC0 + d] = k >= 0 ? s : 0xffffffffu;
     DCI(c, DI_FMIN_SLOT)[d] = k;
-  }
-  dcsim_warp_sync();
-}
-
-/* Warp.  Earliest in-flight transfer -> candidate slot CAND_XFER. */
-DCSIM_DEV void dcsim_rescan_xfer(dcsim_ctx_t& c) {
-  double t; uint32_t s;
-  const int k = dcsim_argmin_ts(dcsim_at<double>(c.blk, DCSIM_OFF_XF_T), dcsim_at<uint32_t>(c.blk, c.P->L.xf_seq),
-                                (int)c.H->n_xfer, c.lane, &t, &s);
-  if (c.lane == 0) {
-    CAND_T(c)[CAND_XFER] = k >= 0 ? t : DCSIM_INF;
-    CAND_SEQ(c)[CAND_XFER] = k >= 0 ? s : 0xffffffffu;
-    c.H->xmin_slot = (uint32_t)k;
   }
   dcsim_warp_sync();
 }
@@ -1076,217 +1159,75 @@ DCSIM_DEV void dcsim_start_by_rule(dcsim_ctx_t& c, int rule, bool at_xfer, int d
   }
 }
 
-/* SIM:537-592, whole warp.  Draw order is the reference's: size -> route -> next inter-arrival (App. A.7).
- * The two rejection loops that dominate the draws — random.choice's bit rejection (random.py:242-250) and the
- * sinusoid "thinning" (arrivals.py:41-45) — are evaluated SPECULATIVELY: lane j computes candidate j from the
- * words candidate j would consume (the Philox window is indexable), a ballot picks the first accepting lane,
- * and the stream position advances by exactly what the sequential loop would have consumed.
- * On entry c.rng_pos is warp-uniform and >= DCSIM_RNG_MARGIN words are staged; on exit it is uniform again. */
-DCSIM_DEV void dcsim_handle_arrival(dcsim_ctx_t& c, int stream) {
-  const dcsim_spec_t& sp = c.P->spec;
-  const dcsim_layout_t& L = c.P->L;
-  dcsim_hdr_t* H = c.H;
-  const int jt = stream & 1, ing = stream >> 1;
-  double size = 0.0;
-  uint32_t jid = 0u;
-  if (c.lane == 0) { /* SIM:539-540 */
-    jid = ++H->jid;
-    H->ev_arr++;
-    size = dcsim_sample_size(c, jt);
-  }
-  uint32_t pos = dcsim_bcast_u32(c.rng_pos, 0);
-
-  int dc_sel = 0;
-  if (sp.route_rule == DCSIM_ROUTE_ECO) { /* SIM:544-553: strict <, first DC wins; no draw */
-    if (c.lane == 0) {
-      double best = sp.dc[0].eco_e_unit[jt] * size;
-      for (int d = 1; d < sp.n_dc; ++d) {
-        const double score = sp.dc[d].eco_e_unit[jt] * size;
-        if (score < best) { best = score; dc_sel = d; }
-      }
-    }
-    dc_sel = (int)dcsim_bcast_u32((uint32_t)dc_sel, 0);
-  } else { /* SIM:575-576 random.choice(names): k = n.bit_length(); redraw until < n */
-    const int n = sp.n_dc, k = dcsim_bit_length((uint32_t)n);
-    for (int it = 0;; it += DCSIM_SPEC_ROUTE) {
-      if (it >= DCSIM_REJECTION_LIMIT) { if (c.lane == 0) H->status |= DCSIM_ST_RNG_RUNAWAY; break; }
-      const bool mine = c.lane < DCSIM_SPEC_ROUTE;
-      const uint32_t v = mine ? dcsim_rng_peek(c, pos + (uint32_t)c.lane) >> (32 - k) : 0xffffffffu;
-      const uint32_t votes = dcsim_warp_ballot(mine && v < (uint32_t)n);
-      if (votes) {
-        const int first = dcsim_ffs(votes) - 1;
-        dc_sel = (int)dcsim_bcast_u32(v, first);
-        pos += (uint32_t)first + 1u;
-        break;
-      }
-      pos += DCSIM_SPEC_ROUTE;
-    }
-  }
-
-  if (c.lane == 0) { /* SIM:580-588 */
-    const double t_x = c.now + sp.transfer_s[ing][dc_sel][jt];
-    if (dcsim_schedulable(c, t_x)) {
-      const uint32_t slot = H->n_xfer;
-      if ((int)slot >= L.cap_xfer) {
-        H->status |= DCSIM_ST_XFER_OVERFLOW;
-      } else {
-        const uint32_t seq = c.seq++;
-        dcsim_at<double>(c.blk, DCSIM_OFF_XF_T)[slot] = t_x;
-        dcsim_at<double>(c.blk, L.xf_size)[slot] = size;
-        dcsim_at<uint32_t>(c.blk, L.xf_seq)[slot] = seq;
-        dcsim_at<uint32_t>(c.blk, L.xf_meta)[slot] = (uint32_t)dc_sel | ((uint32_t)jt << 3) | ((uint32_t)ing << 4);
-        dcsim_at<uint32_t>(c.blk, L.xf_jid)[slot] = jid;
-        H->n_xfer = slot + 1u;
-        if (slot + 1u > H->max_xfer) H->max_xfer = slot + 1u;
-        const double ct = CAND_T(c)[CAND_XFER];
-        if (t_x < ct || (t_x == ct && seq < CAND_SEQ(c)[CAND_XFER])) {
-          CAND_T(c)[CAND_XFER] = t_x; CAND_SEQ(c)[CAND_XFER] = seq; H->xmin_slot = slot;
-        }
-      }
-    }
-  }
-
-  /* SIM:591-592 next inter-arrival of this stream (arrivals.py:35-48) */
-  const dcsim_arrival_t& a = sp.arr[jt];
-  double gap = DCSIM_INF;
-  if (a.mode == DCSIM_ARR_POISSON) {
-    if (a.rate > 0.0) {
-      if (c.lane == 0) gap = -log(1.0 - dcsim_u53(dcsim_rng_peek(c, pos), dcsim_rng_peek(c, pos + 1u))) / a.rate;
-      pos += 2u;
-    }
-  } else if (a.mode == DCSIM_ARR_SINUSOID) {
-    const double abs_amp = a.amp < 0.0 ? -a.amp : a.amp;
-    const double max_rate = a.rate * (1.0 + abs_amp);
-    for (int it = 0;; it += DCSIM_SPEC_THIN) {
-      if (it >= DCSIM_REJECTION_LIMIT) { if (c.lane == 0) H->status |= DCSIM_ST_RNG_RUNAWAY; break; }
-      const bool mine = c.lane < DCSIM_SPEC_THIN;
-      double w = 0.0;
-      bool accept = false;
-      if (mine) {
-        const uint32_t p = pos + 4u * (uint32_t)c.lane;
-        w = -log(1.0 - dcsim_u53(dcsim_rng_peek(c, p), dcsim_rng_peek(c, p + 1u))) / max_rate;
-        const double tc = c.now + w;
-        double lam = a.rate * (1.0 + a.amp * sin(sp.two_pi * dcsim_mod_pos(tc, a.period) / a.period));
-        lam = lam > 0.0 ? lam : 0.0;
-        accept = dcsim_u53(dcsim_rng_peek(c, p + 2u), dcsim_rng_peek(c, p + 3u)) <= lam / max_rate;
-      }
-      const uint32_t votes = dcsim_warp_ballot(mine && accept);
-      if (votes) {
-        const int first = dcsim_ffs(votes) - 1;
-        gap = dcsim_bcast_f64(w, first);
-        pos += 4u * ((uint32_t)first + 1u);
-        break;
-      }
-      pos += 4u * DCSIM_SPEC_THIN;
-    }
-  }
-  c.rng_pos = pos;
-  if (c.lane == 0) {
-    const double t_a = c.now + gap;
-    if (dcsim_schedulable(c, t_a)) {
-      CAND_T(c)[CAND_STREAM0 + stream] = t_a;
-      CAND_SEQ(c)[CAND_STREAM0 + stream] = c.seq++;
-    } else {
-      CAND_T(c)[CAND_STREAM0 + stream] = DCSIM_INF;
-      CAND_SEQ(c)[CAND_STREAM0 + stream] = 0xffffffffu;
-    }
-  }
-}
-
-/* Warp.  Stages entries [base, base+DCSIM_ARR_WINDOW) of the replica's arrival list into shared memory (coalesced). */
-DCSIM_DEV void dcsim_arrivals_stage(dcsim_ctx_t& c, uint64_t r, uint32_t base) {
-  const uint64_t off = r * (uint64_t)c.P->cap_arr + base;
-  const uint32_t count = c.H->arr_count;
-  for (uint32_t i = (uint32_t)c.lane; i < DCSIM_ARR_WINDOW; i += DCSIM_LANES) {
+/* Warp.  Stages entries [base, base + DCSIM_LIST_WINDOW) of the replica's event list into shared memory (coalesced). */
+DCSIM_DEV void dcsim_list_stage(dcsim_ctx_t& c, uint64_t r, uint32_t base) {
+  const uint64_t off = r * 2ull * (uint64_t)c.P->cap_arr + base;
+  const uint32_t count = c.H->ml_count;
+  for (uint32_t i = (uint32_t)c.lane; i < DCSIM_LIST_WINDOW; i += DCSIM_LANES) {
     const bool in = base + i < count;
-    dcsim_at<double>(c.blk, DCSIM_OFF_AW_T)[i] = in ? c.P->arr_t[off + i] : DCSIM_INF;
-    dcsim_at<double>(c.blk, DCSIM_OFF_AW_SIZE)[i] = in ? c.P->arr_size[off + i] : 0.0;
-    dcsim_at<uint32_t>(c.blk, DCSIM_OFF_AW_META)[i] = in ? c.P->arr_meta[off + i] : 0u;
+    LW_T(c)[i] = in ? c.P->ml_t[off + i] : DCSIM_INF;
+    LW_AUX(c)[i] = in ? c.P->ml_aux[off + i] : 0.0;
+    LW_META(c)[i] = in ? c.P->ml_meta[off + i] : 0u;
   }
-  if (c.lane == 0) c.H->aw_base = base;
+  c.lw_base = base;
   dcsim_warp_sync();
 }
 
-/* Lane 0.  Publishes list entry `k` as the (single) arrival candidate; its seq is the one its stream was given
- * when the stream's previous arrival (or the constructor) pushed it. */
-DCSIM_DEV void dcsim_arrival_candidate(dcsim_ctx_t& c, uint32_t k) {
-  if (k < c.H->arr_count) {
-    const uint32_t i = k - c.H->aw_base;
-    const uint32_t stream = dcsim_at<uint32_t>(c.blk, DCSIM_OFF_AW_META)[i] & 15u;
-    CAND_T(c)[CAND_STREAM0] = dcsim_at<double>(c.blk, DCSIM_OFF_AW_T)[i];
-    CAND_SEQ(c)[CAND_STREAM0] = dcsim_at<uint32_t>(c.blk, DCSIM_OFF_PEND_SEQ)[stream];
+/* Lane 0.  Publishes list entry c.cursor as the list candidate.  Its seq was handed out when the push happened: an
+ * arrival's when its stream's previous arrival (or the constructor) pushed it, an xfer_done's when its own arrival did. */
+DCSIM_DEV void dcsim_list_candidate(dcsim_ctx_t& c) {
+  if (c.cursor < c.H->ml_count) {
+    const uint32_t i = c.cursor - c.lw_base;
+    const uint32_t m = LW_META(c)[i];
+    CAND_T(c)[CAND_LIST] = LW_T(c)[i];
+    CAND_SEQ(c)[CAND_LIST] = (m & ML_XFER) ? XRING(c)[c.cursor & (uint32_t)c.P->L.xring_mask] : PEND_SEQ(c)[(m >> 1) & 15u];
   } else {
-    CAND_T(c)[CAND_STREAM0] = DCSIM_INF;
-    CAND_SEQ(c)[CAND_STREAM0] = 0xffffffffu;
+    CAND_T(c)[CAND_LIST] = DCSIM_INF;
+    CAND_SEQ(c)[CAND_LIST] = 0xffffffffu;
   }
 }
 
-/* SIM:537-592 when the arrival list exists: the job's size / DC / "next arrival schedulable" come from the list;
- * what remains is the xfer_done push and the seq bookkeeping.  Whole warp (the window may need re-staging). */
-DCSIM_DEV void dcsim_handle_arrival_listed(dcsim_ctx_t& c, uint64_t r) {
-  const dcsim_spec_t& sp = c.P->spec;
-  const dcsim_layout_t& L = c.P->L;
-  dcsim_hdr_t* H = c.H;
-  /* lane 0 owns cursor / window base (it rewrites them below); the other lanes get them by shuffle */
-  const uint32_t k = dcsim_bcast_u32(c.lane == 0 ? H->arr_cursor : 0u, 0);
-  const uint32_t wbase = dcsim_bcast_u32(c.lane == 0 ? H->aw_base : 0u, 0);
-  if (c.lane == 0) {
-    const uint32_t i = k - wbase;
-    const double size = dcsim_at<double>(c.blk, DCSIM_OFF_AW_SIZE)[i];
-    const uint32_t meta = dcsim_at<uint32_t>(c.blk, DCSIM_OFF_AW_META)[i];
-    const uint32_t stream = meta & 15u;
-    const int jt = (int)(stream & 1u), ing = (int)(stream >> 1), dc_sel = (int)((meta >> 4) & 7u);
-    const uint32_t jid = k + 1u; /* SIM:539: jids count arrivals (H->jid and H->ev_arr follow from the cursor at stage-out) */
-    const double t_x = c.now + sp.transfer_s[ing][dc_sel][jt];
-    if (dcsim_schedulable(c, t_x)) { /* SIM:580-588 */
-      const uint32_t slot = H->n_xfer;
-      if ((int)slot >= L.cap_xfer) {
-        H->status |= DCSIM_ST_XFER_OVERFLOW;
-      } else {
-        const uint32_t seq = c.seq++;
-        dcsim_at<double>(c.blk, DCSIM_OFF_XF_T)[slot] = t_x;
-        dcsim_at<double>(c.blk, L.xf_size)[slot] = size;
-        dcsim_at<uint32_t>(c.blk, L.xf_seq)[slot] = seq;
-        dcsim_at<uint32_t>(c.blk, L.xf_meta)[slot] = (uint32_t)dc_sel | ((uint32_t)jt << 3) | ((uint32_t)ing << 4);
-        dcsim_at<uint32_t>(c.blk, L.xf_jid)[slot] = jid;
-        H->n_xfer = slot + 1u;
-        if (slot + 1u > H->max_xfer) H->max_xfer = slot + 1u;
-        const double ct = CAND_T(c)[CAND_XFER];
-        if (t_x < ct || (t_x == ct && seq < CAND_SEQ(c)[CAND_XFER])) {
-          CAND_T(c)[CAND_XFER] = t_x; CAND_SEQ(c)[CAND_XFER] = seq; H->xmin_slot = slot;
-        }
-      }
-    }
-    if (meta & 0x80u) dcsim_at<uint32_t>(c.blk, DCSIM_OFF_PEND_SEQ)[stream] = c.seq++; /* SIM:591-592 push of the next arrival */
-    H->arr_cursor = k + 1u;
-  }
-  dcsim_warp_sync();
-  if (k + 1u - wbase >= DCSIM_ARR_WINDOW && k + 1u < c.H->arr_count) dcsim_arrivals_stage(c, r, k + 1u);
-  if (c.lane == 0) dcsim_arrival_candidate(c, k + 1u);
-}
-
-/* SIM:595-678 (lane 0 part): consume pool entry `slot`, start the job or queue it. */
+/* SIM:595-678 (lane 0): the transferred job starts if its DC has a free GPU, else it queues. */
 template <bool CAP>
-DCSIM_DEV void dcsim_handle_xfer(dcsim_ctx_t& c, int slot) {
+DCSIM_DEV void dcsim_handle_xfer(dcsim_ctx_t& c, double size, uint32_t meta) {
   const dcsim_spec_t& sp = c.P->spec;
-  const dcsim_layout_t& L = c.P->L;
-  dcsim_hdr_t* H = c.H;
-  double* xt = dcsim_at<double>(c.blk, DCSIM_OFF_XF_T); double* xs = dcsim_at<double>(c.blk, L.xf_size);
-  uint32_t* xq = dcsim_at<uint32_t>(c.blk, L.xf_seq); uint32_t* xm = dcsim_at<uint32_t>(c.blk, L.xf_meta);
-  uint32_t* xj = dcsim_at<uint32_t>(c.blk, L.xf_jid);
-  const double size = xs[slot];
-  const uint32_t meta = xm[slot], jid = xj[slot];
-  const int d = (int)(meta & 7u), jt = (int)((meta >> 3) & 1u);
-  const uint32_t ing = meta >> 4;
-  const uint32_t last = H->n_xfer - 1u; /* unordered pool: move the last entry into the hole */
-  xt[slot] = xt[last]; xs[slot] = xs[last]; xq[slot] = xq[last]; xm[slot] = xm[last]; xj[slot] = xj[last];
-  H->n_xfer = last;
+  const int d = (int)((meta >> 1) & 7u), jt = (int)((meta >> 4) & 1u);
+  const uint32_t ing = (meta >> 5) & 7u, jid = (meta >> 8) + 1u; /* SIM:539: jids count arrivals */
   if (sp.dc[d].total_gpus - DCI(c, DI_BUSY)[d] > 0) {
     dcsim_start_by_rule<CAP>(c, sp.xfer_rule, true, d, jt, size, jid, ing);
     dcsim_refresh_power(c, d);
   } else {
     dcsim_enqueue(c, d, jt, size, jid, ing); /* SIM:678 */
   }
+}
+
+/* The next entry of the event list fires (whole warp: the window may need re-staging).
+ * Arrival, SIM:537-592: everything random about it was drawn by the pre-pass; what remains is handing out the seqs
+ * of its two pushes — the xfer_done's goes into the ring slot of that entry's list position, the stream's next
+ * arrival's into the stream's pending slot.  xfer_done: dcsim_handle_xfer. */
+template <bool CAP>
+DCSIM_DEV void dcsim_handle_list(dcsim_ctx_t& c, uint64_t r) {
+  const uint32_t i = c.cursor - c.lw_base;
+  if (c.lane == 0) {
+    const uint32_t meta = LW_META(c)[i];
+    if (meta & ML_XFER) {
+      dcsim_handle_xfer<CAP>(c, LW_AUX(c)[i], meta);
+    } else {
+      c.H->ev_arr++;
+      if (meta & ML_A_XSCHED) { /* SIM:580-588 */
+        const uint32_t s = c.seq++;
+        if (meta & ML_A_XIN) XRING(c)[dcsim_lo(LW_AUX(c)[i]) & (uint32_t)c.P->L.xring_mask] = s;
+      }
+      if (meta & ML_A_NEXT) PEND_SEQ(c)[(meta >> 1) & 15u] = c.seq++; /* SIM:591-592 */
+    }
+  }
+  c.cursor += 1u;
+  if (c.cursor - c.lw_base >= DCSIM_LIST_WINDOW && c.cursor < c.H->ml_count) {
+    dcsim_warp_sync(); /* lane 0 is done with the old window */
+    dcsim_list_stage(c, r, c.cursor);
+  }
+  if (c.lane == 0) dcsim_list_candidate(c);
+  dcsim_warp_sync();
 }
 
 /* SIM:701-927 minus RL/elastic branches (lane 0 part, after the record was read and before it is erased). */
@@ -1315,16 +1256,35 @@ DCSIM_DEV void dcsim_finish_account(dcsim_ctx_t& c, uint64_t r, int d, int slot)
   }
 }
 
-/* SIM:840-927: start queued jobs while GPUs are free, inference first when inf_priority. */
+/* SIM:840-927: start queued jobs while GPUs are free, inference first when inf_priority.  `pre` is the head entry of
+ * queue `pre_jt` of this DC loaded ahead of time by the caller (-1: none): the queues live in HBM and the first
+ * dequeue's latency is otherwise exposed on every job_finish of a saturated DC. */
+#ifndef DCSIM_PREFETCH_DEQ
+#define DCSIM_PREFETCH_DEQ 1
+#endif
+DCSIM_DEV int dcsim_dequeue_pick(dcsim_ctx_t& c, int d) {
+  if (c.P->spec.inf_priority && dcsim_queue_len(c, d, 0) > 0) return 0;
+  if (dcsim_queue_len(c, d, 1) > 0) return 1;
+  return -1;
+}
 template <bool CAP>
-DCSIM_DEV void dcsim_dequeue_loop(dcsim_ctx_t& c, int d) {
+DCSIM_DEV void dcsim_dequeue_loop(dcsim_ctx_t& c, int d, const dcsim_qent_t& pre, int pre_jt) {
   const dcsim_spec_t& sp = c.P->spec;
+  bool first = true;
   while (sp.dc[d].total_gpus - DCI(c, DI_BUSY)[d] > 0 && c.H->status == 0u) {
-    int jt;
-    if (sp.inf_priority && dcsim_queue_len(c, d, 0) > 0) jt = 0;
-    else if (dcsim_queue_len(c, d, 1) > 0) jt = 1;
-    else break;
-    const dcsim_qent_t e = dcsim_dequeue(c, d, jt);
+    const int jt = dcsim_dequeue_pick(c, d);
+    if (jt < 0) break;
+    dcsim_qent_t e;
+    if (DCSIM_PREFETCH_DEQ && first && jt == pre_jt) { /* the head entry is already here: just advance the ring */
+      int32_t* head = DCI(c, jt ? DI_QH_TRN : DI_QH_INF) + d;
+      const int h = *head;
+      *head = h + 1 >= c.P->L.cap_q[jt] ? 0 : h + 1;
+      DCI(c, jt ? DI_QN_TRN : DI_QN_INF)[d] -= 1;
+      e = pre;
+    } else {
+      e = dcsim_dequeue(c, d, jt);
+    }
+    first = false;
     dcsim_start_by_rule<CAP>(c, sp.deq_rule, false, d, jt, e.size, e.jid, e.ing);
   }
 }
@@ -1334,16 +1294,25 @@ DCSIM_DEV void dcsim_dequeue_loop(dcsim_ctx_t& c, int d) {
  * One pass over the DC's records does everything the reference's `del dc.running_jobs[jid]` + next `_estimate_dc_power`
  * + next heap pop imply: lane j loads record j of the set WITHOUT the finished one (slot j, or j + 1 behind the hole),
  * lanes behind the hole store it one slot down (dict order is start order, models.py:60), the earliest remaining
- * finish is an arg-min over the registers, and the active power is re-summed in dict order from the registers by
- * shuffles.  The records are touched once — which is what lets them live in HBM/L2 instead of shared memory
- * (c.rec) when the block is large: one load round trip per job_finish, stores fire-and-forget. */
-template <bool CAP>
+ * finish is an arg-min over the registers, and the active power is re-summed in dict order (SIM:168-179) — from the
+ * registers by shuffles when the records live in HBM/L2 (RECG: they are touched once per job_finish, one load round
+ * trip, stores fire-and-forget), by lane 0 out of shared memory when they are staged there. */
+template <bool CAP, bool RECG>
 DCSIM_DEV void dcsim_handle_finish(dcsim_ctx_t& c, uint64_t r, int d) {
   const dcsim_layout_t& L = c.P->L;
   const int off = d * L.cap_run;
   const int n = DCI(c, DI_NRUN)[d];
   const int k = DCI(c, DI_FMIN_SLOT)[d];
-  if (c.lane == 0) { c.H->ev_fin++; dcsim_finish_account(c, r, d, k); } /* reads record k; writes no record */
+  dcsim_qent_t pre; pre.size = 0.0; pre.jid = 0u; pre.ing = 0u;
+  int pre_jt = -1;
+  if (c.lane == 0) {
+    c.H->ev_fin++;
+    if (DCSIM_PREFETCH_DEQ) { /* the dequeue loop below will want this entry: have the load in flight meanwhile */
+      pre_jt = dcsim_dequeue_pick(c, d);
+      if (pre_jt >= 0) pre = dcsim_queue_base(c, d, pre_jt)[DCI(c, pre_jt ? DI_QH_TRN : DI_QH_INF)[d]];
+    }
+    dcsim_finish_account(c, r, d, k); /* reads record k; writes no record */
+  }
   double* rt = dcsim_at<double>(c.rec, L.rn_t) + off; double* rp = dcsim_at<double>(c.rec, L.rn_pw) + off;
   double* rv = dcsim_at<double>(c.rec, L.rn_tpt) + off; double* ra = dcsim_at<double>(c.rec, L.rn_start) + off;
   uint32_t* rq = dcsim_at<uint32_t>(c.rec, L.rn_seq) + off; uint32_t* rm = dcsim_at<uint32_t>(c.rec, L.rn_meta) + off;
@@ -1359,15 +1328,18 @@ DCSIM_DEV void dcsim_handle_finish(dcsim_ctx_t& c, uint64_t r, int d) {
     const int src = moved ? j + 1 : j;
     double a_t = DCSIM_INF, a_pw = 0.0, a_tpt = 0.0, a_start = 0.0, a_size = 0.0, a_f = 0.0, a_done = 0.0, a_upd = 0.0;
     uint32_t a_seq = 0xffffffffu, a_meta = 0u, a_jid = 0u;
-    if (act) { a_t = rt[src]; a_seq = rq[src]; a_pw = rp[src]; }
+    if (act) { a_t = rt[src]; a_seq = rq[src]; }
+    if (act && (RECG || moved)) a_pw = rp[src];
     if (moved) {
       a_tpt = rv[src]; a_start = ra[src]; a_meta = rm[src];
       if (full) { a_size = dcsim_at<double>(c.rec, L.rn_size)[off + src]; a_f = dcsim_at<double>(c.rec, L.rn_f)[off + src];
                   a_jid = dcsim_at<uint32_t>(c.rec, L.rn_jid)[off + src]; }
       if constexpr (CAP) { a_done = dcsim_at<double>(c.rec, L.rn_done)[off + src]; a_upd = dcsim_at<double>(c.rec, L.rn_upd)[off + src]; }
     }
-    const int cnt = n1 - base < DCSIM_LANES ? n1 - base : DCSIM_LANES;
-    for (int i = 0; i < cnt; ++i) psum += dcsim_bcast_f64(a_pw, i); /* SIM:168-179: dict order, from 0.0 */
+    if constexpr (RECG) {
+      const int cnt = n1 - base < DCSIM_LANES ? n1 - base : DCSIM_LANES;
+      for (int i = 0; i < cnt; ++i) psum += dcsim_bcast_f64(a_pw, i); /* SIM:168-179: dict order, from 0.0 */
+    }
     {
       const uint32_t h = dcsim_hi(a_t), l = dcsim_lo(a_t);
       if (act && (h < bh || (h == bh && (l < bl || (l == bl && a_seq < bs))))) { bh = h; bl = l; bs = a_seq; bi = j; }
@@ -1393,13 +1365,17 @@ DCSIM_DEV void dcsim_handle_finish(dcsim_ctx_t& c, uint64_t r, int d) {
     win = (int)dcsim_bcast_u32((uint32_t)bi, dcsim_ffs(votes) - 1);
     wt = dcsim_hilo_f64(mh, ml);
   }
+  if constexpr (!RECG) dcsim_warp_sync(); /* the compacted records are visible to lane 0 */
   if (c.lane == 0) {
+    if constexpr (!RECG) {
+      for (int i = 0; i < n1; ++i) psum += rp[i]; /* SIM:168-179: dict order, from 0.0 */
+    }
     CAND_T(c)[CAND_DC0 + d] = wt; CAND_SEQ(c)[CAND_DC0 + d] = ws; DCI(c, DI_FMIN_SLOT)[d] = win;
     DCI(c, DI_NRUN)[d] = n1;
     DCF(c, DF_PSUM)[d] = psum;
+    dcsim_dequeue_loop<CAP>(c, d, pre, pre_jt); /* appends behind the compacted records */
+    dcsim_refresh_power(c, d);
   }
-  dcsim_warp_sync(); /* the compacted records and the new count are visible before the dequeue loop appends */
-  if (c.lane == 0) { dcsim_dequeue_loop<CAP>(c, d); dcsim_refresh_power(c, d); }
   dcsim_warp_sync();
 }
 
@@ -1597,8 +1573,8 @@ DCSIM_DEV void dcsim_handle_log(dcsim_ctx_t& c) {
  * Replica life cycle
  * ============================================================================================== */
 /* SIM:31-157, the parts that touch simulation state: zeroed DCs at default_freq, one pending arrival per
- * (ingress, job type) in dict order inf-then-trn, then the first log tick. */
-template <bool PRE>
+ * (ingress, job type) in dict order inf-then-trn (drawn by the pre-pass; here they get the constructor's seqs), then
+ * the first log tick. */
 DCSIM_DEV void dcsim_replica_init(dcsim_ctx_t& c, uint64_t r) {
   const dcsim_spec_t& sp = c.P->spec;
   const dcsim_layout_t& L = c.P->L;
@@ -1612,40 +1588,20 @@ DCSIM_DEV void dcsim_replica_init(dcsim_ctx_t& c, uint64_t r) {
     DCF(c, DF_POWER)[d] = (double)sp.dc[d].total_gpus * (sp.dc[d].power_gating ? sp.dc[d].p_sleep : sp.dc[d].p_idle);
   }
   dcsim_warp_sync();
-  c.rng_pos = 0u; c.rng_base = 1u; c.seq = 0u; c.now = 0.0;
-  if constexpr (PRE) { /* the pre-pass already drew everything: hand out the constructor's seqs (SIM:154-157) */
-    if (c.lane == 0) {
-      const dcsim_arrhdr_t ah = c.P->arr_hdr[r];
-      c.H->arr_count = ah.count; c.H->arr_cursor = 0u; c.H->status |= ah.status;
-      c.rng_pos = ah.rng_words;
-      for (int s = 0; s < 2 * sp.n_ing; ++s)
-        if ((ah.first_mask >> s) & 1u) dcsim_at<uint32_t>(c.blk, DCSIM_OFF_PEND_SEQ)[s] = c.seq++;
-      const double t = 0.0 + sp.log_interval;
-      if (dcsim_schedulable(c, t)) { CAND_T(c)[CAND_LOG] = t; CAND_SEQ(c)[CAND_LOG] = c.seq++; }
-      c.H->xmin_slot = 0xffffffffu;
-      c.H->initialized = 1u;
-    }
-    dcsim_warp_sync();
-    dcsim_arrivals_stage(c, r, 0u);
-    if (c.lane == 0) dcsim_arrival_candidate(c, 0u);
-    dcsim_warp_sync();
-    return;
-  }
-  for (int s = 0; s < 2 * sp.n_ing; ++s) { /* SIM:154-156 */
-    dcsim_rng_ensure(c, c.rng_pos);
-    if (c.lane == 0) {
-      const double t = 0.0 + dcsim_next_interarrival(c, s & 1, 0.0);
-      if (dcsim_schedulable(c, t)) { CAND_T(c)[CAND_STREAM0 + s] = t; CAND_SEQ(c)[CAND_STREAM0 + s] = c.seq++; }
-    }
-    c.rng_pos = dcsim_bcast_u32(c.rng_pos, 0); /* uniform again; also orders lane 0's reads before the next refill */
-    dcsim_warp_sync();
-  }
+  c.seq = 0u; c.now = 0.0; c.cursor = 0u; c.lw_base = 0u;
   if (c.lane == 0) {
+    const dcsim_arrhdr_t ah = c.P->arr_hdr[r];
+    c.H->ml_count = ah.ml_count; c.H->status |= ah.status;
+    c.H->rng_pos = ah.rng_words; /* every draw of the run happened in the pre-pass */
+    for (int s = 0; s < 2 * sp.n_ing; ++s) /* SIM:154-156 */
+      if ((ah.first_mask >> s) & 1u) PEND_SEQ(c)[s] = c.seq++;
     const double t = 0.0 + sp.log_interval; /* SIM:157 */
     if (dcsim_schedulable(c, t)) { CAND_T(c)[CAND_LOG] = t; CAND_SEQ(c)[CAND_LOG] = c.seq++; }
-    c.H->xmin_slot = 0xffffffffu;
     c.H->initialized = 1u;
   }
+  dcsim_warp_sync();
+  dcsim_list_stage(c, r, 0u);
+  if (c.lane == 0) dcsim_list_candidate(c);
   dcsim_warp_sync();
 }
 
@@ -1676,7 +1632,7 @@ DCSIM_DEV void dcsim_replica_tail(dcsim_ctx_t& c) {
  * Visibility protocol: every branch ends with a warp sync, so at the top of an iteration all shared-memory
  * writes of the previous event are visible to every lane; inside a branch a sync separates lane 0's handler
  * from the warp-parallel step that reads what it wrote. */
-template <bool CAP, bool PRE>
+template <bool CAP, bool RECG>
 DCSIM_DEV uint32_t dcsim_replica_run(dcsim_ctx_t& c, uint64_t r) {
   const dcsim_spec_t& sp = c.P->spec;
   const uint32_t budget = c.P->budget32; /* per-launch event budget; 0xffffffff = unlimited */
@@ -1709,32 +1665,23 @@ DCSIM_DEV uint32_t dcsim_replica_run(dcsim_ctx_t& c, uint64_t r) {
     dcsim_warp_sync(); /* every lane has read its candidate / busy / power before lane 0's handler rewrites them */
     c.now = t;
     /* dispatch on the winning slot itself; the event kind is only spelled out for the (cold) trace */
-    const bool is_arrival = PRE ? (win == CAND_STREAM0) : (win >= CAND_STREAM0 && win < CAND_XFER);
     if (tracing && c.lane == 0) {
-      int kind = win < CAND_STREAM0 ? KIND_FINISH
-                 : (win < CAND_XFER ? (win & 1) : (win == CAND_XFER ? KIND_XFER : (win == CAND_LOG ? KIND_LOG : KIND_FINISH)));
-      if constexpr (PRE) { /* one arrival candidate for all streams: the job type is in the list entry */
-        if (win == CAND_STREAM0) kind = (int)(dcsim_at<uint32_t>(c.blk, DCSIM_OFF_AW_META)[c.H->arr_cursor - c.H->aw_base] & 1u);
+      int kind = KIND_FINISH;
+      if (win == CAND_LIST) {
+        const uint32_t m = LW_META(c)[c.cursor - c.lw_base];
+        kind = (m & ML_XFER) ? KIND_XFER : (int)((m >> 1) & 1u); /* the job type is the stream's low bit */
+      } else if (win == CAND_LOG) {
+        kind = KIND_LOG;
       }
       const uint32_t row = c.P->rec.counts[0];
       if (row < c.P->rec.trace_cap) { c.P->rec.trace[row].t = t; c.P->rec.trace[row].seq = seq; c.P->rec.trace[row].kind = (uint32_t)kind; }
       c.P->rec.counts[0] = row + 1u;
     }
 
-    if (is_arrival) {
-      if constexpr (PRE) {
-        dcsim_handle_arrival_listed(c, r);
-      } else {
-        dcsim_rng_ensure(c, c.rng_pos); /* rng_pos is warp-uniform between arrivals */
-        dcsim_handle_arrival(c, win - CAND_STREAM0);
-      }
-      dcsim_warp_sync();
-    } else if (win == CAND_XFER) {
-      if (c.lane == 0) { c.H->ev_xfer++; dcsim_handle_xfer<CAP>(c, (int)c.H->xmin_slot); }
-      dcsim_warp_sync();
-      dcsim_rescan_xfer(c);
-    } else if (win < CAND_STREAM0) {
-      dcsim_handle_finish<CAP>(c, r, win - CAND_DC0);
+    if (win == CAND_LIST) {
+      dcsim_handle_list<CAP>(c, r);
+    } else if (win < CAND_LIST) {
+      dcsim_handle_finish<CAP, RECG>(c, r, win - CAND_DC0);
     } else if (win == CAND_LOG) {
       if (c.lane == 0) c.H->ev_log++;
       dcsim_handle_log<CAP>(c);
@@ -1784,7 +1731,8 @@ DCSIM_DEV void dcsim_write_summary(dcsim_ctx_t& c, double* out) {
     out[DCSIM_S_EV_ARRIVAL] = (double)H->ev_arr; out[DCSIM_S_EV_XFER] = (double)H->ev_xfer;
     out[DCSIM_S_EV_FINISH] = (double)H->ev_fin; out[DCSIM_S_EV_LOG] = (double)H->ev_log;
     out[DCSIM_S_DONE] = (double)H->done;
-    out[DCSIM_S_MAX_XFER] = (double)H->max_xfer; out[DCSIM_S_MAX_RUN] = (double)H->max_run;
+    out[DCSIM_S_MAX_XFER] = 0.0; /* there is no pool of in-flight transfers to size any more */
+    out[DCSIM_S_MAX_RUN] = (double)H->max_run;
     out[DCSIM_S_MAX_Q] = (double)H->max_q;
   }
   DCSIM_FOR_EACH_DC(d, c, sp.n_dc) {
@@ -1802,29 +1750,28 @@ DCSIM_DEV void dcsim_write_summary(dcsim_ctx_t& c, double* out) {
 
 /* One replica, one launch: (init |) resume -> run -> summary.  `blk` is the working copy of the state
  * block (shared memory on the GPU), already loaded unless `fresh`; `rec` is the base the running-job record offsets
- * apply to (== blk when the records were staged with it, the block's home in HBM when only the head was). */
-template <bool CAP, bool PRE>
+ * apply to (== blk when the records were staged with it, the block's home in HBM when only the head was: RECG). */
+template <bool CAP, bool RECG>
 DCSIM_DEV uint32_t dcsim_replica_step(const dcsim_kparams_t* P, uint64_t r, char* blk, char* rec, bool fresh) {
   dcsim_ctx_t c;
   c.P = P; c.blk = blk; c.rec = rec; c.H = reinterpret_cast<dcsim_hdr_t*>(blk); c.lane = dcsim_lane();
   c.q = P->queues + r * P->L.queue_bytes;
   c.is_traced = ((int64_t)r == P->rec.trace_replica);
   c.is_logged = ((int64_t)r == P->rec.log_replica);
-  const uint64_t key = P->seed0 + r;
-  c.key0 = (uint32_t)key; c.key1 = (uint32_t)(key >> 32);
   if (fresh) {
-    dcsim_replica_init<PRE>(c, r);
+    dcsim_replica_init(c, r);
   } else { /* resume: hot scalars back into registers */
-    c.rng_pos = c.H->rng_pos; c.seq = c.H->seq; c.now = c.H->now;
-    c.rng_base = c.rng_pos + 1u; /* nothing staged */
+    c.seq = c.H->seq; c.now = c.H->now; c.cursor = c.H->ml_cursor; c.lw_base = c.H->lw_base;
   }
   uint32_t n = 0u;
-  if (c.H->done == 0u) n = dcsim_replica_run<CAP, PRE>(c, r);
+  if (c.H->done == 0u) n = dcsim_replica_run<CAP, RECG>(c, r);
   dcsim_warp_sync();
   if (c.lane == 0) {
-    if constexpr (PRE) { c.H->ev_arr = c.H->arr_cursor; c.H->jid = c.H->arr_cursor; } /* one list entry = one arrival = one jid */
+    c.H->ev_xfer = c.cursor - c.H->ev_arr; /* every consumed list entry is an arrival or an xfer_done */
+    c.H->jid = c.H->ev_arr;                /* SIM:539: one jid per arrival */
     c.H->n_events = c.H->ev_arr + c.H->ev_xfer + c.H->ev_fin + c.H->ev_log; /* every processed event is one of these */
-    c.H->rng_pos = c.rng_pos; c.H->seq = c.seq; c.H->now = c.now; c.H->last_t = c.H->n_events ? c.now : 0.0;
+    c.H->seq = c.seq; c.H->now = c.now; c.H->last_t = c.H->n_events ? c.now : 0.0;
+    c.H->ml_cursor = c.cursor; c.H->lw_base = c.lw_base;
   }
   dcsim_warp_sync();
   dcsim_write_summary(c, P->summary + r * DCSIM_SUMMARY_K);

@@ -181,7 +181,7 @@ class BatchedEngine:
 STATUS_NAMES = {S.ST_XFER_OVERFLOW: "in-flight transfer pool", S.ST_RUN_OVERFLOW: "running set",
                 S.ST_QUEUE_OVERFLOW: "FIFO queue", S.ST_STALE_OVERFLOW: "stale-event pool",
                 S.ST_RNG_RUNAWAY: "rejection-sampling runaway", S.ST_ARRIVALS_OVERFLOW: "arrival list",
-                S.ST_ARRIVAL_TIE: "two arrivals at the identical instant"}
+                S.ST_ARRIVAL_TIE: "two arrivals at the identical instant (unused since ABI 2: ties are resolved in push order)"}
 
 
 def describe_status(bits: int) -> str:
@@ -196,7 +196,7 @@ _CACHED_LOGGED = {"key": None, "engine": None}   # the one-replica companion eng
 
 
 def _cache_key(sp, n_replicas, device, cuda_stream):
-    return (sp.to_bytes(), int(n_replicas), int(device), int(cuda_stream), os.environ.get("DCSIM_PREPASS", ""))
+    return (sp.to_bytes(), int(n_replicas), int(device), int(cuda_stream), os.environ.get("DCSIM_RECORDS", ""))
 
 
 def acquire_engine(sp, n_replicas, base_seed, first_replica_id=0, device=0, cuda_stream=0):
@@ -235,7 +235,7 @@ class LoggedReplica:
     finishes long before it.  Results are identical by construction (one replica = one deterministic trajectory)."""
 
     def __init__(self, sp, seed, replica_id, device, job_rows, cluster_rows, rng="philox"):
-        key = (sp.to_bytes(), int(device), os.environ.get("DCSIM_PREPASS", ""))
+        key = (sp.to_bytes(), int(device))
         if _CACHED_LOGGED["engine"] is not None and _CACHED_LOGGED["key"] == key:
             self.eng, _CACHED_LOGGED["engine"], _CACHED_LOGGED["key"] = _CACHED_LOGGED["engine"], None, None
             self.eng.reset(seed, replica_id)
@@ -286,7 +286,8 @@ def run_to_completion(spec_factory, n_replicas, base_seed, first_replica_id=0, d
         if bits == 0:
             return eng, summ
         eng.close()
-        if bits & (S.ST_RNG_RUNAWAY | S.ST_ARRIVAL_TIE) or attempt == max_retries:
+        raisable = S.ST_RUN_OVERFLOW | S.ST_XFER_OVERFLOW | S.ST_ARRIVALS_OVERFLOW | S.ST_QUEUE_OVERFLOW | S.ST_STALE_OVERFLOW
+        if bits & ~raisable or attempt == max_retries:   # a status no capacity can cure (or out of attempts): fail now
             raise RuntimeError(f"replicas stopped: {describe_status(bits)}")
         g_max = max(sp.dc[d].total_gpus for d in range(sp.n_dc))
         if bits & S.ST_RUN_OVERFLOW:
@@ -297,4 +298,6 @@ def run_to_completion(spec_factory, n_replicas, base_seed, first_replica_id=0, d
             caps["cap_arrivals"] = 2 * sp.cap_arrivals
         if bits & S.ST_QUEUE_OVERFLOW:
             caps["cap_q_inf"], caps["cap_q_trn"] = 2 * sp.cap_q_inf, 2 * sp.cap_q_trn
+        if bits & S.ST_STALE_OVERFLOW:                   # cap_greedy: superseded job_finish events still in the event set
+            caps["cap_stale"] = 2 * max(64, sp.cap_stale)
     raise AssertionError("unreachable")

@@ -269,7 +269,9 @@ def flatten(ingresses, dcs, graph, arrival_inf, arrival_train, coeffs_map, polic
     share = 1.0 if algo == "eco_route" else 1.0 / n_dc   # eco_route may send a whole class to one DC
     cap_q = [_poisson_cap(n_ing * p * float(sim_duration) * share, 32) for p in peak]
     sp.cap_xfer, sp.cap_run, sp.cap_q_inf, sp.cap_q_trn = cap_xfer, max(1, cap_run), cap_q[0], cap_q[1]
-    sp.cap_stale = 64 if algo == "cap_greedy" else 0
+    # cap_greedy: every DVFS step of a running job leaves one superseded job_finish event behind (SIM:330-338)
+    n_freq_max = max(len(list(dc.freq_levels)) for dc in dcs.values())
+    sp.cap_stale = min(512, max(64, n_dc * max(1, cap_run) * max(1, n_freq_max - 1) // 4)) if algo == "cap_greedy" else 0
     sp.cap_arrivals = _poisson_cap(n_ing * (peak[0] + peak[1]) * float(sim_duration), 64)
     for key, val in (caps or {}).items():
         if key not in ("cap_xfer", "cap_run", "cap_q_inf", "cap_q_trn", "cap_stale", "cap_arrivals"):

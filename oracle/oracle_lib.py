@@ -32,6 +32,7 @@ def lib():
             build()
         L = C.CDLL(_SO)
         L.dcoracle_sizeof_spec.restype = C.c_size_t
+        L.dcoracle_set_test_time_quantum.argtypes = [C.c_double]
         L.dcoracle_run_batch.restype = C.c_longlong
         L.dcoracle_run_batch.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int,
                                          C.c_void_p]
@@ -52,6 +53,11 @@ def lib():
                                            C.c_void_p, C.c_int]
         _lib = L
     return _lib
+
+
+def set_test_time_quantum(q: float):
+    """TEST HOOK (dcsim_oracle.c g_test_time_quantum): 0 = off.  Rounds arrival / xfer_done instants up to multiples of q."""
+    lib().dcoracle_set_test_time_quantum(float(q))
 
 
 def run_batch(spec_bytes: bytes, n_replicas: int, base_seed: int, first_replica_id: int = 0,

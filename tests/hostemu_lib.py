@@ -20,6 +20,7 @@ _lib_perturbed = None
 def _bind(path):
     L = C.CDLL(path)
     L.hostemu_sizeof_spec.restype = C.c_size_t
+    L.hostemu_set_test_time_quantum.argtypes = [C.c_double]
     L.hostemu_run_batch.restype = C.c_longlong
     L.hostemu_run_batch.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p,
                                     C.c_int64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p,
@@ -42,6 +43,12 @@ def lib(perturbed=False):
         _ensure_built()
         _lib, _lib_perturbed = _bind(_SO), _bind(_SO_PERTURBED)
     return _lib_perturbed if perturbed else _lib
+
+
+def set_test_time_quantum(q):
+    """TEST HOOK (dcsim_core.cuh dcsim_test_quantize): 0 = off."""
+    lib().hostemu_set_test_time_quantum(float(q))
+    lib(perturbed=True).hostemu_set_test_time_quantum(float(q))
 
 
 def run_batch(spec_bytes, n_replicas, seed0, chunk_events=0, trace_cap=0, rec_replica=-1, job_dtype=None,

@@ -128,19 +128,6 @@ def test_thinning_squeeze_fuzz(oracle, hostemu):
         assert _same(got, want), (case, sc, np.argwhere(got != want)[:6])
 
 
-@pytest.mark.parametrize("name", ["cfg3_4x64_sinusoid_120s", "sweep_joint_nf", "cap_greedy_4x64", "full_swing_sinusoid_amp1",
-                                  "no_inf_priority_perf_first", "carbon_cost_8h_2x16"])
-def test_in_loop_sampling_mode_equals_oracle(oracle, hostemu, monkeypatch, name):
-    """DCSIM_PREPASS=0: the single-kernel design (samplers inside the event loop, lane-speculative rejection)."""
-    monkeypatch.setenv("DCSIM_PREPASS", "0")
-    blob = SC.to_spec(SC.BY_NAME[name]).to_bytes()
-    want, total = oracle.run_batch(blob, 2, 31)
-    got = hostemu.run_batch(blob, 2, 31)
-    assert got["events"] == total and _same(got["summary"], want)
-    parts = hostemu.run_batch(blob, 2, 31, chunk_events=997)
-    assert np.array_equal(parts["summary"], got["summary"])
-
-
 def test_latency_histogram_equals_oracle(oracle, hostemu):
     """Same integer binning on both sides (exponent + two mantissa bits) -> identical per-replica histograms."""
     for name in ("cfg3_4x64_sinusoid_120s", "sweep_joint_nf", "trn_only_2x8"):
@@ -177,22 +164,22 @@ def test_wide_seed_against_reference_fixture(hostemu, name):
 
 def test_random_scenarios_equal_oracle(oracle, hostemu, monkeypatch):
     """Differential fuzz (tools/fuzz_core.py, fixed generator seed): random algo / policy / DC shapes / frequency
-    ladders / caps / arrival processes — summaries, traces and both logs bit-identical to the oracle, in the
-    pre-pass and the in-loop sampling mode, with lean and with full running-job records."""
+    ladders / caps / arrival processes — summaries, traces and both logs bit-identical to the oracle, with the
+    running-job records staged and used in place (head-staged mode), with lean and with full records."""
     import os
     import random as pyrandom
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
     import fuzz_core
-    monkeypatch.setenv("DCSIM_PREPASS", "1")  # check() rewrites it; monkeypatch restores the original at teardown
+    monkeypatch.setenv("DCSIM_RECORDS", "shared")  # check() rewrites it; monkeypatch restores the original at teardown
     rnd = pyrandom.Random(20260922)
     for case in range(60):
         sc = fuzz_core.random_scenario(rnd, case)
         seed = rnd.randrange(1, 2 ** 40)
-        for prepass in (True, False):
+        for head_only in (False, True):
             for with_logs in (False, True):
-                res = fuzz_core.check(sc, seed, prepass, with_logs)
-                assert res == "ok" or res.startswith("overflow"), (case, prepass, with_logs, res, sc, seed)
+                res = fuzz_core.check(sc, seed, head_only, with_logs)
+                assert res == "ok" or res.startswith("overflow"), (case, head_only, with_logs, res, sc, seed)
 
 
 def test_device_core_against_reference_on_random_scenarios(hostemu):

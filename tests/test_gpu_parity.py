@@ -230,30 +230,6 @@ def test_cli_runs_a_batch(tmp_path):
     assert stats["energy_j_ci95"] > 0 and os.path.exists(sim.job_log_path) and os.path.exists(sim.cluster_log_path)
 
 
-@pytest.mark.parametrize("name", ["cfg3_4x64_sinusoid_120s", "sweep_bandit", "cap_greedy_4x64", "full_swing_sinusoid_amp1", "sweep_eco_route"])
-def test_in_loop_sampling_mode_on_device(oracle, monkeypatch, name):
-    """DCSIM_PREPASS=0 selects the single-kernel instantiations (Philox window + lane-speculative rejection sampling in
-    the event loop); both designs must give the oracle's numbers — and each other's, bit for bit."""
-    sc = SC.BY_NAME[name]
-    sp = SC.to_spec(sc)
-    with engine_cls()(sp, 6, base_seed=77) as eng:
-        eng.advance(0)
-        split = eng.summary()
-        assert eng.launch_info()["arrivals_prepass"] == 1
-    monkeypatch.setenv("DCSIM_PREPASS", "0")
-    with engine_cls()(sp, 6, base_seed=77) as eng:
-        total = eng.advance(0)
-        fused = eng.summary()
-        assert eng.launch_info()["arrivals_prepass"] == 0
-    want, want_total = oracle.run_batch(sp.to_bytes(), 6, 77, n_threads=os.cpu_count() or 1)
-    assert total == want_total
-    assert_rows_match(fused, want, sc["n_dc"])
-    hw = [S.S_MAX_XFER, S.S_MAX_RUN, S.S_MAX_Q]
-    a, b = split.copy(), fused.copy()
-    a[:, hw] = b[:, hw] = 0
-    assert np.array_equal(a, b)
-
-
 def test_parked_engine_is_reseeded_correctly(tmp_path, oracle):
     """run() parks its device allocations; the next run of the same shape re-seeds them (dcsim_reset) instead of
     re-allocating.  Results, DataCenter write-back and the CSV rows must be those of a fresh engine."""

@@ -55,8 +55,9 @@ def same(a, b):
     return np.array_equal(a, b)
 
 
-def check(sc, seed, prepass, with_logs):
-    os.environ["DCSIM_PREPASS"] = "1" if prepass else "0"
+def check(sc, seed, head_only, with_logs):
+    """head_only: the host build's "head staged" mode (running-job records used at the block's home, DCSIM_RECORDS)."""
+    os.environ["DCSIM_RECORDS"] = "global" if head_only else "shared"
     blob = SC.to_spec(sc).to_bytes()
     want, total = oracle.run_batch(blob, 2, seed, 0)
     kw = dict(rec_replica=1, trace_cap=4000)
@@ -98,17 +99,17 @@ if __name__ == "__main__":
     for case in range(args.cases):
         sc = random_scenario(rnd, case)
         seed = rnd.randrange(1, 2 ** 40)
-        for prepass in (True, False):
+        for head_only in (False, True):
             for with_logs in (False, True):
                 try:
-                    res = check(sc, seed, prepass, with_logs)
+                    res = check(sc, seed, head_only, with_logs)
                 except Exception as e:  # spec rejected etc.
                     res = "EXC " + type(e).__name__ + ": " + str(e)[:120]
                 key = res.split(" ")[0] if not res.startswith("overflow") else res
                 tally[key] = tally.get(key, 0) + 1
                 if res != "ok" and not res.startswith("overflow"):
-                    bad.append((case, prepass, with_logs, res, sc, seed))
-                    print("FAIL", case, "prepass" if prepass else "inloop", "logs" if with_logs else "nolog", res, sc, seed, flush=True)
+                    bad.append((case, head_only, with_logs, res, sc, seed))
+                    print("FAIL", case, "head" if head_only else "staged", "logs" if with_logs else "nolog", res, sc, seed, flush=True)
     print("events compared per oracle batch: see tally;", end=" ")
     print("cases", args.cases, "tally", tally, "failures", len(bad), "in %.0f s" % (time.time() - t0))
     sys.exit(1 if bad else 0)
