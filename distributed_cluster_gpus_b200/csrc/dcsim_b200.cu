@@ -88,12 +88,13 @@ __global__ void __launch_bounds__(DCSIM_ARRIVALS_THREADS) dcsim_arrivals_kernel(
   dcsim_generate_arrivals<MT>(&P, r, clocks, last, ring, (int)blockDim.x);
 }
 
-/* List merge: one WARP per replica (lane-parallel over the replica's arrivals). */
+/* List merge: one WARP per replica (lane-parallel over the replica's arrivals), a sliding window of them in shared memory. */
 #define DCSIM_MERGE_THREADS 128
 __global__ void __launch_bounds__(DCSIM_MERGE_THREADS) dcsim_merge_kernel(const __grid_constant__ dcsim_kparams_t P) {
+  __shared__ dcsim_merge_ring_t rings[DCSIM_MERGE_THREADS / 32];
   const uint64_t r = (uint64_t)blockIdx.x * (DCSIM_MERGE_THREADS / 32) + (threadIdx.x >> 5);
   if (r >= P.n_replicas) return;
-  dcsim_merge_arrivals(&P, r, (int)(threadIdx.x & 31u));
+  dcsim_merge_arrivals(&P, r, (int)(threadIdx.x & 31u), &rings[threadIdx.x >> 5]);
 }
 
 /* Sums the per-replica latency histograms: thread b of every block owns bin b (coalesced 1 KB rows). */
@@ -153,6 +154,8 @@ struct dcsim {
   char* d_queues;
   double* d_summary;
   unsigned long long* d_events;
+  double* d_agg;                 /* DCSIM_AGG_K doubles: scratch of dcsim_all_done */
+  unsigned long long* d_hist_out; /* [2][DCSIM_LAT_BINS]: scratch of dcsim_fetch_latency_histogram */
   uint32_t* d_counts;
   dcsim_trace_rec_t* d_trace;
   dcsim_job_rec_t* d_jobs;
@@ -366,6 +369,8 @@ int dcsim_create(const void* spec_blob, size_t spec_bytes, uint64_t n_replicas, 
     CREATE_TRY(cudaMalloc(&h->d_arr_hdr, (size_t)n_replicas * sizeof(dcsim_arrhdr_t)));
   }
   CREATE_TRY(cudaMalloc(&h->d_events, sizeof(unsigned long long)));
+  CREATE_TRY(cudaMalloc(&h->d_agg, DCSIM_AGG_K * sizeof(double)));
+  CREATE_TRY(cudaMalloc(&h->d_hist_out, 2 * DCSIM_LAT_BINS * sizeof(unsigned long long)));
   CREATE_TRY(cudaMalloc(&h->d_counts, 4 * sizeof(uint32_t)));
   CREATE_TRY(cudaMemsetAsync(h->d_state, 0, state_bytes, h->stream)); /* hdr.initialized == 0 => fresh replica */
   CREATE_TRY(cudaMemsetAsync(h->d_summary, 0, (size_t)n_replicas * DCSIM_SUMMARY_K * sizeof(double), h->stream));
@@ -522,8 +527,7 @@ int dcsim_all_done(dcsim_t* h, int* done_out) {
   *done_out = 0;
   if (!h->launches) return DCSIM_OK;
   CUDA_TRY(h, cudaSetDevice(h->device));
-  double* agg = NULL;
-  CUDA_TRY(h, cudaMalloc(&agg, DCSIM_AGG_K * sizeof(double)));
+  double* agg = h->d_agg; /* allocated once per handle: the chunked-resume loop calls this after every chunk */
   int rc = dcsim_reduce_summary(h, agg);
   double host[DCSIM_AGG_K];
   if (rc == DCSIM_OK) {
@@ -531,7 +535,6 @@ int dcsim_all_done(dcsim_t* h, int* done_out) {
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     if (e != cudaSuccess) rc = set_err(h, DCSIM_E_CUDA, "CUDA error: %s%lld", cudaGetErrorString(e));
   }
-  cudaFree(agg);
   if (rc != DCSIM_OK) return rc;
   /* a replica that stopped on a capacity overflow never finishes, so "done" = nothing is still running */
   *done_out = host[DCSIM_A_RUNNING] == 0.0;
@@ -579,8 +582,7 @@ int dcsim_fetch_latency_histogram(dcsim_t* h, uint64_t* out, size_t out_bytes) {
   if (out_bytes < need) return set_err(h, DCSIM_E_INVALID, "fetch_latency_histogram: buffer too small (need %s%lld bytes)", "", (long long)need);
   if (!h->launches) return set_err(h, DCSIM_E_STATE, "fetch_latency_histogram before the first advance%s%lld");
   CUDA_TRY(h, cudaSetDevice(h->device));
-  unsigned long long* d_out = NULL;
-  CUDA_TRY(h, cudaMalloc(&d_out, need));
+  unsigned long long* d_out = h->d_hist_out;
   cudaError_t e = cudaMemsetAsync(d_out, 0, need, h->stream);
   if (e == cudaSuccess) {
     int blocks = 8 * h->sm_count;
@@ -590,8 +592,17 @@ int dcsim_fetch_latency_histogram(dcsim_t* h, uint64_t* out, size_t out_bytes) {
   }
   if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, need, cudaMemcpyDeviceToHost, h->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-  cudaFree(d_out);
   if (e != cudaSuccess) return set_err(h, DCSIM_E_CUDA, "CUDA error: %s%lld", cudaGetErrorString(e));
+  return DCSIM_OK;
+}
+
+int dcsim_recorder_counts(dcsim_t* h, uint32_t* out3) {
+  if (!h || !out3) return DCSIM_E_INVALID;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  uint32_t counts[4];
+  CUDA_TRY(h, cudaMemcpyAsync(counts, h->d_counts, sizeof(counts), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  out3[0] = counts[0]; out3[1] = counts[1]; out3[2] = counts[2];
   return DCSIM_OK;
 }
 
@@ -650,7 +661,7 @@ void dcsim_destroy(dcsim_t* h) {
   if (h->own_stream) { cudaStreamSynchronize(h->stream); }
   cudaFree(h->d_state); cudaFree(h->d_queues); cudaFree(h->d_summary); cudaFree(h->d_events); cudaFree(h->d_counts);
   cudaFree(h->d_trace); cudaFree(h->d_jobs); cudaFree(h->d_cluster);
-  cudaFree(h->d_hist);
+  cudaFree(h->d_hist); cudaFree(h->d_agg); cudaFree(h->d_hist_out);
   cudaFree(h->d_mt);
   cudaFree(h->d_arr_t); cudaFree(h->d_arr_raw); cudaFree(h->d_arr_meta); cudaFree(h->d_arr_pred); cudaFree(h->d_arr_tx);
   cudaFree(h->d_arr_fin); cudaFree(h->d_ml_t); cudaFree(h->d_ml_aux); cudaFree(h->d_ml_meta); cudaFree(h->d_arr_hdr);

@@ -153,7 +153,8 @@ enum : uint32_t {
 
 enum { /* per-DC f64 arrays inside the state block, each DCSIM_MAX_DC long */
   DF_ENERGY = 0,
-  DF_LAST_T,     /* util_last_ts (SIM:430-436) AND last_energy_time (models.py:100-106): both are 0.0 until the
+  DF_LAST_T,     /* (kept in a register during a launch: dcsim_ctx_t::last_t; this slot holds it between launches)
+                    util_last_ts (SIM:430-436) AND last_energy_time (models.py:100-106): both are 0.0 until the
                     first event and are set to t on every event, so one slot carries both */
   DF_UTIL_TIME, DF_UTIL_BEGIN, DF_ACC_UNIT, DF_CUR_FREQ, DF_POWER,
   DF_PSUM,       /* sum of the running jobs' n*P_gpu(f) in dict (= start) order from 0.0 (SIM:168-179): extended by one
@@ -221,10 +222,12 @@ enum : int32_t {
   DCSIM_OFF_CAND_SEQ = DCSIM_OFF_CAND_T + CAND_N * 8,
   DCSIM_OFF_DC_F64 = DCSIM_OFF_CAND_SEQ + CAND_N * 4,
   DCSIM_OFF_DC_I32 = DCSIM_OFF_DC_F64 + DF_N * DCSIM_MAX_DC * 8,
+  /* the window's t / meta arrays carry one slot more than the window: slot DCSIM_LIST_WINDOW stays (+inf, 0), so that
+     "the entry behind the last staged one" reads as "no event" when the list ends exactly at a window boundary */
   DCSIM_OFF_LW_T = (DCSIM_OFF_DC_I32 + DI_N * DCSIM_MAX_DC * 4 + 15) & ~15,
-  DCSIM_OFF_LW_AUX = DCSIM_OFF_LW_T + (int32_t)DCSIM_LIST_WINDOW * 8,
+  DCSIM_OFF_LW_AUX = DCSIM_OFF_LW_T + ((int32_t)DCSIM_LIST_WINDOW + 1) * 8,
   DCSIM_OFF_LW_META = DCSIM_OFF_LW_AUX + (int32_t)DCSIM_LIST_WINDOW * 8,
-  DCSIM_OFF_PEND_SEQ = DCSIM_OFF_LW_META + (int32_t)DCSIM_LIST_WINDOW * 4,
+  DCSIM_OFF_PEND_SEQ = DCSIM_OFF_LW_META + ((int32_t)DCSIM_LIST_WINDOW + 1) * 4,
   DCSIM_OFF_XRING = (DCSIM_OFF_PEND_SEQ + 2 * DCSIM_MAX_ING * 4 + 15) & ~15
 };
 
@@ -374,6 +377,8 @@ struct dcsim_ctx_t {
   uint32_t cursor;       /* next entry of the event list */
   uint32_t lw_base;      /* list position of the window's first entry */
   double now;
+  double last_t;         /* instant of the previous processed event, 0.0 before the first: util_last_ts / last_energy_time
+                            of EVERY data centre (SIM:429-437 touches them all on every event, so they never differ) */
 };
 
 #define DCF(c, which) (dcsim_at<double>((c).blk, DCSIM_OFF_DC_F64 + (which) * DCSIM_MAX_DC * 8))
@@ -404,7 +409,9 @@ DCSIM_DEV void dcsim_philox_block(uint32_t k0, uint32_t k1, uint32_t b, uint32_t
 }
 
 DCSIM_DEV double dcsim_u53(uint32_t w0, uint32_t w1) { /* genrand_res53 on two given words */
-  return ((double)(w0 >> 5) * 67108864.0 + (double)(w1 >> 6)) * (1.0 / 9007199254740992.0);
+  /* ((w0 >> 5) * 2^26 + (w1 >> 6)) / 2^53 as CPython computes it in doubles; every step there is exact (the sum is an
+   * integer below 2^53), so building the integer first and converting once gives the same bits */
+  return (double)(((uint64_t)(w0 >> 5) << 26) | (uint64_t)(w1 >> 6)) * (1.0 / 9007199254740992.0);
 }
 
 /* ================================================================================================
@@ -544,13 +551,19 @@ __device__ __noinline__
 static
 #endif
 void dcsim_trng_dry(dcsim_trng_t<MT>* g, uint32_t* ring, int stride) { dcsim_trng_block(*g, ring, stride); } /* a sampler out-ran the ring (long rejection run) */
+/* The samplers call dcsim_trng_need(n) once where they are about to draw n words (n <= 4: one block refills the ring
+ * by that much) and then take the words without a check each.  After the per-arrival top-up the ring holds >= 29 words,
+ * so only long rejection runs ever refill here. */
 template <bool MT>
-DCSIM_DEV uint32_t dcsim_trng_word(dcsim_trng_t<MT>& g, uint32_t* ring, int stride) {
-  if (g.pos == g.filled) dcsim_trng_dry(&g, ring, stride);
+DCSIM_DEV void dcsim_trng_need(dcsim_trng_t<MT>& g, uint32_t* ring, int stride, uint32_t n) {
+  if (g.filled - g.pos < n) dcsim_trng_dry(&g, ring, stride);
+}
+template <bool MT>
+DCSIM_DEV uint32_t dcsim_trng_word(dcsim_trng_t<MT>& g, uint32_t* ring, int stride) { /* after dcsim_trng_need */
   return ring[(g.pos++ & (DCSIM_TRNG_RING - 1u)) * stride];
 }
 template <bool MT>
-DCSIM_DEV double dcsim_trng_random(dcsim_trng_t<MT>& g, uint32_t* ring, int stride) {
+DCSIM_DEV double dcsim_trng_random(dcsim_trng_t<MT>& g, uint32_t* ring, int stride) { /* after dcsim_trng_need(2) */
   const uint32_t a = dcsim_trng_word(g, ring, stride), b = dcsim_trng_word(g, ring, stride);
   return dcsim_u53(a, b);
 }
@@ -607,6 +620,7 @@ DCSIM_DEV double dcsim_t_gap(dcsim_trng_t<MT>& g, uint32_t* ring, int stride, co
   double x, rate;
   if (a.mode == DCSIM_ARR_POISSON) {
     if (a.rate <= 0.0) return DCSIM_INF;
+    dcsim_trng_need(g, ring, stride, 2u);
     x = 1.0 - dcsim_trng_random(g, ring, stride);
     rate = a.rate;
   } else if (a.mode == DCSIM_ARR_SINUSOID) {
@@ -616,6 +630,7 @@ DCSIM_DEV double dcsim_t_gap(dcsim_trng_t<MT>& g, uint32_t* ring, int stride, co
     const double p0 = lam0 / max_rate, p_lo = p0 - q.eps, p_hi = p0 + q.eps;
     for (int it = 0;; ++it) {
       if (it >= DCSIM_REJECTION_LIMIT) { *status |= DCSIM_ST_RNG_RUNAWAY; return DCSIM_INF; }
+      dcsim_trng_need(g, ring, stride, 4u);
       const double x1 = 1.0 - dcsim_trng_random(g, ring, stride);
       const double u2 = dcsim_trng_random(g, ring, stride);
       if (x1 >= q.x1_min) {
@@ -643,12 +658,14 @@ DCSIM_DEV double dcsim_t_gap(dcsim_trng_t<MT>& g, uint32_t* ring, int stride, co
 template <bool MT>
 DCSIM_DEV double dcsim_t_size_raw(dcsim_trng_t<MT>& g, uint32_t* ring, int stride, const dcsim_spec_t& sp, int jt, uint32_t* status) {
   if (jt == DCSIM_JT_INFERENCE) {
+    dcsim_trng_need(g, ring, stride, 2u);
     const double x = 1.0 - dcsim_trng_random(g, ring, stride);
     return x > sp.uniform_floor ? x : sp.uniform_floor;
   }
   double z = 0.0;
   for (int it = 0;; ++it) {
     if (it >= DCSIM_REJECTION_LIMIT) { *status |= DCSIM_ST_RNG_RUNAWAY; break; }
+    dcsim_trng_need(g, ring, stride, 4u);
     const double u1 = dcsim_trng_random(g, ring, stride);
     const double u2 = 1.0 - dcsim_trng_random(g, ring, stride);
     z = sp.nv_magicconst * (u1 - 0.5) / u2;
@@ -716,13 +733,16 @@ DCSIM_DEV void dcsim_generate_arrivals(const dcsim_kparams_t* P, uint64_t r, dou
   for (;;) {
     int s = -1;
     double t = DCSIM_INF;
-    for (int q = 0; q < n_streams; ++q) { /* heap order (t, seq): two pending arrivals at the same instant pop in push order */
+    bool tie = false;
+    for (int q = 0; q < n_streams; ++q) {
       const double tq = next_t[q * stride];
-      if (tq < t) { t = tq; s = q; }
-      else if (tq == t && s >= 0 && !(tq == DCSIM_INF) &&
-               dcsim_stream_rank(last_idx[q * stride], q) < dcsim_stream_rank(last_idx[s * stride], s)) s = q;
+      if (tq < t) { t = tq; s = q; tie = false; } else if (tq == t) tie = true;
     }
     if (s < 0 || t > sp.end_time) break; /* heap empty / SIM:427 */
+    if (tie) { /* heap order is (t, seq): pending arrivals at the same instant pop in push order (rare: ~rate * ulp(t)) */
+      for (int q = s + 1; q < n_streams; ++q)
+        if (next_t[q * stride] == t && dcsim_stream_rank(last_idx[q * stride], q) < dcsim_stream_rank(last_idx[s * stride], s)) s = q;
+    }
     if (status) break;
     dcsim_trng_topup(g, ring, stride); /* all lanes refill here, together */
     const int jt = s & 1;
@@ -738,9 +758,11 @@ DCSIM_DEV void dcsim_generate_arrivals(const dcsim_kparams_t* P, uint64_t r, dou
       }
       raw = size; raw_is_size = 0x100u;
     } else { /* random.choice: random.py:242-250 */
+      dcsim_trng_need(g, ring, stride, 1u);
       uint32_t v = dcsim_trng_word(g, ring, stride) >> (32 - k_bits);
       for (int it = 0; v >= (uint32_t)sp.n_dc; ++it) {
         if (it >= DCSIM_REJECTION_LIMIT) { status |= DCSIM_ST_RNG_RUNAWAY; v = 0u; break; }
+        dcsim_trng_need(g, ring, stride, 1u);
         v = dcsim_trng_word(g, ring, stride) >> (32 - k_bits);
       }
       dc_sel = (int)v;
@@ -779,7 +801,19 @@ DCSIM_DEV void dcsim_generate_arrivals(const dcsim_kparams_t* P, uint64_t r, dou
  * ============================================================================================== */
 DCSIM_DEV bool dcsim_finite(double x) { return !(x == DCSIM_INF); }
 
-DCSIM_DEV void dcsim_merge_arrivals(const dcsim_kparams_t* P, uint64_t r, int lane) {
+/* The merge works on a sliding window of the replica's arrivals kept in shared memory (a ring indexed by the arrival
+ * number): what the position scans read — arrival instant, xfer_done instant, running count of finite transfers,
+ * predecessor — plus what the emission needs (size, meta).  Everything is also in HBM (the pre-pass output and the
+ * merge's own scratch), which is where a scan falls back to when it reaches behind the ring (very long transfers). */
+#ifndef DCSIM_MERGE_RING
+#define DCSIM_MERGE_RING 128u /* a power of two >= DCSIM_LANES */
+#endif
+struct dcsim_merge_ring_t {
+  double at[DCSIM_MERGE_RING], tx[DCSIM_MERGE_RING], sz[DCSIM_MERGE_RING];
+  uint32_t fin[DCSIM_MERGE_RING], pred[DCSIM_MERGE_RING], meta[DCSIM_MERGE_RING];
+};
+
+DCSIM_DEV void dcsim_merge_arrivals(const dcsim_kparams_t* P, uint64_t r, int lane, dcsim_merge_ring_t* ring) {
   const dcsim_spec_t& sp = P->spec;
   dcsim_arrhdr_t* hdr = P->arr_hdr + r;
   const uint32_t n = hdr->count;
@@ -794,71 +828,98 @@ DCSIM_DEV void dcsim_merge_arrivals(const dcsim_kparams_t* P, uint64_t r, int la
   double* ma = P->ml_aux + 2ull * ab;
   uint32_t* mm = P->ml_meta + 2ull * ab;
   const double end = sp.end_time, end_eps = P->end_eps, tmax = P->max_transfer;
+  const uint32_t RM = DCSIM_MERGE_RING - 1u;
 
-  /* sweep 1: sizes, xfer_done instants, running count of the finite ones */
-  uint32_t fin_base = 0u;
-  for (uint32_t k0 = 0u; k0 < n; k0 += DCSIM_LANES) {
-    const uint32_t k = k0 + (uint32_t)lane;
-    bool f = false;
-    if (k < n) {
-      const uint32_t meta = am[k];
-      const int stream = (int)(meta & 15u), jt = stream & 1, ing = stream >> 1, dc = (int)((meta >> 4) & 7u);
-      if (!(meta & 0x100u)) raw[k] = dcsim_size_from_raw(sp, raw[k], jt); /* from here on raw[] holds the sizes */
-      const double v = dcsim_test_quantize(at[k] + sp.transfer_s[ing][dc][jt]); /* SIM:580: now + transfer_s, now == the arrival instant */
-      f = dcsim_finite(v);
-      tx[k] = v;
-    }
-    const uint32_t votes = dcsim_warp_ballot(f);
-    if (k < n) fin[k] = fin_base + dcsim_popc(votes & dcsim_lanemask_lt(lane));
-    fin_base += dcsim_popc(votes);
-  }
-  dcsim_warp_sync(); /* tx[] / fin[] / raw[] written by other lanes are read below */
-
-  /* sweep 2: list positions, emission */
+  uint32_t frontier = 0u;  /* arrivals [0, frontier) have their size / xfer_done instant / finite count (ring + HBM) */
+  uint32_t fin_base = 0u;  /* finite xfer_done instants among them */
   uint32_t n_x = 0u, ahead = 0u;
   for (uint32_t k0 = 0u; k0 < n; k0 += DCSIM_LANES) {
-    const uint32_t k = k0 + (uint32_t)lane;
-    if (k >= n) continue;
-    const double tk = at[k], txk = tx[k];
-    const uint32_t meta = am[k], pk = pred[k];
-    /* arrival k: the k earlier arrivals + the transfers that come before it */
-    uint32_t cnt = 0u;
-    for (uint32_t j = k; j > 0u;) {
-      --j;
-      if (at[j] + tmax < tk) { cnt += fin[j] + (dcsim_finite(tx[j]) ? 1u : 0u); break; } /* every finite one up to j is earlier */
-      const double txj = tx[j];
-      if (txj < tk || (txj == tk && pk != DCSIM_NO_PRED && j <= pk)) ++cnt;
+    /* ---- stage 1, as far ahead as this chunk's scans can reach: past the chunk itself and on until an arrival later
+     * than every xfer_done instant of the chunk (<= its last arrival + max_transfer) */
+    const uint32_t k_last = k0 + DCSIM_LANES - 1u < n - 1u ? k0 + DCSIM_LANES - 1u : n - 1u;
+    for (;;) {
+      if (frontier > k_last) {
+        if (frontier >= n) break;
+        const double t_hi = (frontier - k_last <= DCSIM_MERGE_RING ? ring->at[k_last & RM] : at[k_last]) + tmax;
+        if (ring->at[(frontier - 1u) & RM] > t_hi) break;
+      }
+      const uint32_t k = frontier + (uint32_t)lane;
+      bool f = false;
+      double v = DCSIM_INF, size = 0.0, tk = 0.0;
+      uint32_t meta = 0u;
+      if (k < n) {
+        meta = am[k];
+        const int stream = (int)(meta & 15u), jt = stream & 1, ing = stream >> 1, dc = (int)((meta >> 4) & 7u);
+        size = raw[k];
+        if (!(meta & 0x100u)) size = dcsim_size_from_raw(sp, size, jt);
+        tk = at[k];
+        v = dcsim_test_quantize(tk + sp.transfer_s[ing][dc][jt]); /* SIM:580: now + transfer_s, now == the arrival instant */
+        f = dcsim_finite(v);
+      }
+      const uint32_t votes = dcsim_warp_ballot(f);
+      if (k < n) {
+        const uint32_t fk = fin_base + dcsim_popc(votes & dcsim_lanemask_lt(lane));
+        ring->at[k & RM] = tk; ring->tx[k & RM] = v; ring->sz[k & RM] = size;
+        ring->fin[k & RM] = fk; ring->pred[k & RM] = pred[k]; ring->meta[k & RM] = meta;
+        tx[k] = v; fin[k] = fk; raw[k] = size; /* the HBM copies back the ring up */
+      }
+      fin_base += dcsim_popc(votes);
+      frontier += DCSIM_LANES;
+      dcsim_warp_sync(); /* ring / HBM entries written by other lanes are read below */
     }
-    const uint32_t pos_a = k + cnt;
-    const bool xs = dcsim_finite(txk) && !(txk > end_eps); /* SIM:160-163 */
-    const bool xin = xs && !(txk > end);                    /* SIM:427: later events are never processed */
-    uint32_t pos_x = 0xffffffffu;
-    if (xin) {
-      uint32_t ca = k + 1u, cx = 0u; /* arrivals 0..k come first (their pushes precede arrival k's processing) */
+    const uint32_t lo = frontier > DCSIM_MERGE_RING ? frontier - DCSIM_MERGE_RING : 0u; /* ring holds [lo, frontier) */
+
+    /* ---- stage 2: list positions of this chunk's arrivals and their xfer_done events, emission */
+    const uint32_t k = k0 + (uint32_t)lane;
+    if (k < n) {
+      const bool kin = k >= lo;
+      const double tk = kin ? ring->at[k & RM] : at[k], txk = kin ? ring->tx[k & RM] : tx[k];
+      const uint32_t meta = kin ? ring->meta[k & RM] : am[k], pk = kin ? ring->pred[k & RM] : pred[k];
+      /* arrival k: the k earlier arrivals + the transfers that come before it */
+      uint32_t cnt = 0u;
       for (uint32_t j = k; j > 0u;) {
         --j;
-        if (at[j] + tmax < txk) { cx += fin[j] + (dcsim_finite(tx[j]) ? 1u : 0u); break; }
-        if (tx[j] <= txk) ++cx; /* tie: pushed earlier */
+        const bool in = j >= lo;
+        const double tj = in ? ring->at[j & RM] : at[j], txj = in ? ring->tx[j & RM] : tx[j];
+        if (tj + tmax < tk) { cnt += (in ? ring->fin[j & RM] : fin[j]) + (dcsim_finite(txj) ? 1u : 0u); break; } /* every finite one up to j is earlier */
+        if (txj < tk || (txj == tk && pk != DCSIM_NO_PRED && j <= pk)) ++cnt;
       }
-      for (uint32_t i = k + 1u; i < n; ++i) {
-        const double ti = at[i];
-        if (ti > txk) break;
-        if (ti < txk || pred[i] == DCSIM_NO_PRED || pred[i] < k) ++ca; /* tie: arrival i was pushed before arrival k ran */
-        if (tx[i] < txk) ++cx;                                          /* tie: pushed later */
+      const uint32_t pos_a = k + cnt;
+      const bool xs = dcsim_finite(txk) && !(txk > end_eps); /* SIM:160-163 */
+      const bool xin = xs && !(txk > end);                    /* SIM:427: later events are never processed */
+      uint32_t pos_x = 0xffffffffu;
+      if (xin) {
+        uint32_t ca = k + 1u, cx = 0u; /* arrivals 0..k come first (their pushes precede arrival k's processing) */
+        for (uint32_t j = k; j > 0u;) {
+          --j;
+          const bool in = j >= lo;
+          const double tj = in ? ring->at[j & RM] : at[j], txj = in ? ring->tx[j & RM] : tx[j];
+          if (tj + tmax < txk) { cx += (in ? ring->fin[j & RM] : fin[j]) + (dcsim_finite(txj) ? 1u : 0u); break; }
+          if (txj <= txk) ++cx; /* tie: pushed earlier */
+        }
+        for (uint32_t i = k + 1u; i < n; ++i) { /* i < frontier: stage 1 ran until an arrival later than txk */
+          const bool in = i >= lo;
+          const double ti = in ? ring->at[i & RM] : at[i];
+          if (ti > txk) break;
+          const uint32_t pi = in ? ring->pred[i & RM] : pred[i];
+          if (ti < txk || pi == DCSIM_NO_PRED || pi < k) ++ca;          /* tie: arrival i was pushed before arrival k ran */
+          if ((in ? ring->tx[i & RM] : tx[i]) < txk) ++cx;               /* tie: pushed later */
+        }
+        pos_x = ca + cx;
+        ++n_x;
+        ahead = pos_x - pos_a > ahead ? pos_x - pos_a : ahead;
       }
-      pos_x = ca + cx;
-      ++n_x;
-      ahead = pos_x - pos_a > ahead ? pos_x - pos_a : ahead;
+      const uint32_t stream = meta & 15u;
+      mt[pos_a] = tk;
+      ma[pos_a] = dcsim_hilo_f64(0u, pos_x);
+      mm[pos_a] = (stream << 1) | ((meta & 0x80u) ? ML_A_NEXT : 0u) | (xs ? ML_A_XSCHED : 0u) | (xin ? ML_A_XIN : 0u);
+      if (xin) {
+        mt[pos_x] = txk;
+        ma[pos_x] = kin ? ring->sz[k & RM] : raw[k];
+        mm[pos_x] = ML_XFER | (((meta >> 4) & 7u) << 1) | ((stream & 1u) << 4) | ((stream >> 1) << 5) | (k << 8);
+      }
     }
-    const uint32_t stream = meta & 15u;
-    mt[pos_a] = tk;
-    ma[pos_a] = dcsim_hilo_f64(0u, pos_x);
-    mm[pos_a] = (stream << 1) | ((meta & 0x80u) ? ML_A_NEXT : 0u) | (xs ? ML_A_XSCHED : 0u) | (xin ? ML_A_XIN : 0u);
-    if (xin) {
-      mt[pos_x] = txk;
-      ma[pos_x] = raw[k];
-      mm[pos_x] = ML_XFER | (((meta >> 4) & 7u) << 1) | ((stream & 1u) << 4) | ((stream >> 1) << 5) | (k << 8);
-    }
+    dcsim_warp_sync(); /* this chunk's ring reads are done before the next chunk's stage 1 overwrites old entries */
   }
   n_x = dcsim_warp_add_u32(n_x);
   ahead = dcsim_warp_max_u32(ahead);
@@ -917,12 +978,23 @@ DCSIM_DEV int dcsim_argmin_ts(const double* t, const uint32_t* seq, int n, int l
   return win;
 }
 
+/* Seq of the list entry at the cursor.  It was handed out when the push happened: an arrival's when its stream's
+ * previous arrival (or the constructor) pushed it, an xfer_done's when its own arrival did. */
+DCSIM_DEV uint32_t* dcsim_list_seq_slot(dcsim_ctx_t& c, uint32_t m) {
+  return (m & ML_XFER) ? XRING(c) + (c.cursor & (uint32_t)c.P->L.xring_mask) : PEND_SEQ(c) + ((m >> 1) & 15u);
+}
+
 /* Pop-min over the event set itself: exactly one candidate per lane (CAND_N == 32), so no loop and no index
- * bookkeeping — two loads, three REDUX.MIN, one ballot.  Returns the winning candidate slot, -1 if all are +inf. */
+ * bookkeeping — two loads, three REDUX.MIN, one ballot.  Lane CAND_LIST takes its candidate straight from the list
+ * window (entry c.cursor; the slot behind the window reads +inf), so nothing has to "publish" the next list entry.
+ * Returns the winning candidate slot, -1 if all are +inf. */
 DCSIM_DEV int dcsim_argmin_cand(dcsim_ctx_t& c, double* t_out, uint32_t* seq_out) {
+  const uint32_t li = c.cursor - c.lw_base; /* <= DCSIM_LIST_WINDOW */
+  const uint32_t lm = LW_META(c)[li];
 #if DCSIM_LANES == 32
-  const double t = CAND_T(c)[c.lane];
-  const uint32_t s = CAND_SEQ(c)[c.lane];
+  const bool list = c.lane == CAND_LIST;
+  const double t = *(list ? LW_T(c) + li : CAND_T(c) + c.lane);
+  const uint32_t s = *(list ? dcsim_list_seq_slot(c, lm) : CAND_SEQ(c) + c.lane);
   const uint32_t h = dcsim_hi(t), l = dcsim_lo(t);
   const uint32_t mh = dcsim_warp_min_u32(h);
   if (mh >= 0x7ff00000u) return -1;
@@ -934,6 +1006,8 @@ DCSIM_DEV int dcsim_argmin_cand(dcsim_ctx_t& c, double* t_out, uint32_t* seq_out
   *seq_out = ms;
   return dcsim_ffs(votes) - 1;
 #else
+  CAND_T(c)[CAND_LIST] = LW_T(c)[li];
+  CAND_SEQ(c)[CAND_LIST] = *dcsim_list_seq_slot(c, lm);
   return dcsim_argmin_ts(CAND_T(c), CAND_SEQ(c), CAND_N, c.lane, t_out, seq_out);
 #endif
 }
@@ -1173,20 +1247,6 @@ DCSIM_DEV void dcsim_list_stage(dcsim_ctx_t& c, uint64_t r, uint32_t base) {
   dcsim_warp_sync();
 }
 
-/* Lane 0.  Publishes list entry c.cursor as the list candidate.  Its seq was handed out when the push happened: an
- * arrival's when its stream's previous arrival (or the constructor) pushed it, an xfer_done's when its own arrival did. */
-DCSIM_DEV void dcsim_list_candidate(dcsim_ctx_t& c) {
-  if (c.cursor < c.H->ml_count) {
-    const uint32_t i = c.cursor - c.lw_base;
-    const uint32_t m = LW_META(c)[i];
-    CAND_T(c)[CAND_LIST] = LW_T(c)[i];
-    CAND_SEQ(c)[CAND_LIST] = (m & ML_XFER) ? XRING(c)[c.cursor & (uint32_t)c.P->L.xring_mask] : PEND_SEQ(c)[(m >> 1) & 15u];
-  } else {
-    CAND_T(c)[CAND_LIST] = DCSIM_INF;
-    CAND_SEQ(c)[CAND_LIST] = 0xffffffffu;
-  }
-}
-
 /* SIM:595-678 (lane 0): the transferred job starts if its DC has a free GPU, else it queues. */
 template <bool CAP>
 DCSIM_DEV void dcsim_handle_xfer(dcsim_ctx_t& c, double size, uint32_t meta) {
@@ -1226,7 +1286,6 @@ DCSIM_DEV void dcsim_handle_list(dcsim_ctx_t& c, uint64_t r) {
     dcsim_warp_sync(); /* lane 0 is done with the old window */
     dcsim_list_stage(c, r, c.cursor);
   }
-  if (c.lane == 0) dcsim_list_candidate(c);
   dcsim_warp_sync();
 }
 
@@ -1294,9 +1353,10 @@ DCSIM_DEV void dcsim_dequeue_loop(dcsim_ctx_t& c, int d, const dcsim_qent_t& pre
  * One pass over the DC's records does everything the reference's `del dc.running_jobs[jid]` + next `_estimate_dc_power`
  * + next heap pop imply: lane j loads record j of the set WITHOUT the finished one (slot j, or j + 1 behind the hole),
  * lanes behind the hole store it one slot down (dict order is start order, models.py:60), the earliest remaining
- * finish is an arg-min over the registers, and the active power is re-summed in dict order (SIM:168-179) — from the
- * registers by shuffles when the records live in HBM/L2 (RECG: they are touched once per job_finish, one load round
- * trip, stores fire-and-forget), by lane 0 out of shared memory when they are staged there. */
+ * finish is an arg-min over the registers, and the active power is re-summed in dict order (SIM:168-179) from the
+ * registers by shuffles (a lane-0 loop over shared memory measured slower: its loads serialise behind the additions).
+ * The records are touched once per job_finish — one load round trip, stores fire-and-forget — which is what lets them
+ * live in HBM/L2 (RECG) when the block is large. */
 template <bool CAP, bool RECG>
 DCSIM_DEV void dcsim_handle_finish(dcsim_ctx_t& c, uint64_t r, int d) {
   const dcsim_layout_t& L = c.P->L;
@@ -1329,14 +1389,14 @@ DCSIM_DEV void dcsim_handle_finish(dcsim_ctx_t& c, uint64_t r, int d) {
     double a_t = DCSIM_INF, a_pw = 0.0, a_tpt = 0.0, a_start = 0.0, a_size = 0.0, a_f = 0.0, a_done = 0.0, a_upd = 0.0;
     uint32_t a_seq = 0xffffffffu, a_meta = 0u, a_jid = 0u;
     if (act) { a_t = rt[src]; a_seq = rq[src]; }
-    if (act && (RECG || moved)) a_pw = rp[src];
+    if (act) a_pw = rp[src];
     if (moved) {
       a_tpt = rv[src]; a_start = ra[src]; a_meta = rm[src];
       if (full) { a_size = dcsim_at<double>(c.rec, L.rn_size)[off + src]; a_f = dcsim_at<double>(c.rec, L.rn_f)[off + src];
                   a_jid = dcsim_at<uint32_t>(c.rec, L.rn_jid)[off + src]; }
       if constexpr (CAP) { a_done = dcsim_at<double>(c.rec, L.rn_done)[off + src]; a_upd = dcsim_at<double>(c.rec, L.rn_upd)[off + src]; }
     }
-    if constexpr (RECG) {
+    {
       const int cnt = n1 - base < DCSIM_LANES ? n1 - base : DCSIM_LANES;
       for (int i = 0; i < cnt; ++i) psum += dcsim_bcast_f64(a_pw, i); /* SIM:168-179: dict order, from 0.0 */
     }
@@ -1365,11 +1425,7 @@ DCSIM_DEV void dcsim_handle_finish(dcsim_ctx_t& c, uint64_t r, int d) {
     win = (int)dcsim_bcast_u32((uint32_t)bi, dcsim_ffs(votes) - 1);
     wt = dcsim_hilo_f64(mh, ml);
   }
-  if constexpr (!RECG) dcsim_warp_sync(); /* the compacted records are visible to lane 0 */
   if (c.lane == 0) {
-    if constexpr (!RECG) {
-      for (int i = 0; i < n1; ++i) psum += rp[i]; /* SIM:168-179: dict order, from 0.0 */
-    }
     CAND_T(c)[CAND_DC0 + d] = wt; CAND_SEQ(c)[CAND_DC0 + d] = ws; DCI(c, DI_FMIN_SLOT)[d] = win;
     DCI(c, DI_NRUN)[d] = n1;
     DCF(c, DF_PSUM)[d] = psum;
@@ -1588,7 +1644,7 @@ DCSIM_DEV void dcsim_replica_init(dcsim_ctx_t& c, uint64_t r) {
     DCF(c, DF_POWER)[d] = (double)sp.dc[d].total_gpus * (sp.dc[d].power_gating ? sp.dc[d].p_sleep : sp.dc[d].p_idle);
   }
   dcsim_warp_sync();
-  c.seq = 0u; c.now = 0.0; c.cursor = 0u; c.lw_base = 0u;
+  c.seq = 0u; c.now = 0.0; c.last_t = 0.0; c.cursor = 0u; c.lw_base = 0u;
   if (c.lane == 0) {
     const dcsim_arrhdr_t ah = c.P->arr_hdr[r];
     c.H->ml_count = ah.ml_count; c.H->status |= ah.status;
@@ -1600,9 +1656,8 @@ DCSIM_DEV void dcsim_replica_init(dcsim_ctx_t& c, uint64_t r) {
     c.H->initialized = 1u;
   }
   dcsim_warp_sync();
+  if (c.lane == 0) { LW_T(c)[DCSIM_LIST_WINDOW] = DCSIM_INF; LW_META(c)[DCSIM_LIST_WINDOW] = 0u; }
   dcsim_list_stage(c, r, 0u);
-  if (c.lane == 0) dcsim_list_candidate(c);
-  dcsim_warp_sync();
 }
 
 /* SIM:469-475: util to end_time, then accrue_energy(end_time) WITHOUT power_fn => models.py:82-91. */
@@ -1612,7 +1667,7 @@ DCSIM_DEV void dcsim_replica_tail(dcsim_ctx_t& c) {
   DCSIM_FOR_EACH_DC(d, c, sp.n_dc) {
     const dcsim_dc_t& cfg = sp.dc[d];
     const int busy = DCI(c, DI_BUSY)[d];
-    const double last = DCF(c, DF_LAST_T)[d];
+    const double last = c.last_t;
     if (0.0 < last && last < end) DCF(c, DF_UTIL_TIME)[d] += (double)busy * (end - last); /* SIM:471-474 */
     if (last != 0.0) { /* models.py:100-106 with power_fn=None */
       double dt = end - last; dt = dt > 0.0 ? dt : 0.0;
@@ -1622,8 +1677,8 @@ DCSIM_DEV void dcsim_replica_tail(dcsim_ctx_t& c) {
       const double p_idle = (double)(cfg.total_gpus - busy) * (cfg.power_gating ? cfg.p_sleep : cfg.p_idle);
       DCF(c, DF_ENERGY)[d] += (p_active + p_idle) * dt;
     }
-    DCF(c, DF_LAST_T)[d] = end;
   }
+  c.last_t = end;
   dcsim_warp_sync();
 }
 
@@ -1651,17 +1706,18 @@ DCSIM_DEV uint32_t dcsim_replica_run(dcsim_ctx_t& c, uint64_t r) {
     if (win < 0) { finished = true; break; }         /* `while self.event_q` */
     if (t > sp.end_time) { finished = true; break; } /* SIM:427 */
 
-    DCSIM_FOR_EACH_DC(d, c, sp.n_dc) { /* SIM:429-437 + models.py:100-106, state before the event */
-      const double last = DCF(c, DF_LAST_T)[d];
-      if (last == 0.0) {
-        DCF(c, DF_UTIL_BEGIN)[d] = t;
-      } else {
-        double dt = t - last; dt = dt > 0.0 ? dt : 0.0;
+    /* SIM:429-437 + models.py:100-106, state before the event.  Every DC's "last" stamp is the previous event's instant
+     * (one register for all of them); the first event only stamps (0.0 is the reference's "never touched" sentinel). */
+    if (c.last_t == 0.0) {
+      DCSIM_FOR_EACH_DC(d, c, sp.n_dc) DCF(c, DF_UTIL_BEGIN)[d] = t;
+    } else {
+      double dt = t - c.last_t; dt = dt > 0.0 ? dt : 0.0;
+      DCSIM_FOR_EACH_DC(d, c, sp.n_dc) {
         DCF(c, DF_UTIL_TIME)[d] += (double)DCI(c, DI_BUSY)[d] * dt;
         DCF(c, DF_ENERGY)[d] += DCF(c, DF_POWER)[d] * dt;
       }
-      DCF(c, DF_LAST_T)[d] = t;
     }
+    c.last_t = t;
     dcsim_warp_sync(); /* every lane has read its candidate / busy / power before lane 0's handler rewrites them */
     c.now = t;
     /* dispatch on the winning slot itself; the event kind is only spelled out for the (cold) trace */
@@ -1734,6 +1790,7 @@ DCSIM_DEV void dcsim_write_summary(dcsim_ctx_t& c, double* out) {
     out[DCSIM_S_MAX_XFER] = 0.0; /* there is no pool of in-flight transfers to size any more */
     out[DCSIM_S_MAX_RUN] = (double)H->max_run;
     out[DCSIM_S_MAX_Q] = (double)H->max_q;
+    out[DCSIM_S_UTIL_BEGIN] = DCF(c, DF_UTIL_BEGIN)[0];
   }
   DCSIM_FOR_EACH_DC(d, c, sp.n_dc) {
     double* o = out + DCSIM_S_DC0 + d * DCSIM_S_DC_STRIDE;
@@ -1762,6 +1819,7 @@ DCSIM_DEV uint32_t dcsim_replica_step(const dcsim_kparams_t* P, uint64_t r, char
     dcsim_replica_init(c, r);
   } else { /* resume: hot scalars back into registers */
     c.seq = c.H->seq; c.now = c.H->now; c.cursor = c.H->ml_cursor; c.lw_base = c.H->lw_base;
+    c.last_t = DCF(c, DF_LAST_T)[0];
   }
   uint32_t n = 0u;
   if (c.H->done == 0u) n = dcsim_replica_run<CAP, RECG>(c, r);
@@ -1772,6 +1830,7 @@ DCSIM_DEV uint32_t dcsim_replica_step(const dcsim_kparams_t* P, uint64_t r, char
     c.H->n_events = c.H->ev_arr + c.H->ev_xfer + c.H->ev_fin + c.H->ev_log; /* every processed event is one of these */
     c.H->seq = c.seq; c.H->now = c.now; c.H->last_t = c.H->n_events ? c.now : 0.0;
     c.H->ml_cursor = c.cursor; c.H->lw_base = c.lw_base;
+    for (int d = 0; d < P->spec.n_dc; ++d) DCF(c, DF_LAST_T)[d] = c.last_t;
   }
   dcsim_warp_sync();
   dcsim_write_summary(c, P->summary + r * DCSIM_SUMMARY_K);

@@ -46,6 +46,14 @@ def latency_quantiles(hist_row, qs=(0.5, 0.9, 0.99)):
 RNG_KINDS = {"philox": 0, "mt19937": 1}
 
 
+class RecorderOverflow(RuntimeError):
+    """A recorder (0 trace, 1 job log, 2 cluster log) saw more rows than its capacity; `.needed` says how many."""
+
+    def __init__(self, which, needed, capacity):
+        super().__init__(f"{('trace', 'job log', 'cluster log')[which]} needs {needed} rows, capacity {capacity}")
+        self.which, self.needed, self.capacity = which, needed, capacity
+
+
 class BatchedEngine:
     """R independent replicas of one scenario on one GPU.
 
@@ -140,20 +148,30 @@ class BatchedEngine:
         return out
 
     # -- recorders -------------------------------------------------------------------------------
-    def _fetch(self, fn, dtype, cap):
+    def recorder_counts(self):
+        """(trace, job_log, cluster_log) rows the recorders WOULD have written: more than a recorder's capacity means
+        its rows are a truncated prefix (the kernels keep counting and stop writing)."""
+        out = (C.c_uint32 * 3)()
+        N.check(self._lib.dcsim_recorder_counts(self._h, C.byref(out)), self._h)
+        return int(out[0]), int(out[1]), int(out[2])
+
+    def _fetch(self, fn, dtype, cap, which):
         arr = np.zeros(max(cap, 1), dtype=dtype)
         n = C.c_uint32(0)
         N.check(fn(self._h, C.c_void_p(arr.ctypes.data), cap, C.byref(n)), self._h)
+        if cap and which is not None and self.recorder_counts()[which] > cap:     # never hand a silently truncated log to a caller
+            raise RecorderOverflow(which, self.recorder_counts()[which], cap)
         return arr[: n.value]
 
     def trace(self):
-        return self._fetch(self._lib.dcsim_fetch_trace, TRACE_DTYPE, self._trace_cap)
+        """The first `capacity` processed events of the traced replica (a debug aid: a prefix by design)."""
+        return self._fetch(self._lib.dcsim_fetch_trace, TRACE_DTYPE, self._trace_cap, None)
 
     def job_log(self):
-        return self._fetch(self._lib.dcsim_fetch_job_log, JOB_DTYPE, self._jobs_cap)
+        return self._fetch(self._lib.dcsim_fetch_job_log, JOB_DTYPE, self._jobs_cap, 1)
 
     def cluster_log(self):
-        return self._fetch(self._lib.dcsim_fetch_cluster_log, CLUSTER_DTYPE, self._cluster_cap)
+        return self._fetch(self._lib.dcsim_fetch_cluster_log, CLUSTER_DTYPE, self._cluster_cap, 2)
 
     def launch_info(self) -> dict:
         li = S.LaunchInfo()

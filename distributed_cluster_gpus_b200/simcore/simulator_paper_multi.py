@@ -17,7 +17,7 @@ from typing import Dict, Optional, Tuple, Union
 import numpy as np
 
 from .. import spec as S
-from ..engine import RNG_KINDS, LoggedReplica, release_engine, run_to_completion
+from ..engine import RNG_KINDS, LoggedReplica, RecorderOverflow, release_engine, run_to_completion
 from .arrivals import ArrivalConfig
 from .models import DataCenter
 from .network import Graph, Ingress
@@ -130,7 +130,11 @@ class MultiIngressPaperSimulator:
             # the companion's single replica is done long before the batch: fetch its rows and write the CSV files
             # while the GPU is still busy with the batch
             if companion is not None:
-                bits, jobs, cluster = companion.collect()
+                try:
+                    bits, jobs, cluster = companion.collect()
+                except RecorderOverflow:
+                    early["bits"] = -1               # a recorder was too small: replica 0 is logged again below
+                    return
                 early["bits"] = bits
                 if bits == 0:
                     self._write_csvs(jobs, cluster)
@@ -149,20 +153,16 @@ class MultiIngressPaperSimulator:
             self.launch_info = eng.launch_info()
             self._store_replica0(summ[0])
             if in_batch_log:
-                self._write_csvs(eng.job_log(), eng.cluster_log())
+                try:
+                    self._write_csvs(eng.job_log(), eng.cluster_log())
+                except RecorderOverflow:
+                    self._log_one_replica(eng.spec, job_cap * 2, cluster_cap * 2)
             elif companion is not None:
                 if not early.get("written") or eng.spec.to_bytes() != self._spec.to_bytes():
                     # the batch (or the companion) needed larger capacities: log replica 0 again under the final spec
                     companion.release(keep=False)
                     companion = None
-
-                    def configure_one(e):
-                        e.set_rng(self.rng)
-                        e.set_logging(0, job_cap, cluster_cap)
-                    one, _ = run_to_completion(lambda caps: eng.spec, 1, self.rng_seed, self.first_replica_id, self.device,
-                                               0, configure=configure_one)
-                    self._write_csvs(one.job_log(), one.cluster_log())
-                    one.close()
+                    self._log_one_replica(eng.spec, job_cap, cluster_cap)
         except BaseException:
             eng.close()
             if companion is not None:
@@ -178,7 +178,13 @@ class MultiIngressPaperSimulator:
 
     # ------------------------------------------------------------------------------------------------
     def _store_replica0(self, row):
+        """Replica 0 -> the caller's DataCenter objects, as the reference leaves them after run() (SIM:469-475,
+        models.py:93-106).  What cannot be materialised — the Job objects still queued or running — is represented by
+        its COUNT: `len(dc.q_inf)`, `len(dc.q_train)` and `len(dc.running_jobs)` are right, the elements are
+        placeholders (None / jid-less keys); the same counts are also plain attributes (q_inf_len, q_train_len,
+        running_count)."""
         self.now = float(row[S.S_LAST_T])
+        any_event = row[S.S_EVENTS] > 0
         for d, dc in enumerate(self.dcs.values()):
             g = row[S.S_DC0 + d * S.S_DC_STRIDE: S.S_DC0 + (d + 1) * S.S_DC_STRIDE]
             dc.energy_joules = float(g[S.SD_ENERGY_J])
@@ -186,8 +192,37 @@ class MultiIngressPaperSimulator:
             dc.accumulated_job_unit = float(g[S.SD_ACC_JOB_UNIT])
             dc.busy_gpus = int(g[S.SD_BUSY])
             dc.current_freq = float(g[S.SD_CURRENT_FREQ])
-            dc.last_energy_time = self.end_time
-            dc.util_last_ts = self.end_time
+            dc.last_energy_time = self.end_time                       # accrue_energy(end_time) always stamps it
+            dc.util_last_ts = self.end_time if any_event else 0.0     # SIM:471-474: untouched (0.0) without events
+            dc.util_begin_ts = float(row[S.S_UTIL_BEGIN])             # instant of the first processed event
+            dc.q_inf_len, dc.q_train_len, dc.running_count = int(g[S.SD_Q_INF]), int(g[S.SD_Q_TRN]), int(g[S.SD_RUNNING])
+            dc.q_inf = [None] * dc.q_inf_len
+            dc.q_train = [None] * dc.q_train_len
+            dc.running_jobs = {-(i + 1): None for i in range(dc.running_count)}
+
+    def _log_one_replica(self, spec, job_cap, cluster_cap):
+        """Replica 0's CSV rows from a one-replica engine of its own; a recorder that turns out too small is
+        re-run at the size the device counted (never a silently truncated file)."""
+        from ..engine import RecorderOverflow
+        for _ in range(4):
+            def configure_one(e, jc=job_cap, cc=cluster_cap):
+                e.set_rng(self.rng)
+                e.set_logging(0, jc, cc)
+            one, _s = run_to_completion(lambda caps: spec, 1, self.rng_seed, self.first_replica_id, self.device, 0,
+                                        configure=configure_one)
+            try:
+                jobs, cluster = one.job_log(), one.cluster_log()
+            except RecorderOverflow as e:
+                if e.which == 1:
+                    job_cap = e.needed + 64
+                else:
+                    cluster_cap = e.needed + 64
+                continue
+            finally:
+                one.close()
+            self._write_csvs(jobs, cluster)
+            return
+        raise RuntimeError("could not size the log recorders")
 
     def _write_csvs(self, jobs, cluster):
         write_csv_logs(jobs, cluster, self.dcs, list(self.ingresses), self.coeffs_map, self._spec.net_lat_s,

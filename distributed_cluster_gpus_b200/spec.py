@@ -31,6 +31,7 @@ START_POLICY, START_NF_LUT, START_BANDIT = 0, 1, 2
 S_STATUS, S_EVENTS, S_JOBS_FINISHED, S_JOBS_CREATED, S_TOTAL_ENERGY_J, S_LAT_SUM = 0, 1, 2, 3, 4, 5
 S_LAT_SUM_INF, S_FIN_INF, S_LAT_SUM_TRN, S_FIN_TRN, S_RNG_WORDS, S_LAST_T, S_SEQ = 6, 7, 8, 9, 10, 11, 12
 S_EV_ARRIVAL, S_EV_XFER, S_EV_FINISH, S_EV_LOG, S_DONE, S_MAX_XFER, S_MAX_RUN, S_MAX_Q = 13, 14, 15, 16, 17, 18, 19, 20
+S_UTIL_BEGIN = 21
 S_DC0, S_DC_STRIDE = 24, 8
 SUMMARY_K = 24 + 8 * MAX_DC
 SD_ENERGY_J, SD_UTIL_GPU_TIME, SD_ACC_JOB_UNIT, SD_BUSY, SD_CURRENT_FREQ, SD_Q_INF, SD_Q_TRN, SD_RUNNING = range(8)

@@ -161,7 +161,7 @@ enum {
   DCSIM_S_MAX_XFER = 18,     /* high-water marks, for capacity tuning */
   DCSIM_S_MAX_RUN = 19,
   DCSIM_S_MAX_Q = 20,
-  DCSIM_S_RESERVED = 21,
+  DCSIM_S_UTIL_BEGIN = 21,   /* util_begin_ts: the instant of the first processed event (the same for every DC: the sweep :429-437 touches all of them) */
   DCSIM_S_DC0 = 24,          /* then DCSIM_S_DC_STRIDE doubles per DC */
   DCSIM_S_DC_STRIDE = 8,
   DCSIM_SUMMARY_K = 24 + 8 * DCSIM_MAX_DC
@@ -291,6 +291,11 @@ int dcsim_fetch_latency_histogram(dcsim_t* h, uint64_t* out, size_t out_bytes);
 #define DCSIM_RNG_PHILOX 0
 #define DCSIM_RNG_MT19937 1
 int dcsim_set_rng(dcsim_t* h, int rng_kind);
+
+/* Rows the recorders WOULD have written so far: out3 = {trace, job_log, cluster_log}.  The kernels keep counting past
+ * a recorder's capacity (and stop writing), so out3[i] > capacity means the fetched rows are a truncated prefix —
+ * callers that need every row (the CSV wire formats) check this and re-run with a larger capacity. */
+int dcsim_recorder_counts(dcsim_t* h, uint32_t* out3);
 
 int dcsim_fetch_trace(dcsim_t* h, dcsim_trace_rec_t* out, uint32_t capacity, uint32_t* n_out);
 int dcsim_fetch_job_log(dcsim_t* h, dcsim_job_rec_t* out, uint32_t capacity, uint32_t* n_out);

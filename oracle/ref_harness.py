@@ -201,3 +201,23 @@ def run_reference(sc, seed, rng="philox", trace_events=0, log_dir=None):
     if trace_events:
         out["trace"] = st["trace"]
     return out
+
+
+def time_reference_as_shipped(sc, seed):
+    """Wall seconds of ONE reference run exactly as shipped — its own Mersenne Twister (SIM:71), CSV logging to a
+    tmpfs directory, no progress bar, nothing wrapped or re-bound.  The number of events that run processes is the
+    oracle's for the same seed in MT19937 mode (the oracle reproduces the stock run event for event), so the caller
+    divides.  Used by bench.py's optional `kind: "python"` leg, only where the reference tree is present."""
+    Sim, _, _, _ = _import_reference()
+    inputs = build_reference_inputs(sc)
+    logger = logging.getLogger("dcsim-ref-harness")
+    logger.addHandler(logging.NullHandler())
+    logger.propagate = False
+    logger.setLevel(logging.CRITICAL)
+    with tempfile.TemporaryDirectory(prefix="dcsim_ref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as log_dir:
+        sim = Sim(logger=logger, sim_duration=sc["duration"], log_interval=sc["log_interval"], log_path=log_dir,
+                  rng_seed=seed, algo=sc["algo"], power_cap=sc["power_cap"], show_progress=False,
+                  num_fixed_gpus=sc["num_fixed_gpus"], fixed_freq=sc["fixed_freq"], **inputs)
+        t0 = time.perf_counter()
+        sim.run()
+        return time.perf_counter() - t0

@@ -8,3 +8,6 @@ g++ -O2 -fPIC -shared -std=gnu++17 -ffp-contract=off -fno-fast-math -Wall -Wno-u
 # conditioning probe: the same build with every 5th pow() result moved by one ulp (see hostemu.cpp)
 g++ -O2 -fPIC -shared -std=gnu++17 -ffp-contract=off -fno-fast-math -Wall -Wno-unused-function -Wno-unknown-pragmas \
     -DDCSIM_HOSTEMU_PERTURB -o _build/libdcsim_hostemu_perturbed.so hostemu.cpp -lm
+# the list merge with a ring of one chunk only: every scan that reaches back or ahead takes the HBM fall-back path
+g++ -O2 -fPIC -shared -std=gnu++17 -ffp-contract=off -fno-fast-math -Wall -Wno-unused-function -Wno-unknown-pragmas \
+    -DDCSIM_MERGE_RING=32u -o _build/libdcsim_hostemu_smallring.so hostemu.cpp -lm

@@ -82,10 +82,11 @@ long long hostemu_run_batch(const void* spec_blob, size_t spec_bytes, uint64_t n
     double clocks[2 * DCSIM_MAX_ING];
     uint32_t last[2 * DCSIM_MAX_ING];
     uint32_t ring[DCSIM_TRNG_RING];
+    static dcsim_merge_ring_t merge_ring;
     if (rng_kind == 1) P->mt_state = (uint32_t*)calloc(n_replicas * (size_t)DCSIM_MT_N, sizeof(uint32_t));
     for (uint64_t r = 0; r < n_replicas; ++r) {
       if (rng_kind == 1) dcsim_generate_arrivals<true>(P, r, clocks, last, ring, 1); else dcsim_generate_arrivals<false>(P, r, clocks, last, ring, 1);
-      dcsim_merge_arrivals(P, r, 0);
+      dcsim_merge_arrivals(P, r, 0, &merge_ring);
       /* self-check: the merged list is a gap-free, (t)-sorted permutation of the replica's events */
       const dcsim_arrhdr_t* ah = P->arr_hdr + r;
       const double* mt = P->ml_t + 2 * r * (uint64_t)P->cap_arr;

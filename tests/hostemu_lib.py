@@ -13,6 +13,8 @@ _HDR = os.path.join(_HERE, "..", "include", "dcsim_b200.h")
 SUMMARY_K = 24 + 8 * 8
 TRACE_DTYPE = np.dtype([("t", "<f8"), ("seq", "<u4"), ("kind", "<u4")])
 _SO_PERTURBED = os.path.join(_DIR, "_build", "libdcsim_hostemu_perturbed.so")
+_SO_SMALLRING = os.path.join(_DIR, "_build", "libdcsim_hostemu_smallring.so")
+_lib_smallring = None
 _lib = None
 _lib_perturbed = None
 
@@ -30,29 +32,31 @@ def _bind(path):
 
 def _ensure_built():
     srcs = (os.path.join(_DIR, "hostemu.cpp"), os.path.join(_DIR, "build.sh"), _CORE, _HDR)
-    for so in (_SO, _SO_PERTURBED):
+    for so in (_SO, _SO_PERTURBED, _SO_SMALLRING):
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
             subprocess.run([os.path.join(_DIR, "build.sh")], check=True, capture_output=True)
             return
 
 
-def lib(perturbed=False):
-    """perturbed=True: the conditioning probe (every 5th pow() result moved by one ulp, see hostemu.cpp)."""
-    global _lib, _lib_perturbed
+def lib(perturbed=False, smallring=False):
+    """perturbed=True: the conditioning probe (every 5th pow() result moved by one ulp, see hostemu.cpp);
+    smallring=True: the list merge built with a one-chunk ring (its HBM fall-back paths do all the work)."""
+    global _lib, _lib_perturbed, _lib_smallring
     if _lib is None:
         _ensure_built()
-        _lib, _lib_perturbed = _bind(_SO), _bind(_SO_PERTURBED)
-    return _lib_perturbed if perturbed else _lib
+        _lib, _lib_perturbed, _lib_smallring = _bind(_SO), _bind(_SO_PERTURBED), _bind(_SO_SMALLRING)
+    return _lib_smallring if smallring else (_lib_perturbed if perturbed else _lib)
 
 
 def set_test_time_quantum(q):
     """TEST HOOK (dcsim_core.cuh dcsim_test_quantize): 0 = off."""
     lib().hostemu_set_test_time_quantum(float(q))
     lib(perturbed=True).hostemu_set_test_time_quantum(float(q))
+    lib(smallring=True).hostemu_set_test_time_quantum(float(q))
 
 
 def run_batch(spec_bytes, n_replicas, seed0, chunk_events=0, trace_cap=0, rec_replica=-1, job_dtype=None,
-              jobs_cap=0, cluster_dtype=None, cluster_cap=0, rng_kind=0, perturbed=False):
+              jobs_cap=0, cluster_dtype=None, cluster_cap=0, rng_kind=0, perturbed=False, smallring=False):
     out = np.zeros((n_replicas, SUMMARY_K))
     buf = C.create_string_buffer(spec_bytes, len(spec_bytes))
     trace = np.zeros(max(trace_cap, 1), dtype=TRACE_DTYPE)
@@ -61,7 +65,7 @@ def run_batch(spec_bytes, n_replicas, seed0, chunk_events=0, trace_cap=0, rec_re
     counts = np.zeros(4, dtype=np.uint32)
     layout = np.zeros(8, dtype=np.int32)
     hist = np.zeros((n_replicas, 2, 128), dtype=np.uint32)
-    total = lib(perturbed).hostemu_run_batch(buf, len(spec_bytes), n_replicas, seed0 & (2**64 - 1), chunk_events,
+    total = lib(perturbed, smallring).hostemu_run_batch(buf, len(spec_bytes), n_replicas, seed0 & (2**64 - 1), chunk_events,
                                     out.ctypes.data, rec_replica,
                                     trace.ctypes.data if trace_cap else None, trace_cap,
                                     jobs.ctypes.data if jobs is not None and jobs_cap else None, jobs_cap,

@@ -62,3 +62,19 @@ def test_chunked_resume_with_ties(oracle, hostemu, quantum):
     whole = hostemu.run_batch(blob, 2, 5)
     parts = hostemu.run_batch(blob, 2, 5, chunk_events=7)
     assert np.array_equal(whole["summary"], parts["summary"]) and whole["events"] == parts["events"]
+
+
+@pytest.mark.parametrize("name", ["cfg3_4x64_sinusoid_120s", "cfg5_8x256_sinusoid_60s", "ragged_3dc_12_5_40", "sweep_eco_route"])
+@pytest.mark.parametrize("q", [0.0, 0.25])
+def test_merge_fallback_paths(oracle, hostemu, quantum, name, q):
+    """The list merge keeps a sliding window of arrivals in shared memory and reads HBM where a scan leaves it.  A host
+    build with a ring of ONE chunk sends nearly every scan down that path; results must not change."""
+    sc = dict(SC.BY_NAME[name])
+    sc["duration"] = min(sc["duration"], 40.0)
+    blob = SC.to_spec(sc, caps={"cap_xfer": 4096}).to_bytes()
+    quantum(q)
+    want, total = oracle.run_batch(blob, 2, 31, 0)
+    got = hostemu.run_batch(blob, 2, 31, smallring=True)
+    a, b = got["summary"].copy(), want.copy()
+    a[:, HIGH_WATER] = b[:, HIGH_WATER] = 0
+    assert got["events"] == total and np.array_equal(a, b)
