@@ -20,7 +20,7 @@ EXPORTS = (
     "dcsim_set_trace", "dcsim_set_logging", "dcsim_prepare", "dcsim_advance", "dcsim_all_done", "dcsim_fetch_summary",
     "dcsim_summary_device_ptr", "dcsim_reduce_summary", "dcsim_enable_latency_histogram", "dcsim_fetch_latency_histogram", "dcsim_fetch_trace", "dcsim_fetch_job_log",
     "dcsim_fetch_cluster_log", "dcsim_launch_info", "dcsim_last_error", "dcsim_destroy", "dcsim_set_rng",
-    "dcsim_recorder_counts",
+    "dcsim_recorder_counts", "dcsim_allreduce_summary",
 )
 
 _lib = None
@@ -81,6 +81,8 @@ def load():
     for name in ("dcsim_fetch_trace", "dcsim_fetch_job_log", "dcsim_fetch_cluster_log"):
         getattr(L, name).restype = i32
         getattr(L, name).argtypes = [vp, vp, u32, C.POINTER(u32)]
+    L.dcsim_allreduce_summary.restype = i32
+    L.dcsim_allreduce_summary.argtypes = [vp, vp, vp]
     L.dcsim_recorder_counts.restype = i32
     L.dcsim_recorder_counts.argtypes = [vp, C.POINTER(u32 * 3)]
     L.dcsim_launch_info.restype = i32

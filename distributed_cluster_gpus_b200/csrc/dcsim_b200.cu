@@ -15,6 +15,7 @@
  * -fmad=false matters: the reference is CPython float arithmetic, one rounding per operation.
  */
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <new>
 #include <stdio.h>
@@ -550,6 +551,32 @@ int dcsim_reduce_summary(dcsim_t* h, double* dev_out) {
   if (blocks > 4 * h->sm_count) blocks = 4 * h->sm_count;
   dcsim_reduce_kernel<<<blocks, 256, 0, h->stream>>>(h->d_summary, h->n_replicas, dev_out);
   CUDA_TRY(h, cudaGetLastError());
+  return DCSIM_OK;
+}
+
+/* The run's only collective for callers that own an NCCL communicator (C / C++ hosts; Python callers use
+ * dcsim_reduce_summary + torch.distributed).  NCCL is resolved at run time from whatever the process has loaded (or
+ * libnccl.so.2), so the library carries no link-time dependency on a particular NCCL build. */
+typedef int (*dcsim_nccl_allreduce_fn)(const void*, void*, size_t, int /*ncclDataType_t*/, int /*ncclRedOp_t*/, void* /*ncclComm_t*/, cudaStream_t);
+int dcsim_allreduce_summary(dcsim_t* h, void* nccl_comm, double* out) {
+  if (!h || !out) return DCSIM_E_INVALID;
+  if (!nccl_comm) return set_err(h, DCSIM_E_INVALID, "allreduce_summary: nccl_comm is NULL%s%lld");
+  static dcsim_nccl_allreduce_fn fn = NULL;
+  if (!fn) {
+    void* sym = dlsym(RTLD_DEFAULT, "ncclAllReduce");
+    if (!sym) {
+      void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+      if (lib) sym = dlsym(lib, "ncclAllReduce");
+    }
+    if (!sym) return set_err(h, DCSIM_E_UNSUPPORTED, "allreduce_summary: no NCCL in this process (ncclAllReduce not found)%s%lld");
+    fn = (dcsim_nccl_allreduce_fn)sym;
+  }
+  int rc = dcsim_reduce_summary(h, h->d_agg);
+  if (rc != DCSIM_OK) return rc;
+  const int nccl_rc = fn(h->d_agg, h->d_agg, DCSIM_AGG_K, /*ncclFloat64*/ 8, /*ncclSum*/ 0, nccl_comm, h->stream);
+  if (nccl_rc != 0) return set_err(h, DCSIM_E_CUDA, "allreduce_summary: ncclAllReduce failed with code %s%lld", "", (long long)nccl_rc);
+  CUDA_TRY(h, cudaMemcpyAsync(out, h->d_agg, DCSIM_AGG_K * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   return DCSIM_OK;
 }
 

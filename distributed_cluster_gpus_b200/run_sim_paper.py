@@ -145,16 +145,21 @@ def _main_sharded(args, world, rank):
     import torch
     import torch.distributed as dist
     from . import sharding
-    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    backend = os.environ.get("DCSIM_DIST_BACKEND", "nccl")     # "gloo": several ranks may share a GPU (tests on a 1-GPU box)
+    local = int(os.environ.get("LOCAL_RANK", str(rank))) % max(1, torch.cuda.device_count())
     torch.cuda.set_device(local)
+    dev = torch.device("cuda", local) if backend == "nccl" else torch.device("cpu")
     if not dist.is_initialized():
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if backend == "nccl":
+            dist.init_process_group("nccl", device_id=dev)
+        else:
+            dist.init_process_group(backend)
     first, count = sharding.shard(args.replicas, rank, world)
     sim = build_simulator(args, replicas=max(count, 1), first_replica_id=first, device=local, write_logs=(rank == 0))
     sim.run()
     summ = sim.summary if count > 0 else sim.summary[:0]
-    agg = torch.from_numpy(sharding.aggregate_rows(summ)).cuda()
-    hist = torch.from_numpy(sim.latency_histogram.astype(np.int64) if count > 0 else np.zeros((2, 128), np.int64)).cuda()
+    agg = torch.from_numpy(sharding.aggregate_rows(summ)).to(dev)
+    hist = torch.from_numpy(sim.latency_histogram.astype(np.int64) if count > 0 else np.zeros((2, 128), np.int64)).to(dev)
     sharding.allreduce_aggregate(agg)
     dist.all_reduce(hist, op=dist.ReduceOp.SUM)
     # per-replica energies / mean latencies for the percentile rows: gathered (8 bytes per replica and column)
@@ -162,9 +167,9 @@ def _main_sharded(args, world, rank):
     fin = summ[:, S.S_JOBS_FINISHED]
     ml = np.divide(summ[:, S.S_LAT_SUM], fin, out=np.zeros_like(fin), where=fin > 0)
     width = -(-args.replicas // world)
-    mine = torch.full((2, width), float("nan"), dtype=torch.float64, device="cuda")
-    mine[0, :count] = torch.from_numpy(np.ascontiguousarray(e)).cuda()
-    mine[1, :count] = torch.from_numpy(np.ascontiguousarray(ml)).cuda()
+    mine = torch.full((2, width), float("nan"), dtype=torch.float64, device=dev)
+    mine[0, :count] = torch.from_numpy(np.ascontiguousarray(e)).to(dev)
+    mine[1, :count] = torch.from_numpy(np.ascontiguousarray(ml)).to(dev)
     everyone = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(everyone, mine)
     stats = None

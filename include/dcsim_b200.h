@@ -271,6 +271,12 @@ int dcsim_summary_device_ptr(dcsim_t* h, void** dev_ptr_out);
  * all-reduces over NCCL at end of run; no other data crosses GPUs. */
 int dcsim_reduce_summary(dcsim_t* h, double* dev_out);
 
+/* The same vector summed over all ranks of `nccl_comm` (an ncclComm_t the caller created, one rank per GPU): reduces on
+ * the device, ncclAllReduce(sum, double, DCSIM_AGG_K) on the handle's stream, copies the result to `out` (host memory,
+ * DCSIM_AGG_K doubles) and synchronises.  The run's only collective, for hosts that drive NCCL themselves (SURVEY.md
+ * App. D b200sim_allreduce_summary); NCCL is looked up at run time, DCSIM_E_UNSUPPORTED if the process has none. */
+int dcsim_allreduce_summary(dcsim_t* h, void* nccl_comm, double* out);
+
 /* Job-latency histogram of the whole batch (latency = finish - start, the job_log.csv latency_s column,
  * simulator_paper_multi.py:820): DCSIM_LAT_BINS bins per job type, 4 per octave starting at 2^-20 s — bin index =
  * 4 * (exponent + 20) + top two mantissa bits, clamped — summed over all replicas on the device.  `out` receives

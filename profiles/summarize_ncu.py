@@ -32,7 +32,8 @@ def main():
     rows = list(csv.reader(io.StringIO(ncu(rep, "--page", "raw", "--csv"))))
     hdr, units, vals = rows[0], rows[1], rows[2]
     m = {h: (vals[i], units[i]) for i, h in enumerate(hdr)}
-    print(f"# ncu summary of `{rep.split('/')[-1]}` — dcsim_advance_kernel, {events:.0f} events in the profiled launch\n")
+    kname = m.get("Kernel Name", ("?", ""))[0].split("(")[0].replace("void ", "")
+    print(f"# ncu summary of `{rep.split('/')[-1]}` — `{kname}`, {events:.0f} events in the profiled launch\n")
     print("| metric | value | unit |\n|---|---|---|")
     for k in KEYS:
         if k in m:
@@ -67,7 +68,19 @@ def main():
             a[2] = r[1].strip()[:100]
     ti = sum(v[0] for v in agg.values()) or 1
     ts = sum(v[1] for v in agg.values()) or 1
-    print(f"\n## per-event cost\n\n* warp-instructions executed: {ti:.4g} = **{ti / events:.0f} per event**")
+    # The source page lists an instruction once per source FILE of its inline stack (callee line, wrapper line, call
+    # site), so summing its rows counts inlined code several times (round 1's "303 per event" was that sum; the same
+    # report's sm__inst_executed gave 235).  The per-event figure therefore comes from the hardware counter:
+    try:
+        cyc = float(m["sm__cycles_elapsed.avg"][0].replace(",", ""))
+        ipc = float(m["sm__inst_executed.sum.per_cycle_elapsed"][0].replace(",", ""))
+        executed = cyc * ipc
+    except (KeyError, ValueError):
+        executed = float("nan")
+    print(f"\n## per-event cost\n\n* warp-instructions executed (`sm__inst_executed.sum` = sum.per_cycle_elapsed x cycles): "
+          f"{executed:.4g} = **{executed / events:.0f} per event**")
+    print(f"* (sum over the source page's line rows, which repeats inlined instructions once per file of the inline stack: "
+          f"{ti / events:.0f} per event — the table below is INCLUSIVE in that sense; percentages are of this sum)")
     if "dram__bytes_read.sum" in m:
         print(f"* DRAM bytes (read+write) as reported above; algorithmic bytes per event = 96 + 76*D")
     print("\n## top source lines by executed warp-instructions\n\n| file:line | instr/event | % instr | % stall samples | source |\n|---|---|---|---|---|")

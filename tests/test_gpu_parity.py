@@ -401,3 +401,92 @@ def test_set_rng_rejects_bad_use():
         eng.advance(10)
         with pytest.raises(N.DcsimError):
             eng.set_rng("philox")      # the batch has started
+
+
+def _full_batch_parity(oracle, name, n, seed):
+    sc = SC.BY_NAME[name]
+    sp = SC.to_spec(sc)
+    with engine_cls()(sp, n, base_seed=seed) as eng:
+        total = eng.advance(0)
+        got = eng.summary()
+        info = eng.launch_info()
+    want, want_total = oracle.run_batch(sp.to_bytes(), n, seed, 0, n_threads=os.cpu_count() or 1)
+    assert total == want_total
+    worst = assert_rows_match(got, want, sc["n_dc"])
+    print(f"{name}: ALL {n} replicas, {total} events, worst float rel err {worst:.2e}, "
+          f"{info['resident_warps_per_sm']} warps/SM, staging mode {info['staging_mode']}")
+
+
+def test_bench_batch_matches_oracle_replica_by_replica(oracle):
+    """The bench workload at bench size: all 65 536 replicas of 4 DC x 64 / 120 s against the (threaded) oracle — every
+    count exact, every float of every replica's summary within 1e-9."""
+    _full_batch_parity(oracle, "cfg3_4x64_sinusoid_120s", 65536, 123)
+
+
+def test_cfg5_batch_matches_oracle_replica_by_replica(oracle):
+    """8 DC x 256 (head-staged launch mode: running-job records in HBM/L2), 4096 replicas, full duration."""
+    _full_batch_parity(oracle, "cfg5_8x256_sinusoid_60s", 4096, 777)
+
+
+def test_recorder_overflow_is_reported_not_truncated(tmp_path):
+    """A job / cluster log that does not fit its recorder raises (with the row count the device saw) instead of
+    handing back a truncated prefix; the drop-in re-runs the logged replica at that size."""
+    import csv
+    import logging
+    from distributed_cluster_gpus_b200.engine import RecorderOverflow
+    from distributed_cluster_gpus_b200.configs import paper_config as pc
+    from distributed_cluster_gpus_b200.simcore.simulator_paper_multi import MultiIngressPaperSimulator
+    sc = SC.BY_NAME["ragged_3dc_12_5_40"]
+    sp = SC.to_spec(sc)
+    with engine_cls()(sp, 2, base_seed=3) as eng:
+        eng.set_logging(1, 50, 9)
+        eng.advance(0)
+        fin = int(eng.summary()[1, S.S_JOBS_FINISHED])
+        with pytest.raises(RecorderOverflow) as ei:
+            eng.job_log()
+        assert ei.value.needed == fin and ei.value.capacity == 50
+        with pytest.raises(RecorderOverflow):
+            eng.cluster_log()
+    kw = SC.build_inputs(sc)
+    sim = MultiIngressPaperSimulator(router_policy=pc.build_router_policy(), logger=logging.getLogger("t"),
+                                     sim_duration=sc["duration"], log_interval=sc["log_interval"], log_path=str(tmp_path),
+                                     rng_seed=3, algo=sc["algo"], show_progress=False, replicas=4, keep_engine=False, **kw)
+    sim._log_one_replica(sim._spec, 40, 7)                            # far too small: must grow, not truncate
+    rows = list(csv.reader(open(sim.job_log_path)))
+    with engine_cls()(sp, 1, base_seed=3) as eng:
+        eng.advance(0)
+        assert len(rows) - 1 == int(eng.summary()[0, S.S_JOBS_FINISHED])
+
+
+def _run_cli(args, env_extra=None, timeout=900):
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, **(env_extra or {}))
+    env["PYTHONPATH"] = root + os.pathsep + env.get("PYTHONPATH", "")
+    return subprocess.run([sys.executable, "-m", "distributed_cluster_gpus_b200.run_sim_paper"] + args, capture_output=True,
+                          text=True, timeout=timeout, cwd=root, env=env)
+
+
+def test_cli_sharded_over_ranks_is_invariant(tmp_path):
+    """`run_sim_paper --gpus 2`: two ranks (one process per GPU; on a one-GPU box both share it and talk over gloo),
+    replicas sharded by global id, one all-reduce of the aggregate.  Statistics and replica 0's CSVs must equal the
+    single-process run's."""
+    import json
+    import torch
+    common = ["--duration", "20", "--inf-mode", "sinusoid", "--inf-rate", "10", "--inf-period", "3600", "--trn-rate", "1",
+              "--n-dc", "4", "--gpus-per-dc", "64", "--replicas", "301", "--seed", "77", "--progress", ""]
+    one = _run_cli(common + ["--log-path", str(tmp_path / "one" / "x"), "--summary-json", str(tmp_path / "one.json")])
+    assert one.returncode == 0, one.stderr[-2000:]
+    extra = {} if torch.cuda.device_count() >= 2 else {"DCSIM_DIST_BACKEND": "gloo"}
+    two = _run_cli(common + ["--gpus", "2", "--log-path", str(tmp_path / "two" / "x"), "--summary-json", str(tmp_path / "two.json")], extra)
+    assert two.returncode == 0, two.stderr[-3000:]
+    a, b = json.load(open(tmp_path / "one.json")), json.load(open(tmp_path / "two.json"))
+    assert b["gpus"] == 2 and a["replicas"] == b["replicas"] == 301
+    assert a["events_total"] == b["events_total"] and a["jobs_finished_total"] == b["jobs_finished_total"]
+    for k in ("energy_j_mean", "mean_latency_s_mean", "energy_j_ci95", "mean_latency_s_ci95"):
+        assert abs(a[k] - b[k]) <= 1e-9 * abs(a[k]), k
+    for k in ("energy_j_p05_p50_p95", "mean_latency_s_p05_p50_p95"):
+        assert np.allclose(a[k], b[k], rtol=1e-12), k
+    for f in ("job_log.csv", "cluster_log.csv"):
+        assert open(tmp_path / "one" / "x" / f).read() == open(tmp_path / "two" / "x" / f).read(), f
