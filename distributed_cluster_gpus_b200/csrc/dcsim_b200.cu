@@ -22,55 +22,17 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "dcsim_core.cuh"
-
-#define DCSIM_MAX_WARPS_PER_CTA 4
-
-extern __shared__ __align__(16) char dcsim_smem[];
-
-#ifndef DCSIM_MIN_CTAS_PER_SM
-#define DCSIM_MIN_CTAS_PER_SM 8 /* 8 CTAs x 4 warps = 32 warps/SM -> ptxas keeps the kernel within 64 registers */
+#ifndef DCSIM_DEFAULT_GROUP
+#define DCSIM_DEFAULT_GROUP 32 /* lanes per replica when DCSIM_GROUP is not set */
 #endif
+#define DCSIM_ADV_SUFFIX _g32
+#include "dcsim_advance_impl.cuh" /* the 32-lanes-per-replica event loop (and dcsim_core.cuh) */
 
-/* CAP = the power-cap controller (algo = cap_greedy with power_cap > 0: SIM:207-338) is compiled in.  It is a
- * separate instantiation because merely inlining that cold code costs the common path 17 % (measured,
- * profiles/r01_variants_ab.md). */
-/* MODE = where the replica's state block lives during the launch (a compile-time switch: a run-time select would turn
- * every state access into a generic load/store, measured -15 %):
- *   DCSIM_MODE_STAGED  the whole block is staged in shared memory (small blocks: 4 DC x 64 is ~5 kB, 32 warps/SM);
- *   DCSIM_MODE_HEAD    only the head [0, L.rec_off) — header, event set, per-DC arrays, list window, seq ring —
- *                      is staged; the running-job records stay at the block's home in HBM/L2 and are touched once per
- *                      job_finish (dcsim_handle_finish) and written once per start.  Picked when the whole block would
- *                      leave the SM below its 32 warps (8 DC x 256: 17 kB -> 12 warps/SM; head ~4 kB -> 32);
- *   DCSIM_MODE_INPLACE nothing is staged (even the head exceeds a CTA's shared memory): same core on the HBM copy. */
-enum { DCSIM_MODE_INPLACE = 0, DCSIM_MODE_STAGED = 1, DCSIM_MODE_HEAD = 2 };
-template <bool CAP, int MODE>
-__global__ void __launch_bounds__(DCSIM_MAX_WARPS_PER_CTA * 32, DCSIM_MIN_CTAS_PER_SM)
-dcsim_advance_kernel(const __grid_constant__ dcsim_kparams_t P, unsigned long long* __restrict__ events_total) {
-  const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31u);
-  const int wpc = (int)(blockDim.x >> 5);
-  const uint64_t r = (uint64_t)blockIdx.x * (uint64_t)wpc + (uint64_t)warp;
-  if (r >= P.n_replicas) return; /* whole warps leave together */
-  const int bytes = MODE == DCSIM_MODE_HEAD ? P.L.rec_off : P.L.total_bytes; /* what is staged */
-  char* home = P.state + r * (uint64_t)P.L.total_bytes;
-  char* blk = MODE != DCSIM_MODE_INPLACE ? dcsim_smem + (size_t)warp * (size_t)bytes : home;
-  char* rec = MODE == DCSIM_MODE_STAGED ? blk : home;
-  const bool fresh = reinterpret_cast<const dcsim_hdr_t*>(home)->initialized == 0u;
-  if (MODE != DCSIM_MODE_INPLACE && !fresh) { /* resume: coalesced 16-byte loads of the replica's block */
-    const uint4* src = reinterpret_cast<const uint4*>(home);
-    uint4* dst = reinterpret_cast<uint4*>(blk);
-    for (int i = lane; i < bytes / 16; i += 32) dst[i] = src[i];
-  }
-  __syncwarp();
-  const uint32_t n = dcsim_replica_step<CAP, MODE != DCSIM_MODE_STAGED>(&P, r, blk, rec, fresh);
-  __syncwarp();
-  if (MODE != DCSIM_MODE_INPLACE) {
-    const uint4* src = reinterpret_cast<const uint4*>(blk);
-    uint4* dst = reinterpret_cast<uint4*>(home);
-    for (int i = lane; i < bytes / 16; i += 32) dst[i] = src[i];
-  }
-  if (lane == 0 && n) atomicAdd(events_total, (unsigned long long)n);
-}
+/* the builds with several replicas per warp live in their own translation units (dcsim_advance_g8.cu, _g16.cu) */
+cudaError_t dcsim_adv_launch_g16(const dcsim_kparams_t*, unsigned long long*, int, int, int, int, int, cudaStream_t);
+cudaError_t dcsim_adv_attrs_g16(int, int, int, int, int, int*, int*, int*);
+cudaError_t dcsim_adv_launch_g8(const dcsim_kparams_t*, unsigned long long*, int, int, int, int, int, cudaStream_t);
+cudaError_t dcsim_adv_attrs_g8(int, int, int, int, int, int*, int*, int*);
 
 /* Arrival pre-pass: one THREAD per replica draws that replica's whole arrival sequence in the reference's draw order;
  * consecutive threads = consecutive replicas, so all 32 lanes of a warp run the samplers that the event loop would
@@ -103,14 +65,6 @@ __global__ void dcsim_hist_reduce_kernel(const uint32_t* __restrict__ hist, uint
   unsigned long long acc = 0ull;
   for (uint64_t r = blockIdx.x; r < n; r += gridDim.x) acc += hist[r * (2 * DCSIM_LAT_BINS) + threadIdx.x];
   if (acc) atomicAdd(out + threadIdx.x, acc);
-}
-
-typedef void (*dcsim_advance_fn)(const dcsim_kparams_t, unsigned long long*);
-static dcsim_advance_fn dcsim_pick_kernel(bool cap, int mode) {
-  static const dcsim_advance_fn table[6] = {
-      dcsim_advance_kernel<false, 0>, dcsim_advance_kernel<false, 1>, dcsim_advance_kernel<false, 2>,
-      dcsim_advance_kernel<true, 0>,  dcsim_advance_kernel<true, 1>,  dcsim_advance_kernel<true, 2>};
-  return table[(cap ? 3 : 0) + mode];
 }
 
 /* Aggregates the summaries; every block reduces a slice, then one atomicAdd per component. */
@@ -150,6 +104,7 @@ struct dcsim {
   dcsim_layout_t L;
   uint64_t n_replicas, seed0;
   int device, sm_count, warps_per_cta, ctas, smem_bytes, regs, resident_warps;
+  int lanes; /* lanes per replica of the advance kernel picked for this handle: 32, 16 or 8 */
   cudaStream_t stream, own_stream;
   char* d_state;
   char* d_queues;
@@ -239,9 +194,17 @@ static int validate_spec(const dcsim_spec_t* sp) {
   return DCSIM_OK;
 }
 
-/* Launch geometry for the handle's current state-block layout: what is staged (whole block / head only / nothing),
- * warps per CTA, shared memory.  DCSIM_RECORDS=shared|global forces the whole-block / head-only mode (A/B runs). */
-static int resident_warps_for(int bytes_per_warp, int smem_optin, int smem_sm, int* wpc_out) {
+/* Launch geometry for the handle's current state-block layout: lanes per replica (32 / 16 / 8), what is staged (whole
+ * block / head only / nothing), warps per CTA, shared memory.
+ *   DCSIM_GROUP=32|16|8     forces the lanes per replica (default: see pick below);
+ *   DCSIM_RECORDS=shared|global forces the whole-block / head-only staging (A/B runs). */
+typedef cudaError_t (*dcsim_adv_launch_fn)(const dcsim_kparams_t*, unsigned long long*, int, int, int, int, int, cudaStream_t);
+typedef cudaError_t (*dcsim_adv_attrs_fn)(int, int, int, int, int, int*, int*, int*);
+static dcsim_adv_launch_fn adv_launch_for(int lanes) { return lanes == 8 ? dcsim_adv_launch_g8 : (lanes == 16 ? dcsim_adv_launch_g16 : dcsim_adv_launch_g32); }
+static dcsim_adv_attrs_fn adv_attrs_for(int lanes) { return lanes == 8 ? dcsim_adv_attrs_g8 : (lanes == 16 ? dcsim_adv_attrs_g16 : dcsim_adv_attrs_g32); }
+static int min_ctas_for(int lanes) { return lanes == 32 ? 8 : (lanes == 16 ? 6 : 4); } /* DCSIM_MIN_CTAS_PER_SM of that build */
+
+static int resident_warps_for(int bytes_per_warp, int smem_optin, int smem_sm, int max_warps, int* wpc_out) {
   /* warps per CTA: whichever of 4 / 2 / 1 keeps the most warps resident (each CTA also reserves 1 KB of shared
    * memory and an SM holds at most 32 CTAs); small state blocks end up at 4 x 8 CTAs, large ones at 1 or 2 */
   int wpc = 0, best_warps = 0;
@@ -251,7 +214,7 @@ static int resident_warps_for(int bytes_per_warp, int smem_optin, int smem_sm, i
     int ctas = (int)(smem_sm / (per_cta + 1024));
     if (ctas > 32) ctas = 32;
     int warps = ctas * cand;
-    if (warps > DCSIM_MIN_CTAS_PER_SM * DCSIM_MAX_WARPS_PER_CTA) warps = DCSIM_MIN_CTAS_PER_SM * DCSIM_MAX_WARPS_PER_CTA; /* register bound */
+    if (warps > max_warps) warps = max_warps; /* register bound */
     if (warps > best_warps) { best_warps = warps; wpc = cand; }
   }
   *wpc_out = wpc;
@@ -263,9 +226,13 @@ static cudaError_t size_launch(dcsim_t* h) {
   int smem_optin = 0, smem_sm = 0;
   if ((e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device)) != cudaSuccess) return e;
   if ((e = cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, h->device)) != cudaSuccess) return e;
+  int lanes = DCSIM_DEFAULT_GROUP;
+  { const char* g = getenv("DCSIM_GROUP"); if (g) { const int v = atoi(g); if (v == 8 || v == 16 || v == 32) lanes = v; } }
+  const int rpw = 32 / lanes; /* replicas per warp */
+  const int max_warps = min_ctas_for(lanes) * DCSIM_MAX_WARPS_PER_CTA;
   int wpc_full = 0, wpc_head = 0;
-  const int warps_full = resident_warps_for(h->L.total_bytes, smem_optin, smem_sm, &wpc_full);
-  const int warps_head = resident_warps_for(h->L.rec_off, smem_optin, smem_sm, &wpc_head);
+  const int warps_full = resident_warps_for(rpw * h->L.total_bytes, smem_optin, smem_sm, max_warps, &wpc_full);
+  const int warps_head = resident_warps_for(rpw * h->L.rec_off, smem_optin, smem_sm, max_warps, &wpc_head);
   const char* force = getenv("DCSIM_RECORDS");
   int mode, wpc, bytes;
   if (wpc_full >= 1 && (warps_full >= warps_head || (force && force[0] == 's')) && !(force && force[0] == 'g' && wpc_head >= 1)) {
@@ -275,17 +242,14 @@ static cudaError_t size_launch(dcsim_t* h) {
   } else { /* not even the head fits a CTA's shared memory: run in place out of HBM/L2 */
     mode = DCSIM_MODE_INPLACE; wpc = DCSIM_MAX_WARPS_PER_CTA; bytes = 0;
   }
+  h->lanes = lanes;
   h->mode = mode;
   h->warps_per_cta = wpc;
-  h->smem_bytes = wpc * bytes;
-  h->ctas = (int)((h->n_replicas + (uint64_t)wpc - 1) / (uint64_t)wpc);
-  const dcsim_advance_fn kern = dcsim_pick_kernel(h->L.cap_stale != 0, h->mode);
-  if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin)) != cudaSuccess) return e;
-  cudaFuncAttributes fa;
-  if ((e = cudaFuncGetAttributes(&fa, kern)) != cudaSuccess) return e;
-  h->regs = fa.numRegs;
-  int blocks_per_sm = 0;
-  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, wpc * 32, h->smem_bytes)) != cudaSuccess) return e;
+  h->smem_bytes = wpc * rpw * bytes;
+  const uint64_t per_cta = (uint64_t)wpc * (uint64_t)rpw;
+  h->ctas = (int)((h->n_replicas + per_cta - 1) / per_cta);
+  int blocks_per_sm = 0, min_ctas = 0;
+  if ((e = adv_attrs_for(lanes)(h->L.cap_stale != 0, h->mode, wpc * 32, h->smem_bytes, smem_optin, &h->regs, &blocks_per_sm, &min_ctas)) != cudaSuccess) return e;
   h->resident_warps = blocks_per_sm * wpc;
   return cudaSuccess;
 }
@@ -492,9 +456,7 @@ int dcsim_advance(dcsim_t* h, uint64_t max_events_per_replica, uint64_t* total_e
   if (rc != DCSIM_OK) return rc;
   dcsim_kparams_t P;
   fill_kparams(h, &P, max_events_per_replica);
-  const dim3 grid(h->ctas), block(h->warps_per_cta * 32);
-  dcsim_pick_kernel(h->L.cap_stale != 0, h->mode)<<<grid, block, h->smem_bytes, h->stream>>>(P, h->d_events);
-  CUDA_TRY(h, cudaGetLastError());
+  CUDA_TRY(h, adv_launch_for(h->lanes)(&P, h->d_events, h->L.cap_stale != 0, h->mode, h->ctas, h->warps_per_cta * 32, h->smem_bytes, h->stream));
   h->launches++;
   if (total_events_out) {
     unsigned long long total = 0;
@@ -675,8 +637,8 @@ int dcsim_launch_info(dcsim_t* h, dcsim_launch_info_t* out) {
   /* per arrival: pre-pass output 24 B + merge scratch 12 B + two list entries of 20 B */
   out->hbm_bytes_arrivals = (uint64_t)h->n_replicas * ((uint64_t)h->cap_arr * 76ull + sizeof(dcsim_arrhdr_t));
   out->staging_mode = h->mode; out->state_block_bytes = h->L.total_bytes;
-  out->staged_bytes_per_replica = h->warps_per_cta ? h->smem_bytes / h->warps_per_cta : 0;
-  out->cap_stale = h->L.cap_stale;
+  out->staged_bytes_per_replica = h->warps_per_cta ? h->smem_bytes / (h->warps_per_cta * (32 / h->lanes)) : 0;
+  out->lanes_per_replica = h->lanes;
   return DCSIM_OK;
 }
 

@@ -67,12 +67,39 @@ static inline uint32_t dcsim_warp_max_u32(uint32_t x) { return x; }
 #define DCSIM_INF (__builtin_inf())
 #else
 #define DCSIM_DEV __device__ __forceinline__
+/* Lanes per replica.  32: one warp owns one replica.  8 / 16: a warp carries 4 / 2 replicas, each on an aligned group of
+ * lanes; every collective below is then relative to the caller's group (the groups of a warp run different handlers
+ * and only ever synchronise among themselves).  The merge kernel always uses 32. */
+#ifndef DCSIM_LANES
 #define DCSIM_LANES 32
-DCSIM_DEV int dcsim_lane() { return (int)(threadIdx.x & 31u); }
-DCSIM_DEV void dcsim_warp_sync() { __syncwarp(); }
-DCSIM_DEV uint32_t dcsim_warp_min_u32(uint32_t x) { return __reduce_min_sync(0xffffffffu, x); }
-DCSIM_DEV uint32_t dcsim_warp_ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
-DCSIM_DEV uint32_t dcsim_bcast_u32(uint32_t x, int src) { return __shfl_sync(0xffffffffu, x, src); }
+#endif
+#if DCSIM_LANES == 32
+#define DCSIM_GROUP_SHIFT 0u
+#define DCSIM_GROUP_MASK 0xffffffffu
+#else
+#define DCSIM_GROUP_SHIFT ((threadIdx.x & 31u) & ~(unsigned)(DCSIM_LANES - 1))
+#define DCSIM_GROUP_MASK ((((1u << DCSIM_LANES) - 1u)) << DCSIM_GROUP_SHIFT)
+#endif
+DCSIM_DEV int dcsim_lane() { return (int)(threadIdx.x & (unsigned)(DCSIM_LANES - 1)); }
+DCSIM_DEV void dcsim_warp_sync() { __syncwarp(DCSIM_GROUP_MASK); }
+DCSIM_DEV uint32_t dcsim_warp_min_u32(uint32_t x) {
+#if DCSIM_LANES == 32
+  return __reduce_min_sync(0xffffffffu, x);
+#else
+  const unsigned gm = DCSIM_GROUP_MASK;
+#pragma unroll
+  for (int o = DCSIM_LANES / 2; o > 0; o >>= 1) { const uint32_t y = __shfl_xor_sync(gm, x, o); x = y < x ? y : x; }
+  return x;
+#endif
+}
+DCSIM_DEV uint32_t dcsim_warp_ballot(bool p) {
+#if DCSIM_LANES == 32
+  return __ballot_sync(0xffffffffu, p);
+#else
+  return (__ballot_sync(DCSIM_GROUP_MASK, p) >> DCSIM_GROUP_SHIFT) & ((1u << DCSIM_LANES) - 1u);
+#endif
+}
+DCSIM_DEV uint32_t dcsim_bcast_u32(uint32_t x, int src) { return __shfl_sync(DCSIM_GROUP_MASK, x, src, DCSIM_LANES); }
 DCSIM_DEV int dcsim_ffs(uint32_t x) { return __ffs((int)x); }
 DCSIM_DEV uint32_t dcsim_hi(double x) { return (uint32_t)__double2hiint(x); }
 DCSIM_DEV uint32_t dcsim_lo(double x) { return (uint32_t)__double2loint(x); }
@@ -80,8 +107,21 @@ DCSIM_DEV uint32_t dcsim_mulhi(uint32_t a, uint32_t b) { return __umulhi(a, b); 
 DCSIM_DEV int dcsim_bit_length(uint32_t n) { return 32 - __clz((int)n); }
 DCSIM_DEV uint32_t dcsim_popc(uint32_t x) { return (uint32_t)__popc(x); }
 DCSIM_DEV uint32_t dcsim_lanemask_lt(int lane) { return (1u << lane) - 1u; }
+#if DCSIM_LANES == 32
 DCSIM_DEV uint32_t dcsim_warp_add_u32(uint32_t x) { return __reduce_add_sync(0xffffffffu, x); }
 DCSIM_DEV uint32_t dcsim_warp_max_u32(uint32_t x) { return __reduce_max_sync(0xffffffffu, x); }
+#else
+DCSIM_DEV uint32_t dcsim_warp_add_u32(uint32_t x) {
+#pragma unroll
+  for (int o = DCSIM_LANES / 2; o > 0; o >>= 1) x += __shfl_xor_sync(DCSIM_GROUP_MASK, x, o);
+  return x;
+}
+DCSIM_DEV uint32_t dcsim_warp_max_u32(uint32_t x) {
+#pragma unroll
+  for (int o = DCSIM_LANES / 2; o > 0; o >>= 1) { const uint32_t y = __shfl_xor_sync(DCSIM_GROUP_MASK, x, o); x = y > x ? y : x; }
+  return x;
+}
+#endif
 #define DCSIM_INF (__longlong_as_double(0x7ff0000000000000LL))
 #endif
 
@@ -114,7 +154,7 @@ DCSIM_DEV int dcsim_lat_bin(double lat) {
 /* Cold helpers are kept OUT OF LINE (by-value arguments only, so the context stays in registers): inlining them
  * costs the event loop registers and instruction-cache footprint on paths most launches never take. */
 #ifndef DCSIM_HOST_EMU
-#define DCSIM_COLD __device__ __noinline__
+#define DCSIM_COLD static __device__ __noinline__ /* static: the core is compiled into several translation units */
 #else
 #define DCSIM_COLD static
 #endif
@@ -135,7 +175,7 @@ enum {
   CAND_LIST = 8,     /* the next entry of the replica's {arrival, xfer_done} list */
   CAND_LOG = 9,      /* the log tick */
   CAND_STALE = 10,   /* earliest superseded job_finish (cap_greedy re-scheduling leaves the old event in the heap, SIM:330-338) */
-  CAND_N = 32
+  CAND_N = 16
 };
 enum { KIND_ARR_INF = 0, KIND_ARR_TRN = 1, KIND_XFER = 2, KIND_FINISH = 3, KIND_LOG = 4, KIND_STALE = 5 };
 
@@ -984,27 +1024,38 @@ DCSIM_DEV uint32_t* dcsim_list_seq_slot(dcsim_ctx_t& c, uint32_t m) {
   return (m & ML_XFER) ? XRING(c) + (c.cursor & (uint32_t)c.P->L.xring_mask) : PEND_SEQ(c) + ((m >> 1) & 15u);
 }
 
-/* Pop-min over the event set itself: exactly one candidate per lane (CAND_N == 32), so no loop and no index
- * bookkeeping — two loads, three REDUX.MIN, one ballot.  Lane CAND_LIST takes its candidate straight from the list
+/* Pop-min over the event set itself: one candidate slot per lane (two with 8 lanes per replica), three
+ * min-reductions (REDUX.MIN on a whole warp, shuffle butterflies inside a lane group), one ballot.  The lane of slot
+ * CAND_LIST takes its candidate straight from the list
  * window (entry c.cursor; the slot behind the window reads +inf), so nothing has to "publish" the next list entry.
  * Returns the winning candidate slot, -1 if all are +inf. */
 DCSIM_DEV int dcsim_argmin_cand(dcsim_ctx_t& c, double* t_out, uint32_t* seq_out) {
   const uint32_t li = c.cursor - c.lw_base; /* <= DCSIM_LIST_WINDOW */
   const uint32_t lm = LW_META(c)[li];
-#if DCSIM_LANES == 32
-  const bool list = c.lane == CAND_LIST;
-  const double t = *(list ? LW_T(c) + li : CAND_T(c) + c.lane);
-  const uint32_t s = *(list ? dcsim_list_seq_slot(c, lm) : CAND_SEQ(c) + c.lane);
-  const uint32_t h = dcsim_hi(t), l = dcsim_lo(t);
-  const uint32_t mh = dcsim_warp_min_u32(h);
+#ifndef DCSIM_HOST_EMU
+  uint32_t bh = 0x7ff00000u, bl = 0u, bs = 0xffffffffu;
+  int bi = -1;
+#pragma unroll
+  for (int i0 = 0; i0 < CAND_N; i0 += DCSIM_LANES) { /* one slot per lane (32 lanes) or two (8 lanes) */
+    const int i = i0 + c.lane;
+    if (DCSIM_LANES <= CAND_N || i < CAND_N) {
+      const bool list = i == CAND_LIST;
+      const double t = *(list ? LW_T(c) + li : CAND_T(c) + i);
+      const uint32_t s = *(list ? dcsim_list_seq_slot(c, lm) : CAND_SEQ(c) + i);
+      const uint32_t h = dcsim_hi(t), l = dcsim_lo(t);
+      if (i0 == 0 || h < bh || (h == bh && (l < bl || (l == bl && s < bs)))) { bh = h; bl = l; bs = s; bi = i; }
+    }
+  }
+  const uint32_t mh = dcsim_warp_min_u32(bh);
   if (mh >= 0x7ff00000u) return -1;
-  const uint32_t ml = dcsim_warp_min_u32(h == mh ? l : 0xffffffffu);
-  const bool m = (h == mh) && (l == ml);
-  const uint32_t ms = dcsim_warp_min_u32(m ? s : 0xffffffffu);
-  const uint32_t votes = dcsim_warp_ballot(m && s == ms);
+  const uint32_t ml = dcsim_warp_min_u32(bh == mh ? bl : 0xffffffffu);
+  const bool m = (bh == mh) && (bl == ml);
+  const uint32_t ms = dcsim_warp_min_u32(m ? bs : 0xffffffffu);
+  const uint32_t votes = dcsim_warp_ballot(m && bs == ms);
   *t_out = __hiloint2double((int)mh, (int)ml);
   *seq_out = ms;
-  return dcsim_ffs(votes) - 1;
+  const int src = dcsim_ffs(votes) - 1;
+  return DCSIM_LANES >= CAND_N ? src : (int)dcsim_bcast_u32((uint32_t)bi, src); /* one slot per lane: slot == lane */
 #else
   CAND_T(c)[CAND_LIST] = LW_T(c)[li];
   CAND_SEQ(c)[CAND_LIST] = *dcsim_list_seq_slot(c, lm);

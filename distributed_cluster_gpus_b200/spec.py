@@ -112,7 +112,7 @@ class LaunchInfo(C.Structure):
                 ("kernel_launches", C.c_int32), ("arrivals_prepass", C.c_int32),
                 ("hbm_bytes_state", C.c_uint64), ("hbm_bytes_queues", C.c_uint64), ("hbm_bytes_arrivals", C.c_uint64),
                 ("staging_mode", C.c_int32), ("state_block_bytes", C.c_int32), ("staged_bytes_per_replica", C.c_int32),
-                ("cap_stale", C.c_int32)]
+                ("lanes_per_replica", C.c_int32)]
 
 
 def _price_for(energy_price, dc_name: str, hour: int) -> float:

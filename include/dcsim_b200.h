@@ -317,7 +317,7 @@ typedef struct dcsim_launch_info {
                                       HBM/L2), 0 nothing (in place) */
   int32_t state_block_bytes;       /* one replica's state block */
   int32_t staged_bytes_per_replica;/* the part of it that is staged in shared memory during a launch */
-  int32_t cap_stale;
+  int32_t lanes_per_replica;       /* 32: one warp per replica; 16 / 8: a warp carries 2 / 4 replicas on lane groups */
 } dcsim_launch_info_t;
 int dcsim_launch_info(dcsim_t* h, dcsim_launch_info_t* out);
 

@@ -16,7 +16,8 @@ def _ensure_native_artifacts():
     """A fresh checkout has no built artefacts (they are git-ignored): build them once (nvcc cross-compiles
     without a GPU).  Tests never fall back to anything else if this fails."""
     lib = os.path.join(ROOT, "distributed_cluster_gpus_b200", "csrc", "libdcsim_b200.so")
-    srcs = [os.path.join(ROOT, "distributed_cluster_gpus_b200", "csrc", f) for f in ("dcsim_b200.cu", "dcsim_core.cuh")]
+    srcs = [os.path.join(ROOT, "distributed_cluster_gpus_b200", "csrc", f)
+            for f in ("dcsim_b200.cu", "dcsim_core.cuh", "dcsim_advance_impl.cuh", "dcsim_advance_g8.cu", "dcsim_advance_g16.cu")]
     stale = (not os.path.exists(lib)) or any(os.path.getmtime(s) > os.path.getmtime(lib) for s in srcs)
     if stale:
         import __graft_entry__
