@@ -81,10 +81,12 @@ def load():
     for name in ("dcsim_fetch_trace", "dcsim_fetch_job_log", "dcsim_fetch_cluster_log"):
         getattr(L, name).restype = i32
         getattr(L, name).argtypes = [vp, vp, u32, C.POINTER(u32)]
-    L.dcsim_allreduce_summary.restype = i32
-    L.dcsim_allreduce_summary.argtypes = [vp, vp, vp]
-    L.dcsim_recorder_counts.restype = i32
-    L.dcsim_recorder_counts.argtypes = [vp, C.POINTER(u32 * 3)]
+    if hasattr(L, "dcsim_allreduce_summary"):      # (older tuning builds selected with DCSIM_B200_LIB may lack the newest entry points)
+        L.dcsim_allreduce_summary.restype = i32
+        L.dcsim_allreduce_summary.argtypes = [vp, vp, vp]
+    if hasattr(L, "dcsim_recorder_counts"):
+        L.dcsim_recorder_counts.restype = i32
+        L.dcsim_recorder_counts.argtypes = [vp, C.POINTER(u32 * 3)]
     L.dcsim_launch_info.restype = i32
     L.dcsim_launch_info.argtypes = [vp, C.POINTER(S.LaunchInfo)]
     L.dcsim_last_error.restype = C.c_char_p

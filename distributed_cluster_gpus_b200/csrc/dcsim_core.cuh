@@ -853,6 +853,56 @@ struct dcsim_merge_ring_t {
   uint32_t fin[DCSIM_MERGE_RING], pred[DCSIM_MERGE_RING], meta[DCSIM_MERGE_RING];
 };
 
+/* List positions of arrival k (pos_a) and of its xfer_done (pos_x, when `xin`): the number of list events before each.
+ * CHECKED = false: every index the scans touch is known to be in the ring (the common case, decided once per chunk);
+ * CHECKED = true: indices below `lo` are read from HBM.  `thr_gap` = max_transfer plus a margin far above any rounding:
+ * an arrival earlier than (t - thr_gap) has its xfer_done — if it has one — before t, and so have all before it. */
+template <bool CHECKED>
+DCSIM_DEV void dcsim_merge_positions(const dcsim_merge_ring_t* ring, const double* at, const double* tx, const uint32_t* fin,
+                                     const uint32_t* pred, uint32_t lo, uint32_t n, uint32_t k, double tk, double txk, uint32_t pk,
+                                     double thr_gap, bool xin, uint32_t* pos_a, uint32_t* pos_x) {
+  const uint32_t RM = DCSIM_MERGE_RING - 1u;
+#define MR_AT(j) ((!CHECKED || (j) >= lo) ? ring->at[(j) & RM] : at[(j)])
+#define MR_TX(j) ((!CHECKED || (j) >= lo) ? ring->tx[(j) & RM] : tx[(j)])
+#define MR_FIN(j) ((!CHECKED || (j) >= lo) ? ring->fin[(j) & RM] : fin[(j)])
+#define MR_PRED(j) ((!CHECKED || (j) >= lo) ? ring->pred[(j) & RM] : pred[(j)])
+  /* arrival k: the k earlier arrivals + the transfers that come before it */
+  uint32_t cnt = 0u;
+  {
+    const double far = tk - thr_gap;
+    for (uint32_t j = k; j > 0u;) {
+      --j;
+      const double tj = MR_AT(j), txj = MR_TX(j);
+      if (tj < far) { cnt += MR_FIN(j) + (dcsim_finite(txj) ? 1u : 0u); break; } /* every finite one up to j is earlier */
+      if (txj < tk || (txj == tk && pk != DCSIM_NO_PRED && j <= pk)) ++cnt;
+    }
+  }
+  *pos_a = k + cnt;
+  *pos_x = 0xffffffffu;
+  if (xin) {
+    uint32_t ca = k + 1u, cx = 0u; /* arrivals 0..k come first (their pushes precede arrival k's processing) */
+    const double far = txk - thr_gap;
+    for (uint32_t j = k; j > 0u;) {
+      --j;
+      const double tj = MR_AT(j), txj = MR_TX(j);
+      if (tj < far) { cx += MR_FIN(j) + (dcsim_finite(txj) ? 1u : 0u); break; }
+      if (txj <= txk) ++cx; /* tie: pushed earlier */
+    }
+    for (uint32_t i = k + 1u; i < n; ++i) { /* i < frontier: stage 1 ran until an arrival later than txk */
+      const double ti = MR_AT(i);
+      if (ti > txk) break;
+      if (ti < txk) ++ca;
+      else { const uint32_t pi = MR_PRED(i); if (pi == DCSIM_NO_PRED || pi < k) ++ca; } /* tie: arrival i was pushed before arrival k ran */
+      if (MR_TX(i) < txk) ++cx;                                                         /* tie: pushed later */
+    }
+    *pos_x = ca + cx;
+  }
+#undef MR_AT
+#undef MR_TX
+#undef MR_FIN
+#undef MR_PRED
+}
+
 DCSIM_DEV void dcsim_merge_arrivals(const dcsim_kparams_t* P, uint64_t r, int lane, dcsim_merge_ring_t* ring) {
   const dcsim_spec_t& sp = P->spec;
   dcsim_arrhdr_t* hdr = P->arr_hdr + r;
@@ -868,6 +918,7 @@ DCSIM_DEV void dcsim_merge_arrivals(const dcsim_kparams_t* P, uint64_t r, int la
   double* ma = P->ml_aux + 2ull * ab;
   uint32_t* mm = P->ml_meta + 2ull * ab;
   const double end = sp.end_time, end_eps = P->end_eps, tmax = P->max_transfer;
+  const double thr_gap = tmax + (end + 1.0) * 1e-12 + 1e-300; /* > max_transfer by far more than any rounding at t <= end */
   const uint32_t RM = DCSIM_MERGE_RING - 1u;
 
   uint32_t frontier = 0u;  /* arrivals [0, frontier) have their size / xfer_done instant / finite count (ring + HBM) */
@@ -880,7 +931,7 @@ DCSIM_DEV void dcsim_merge_arrivals(const dcsim_kparams_t* P, uint64_t r, int la
     for (;;) {
       if (frontier > k_last) {
         if (frontier >= n) break;
-        const double t_hi = (frontier - k_last <= DCSIM_MERGE_RING ? ring->at[k_last & RM] : at[k_last]) + tmax;
+        const double t_hi = (frontier - k_last <= DCSIM_MERGE_RING ? ring->at[k_last & RM] : at[k_last]) + thr_gap;
         if (ring->at[(frontier - 1u) & RM] > t_hi) break;
       }
       const uint32_t k = frontier + (uint32_t)lane;
@@ -908,6 +959,9 @@ DCSIM_DEV void dcsim_merge_arrivals(const dcsim_kparams_t* P, uint64_t r, int la
       dcsim_warp_sync(); /* ring / HBM entries written by other lanes are read below */
     }
     const uint32_t lo = frontier > DCSIM_MERGE_RING ? frontier - DCSIM_MERGE_RING : 0u; /* ring holds [lo, frontier) */
+    /* every backward scan of this chunk stops at or before `lo` when the oldest ring entry is already "far" from the
+       chunk's first arrival (forward scans end below the frontier by construction of stage 1) */
+    const bool covered = lo == 0u || (k0 >= lo && ring->at[lo & RM] < ring->at[k0 & RM] - thr_gap);
 
     /* ---- stage 2: list positions of this chunk's arrivals and their xfer_done events, emission */
     const uint32_t k = k0 + (uint32_t)lane;
@@ -915,40 +969,12 @@ DCSIM_DEV void dcsim_merge_arrivals(const dcsim_kparams_t* P, uint64_t r, int la
       const bool kin = k >= lo;
       const double tk = kin ? ring->at[k & RM] : at[k], txk = kin ? ring->tx[k & RM] : tx[k];
       const uint32_t meta = kin ? ring->meta[k & RM] : am[k], pk = kin ? ring->pred[k & RM] : pred[k];
-      /* arrival k: the k earlier arrivals + the transfers that come before it */
-      uint32_t cnt = 0u;
-      for (uint32_t j = k; j > 0u;) {
-        --j;
-        const bool in = j >= lo;
-        const double tj = in ? ring->at[j & RM] : at[j], txj = in ? ring->tx[j & RM] : tx[j];
-        if (tj + tmax < tk) { cnt += (in ? ring->fin[j & RM] : fin[j]) + (dcsim_finite(txj) ? 1u : 0u); break; } /* every finite one up to j is earlier */
-        if (txj < tk || (txj == tk && pk != DCSIM_NO_PRED && j <= pk)) ++cnt;
-      }
-      const uint32_t pos_a = k + cnt;
       const bool xs = dcsim_finite(txk) && !(txk > end_eps); /* SIM:160-163 */
       const bool xin = xs && !(txk > end);                    /* SIM:427: later events are never processed */
-      uint32_t pos_x = 0xffffffffu;
-      if (xin) {
-        uint32_t ca = k + 1u, cx = 0u; /* arrivals 0..k come first (their pushes precede arrival k's processing) */
-        for (uint32_t j = k; j > 0u;) {
-          --j;
-          const bool in = j >= lo;
-          const double tj = in ? ring->at[j & RM] : at[j], txj = in ? ring->tx[j & RM] : tx[j];
-          if (tj + tmax < txk) { cx += (in ? ring->fin[j & RM] : fin[j]) + (dcsim_finite(txj) ? 1u : 0u); break; }
-          if (txj <= txk) ++cx; /* tie: pushed earlier */
-        }
-        for (uint32_t i = k + 1u; i < n; ++i) { /* i < frontier: stage 1 ran until an arrival later than txk */
-          const bool in = i >= lo;
-          const double ti = in ? ring->at[i & RM] : at[i];
-          if (ti > txk) break;
-          const uint32_t pi = in ? ring->pred[i & RM] : pred[i];
-          if (ti < txk || pi == DCSIM_NO_PRED || pi < k) ++ca;          /* tie: arrival i was pushed before arrival k ran */
-          if ((in ? ring->tx[i & RM] : tx[i]) < txk) ++cx;               /* tie: pushed later */
-        }
-        pos_x = ca + cx;
-        ++n_x;
-        ahead = pos_x - pos_a > ahead ? pos_x - pos_a : ahead;
-      }
+      uint32_t pos_a, pos_x;
+      if (covered) dcsim_merge_positions<false>(ring, at, tx, fin, pred, lo, n, k, tk, txk, pk, thr_gap, xin, &pos_a, &pos_x);
+      else dcsim_merge_positions<true>(ring, at, tx, fin, pred, lo, n, k, tk, txk, pk, thr_gap, xin, &pos_a, &pos_x);
+      if (xin) { ++n_x; ahead = pos_x - pos_a > ahead ? pos_x - pos_a : ahead; }
       const uint32_t stream = meta & 15u;
       mt[pos_a] = tk;
       ma[pos_a] = dcsim_hilo_f64(0u, pos_x);

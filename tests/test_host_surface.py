@@ -145,3 +145,34 @@ def test_energy_price_map_forms():
     assert sp.dc[0].carbon_intensity == 0.0
     # price 0 everywhere -> the carbon objective with CI = 0: every score is 0, the first grid point wins (n=1, f=levels[0])
     assert (sp.dc[0].nf_xfer[0][12].n, sp.dc[0].nf_xfer[0][12].f) == (1, 0.5)
+
+
+def test_cli_gpus_flag_relaunches_through_torchrun(monkeypatch):
+    """`run_sim_paper --gpus N` outside a launcher re-launches itself as N ranks (one process per GPU, rendezvous on
+    127.0.0.1) with its own arguments; under a launcher (WORLD_SIZE set) it does not."""
+    import subprocess
+    from distributed_cluster_gpus_b200 import run_sim_paper as cli
+    seen = {}
+
+    class Done:
+        returncode = 0
+
+    def fake_run(cmd, check=False):
+        seen["cmd"] = cmd
+        return Done()
+    monkeypatch.setattr(subprocess, "run", fake_run)
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    argv = ["--gpus", "4", "--replicas", "1000", "--n-dc", "4", "--gpus-per-dc", "64", "--duration", "5"]
+    assert cli.main(argv) is None
+    cmd = seen["cmd"]
+    assert "torch.distributed.run" in cmd and "--nproc-per-node=4" in cmd and "127.0.0.1" in cmd
+    assert cmd[cmd.index("distributed_cluster_gpus_b200.run_sim_paper") + 1:] == argv
+
+
+def test_shard_covers_every_replica_once():
+    from distributed_cluster_gpus_b200 import sharding
+    for total, world in ((1048576, 8), (65536, 3), (5, 8), (301, 2)):
+        spans = [sharding.shard(total, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and sum(c for _, c in spans) == total
+        for (f0, c0), (f1, _c1) in zip(spans, spans[1:]):
+            assert f0 + c0 == f1
