@@ -73,6 +73,9 @@ static DCSIM_ADV(dcsim_advance_fn) DCSIM_ADV(dcsim_pick_kernel)(bool cap, int mo
   return table[(cap ? 3 : 0) + mode];
 }
 
+/* Resident CTAs per SM this build's register budget was chosen for (its __launch_bounds__). */
+int DCSIM_ADV(dcsim_adv_min_ctas)(void) { return DCSIM_MIN_CTAS_PER_SM; }
+
 /* Launch on `stream`: `ctas` CTAs of `threads` threads (threads / DCSIM_LANES replicas each), `smem` dynamic bytes. */
 cudaError_t DCSIM_ADV(dcsim_adv_launch)(const dcsim_kparams_t* P, unsigned long long* events, int cap, int mode, int ctas, int threads,
                                         int smem, cudaStream_t stream) {

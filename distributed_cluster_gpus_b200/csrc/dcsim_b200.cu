@@ -22,9 +22,6 @@
 #include <stdlib.h>
 #include <string.h>
 
-#ifndef DCSIM_DEFAULT_GROUP
-#define DCSIM_DEFAULT_GROUP 32 /* lanes per replica when DCSIM_GROUP is not set */
-#endif
 #define DCSIM_ADV_SUFFIX _g32
 #include "dcsim_advance_impl.cuh" /* the 32-lanes-per-replica event loop (and dcsim_core.cuh) */
 
@@ -33,6 +30,8 @@ cudaError_t dcsim_adv_launch_g16(const dcsim_kparams_t*, unsigned long long*, in
 cudaError_t dcsim_adv_attrs_g16(int, int, int, int, int, int*, int*, int*);
 cudaError_t dcsim_adv_launch_g8(const dcsim_kparams_t*, unsigned long long*, int, int, int, int, int, cudaStream_t);
 cudaError_t dcsim_adv_attrs_g8(int, int, int, int, int, int*, int*, int*);
+int dcsim_adv_min_ctas_g16(void);
+int dcsim_adv_min_ctas_g8(void);
 
 /* Arrival pre-pass: one THREAD per replica draws that replica's whole arrival sequence in the reference's draw order;
  * consecutive threads = consecutive replicas, so all 32 lanes of a warp run the samplers that the event loop would
@@ -202,7 +201,7 @@ typedef cudaError_t (*dcsim_adv_launch_fn)(const dcsim_kparams_t*, unsigned long
 typedef cudaError_t (*dcsim_adv_attrs_fn)(int, int, int, int, int, int*, int*, int*);
 static dcsim_adv_launch_fn adv_launch_for(int lanes) { return lanes == 8 ? dcsim_adv_launch_g8 : (lanes == 16 ? dcsim_adv_launch_g16 : dcsim_adv_launch_g32); }
 static dcsim_adv_attrs_fn adv_attrs_for(int lanes) { return lanes == 8 ? dcsim_adv_attrs_g8 : (lanes == 16 ? dcsim_adv_attrs_g16 : dcsim_adv_attrs_g32); }
-static int min_ctas_for(int lanes) { return lanes == 32 ? 8 : (lanes == 16 ? 6 : 4); } /* DCSIM_MIN_CTAS_PER_SM of that build */
+static int min_ctas_for(int lanes) { return lanes == 8 ? dcsim_adv_min_ctas_g8() : (lanes == 16 ? dcsim_adv_min_ctas_g16() : dcsim_adv_min_ctas_g32()); }
 
 static int resident_warps_for(int bytes_per_warp, int smem_optin, int smem_sm, int max_warps, int* wpc_out) {
   /* warps per CTA: whichever of 4 / 2 / 1 keeps the most warps resident (each CTA also reserves 1 KB of shared
@@ -226,7 +225,11 @@ static cudaError_t size_launch(dcsim_t* h) {
   int smem_optin = 0, smem_sm = 0;
   if ((e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device)) != cudaSuccess) return e;
   if ((e = cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, h->device)) != cudaSuccess) return e;
-  int lanes = DCSIM_DEFAULT_GROUP;
+  /* Lanes per replica.  Four replicas per warp pay when an event's warp-wide part (pop-min, DC sweep, lane-0 handler)
+   * dominates: few DCs (their finish slots + list + log fit one round of 8 lanes) and short running sets (a job_finish
+   * walks the DC's records 8 at a time).  Measured (profiles/r02_ab_lane_groups.jsonl): 4 DC x 64 +20 %, 1 DC x 64 +10 %,
+   * but 8 DC x 256 -16 % and joint_nf (up to 64 running jobs per DC) -23 % — those keep the whole warp. */
+  int lanes = (h->spec.n_dc <= 5 && h->L.cap_run <= 16) ? 8 : 32;
   { const char* g = getenv("DCSIM_GROUP"); if (g) { const int v = atoi(g); if (v == 8 || v == 16 || v == 32) lanes = v; } }
   const int rpw = 32 / lanes; /* replicas per warp */
   const int max_warps = min_ctas_for(lanes) * DCSIM_MAX_WARPS_PER_CTA;

@@ -172,11 +172,15 @@ DCSIM_COLD void dcsim_hist_add(uint32_t* hist, uint64_t r, int jt, double lat) {
 /* ---- candidate slots (the event set, one slot per lane) -------------------------------------- */
 enum {
   CAND_DC0 = 0,      /* + d   : earliest job_finish among DC d's running jobs */
-  CAND_LIST = 8,     /* the next entry of the replica's {arrival, xfer_done} list */
-  CAND_LOG = 9,      /* the log tick */
-  CAND_STALE = 10,   /* earliest superseded job_finish (cap_greedy re-scheduling leaves the old event in the heap, SIM:330-338) */
-  CAND_N = 16
+  /* behind the n_dc finish slots, densely (so that 4 DCs + 3 fit the 8 lanes of a lane group in one round):
+     n_dc     the next entry of the replica's {arrival, xfer_done} list  (CAND_LIST(c))
+     n_dc + 1 the log tick                                               (CAND_LOG(c))
+     n_dc + 2 earliest superseded job_finish (cap_greedy re-scheduling leaves the old event in the heap, SIM:330-338) */
+  CAND_N = 16        /* slots allocated (DCSIM_MAX_DC + 3 used at most); unused ones stay +inf */
 };
+#define CAND_LIST(c) ((c).P->spec.n_dc)
+#define CAND_LOG(c) ((c).P->spec.n_dc + 1)
+#define CAND_STALE(c) ((c).P->spec.n_dc + 2)
 enum { KIND_ARR_INF = 0, KIND_ARR_TRN = 1, KIND_XFER = 2, KIND_FINISH = 3, KIND_LOG = 4, KIND_STALE = 5 };
 
 /* ---- one entry of a replica's event list (SoA: t f64, aux f64, meta u32) ----------------------
@@ -580,8 +584,36 @@ DCSIM_DEV void dcsim_trng_block(dcsim_trng_t<MT>& g, uint32_t* ring, int stride)
   ring[(i + 2u) * stride] = w[2]; ring[(i + 3u) * stride] = w[3];
   g.filled += 4u;
 }
+/* Two consecutive Philox blocks with their rounds interleaved: each block is a chain of 10 dependent multiply rounds,
+ * two independent chains side by side fill the latency of one (the pre-pass is latency-bound: ~3.5 warps per scheduler). */
+DCSIM_DEV void dcsim_philox_block2(uint32_t k0, uint32_t k1, uint32_t b, uint32_t out[8]) {
+  uint32_t a0 = b, a1 = 0u, a2 = 0u, a3 = 0u, e0 = b + 1u, e1 = 0u, e2 = 0u, e3 = 0u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t ah0 = dcsim_mulhi(0xD2511F53u, a0), al0 = 0xD2511F53u * a0, ah1 = dcsim_mulhi(0xCD9E8D57u, a2), al1 = 0xCD9E8D57u * a2;
+    const uint32_t eh0 = dcsim_mulhi(0xD2511F53u, e0), el0 = 0xD2511F53u * e0, eh1 = dcsim_mulhi(0xCD9E8D57u, e2), el1 = 0xCD9E8D57u * e2;
+    const uint32_t an0 = ah1 ^ a1 ^ k0, an2 = ah0 ^ a3 ^ k1, en0 = eh1 ^ e1 ^ k0, en2 = eh0 ^ e3 ^ k1;
+    a0 = an0; a1 = al1; a2 = an2; a3 = al0;
+    e0 = en0; e1 = el1; e2 = en2; e3 = el0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = a0; out[1] = a1; out[2] = a2; out[3] = a3; out[4] = e0; out[5] = e1; out[6] = e2; out[7] = e3;
+}
+
 template <bool MT>
 DCSIM_DEV void dcsim_trng_topup(dcsim_trng_t<MT>& g, uint32_t* ring, int stride) {
+  if constexpr (!MT) {
+    while (g.filled - g.pos <= DCSIM_TRNG_RING - 8u) { /* room for two blocks */
+      uint32_t w[8];
+      dcsim_philox_block2(g.k0, g.k1, g.filled >> 2, w);
+      const uint32_t i = g.filled & (DCSIM_TRNG_RING - 1u); /* filled is a multiple of 4, the ring of 8: no wrap inside a block */
+      const uint32_t j = (g.filled + 4u) & (DCSIM_TRNG_RING - 1u);
+      ring[(i + 0u) * stride] = w[0]; ring[(i + 1u) * stride] = w[1]; ring[(i + 2u) * stride] = w[2]; ring[(i + 3u) * stride] = w[3];
+      ring[(j + 0u) * stride] = w[4]; ring[(j + 1u) * stride] = w[5]; ring[(j + 2u) * stride] = w[6]; ring[(j + 3u) * stride] = w[7];
+      g.filled += 8u;
+    }
+  }
   while (g.filled - g.pos <= DCSIM_TRNG_RING - 4u) dcsim_trng_block(g, ring, stride);
 }
 template <bool MT>
@@ -866,28 +898,26 @@ DCSIM_DEV void dcsim_merge_positions(const dcsim_merge_ring_t* ring, const doubl
 #define MR_TX(j) ((!CHECKED || (j) >= lo) ? ring->tx[(j) & RM] : tx[(j)])
 #define MR_FIN(j) ((!CHECKED || (j) >= lo) ? ring->fin[(j) & RM] : fin[(j)])
 #define MR_PRED(j) ((!CHECKED || (j) >= lo) ? ring->pred[(j) & RM] : pred[(j)])
-  /* arrival k: the k earlier arrivals + the transfers that come before it */
-  uint32_t cnt = 0u;
-  {
-    const double far = tk - thr_gap;
-    for (uint32_t j = k; j > 0u;) {
-      --j;
-      const double tj = MR_AT(j), txj = MR_TX(j);
-      if (tj < far) { cnt += MR_FIN(j) + (dcsim_finite(txj) ? 1u : 0u); break; } /* every finite one up to j is earlier */
-      if (txj < tk || (txj == tk && pk != DCSIM_NO_PRED && j <= pk)) ++cnt;
+  /* One walk back over the earlier arrivals j serves both positions: transfer j precedes arrival k if tx_j < t_k (or
+   * ties and was pushed first), and precedes transfer k if tx_j <= tx_k.  tx_k >= t_k, so the second question is
+   * settled ("everything further back is earlier") no later than the first. */
+  uint32_t cnt = 0u, cx = 0u;
+  const double far_a = tk - thr_gap, far_x = xin ? txk - thr_gap : DCSIM_INF;
+  bool x_open = xin;
+  for (uint32_t j = k; j > 0u;) {
+    --j;
+    const double tj = MR_AT(j), txj = MR_TX(j);
+    if (x_open) {
+      if (tj < far_x) { cx += MR_FIN(j) + (dcsim_finite(txj) ? 1u : 0u); x_open = false; }
+      else if (txj <= txk) ++cx; /* tie: pushed earlier */
     }
+    if (tj < far_a) { cnt += MR_FIN(j) + (dcsim_finite(txj) ? 1u : 0u); break; } /* every finite one up to j is earlier */
+    if (txj < tk || (txj == tk && pk != DCSIM_NO_PRED && j <= pk)) ++cnt;
   }
   *pos_a = k + cnt;
   *pos_x = 0xffffffffu;
   if (xin) {
-    uint32_t ca = k + 1u, cx = 0u; /* arrivals 0..k come first (their pushes precede arrival k's processing) */
-    const double far = txk - thr_gap;
-    for (uint32_t j = k; j > 0u;) {
-      --j;
-      const double tj = MR_AT(j), txj = MR_TX(j);
-      if (tj < far) { cx += MR_FIN(j) + (dcsim_finite(txj) ? 1u : 0u); break; }
-      if (txj <= txk) ++cx; /* tie: pushed earlier */
-    }
+    uint32_t ca = k + 1u; /* arrivals 0..k come first (their pushes precede arrival k's processing) */
     for (uint32_t i = k + 1u; i < n; ++i) { /* i < frontier: stage 1 ran until an arrival later than txk */
       const double ti = MR_AT(i);
       if (ti > txk) break;
@@ -1052,7 +1082,7 @@ DCSIM_DEV uint32_t* dcsim_list_seq_slot(dcsim_ctx_t& c, uint32_t m) {
 
 /* Pop-min over the event set itself: one candidate slot per lane (two with 8 lanes per replica), three
  * min-reductions (REDUX.MIN on a whole warp, shuffle butterflies inside a lane group), one ballot.  The lane of slot
- * CAND_LIST takes its candidate straight from the list
+ * CAND_LIST(c) takes its candidate straight from the list
  * window (entry c.cursor; the slot behind the window reads +inf), so nothing has to "publish" the next list entry.
  * Returns the winning candidate slot, -1 if all are +inf. */
 DCSIM_DEV int dcsim_argmin_cand(dcsim_ctx_t& c, double* t_out, uint32_t* seq_out) {
@@ -1061,16 +1091,15 @@ DCSIM_DEV int dcsim_argmin_cand(dcsim_ctx_t& c, double* t_out, uint32_t* seq_out
 #ifndef DCSIM_HOST_EMU
   uint32_t bh = 0x7ff00000u, bl = 0u, bs = 0xffffffffu;
   int bi = -1;
-#pragma unroll
-  for (int i0 = 0; i0 < CAND_N; i0 += DCSIM_LANES) { /* one slot per lane (32 lanes) or two (8 lanes) */
-    const int i = i0 + c.lane;
-    if (DCSIM_LANES <= CAND_N || i < CAND_N) {
-      const bool list = i == CAND_LIST;
-      const double t = *(list ? LW_T(c) + li : CAND_T(c) + i);
-      const uint32_t s = *(list ? dcsim_list_seq_slot(c, lm) : CAND_SEQ(c) + i);
-      const uint32_t h = dcsim_hi(t), l = dcsim_lo(t);
-      if (i0 == 0 || h < bh || (h == bh && (l < bl || (l == bl && s < bs)))) { bh = h; bl = l; bs = s; bi = i; }
-    }
+  const int n_slots = c.P->spec.n_dc + 3, slot_list = c.P->spec.n_dc;
+  for (int i0 = 0; i0 < n_slots; i0 += DCSIM_LANES) { /* one round with 32 lanes; with 8, one up to 5 DCs, else two */
+    /* with more lanes than slots the surplus lanes all look at the last slot, which is never used (+inf): no branch */
+    const int i = DCSIM_LANES > CAND_N ? (c.lane < CAND_N ? c.lane : CAND_N - 1) : i0 + c.lane;
+    const bool list = i == slot_list;
+    const double t = *(list ? LW_T(c) + li : CAND_T(c) + i);
+    const uint32_t s = *(list ? dcsim_list_seq_slot(c, lm) : CAND_SEQ(c) + i);
+    const uint32_t h = dcsim_hi(t), l = dcsim_lo(t);
+    if (i0 == 0 || h < bh || (h == bh && (l < bl || (l == bl && s < bs)))) { bh = h; bl = l; bs = s; bi = i; }
   }
   const uint32_t mh = dcsim_warp_min_u32(bh);
   if (mh >= 0x7ff00000u) return -1;
@@ -1083,8 +1112,8 @@ DCSIM_DEV int dcsim_argmin_cand(dcsim_ctx_t& c, double* t_out, uint32_t* seq_out
   const int src = dcsim_ffs(votes) - 1;
   return DCSIM_LANES >= CAND_N ? src : (int)dcsim_bcast_u32((uint32_t)bi, src); /* one slot per lane: slot == lane */
 #else
-  CAND_T(c)[CAND_LIST] = LW_T(c)[li];
-  CAND_SEQ(c)[CAND_LIST] = *dcsim_list_seq_slot(c, lm);
+  CAND_T(c)[CAND_LIST(c)] = LW_T(c)[li];
+  CAND_SEQ(c)[CAND_LIST(c)] = *dcsim_list_seq_slot(c, lm);
   return dcsim_argmin_ts(CAND_T(c), CAND_SEQ(c), CAND_N, c.lane, t_out, seq_out);
 #endif
 }
@@ -1512,14 +1541,14 @@ DCSIM_DEV void dcsim_handle_finish(dcsim_ctx_t& c, uint64_t r, int d) {
   dcsim_warp_sync();
 }
 
-/* Warp.  Earliest superseded job_finish -> candidate slot CAND_STALE. */
+/* Warp.  Earliest superseded job_finish -> candidate slot CAND_STALE(c). */
 DCSIM_DEV void dcsim_rescan_stale(dcsim_ctx_t& c) {
   double t; uint32_t s;
   const int k = dcsim_argmin_ts(dcsim_at<double>(c.blk, c.P->L.st_t), dcsim_at<uint32_t>(c.blk, c.P->L.st_seq),
                                 (int)c.H->n_stale, c.lane, &t, &s);
   if (c.lane == 0) {
-    CAND_T(c)[CAND_STALE] = k >= 0 ? t : DCSIM_INF;
-    CAND_SEQ(c)[CAND_STALE] = k >= 0 ? s : 0xffffffffu;
+    CAND_T(c)[CAND_STALE(c)] = k >= 0 ? t : DCSIM_INF;
+    CAND_SEQ(c)[CAND_STALE(c)] = k >= 0 ? s : 0xffffffffu;
     c.H->smin_slot = (uint32_t)k;
   }
   dcsim_warp_sync();
@@ -1696,8 +1725,8 @@ DCSIM_DEV void dcsim_handle_log(dcsim_ctx_t& c) {
   if (c.lane == 0) {
     if (rec) c.P->rec.counts[2] += (uint32_t)sp.n_dc;
     const double t = c.now + interval; /* SIM:949 */
-    if (dcsim_schedulable(c, t)) { CAND_T(c)[CAND_LOG] = t; CAND_SEQ(c)[CAND_LOG] = c.seq++; }
-    else { CAND_T(c)[CAND_LOG] = DCSIM_INF; CAND_SEQ(c)[CAND_LOG] = 0xffffffffu; }
+    if (dcsim_schedulable(c, t)) { CAND_T(c)[CAND_LOG(c)] = t; CAND_SEQ(c)[CAND_LOG(c)] = c.seq++; }
+    else { CAND_T(c)[CAND_LOG(c)] = DCSIM_INF; CAND_SEQ(c)[CAND_LOG(c)] = 0xffffffffu; }
   }
   dcsim_warp_sync();
 }
@@ -1729,7 +1758,7 @@ DCSIM_DEV void dcsim_replica_init(dcsim_ctx_t& c, uint64_t r) {
     for (int s = 0; s < 2 * sp.n_ing; ++s) /* SIM:154-156 */
       if ((ah.first_mask >> s) & 1u) PEND_SEQ(c)[s] = c.seq++;
     const double t = 0.0 + sp.log_interval; /* SIM:157 */
-    if (dcsim_schedulable(c, t)) { CAND_T(c)[CAND_LOG] = t; CAND_SEQ(c)[CAND_LOG] = c.seq++; }
+    if (dcsim_schedulable(c, t)) { CAND_T(c)[CAND_LOG(c)] = t; CAND_SEQ(c)[CAND_LOG(c)] = c.seq++; }
     c.H->initialized = 1u;
   }
   dcsim_warp_sync();
@@ -1800,10 +1829,10 @@ DCSIM_DEV uint32_t dcsim_replica_run(dcsim_ctx_t& c, uint64_t r) {
     /* dispatch on the winning slot itself; the event kind is only spelled out for the (cold) trace */
     if (tracing && c.lane == 0) {
       int kind = KIND_FINISH;
-      if (win == CAND_LIST) {
+      if (win == CAND_LIST(c)) {
         const uint32_t m = LW_META(c)[c.cursor - c.lw_base];
         kind = (m & ML_XFER) ? KIND_XFER : (int)((m >> 1) & 1u); /* the job type is the stream's low bit */
-      } else if (win == CAND_LOG) {
+      } else if (win == CAND_LOG(c)) {
         kind = KIND_LOG;
       }
       const uint32_t row = c.P->rec.counts[0];
@@ -1811,11 +1840,11 @@ DCSIM_DEV uint32_t dcsim_replica_run(dcsim_ctx_t& c, uint64_t r) {
       c.P->rec.counts[0] = row + 1u;
     }
 
-    if (win == CAND_LIST) {
+    if (win == CAND_LIST(c)) {
       dcsim_handle_list<CAP>(c, r);
-    } else if (win < CAND_LIST) {
+    } else if (win < CAND_LIST(c)) {
       dcsim_handle_finish<CAP, RECG>(c, r, win - CAND_DC0);
-    } else if (win == CAND_LOG) {
+    } else if (win == CAND_LOG(c)) {
       if (c.lane == 0) c.H->ev_log++;
       dcsim_handle_log<CAP>(c);
     } else if constexpr (CAP) { /* a superseded job_finish: it advanced the clock and accrued energy, nothing else (SIM:456-461) */
