@@ -18,8 +18,10 @@
 #define DCSIM_REPLICAS_PER_WARP (32 / DCSIM_LANES)
 #ifndef DCSIM_MIN_CTAS_PER_SM
 /* 32 lanes per replica: 8 CTAs x 4 warps = 32 warps/SM -> ptxas keeps the kernel within 64 registers.  With several
- * replicas per warp shared memory allows fewer warps anyway, so the register budget per thread is left wider. */
-#define DCSIM_MIN_CTAS_PER_SM (DCSIM_LANES == 32 ? 8 : (DCSIM_LANES == 16 ? 6 : 4))
+ * replicas per warp shared memory allows fewer warps anyway, so the register budget per thread is wider: 8 lanes run
+ * best at 5 CTAs (96 registers, 80 replicas per SM) — 4 CTAs / 118 registers measured -13 %, 6 CTAs / 80 registers
+ * (spills) -12 % (profiles/r02_ab_lane_group_occupancy.jsonl). */
+#define DCSIM_MIN_CTAS_PER_SM (DCSIM_LANES == 32 ? 8 : (DCSIM_LANES == 16 ? 6 : 5))
 #endif
 
 extern __shared__ __align__(16) char dcsim_smem[];

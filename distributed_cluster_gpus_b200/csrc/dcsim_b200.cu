@@ -38,15 +38,21 @@ int dcsim_adv_min_ctas_g8(void);
  * otherwise run on one lane.  Per-thread scratch in shared memory, [slot][thread]: 2*MAX_ING stream clocks (f64),
  * 2*MAX_ING "latest arrival of the stream" indices (u32), DCSIM_TRNG_RING staged random words (u32). */
 #define DCSIM_ARRIVALS_THREADS 128
-#define DCSIM_ARRIVALS_SCRATCH_PER_THREAD (2 * DCSIM_MAX_ING * (sizeof(double) + sizeof(uint32_t)) + DCSIM_TRNG_RING * sizeof(uint32_t))
+/* 7 resident CTAs per SM (<= 73 registers, <= 32 kB of scratch each): 148 x 7 x 128 = 132 608 threads, so that a batch of
+ * 131 072 replicas (BASELINE config 5 per GPU) is still ONE wave of this latency-bound kernel. */
+#define DCSIM_ARRIVALS_MIN_CTAS 7
+static size_t dcsim_arrivals_scratch_bytes(int n_ing) { /* per CTA: [slot][thread] arrays for 2 * n_ing streams */
+  return (size_t)DCSIM_ARRIVALS_THREADS * ((size_t)(2 * n_ing) * (sizeof(double) + sizeof(uint32_t)) + DCSIM_TRNG_RING * sizeof(uint32_t));
+}
 extern __shared__ __align__(16) double dcsim_arr_scratch[];
 template <bool MT>
-__global__ void __launch_bounds__(DCSIM_ARRIVALS_THREADS) dcsim_arrivals_kernel(const __grid_constant__ dcsim_kparams_t P) {
+__global__ void __launch_bounds__(DCSIM_ARRIVALS_THREADS, DCSIM_ARRIVALS_MIN_CTAS) dcsim_arrivals_kernel(const __grid_constant__ dcsim_kparams_t P) {
   const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= P.n_replicas) return;
-  double* clocks = dcsim_arr_scratch + threadIdx.x;                                                   /* [stream][thread] */
-  uint32_t* last = reinterpret_cast<uint32_t*>(dcsim_arr_scratch + 2 * DCSIM_MAX_ING * blockDim.x) + threadIdx.x; /* [stream][thread] */
-  uint32_t* ring = last + 2 * DCSIM_MAX_ING * blockDim.x;                                             /* [word][thread] */
+  const int n_streams = 2 * P.spec.n_ing;
+  double* clocks = dcsim_arr_scratch + threadIdx.x;                                             /* [stream][thread] */
+  uint32_t* last = reinterpret_cast<uint32_t*>(dcsim_arr_scratch + n_streams * blockDim.x) + threadIdx.x; /* [stream][thread] */
+  uint32_t* ring = last + n_streams * blockDim.x;                                               /* [word][thread] */
   dcsim_generate_arrivals<MT>(&P, r, clocks, last, ring, (int)blockDim.x);
 }
 
@@ -439,7 +445,7 @@ int dcsim_prepare(dcsim_t* h) {
   dcsim_kparams_t P;
   fill_kparams(h, &P, 0);
   const int nb = (int)((h->n_replicas + DCSIM_ARRIVALS_THREADS - 1) / DCSIM_ARRIVALS_THREADS);
-  const size_t scratch = (size_t)DCSIM_ARRIVALS_THREADS * DCSIM_ARRIVALS_SCRATCH_PER_THREAD;
+  const size_t scratch = dcsim_arrivals_scratch_bytes(h->spec.n_ing);
   if (h->rng_kind == DCSIM_RNG_MT19937) dcsim_arrivals_kernel<true><<<nb, DCSIM_ARRIVALS_THREADS, scratch, h->stream>>>(P);
   else dcsim_arrivals_kernel<false><<<nb, DCSIM_ARRIVALS_THREADS, scratch, h->stream>>>(P);
   CUDA_TRY(h, cudaGetLastError());

@@ -1088,13 +1088,28 @@ DCSIM_DEV uint32_t* dcsim_list_seq_slot(dcsim_ctx_t& c, uint32_t m) {
 DCSIM_DEV int dcsim_argmin_cand(dcsim_ctx_t& c, double* t_out, uint32_t* seq_out) {
   const uint32_t li = c.cursor - c.lw_base; /* <= DCSIM_LIST_WINDOW */
   const uint32_t lm = LW_META(c)[li];
-#ifndef DCSIM_HOST_EMU
+#if !defined(DCSIM_HOST_EMU) && DCSIM_LANES >= CAND_N
+  /* one slot per lane, no loop; the surplus lanes all look at the last slot, which is never used (+inf) */
+  const int i = c.lane < CAND_N ? c.lane : CAND_N - 1;
+  const bool list = i == c.P->spec.n_dc;
+  const double t = *(list ? LW_T(c) + li : CAND_T(c) + i);
+  const uint32_t s = *(list ? dcsim_list_seq_slot(c, lm) : CAND_SEQ(c) + i);
+  const uint32_t h = dcsim_hi(t), l = dcsim_lo(t);
+  const uint32_t mh = dcsim_warp_min_u32(h);
+  if (mh >= 0x7ff00000u) return -1;
+  const uint32_t ml = dcsim_warp_min_u32(h == mh ? l : 0xffffffffu);
+  const bool m = (h == mh) && (l == ml);
+  const uint32_t ms = dcsim_warp_min_u32(m ? s : 0xffffffffu);
+  const uint32_t votes = dcsim_warp_ballot(m && s == ms);
+  *t_out = __hiloint2double((int)mh, (int)ml);
+  *seq_out = ms;
+  return dcsim_ffs(votes) - 1; /* slot == lane */
+#elif !defined(DCSIM_HOST_EMU)
   uint32_t bh = 0x7ff00000u, bl = 0u, bs = 0xffffffffu;
   int bi = -1;
   const int n_slots = c.P->spec.n_dc + 3, slot_list = c.P->spec.n_dc;
-  for (int i0 = 0; i0 < n_slots; i0 += DCSIM_LANES) { /* one round with 32 lanes; with 8, one up to 5 DCs, else two */
-    /* with more lanes than slots the surplus lanes all look at the last slot, which is never used (+inf): no branch */
-    const int i = DCSIM_LANES > CAND_N ? (c.lane < CAND_N ? c.lane : CAND_N - 1) : i0 + c.lane;
+  for (int i0 = 0; i0 < n_slots; i0 += DCSIM_LANES) { /* with 8 lanes: one round up to 5 DCs, else two */
+    const int i = i0 + c.lane; /* < CAND_N: unused slots read +inf */
     const bool list = i == slot_list;
     const double t = *(list ? LW_T(c) + li : CAND_T(c) + i);
     const uint32_t s = *(list ? dcsim_list_seq_slot(c, lm) : CAND_SEQ(c) + i);
@@ -1109,8 +1124,7 @@ DCSIM_DEV int dcsim_argmin_cand(dcsim_ctx_t& c, double* t_out, uint32_t* seq_out
   const uint32_t votes = dcsim_warp_ballot(m && bs == ms);
   *t_out = __hiloint2double((int)mh, (int)ml);
   *seq_out = ms;
-  const int src = dcsim_ffs(votes) - 1;
-  return DCSIM_LANES >= CAND_N ? src : (int)dcsim_bcast_u32((uint32_t)bi, src); /* one slot per lane: slot == lane */
+  return (int)dcsim_bcast_u32((uint32_t)bi, dcsim_ffs(votes) - 1);
 #else
   CAND_T(c)[CAND_LIST(c)] = LW_T(c)[li];
   CAND_SEQ(c)[CAND_LIST(c)] = *dcsim_list_seq_slot(c, lm);
