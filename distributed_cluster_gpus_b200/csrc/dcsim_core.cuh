@@ -151,12 +151,17 @@ DCSIM_DEV int dcsim_lat_bin(double lat) {
   return idx > DCSIM_LAT_BINS - 1 ? DCSIM_LAT_BINS - 1 : idx;
 }
 
-/* Cold helpers are kept OUT OF LINE (by-value arguments only, so the context stays in registers): inlining them
- * costs the event loop registers and instruction-cache footprint on paths most launches never take. */
-#ifndef DCSIM_HOST_EMU
+/* Cold helpers are kept OUT OF LINE in the one-replica-per-warp build (by-value arguments only, so the context stays in
+ * registers): inlining them costs the event loop registers and instruction-cache footprint on paths most launches never
+ * take.  When a warp carries several replicas they are INLINED instead: a call made by one lane group while its
+ * siblings are elsewhere in the loop is ruinous (the job-latency histogram's one-instruction helper measured +130 % on
+ * the whole event loop as a call, < 1 % inlined: tools/hist_probe.py), and that build has registers to spare. */
+#if defined(DCSIM_HOST_EMU)
+#define DCSIM_COLD static
+#elif DCSIM_LANES == 32
 #define DCSIM_COLD static __device__ __noinline__ /* static: the core is compiled into several translation units */
 #else
-#define DCSIM_COLD static
+#define DCSIM_COLD static __device__ __forceinline__
 #endif
 
 /* One count into replica r's [2][DCSIM_LAT_BINS] histogram in HBM — fire-and-forget, nothing waits for it. */
