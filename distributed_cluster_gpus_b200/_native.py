@@ -20,7 +20,7 @@ EXPORTS = (
     "dcsim_set_trace", "dcsim_set_logging", "dcsim_prepare", "dcsim_advance", "dcsim_all_done", "dcsim_fetch_summary",
     "dcsim_summary_device_ptr", "dcsim_reduce_summary", "dcsim_enable_latency_histogram", "dcsim_fetch_latency_histogram", "dcsim_fetch_trace", "dcsim_fetch_job_log",
     "dcsim_fetch_cluster_log", "dcsim_launch_info", "dcsim_last_error", "dcsim_destroy", "dcsim_set_rng",
-    "dcsim_recorder_counts", "dcsim_allreduce_summary",
+    "dcsim_recorder_counts", "dcsim_allreduce_summary", "dcsim_fetch_summary_host",
 )
 
 _lib = None
@@ -84,6 +84,9 @@ def load():
     if hasattr(L, "dcsim_allreduce_summary"):      # (older tuning builds selected with DCSIM_B200_LIB may lack the newest entry points)
         L.dcsim_allreduce_summary.restype = i32
         L.dcsim_allreduce_summary.argtypes = [vp, vp, vp]
+    if hasattr(L, "dcsim_fetch_summary_host"):
+        L.dcsim_fetch_summary_host.restype = i32
+        L.dcsim_fetch_summary_host.argtypes = [vp, C.POINTER(C.POINTER(C.c_double))]
     if hasattr(L, "dcsim_recorder_counts"):
         L.dcsim_recorder_counts.restype = i32
         L.dcsim_recorder_counts.argtypes = [vp, C.POINTER(u32 * 3)]

@@ -114,6 +114,7 @@ struct dcsim {
   char* d_state;
   char* d_queues;
   double* d_summary;
+  double* h_summary_pinned; /* page-locked host mirror of d_summary, allocated on first use (dcsim_fetch_summary_host) */
   unsigned long long* d_events;
   double* d_agg;                 /* DCSIM_AGG_K doubles: scratch of dcsim_all_done */
   unsigned long long* d_hist_out; /* [2][DCSIM_LAT_BINS]: scratch of dcsim_fetch_latency_histogram */
@@ -488,6 +489,19 @@ int dcsim_fetch_summary(dcsim_t* h, double* out, size_t out_bytes) {
   return DCSIM_OK;
 }
 
+int dcsim_fetch_summary_host(dcsim_t* h, const double** host_ptr_out) {
+  if (!h || !host_ptr_out) return DCSIM_E_INVALID;
+  *host_ptr_out = NULL;
+  if (!h->launches) return set_err(h, DCSIM_E_STATE, "fetch_summary_host before the first advance%s%lld");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const size_t need = (size_t)h->n_replicas * DCSIM_SUMMARY_K * sizeof(double);
+  if (!h->h_summary_pinned) CUDA_TRY(h, cudaHostAlloc(&h->h_summary_pinned, need, cudaHostAllocDefault));
+  CUDA_TRY(h, cudaMemcpyAsync(h->h_summary_pinned, h->d_summary, need, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  *host_ptr_out = h->h_summary_pinned;
+  return DCSIM_OK;
+}
+
 int dcsim_summary_device_ptr(dcsim_t* h, void** dev_ptr_out) {
   if (!h || !dev_ptr_out) return DCSIM_E_INVALID;
   *dev_ptr_out = h->d_summary;
@@ -660,6 +674,7 @@ void dcsim_destroy(dcsim_t* h) {
   cudaFree(h->d_state); cudaFree(h->d_queues); cudaFree(h->d_summary); cudaFree(h->d_events); cudaFree(h->d_counts);
   cudaFree(h->d_trace); cudaFree(h->d_jobs); cudaFree(h->d_cluster);
   cudaFree(h->d_hist); cudaFree(h->d_agg); cudaFree(h->d_hist_out);
+  if (h->h_summary_pinned) cudaFreeHost(h->h_summary_pinned);
   cudaFree(h->d_mt);
   cudaFree(h->d_arr_t); cudaFree(h->d_arr_raw); cudaFree(h->d_arr_meta); cudaFree(h->d_arr_pred); cudaFree(h->d_arr_tx);
   cudaFree(h->d_arr_fin); cudaFree(h->d_ml_t); cudaFree(h->d_ml_aux); cudaFree(h->d_ml_meta); cudaFree(h->d_arr_hdr);

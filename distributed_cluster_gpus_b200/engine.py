@@ -120,6 +120,12 @@ class BatchedEngine:
 
     def summary(self, out=None) -> np.ndarray:
         """[n_replicas, SUMMARY_K] float64; ``out`` may be a (pinned) preallocated array."""
+        if out is None and hasattr(self._lib, "dcsim_fetch_summary_host"):
+            # through the library's page-locked mirror (a full-rate DMA), then one host copy: the mirror is reused by
+            # the next fetch on this handle, the returned array is the caller's
+            p = C.POINTER(C.c_double)()
+            N.check(self._lib.dcsim_fetch_summary_host(self._h, C.byref(p)), self._h)
+            return np.ctypeslib.as_array(p, shape=(self.n_replicas, S.SUMMARY_K)).copy()
         if out is None:
             out = np.empty((self.n_replicas, S.SUMMARY_K), dtype=np.float64)
         N.check(self._lib.dcsim_fetch_summary(self._h, C.c_void_p(out.ctypes.data), out.nbytes), self._h)

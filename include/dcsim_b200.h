@@ -263,6 +263,11 @@ int dcsim_all_done(dcsim_t* h, int* done_out);
 /* Copies [n_replicas][DCSIM_SUMMARY_K] doubles to host memory (synchronises). */
 int dcsim_fetch_summary(dcsim_t* h, double* out, size_t out_bytes);
 
+/* The same rows through a page-locked host buffer the library owns (allocated on first use): a full-rate DMA instead of a
+ * pageable copy (46 MB for 65 536 replicas: ~2 ms instead of ~20).  *host_ptr_out stays valid until the next call on
+ * this handle or dcsim_destroy(); synchronises. */
+int dcsim_fetch_summary_host(dcsim_t* h, const double** host_ptr_out);
+
 /* Device pointer of the same array, for zero-copy consumers on the same device. */
 int dcsim_summary_device_ptr(dcsim_t* h, void** dev_ptr_out);
 
