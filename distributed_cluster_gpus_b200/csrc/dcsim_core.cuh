@@ -589,36 +589,10 @@ DCSIM_DEV void dcsim_trng_block(dcsim_trng_t<MT>& g, uint32_t* ring, int stride)
   ring[(i + 2u) * stride] = w[2]; ring[(i + 3u) * stride] = w[3];
   g.filled += 4u;
 }
-/* Two consecutive Philox blocks with their rounds interleaved: each block is a chain of 10 dependent multiply rounds,
- * two independent chains side by side fill the latency of one (the pre-pass is latency-bound: ~3.5 warps per scheduler). */
-DCSIM_DEV void dcsim_philox_block2(uint32_t k0, uint32_t k1, uint32_t b, uint32_t out[8]) {
-  uint32_t a0 = b, a1 = 0u, a2 = 0u, a3 = 0u, e0 = b + 1u, e1 = 0u, e2 = 0u, e3 = 0u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t ah0 = dcsim_mulhi(0xD2511F53u, a0), al0 = 0xD2511F53u * a0, ah1 = dcsim_mulhi(0xCD9E8D57u, a2), al1 = 0xCD9E8D57u * a2;
-    const uint32_t eh0 = dcsim_mulhi(0xD2511F53u, e0), el0 = 0xD2511F53u * e0, eh1 = dcsim_mulhi(0xCD9E8D57u, e2), el1 = 0xCD9E8D57u * e2;
-    const uint32_t an0 = ah1 ^ a1 ^ k0, an2 = ah0 ^ a3 ^ k1, en0 = eh1 ^ e1 ^ k0, en2 = eh0 ^ e3 ^ k1;
-    a0 = an0; a1 = al1; a2 = an2; a3 = al0;
-    e0 = en0; e1 = el1; e2 = en2; e3 = el0;
-    k0 += 0x9E3779B9u;
-    k1 += 0xBB67AE85u;
-  }
-  out[0] = a0; out[1] = a1; out[2] = a2; out[3] = a3; out[4] = e0; out[5] = e1; out[6] = e2; out[7] = e3;
-}
-
 template <bool MT>
 DCSIM_DEV void dcsim_trng_topup(dcsim_trng_t<MT>& g, uint32_t* ring, int stride) {
-  if constexpr (!MT) {
-    while (g.filled - g.pos <= DCSIM_TRNG_RING - 8u) { /* room for two blocks */
-      uint32_t w[8];
-      dcsim_philox_block2(g.k0, g.k1, g.filled >> 2, w);
-      const uint32_t i = g.filled & (DCSIM_TRNG_RING - 1u); /* filled is a multiple of 4, the ring of 8: no wrap inside a block */
-      const uint32_t j = (g.filled + 4u) & (DCSIM_TRNG_RING - 1u);
-      ring[(i + 0u) * stride] = w[0]; ring[(i + 1u) * stride] = w[1]; ring[(i + 2u) * stride] = w[2]; ring[(i + 3u) * stride] = w[3];
-      ring[(j + 0u) * stride] = w[4]; ring[(j + 1u) * stride] = w[5]; ring[(j + 2u) * stride] = w[6]; ring[(j + 3u) * stride] = w[7];
-      g.filled += 8u;
-    }
-  }
+  /* one block at a time: generating two with interleaved rounds (more ILP for a latency-bound kernel) measured 4 %
+     SLOWER — the longer live ranges cost more than the overlap gains (profiles/r02_variants_ab.md) */
   while (g.filled - g.pos <= DCSIM_TRNG_RING - 4u) dcsim_trng_block(g, ring, stride);
 }
 template <bool MT>
