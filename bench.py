@@ -341,10 +341,6 @@ def run_b200(args, world, rank, local_rank):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device; there is no CPU fallback")
     torch.cuda.set_device(local_rank)
-    if "NCCL_DEBUG" not in os.environ:        # NCCL's init lines (nranks, NVLS, ...) go to stderr: stdout stays one JSON line
-        os.environ["NCCL_DEBUG"] = "INFO"
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     sc = workload(args)
@@ -539,6 +535,14 @@ def main():
     if args.impl == "reference":
         run_reference_arm(args, world, rank)
         return
+    if world > 1:
+        # BEFORE torch is imported (NCCL reads its environment once): the communicator's init lines (nranks, NVLS, ...) are
+        # wanted as evidence that N ranks really talk, but stdout must stay ONE JSON line — so they go to stderr unless the
+        # caller routed them somewhere itself.  A caller's own NCCL_DEBUG level is respected.
+        if "NCCL_DEBUG" not in os.environ:
+            os.environ["NCCL_DEBUG"] = "INFO"
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     run_b200(args, world, rank, local_rank)
 
 
