@@ -44,6 +44,9 @@
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
+#if !defined(DCSIM_HOST_EMU)
+#include <cuda_pipeline.h>
+#endif
 
 #include "../../include/dcsim_b200.h"
 
@@ -221,7 +224,8 @@ enum { /* per-DC i32 arrays; FIFO rings are (head index, length) so no modulo is
 #define DCSIM_FOR_EACH_DC(d, c, n) for (int d = 0; d < (n); ++d)
 #endif
 
-#define DCSIM_LIST_WINDOW 32u   /* event-list entries staged in shared memory at a time: one per lane */
+#define DCSIM_LIST_WINDOW 32u   /* slots of the event-list ring in shared memory (list position p lives in slot p & 31) */
+#define DCSIM_LIST_HALF 16u     /* refill granularity: while one half is consumed the other is (asynchronously) loaded */
 /* A rejection loop that has not accepted after this many draws stops the replica with DCSIM_ST_RNG_RUNAWAY
  * instead of spinning (the reference would spin: e.g. arrivals.py:41-45 under a clipped lambda). */
 #define DCSIM_REJECTION_LIMIT (1 << 24)
@@ -234,7 +238,7 @@ struct dcsim_hdr_t {
   uint32_t n_fin_inf, n_fin_trn, ev_arr, ev_xfer;
   uint32_t ev_fin, ev_log, _r1, max_run;
   uint32_t max_q, _r2, bandit_t, n_stale;
-  uint32_t smin_slot, ml_cursor, ml_count, lw_base; /* event-list cursor / length / first staged entry */
+  uint32_t smin_slot, ml_cursor, ml_count, _r3; /* event-list cursor / length */
 };
 
 /* Byte offsets of the arrays inside a state block; computed once per handle on the host. */
@@ -271,12 +275,10 @@ enum : int32_t {
   DCSIM_OFF_CAND_SEQ = DCSIM_OFF_CAND_T + CAND_N * 8,
   DCSIM_OFF_DC_F64 = DCSIM_OFF_CAND_SEQ + CAND_N * 4,
   DCSIM_OFF_DC_I32 = DCSIM_OFF_DC_F64 + DF_N * DCSIM_MAX_DC * 8,
-  /* the window's t / meta arrays carry one slot more than the window: slot DCSIM_LIST_WINDOW stays (+inf, 0), so that
-     "the entry behind the last staged one" reads as "no event" when the list ends exactly at a window boundary */
   DCSIM_OFF_LW_T = (DCSIM_OFF_DC_I32 + DI_N * DCSIM_MAX_DC * 4 + 15) & ~15,
-  DCSIM_OFF_LW_AUX = DCSIM_OFF_LW_T + ((int32_t)DCSIM_LIST_WINDOW + 1) * 8,
+  DCSIM_OFF_LW_AUX = DCSIM_OFF_LW_T + (int32_t)DCSIM_LIST_WINDOW * 8,
   DCSIM_OFF_LW_META = DCSIM_OFF_LW_AUX + (int32_t)DCSIM_LIST_WINDOW * 8,
-  DCSIM_OFF_PEND_SEQ = DCSIM_OFF_LW_META + ((int32_t)DCSIM_LIST_WINDOW + 1) * 4,
+  DCSIM_OFF_PEND_SEQ = DCSIM_OFF_LW_META + (int32_t)DCSIM_LIST_WINDOW * 4,
   DCSIM_OFF_XRING = (DCSIM_OFF_PEND_SEQ + 2 * DCSIM_MAX_ING * 4 + 15) & ~15
 };
 
@@ -424,7 +426,6 @@ struct dcsim_ctx_t {
    * authoritative (only lane 0 runs handlers); the others are warp-uniform. */
   uint32_t seq;          /* successful pushes (SIM:163) */
   uint32_t cursor;       /* next entry of the event list */
-  uint32_t lw_base;      /* list position of the window's first entry */
   double now;
   double last_t;         /* instant of the previous processed event, 0.0 before the first: util_last_ts / last_energy_time
                             of EVERY data centre (SIM:429-437 touches them all on every event, so they never differ) */
@@ -1065,7 +1066,7 @@ DCSIM_DEV uint32_t* dcsim_list_seq_slot(dcsim_ctx_t& c, uint32_t m) {
  * window (entry c.cursor; the slot behind the window reads +inf), so nothing has to "publish" the next list entry.
  * Returns the winning candidate slot, -1 if all are +inf. */
 DCSIM_DEV int dcsim_argmin_cand(dcsim_ctx_t& c, double* t_out, uint32_t* seq_out) {
-  const uint32_t li = c.cursor - c.lw_base; /* <= DCSIM_LIST_WINDOW */
+  const uint32_t li = c.cursor & (DCSIM_LIST_WINDOW - 1u); /* entries at and past the end of the list read (+inf, 0) */
   const uint32_t lm = LW_META(c)[li];
 #if !defined(DCSIM_HOST_EMU) && DCSIM_LANES >= CAND_N
   /* one slot per lane, no loop; the surplus lanes all look at the last slot, which is never used (+inf) */
@@ -1332,17 +1333,40 @@ DCSIM_DEV void dcsim_start_by_rule(dcsim_ctx_t& c, int rule, bool at_xfer, int d
   }
 }
 
-/* Warp.  Stages entries [base, base + DCSIM_LIST_WINDOW) of the replica's event list into shared memory (coalesced). */
-DCSIM_DEV void dcsim_list_stage(dcsim_ctx_t& c, uint64_t r, uint32_t base) {
-  const uint64_t off = r * 2ull * (uint64_t)c.P->cap_arr + base;
+/* The event list is streamed through a 32-slot ring in the state block, half a ring (16 entries) at a time: when the
+ * cursor enters one half, the other half — just consumed — is refilled with the 16 entries after the current half.  On
+ * the GPU the refill is ASYNCHRONOUS (cp.async: HBM -> shared memory without registers), so its latency, which a whole
+ * warp (all of its lane groups) would otherwise sit out every 16 list events, hides behind the events of the current
+ * half; dcsim_list_wait() is called before the first entry of a freshly filled half is looked at.  Slots of list
+ * positions at or past the end of the list get (+inf, 0): "no event". */
+DCSIM_DEV void dcsim_list_fill(dcsim_ctx_t& c, uint64_t r, uint32_t first, uint32_t n_entries) {
+  const uint64_t off = r * 2ull * (uint64_t)c.P->cap_arr;
   const uint32_t count = c.H->ml_count;
-  for (uint32_t i = (uint32_t)c.lane; i < DCSIM_LIST_WINDOW; i += DCSIM_LANES) {
-    const bool in = base + i < count;
-    LW_T(c)[i] = in ? c.P->ml_t[off + i] : DCSIM_INF;
-    LW_AUX(c)[i] = in ? c.P->ml_aux[off + i] : 0.0;
-    LW_META(c)[i] = in ? c.P->ml_meta[off + i] : 0u;
+  for (uint32_t i = (uint32_t)c.lane; i < n_entries; i += DCSIM_LANES) {
+    const uint32_t p = first + i, slot = p & (DCSIM_LIST_WINDOW - 1u);
+    if (p < count) {
+#if !defined(DCSIM_HOST_EMU)
+      if (__isShared(c.blk)) {
+        __pipeline_memcpy_async(LW_T(c) + slot, c.P->ml_t + off + p, 8);
+        __pipeline_memcpy_async(LW_AUX(c) + slot, c.P->ml_aux + off + p, 8);
+        __pipeline_memcpy_async(LW_META(c) + slot, c.P->ml_meta + off + p, 4);
+        continue;
+      }
+#endif
+      LW_T(c)[slot] = c.P->ml_t[off + p]; LW_AUX(c)[slot] = c.P->ml_aux[off + p]; LW_META(c)[slot] = c.P->ml_meta[off + p];
+    } else {
+      LW_T(c)[slot] = DCSIM_INF; LW_AUX(c)[slot] = 0.0; LW_META(c)[slot] = 0u;
+    }
   }
-  c.lw_base = base;
+#if !defined(DCSIM_HOST_EMU)
+  __pipeline_commit();
+#endif
+}
+/* Whole lane group: every refill issued so far has landed and is visible to all lanes. */
+DCSIM_DEV void dcsim_list_wait() {
+#if !defined(DCSIM_HOST_EMU)
+  __pipeline_wait_prior(0);
+#endif
   dcsim_warp_sync();
 }
 
@@ -1366,7 +1390,7 @@ DCSIM_DEV void dcsim_handle_xfer(dcsim_ctx_t& c, double size, uint32_t meta) {
  * arrival's into the stream's pending slot.  xfer_done: dcsim_handle_xfer. */
 template <bool CAP>
 DCSIM_DEV void dcsim_handle_list(dcsim_ctx_t& c, uint64_t r) {
-  const uint32_t i = c.cursor - c.lw_base;
+  const uint32_t i = c.cursor & (DCSIM_LIST_WINDOW - 1u);
   if (c.lane == 0) {
     const uint32_t meta = LW_META(c)[i];
     if (meta & ML_XFER) {
@@ -1381,11 +1405,12 @@ DCSIM_DEV void dcsim_handle_list(dcsim_ctx_t& c, uint64_t r) {
     }
   }
   c.cursor += 1u;
-  if (c.cursor - c.lw_base >= DCSIM_LIST_WINDOW && c.cursor < c.H->ml_count) {
-    dcsim_warp_sync(); /* lane 0 is done with the old window */
-    dcsim_list_stage(c, r, c.cursor);
+  if ((c.cursor & (DCSIM_LIST_HALF - 1u)) == 0u) { /* entering the other half: it was refilled half a ring ago */
+    dcsim_list_wait();                              /* (also: lane 0 is done with the half just left) */
+    dcsim_list_fill(c, r, c.cursor + DCSIM_LIST_HALF, DCSIM_LIST_HALF);
+  } else {
+    dcsim_warp_sync();
   }
-  dcsim_warp_sync();
 }
 
 /* SIM:701-927 minus RL/elastic branches (lane 0 part, after the record was read and before it is erased). */
@@ -1743,7 +1768,7 @@ DCSIM_DEV void dcsim_replica_init(dcsim_ctx_t& c, uint64_t r) {
     DCF(c, DF_POWER)[d] = (double)sp.dc[d].total_gpus * (sp.dc[d].power_gating ? sp.dc[d].p_sleep : sp.dc[d].p_idle);
   }
   dcsim_warp_sync();
-  c.seq = 0u; c.now = 0.0; c.last_t = 0.0; c.cursor = 0u; c.lw_base = 0u;
+  c.seq = 0u; c.now = 0.0; c.last_t = 0.0; c.cursor = 0u;
   if (c.lane == 0) {
     const dcsim_arrhdr_t ah = c.P->arr_hdr[r];
     c.H->ml_count = ah.ml_count; c.H->status |= ah.status;
@@ -1755,8 +1780,8 @@ DCSIM_DEV void dcsim_replica_init(dcsim_ctx_t& c, uint64_t r) {
     c.H->initialized = 1u;
   }
   dcsim_warp_sync();
-  if (c.lane == 0) { LW_T(c)[DCSIM_LIST_WINDOW] = DCSIM_INF; LW_META(c)[DCSIM_LIST_WINDOW] = 0u; }
-  dcsim_list_stage(c, r, 0u);
+  dcsim_list_fill(c, r, 0u, DCSIM_LIST_WINDOW);
+  dcsim_list_wait();
 }
 
 /* SIM:469-475: util to end_time, then accrue_energy(end_time) WITHOUT power_fn => models.py:82-91. */
@@ -1823,7 +1848,7 @@ DCSIM_DEV uint32_t dcsim_replica_run(dcsim_ctx_t& c, uint64_t r) {
     if (tracing && c.lane == 0) {
       int kind = KIND_FINISH;
       if (win == CAND_LIST(c)) {
-        const uint32_t m = LW_META(c)[c.cursor - c.lw_base];
+        const uint32_t m = LW_META(c)[c.cursor & (DCSIM_LIST_WINDOW - 1u)];
         kind = (m & ML_XFER) ? KIND_XFER : (int)((m >> 1) & 1u); /* the job type is the stream's low bit */
       } else if (win == CAND_LOG(c)) {
         kind = KIND_LOG;
@@ -1917,18 +1942,18 @@ DCSIM_DEV uint32_t dcsim_replica_step(const dcsim_kparams_t* P, uint64_t r, char
   if (fresh) {
     dcsim_replica_init(c, r);
   } else { /* resume: hot scalars back into registers */
-    c.seq = c.H->seq; c.now = c.H->now; c.cursor = c.H->ml_cursor; c.lw_base = c.H->lw_base;
+    c.seq = c.H->seq; c.now = c.H->now; c.cursor = c.H->ml_cursor;
     c.last_t = DCF(c, DF_LAST_T)[0];
   }
   uint32_t n = 0u;
   if (c.H->done == 0u) n = dcsim_replica_run<CAP, RECG>(c, r);
-  dcsim_warp_sync();
+  dcsim_list_wait(); /* a refill still in flight lands before the block is staged out (the ring is part of it) */
   if (c.lane == 0) {
     c.H->ev_xfer = c.cursor - c.H->ev_arr; /* every consumed list entry is an arrival or an xfer_done */
     c.H->jid = c.H->ev_arr;                /* SIM:539: one jid per arrival */
     c.H->n_events = c.H->ev_arr + c.H->ev_xfer + c.H->ev_fin + c.H->ev_log; /* every processed event is one of these */
     c.H->seq = c.seq; c.H->now = c.now; c.H->last_t = c.H->n_events ? c.now : 0.0;
-    c.H->ml_cursor = c.cursor; c.H->lw_base = c.lw_base;
+    c.H->ml_cursor = c.cursor;
     for (int d = 0; d < P->spec.n_dc; ++d) DCF(c, DF_LAST_T)[d] = c.last_t;
   }
   dcsim_warp_sync();
