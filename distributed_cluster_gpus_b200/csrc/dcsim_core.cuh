@@ -1096,32 +1096,21 @@ DCSIM_DEV int dcsim_argmin_cand(dcsim_ctx_t& c, double* t_out, uint32_t* seq_out
     const uint32_t h = dcsim_hi(t), l = dcsim_lo(t);
     if (i0 == 0 || h < bh || (h == bh && (l < bl || (l == bl && s < bs)))) { bh = h; bl = l; bs = s; bi = i; }
   }
-  dcsim_group_min_tuple(bh, bl, bs, bi);
-  if (bh >= 0x7ff00000u) return -1;
-  *t_out = __hiloint2double((int)bh, (int)bl);
-  *seq_out = bs;
-  return bi;
+  const uint32_t mh = dcsim_warp_min_u32(bh);
+  if (mh >= 0x7ff00000u) return -1;
+  const uint32_t ml = dcsim_warp_min_u32(bh == mh ? bl : 0xffffffffu);
+  const bool m = (bh == mh) && (bl == ml);
+  const uint32_t ms = dcsim_warp_min_u32(m ? bs : 0xffffffffu);
+  const uint32_t votes = dcsim_warp_ballot(m && bs == ms);
+  *t_out = __hiloint2double((int)mh, (int)ml);
+  *seq_out = ms;
+  return (int)dcsim_bcast_u32((uint32_t)bi, dcsim_ffs(votes) - 1);
 #else
   CAND_T(c)[CAND_LIST(c)] = LW_T(c)[li];
   CAND_SEQ(c)[CAND_LIST(c)] = *dcsim_list_seq_slot(c, lm);
   return dcsim_argmin_ts(CAND_T(c), CAND_SEQ(c), CAND_N, c.lane, t_out, seq_out);
 #endif
 }
-
-#if !defined(DCSIM_HOST_EMU) && DCSIM_LANES < 32
-/* Lane group: lexicographic minimum of per-lane (hi, lo, seq, index) tuples, to every lane — one butterfly over whole
- * tuples (a lane group pays a member-mask check per collective sequence, so one fat exchange beats three reductions and a
- * ballot, and the dependent chain is log2(lanes) shuffle steps). */
-DCSIM_DEV void dcsim_group_min_tuple(uint32_t& bh, uint32_t& bl, uint32_t& bs, int& bi) {
-  const unsigned gm = DCSIM_GROUP_MASK;
-#pragma unroll
-  for (int o = DCSIM_LANES / 2; o > 0; o >>= 1) {
-    const uint32_t oh = __shfl_xor_sync(gm, bh, o), ol = __shfl_xor_sync(gm, bl, o), os = __shfl_xor_sync(gm, bs, o);
-    const int oi = (int)__shfl_xor_sync(gm, (uint32_t)bi, o);
-    if (oh < bh || (oh == bh && (ol < bl || (ol == bl && os < bs)))) { bh = oh; bl = ol; bs = os; bi = oi; }
-  }
-}
-#endif
 
 /* SIM:160-163: an event later than end_time + 1e-9 (or at +inf) is never scheduled and takes no seq. */
 DCSIM_DEV bool dcsim_schedulable(const dcsim_ctx_t& c, double t) { return !(t == DCSIM_INF) && !(t > c.P->end_eps); }
@@ -1548,14 +1537,10 @@ DCSIM_DEV void dcsim_handle_finish(dcsim_ctx_t& c, uint64_t r, int d) {
     }
   }
   /* earliest remaining finish of DC d, in (t, seq) order */
+  const uint32_t mh = dcsim_warp_min_u32(bh);
   int win = -1;
   double wt = DCSIM_INF;
   uint32_t ws = 0xffffffffu;
-#if !defined(DCSIM_HOST_EMU) && DCSIM_LANES < 32
-  dcsim_group_min_tuple(bh, bl, bs, bi);
-  if (bh < 0x7ff00000u) { win = bi; ws = bs; wt = dcsim_hilo_f64(bh, bl); }
-#else
-  const uint32_t mh = dcsim_warp_min_u32(bh);
   if (mh < 0x7ff00000u) {
     const uint32_t ml = dcsim_warp_min_u32(bh == mh ? bl : 0xffffffffu);
     const bool m = (bh == mh) && (bl == ml);
@@ -1564,7 +1549,6 @@ DCSIM_DEV void dcsim_handle_finish(dcsim_ctx_t& c, uint64_t r, int d) {
     win = (int)dcsim_bcast_u32((uint32_t)bi, dcsim_ffs(votes) - 1);
     wt = dcsim_hilo_f64(mh, ml);
   }
-#endif
   if (c.lane == 0) {
     CAND_T(c)[CAND_DC0 + d] = wt; CAND_SEQ(c)[CAND_DC0 + d] = ws; DCI(c, DI_FMIN_SLOT)[d] = win;
     DCI(c, DI_NRUN)[d] = n1;
