@@ -730,6 +730,17 @@ DCSIM_DEV double dcsim_t_size_raw(dcsim_trng_t<MT>& g, uint32_t* ring, int strid
   return z;
 }
 
+/* x % y as above when a guess of the quotient is at hand (finish_time % log_interval with the number of log ticks so
+ * far: exact whenever the clock is between the q-th and the (q+1)-th multiple of y, which is where it is unless a tick
+ * instant has drifted by an ulp).  With the right q the remainder x - q*y is exact in one fma (it is representable: it
+ * is what fmod returns); a wrong q puts the true value outside [0, y), and no rounding can move it back inside, so
+ * "the result lies in [0, y)" certifies both q and the result.  Otherwise: the division. */
+DCSIM_DEV double dcsim_mod_pos_hint(double x, double y, uint32_t q_guess) {
+  const double r = fma(-(double)q_guess, y, x);
+  if (r >= 0.0 && r < y) return r;
+  return dcsim_mod_pos(x, y);
+}
+
 /* arrivals.py:7-8 / 10-11 from the stored deviate. */
 DCSIM_DEV double dcsim_size_from_raw(const dcsim_spec_t& sp, double raw, int jt) {
   if (jt == DCSIM_JT_INFERENCE) return sp.pareto_xm / pow(raw, sp.pareto_inv_alpha);
@@ -1424,7 +1435,7 @@ DCSIM_DEV void dcsim_finish_account(dcsim_ctx_t& c, uint64_t r, int d, int slot)
   int32_t* busy = DCI(c, DI_BUSY) + d;
   *busy = *busy - g > 0 ? *busy - g : 0; /* SIM:707 */
   const double now = c.now;
-  DCF(c, DF_ACC_UNIT)[d] += dcsim_at<double>(c.rec, L.rn_tpt)[i] * dcsim_mod_pos(now, sp.log_interval); /* SIM:711 */
+  DCF(c, DF_ACC_UNIT)[d] += dcsim_at<double>(c.rec, L.rn_tpt)[i] * dcsim_mod_pos_hint(now, sp.log_interval, H->ev_log); /* SIM:711 */
   const double lat = now - dcsim_at<double>(c.rec, L.rn_start)[i]; /* SIM:820 */
   H->lat_sum += lat;
   if (jt == DCSIM_JT_INFERENCE) { H->lat_sum_inf += lat; H->n_fin_inf++; } else { H->lat_sum_trn += lat; H->n_fin_trn++; }
@@ -1489,14 +1500,6 @@ DCSIM_DEV void dcsim_handle_finish(dcsim_ctx_t& c, uint64_t r, int d) {
   const int k = DCI(c, DI_FMIN_SLOT)[d];
   dcsim_qent_t pre; pre.size = 0.0; pre.jid = 0u; pre.ing = 0u;
   int pre_jt = -1;
-  if (c.lane == 0) {
-    c.H->ev_fin++;
-    if (DCSIM_PREFETCH_DEQ) { /* the dequeue loop below will want this entry: have the load in flight meanwhile */
-      pre_jt = dcsim_dequeue_pick(c, d);
-      if (pre_jt >= 0) pre = dcsim_queue_base(c, d, pre_jt)[DCI(c, pre_jt ? DI_QH_TRN : DI_QH_INF)[d]];
-    }
-    dcsim_finish_account(c, r, d, k); /* reads record k; writes no record */
-  }
   double* rt = dcsim_at<double>(c.rec, L.rn_t) + off; double* rp = dcsim_at<double>(c.rec, L.rn_pw) + off;
   double* rv = dcsim_at<double>(c.rec, L.rn_tpt) + off; double* ra = dcsim_at<double>(c.rec, L.rn_start) + off;
   uint32_t* rq = dcsim_at<uint32_t>(c.rec, L.rn_seq) + off; uint32_t* rm = dcsim_at<uint32_t>(c.rec, L.rn_meta) + off;
@@ -1505,20 +1508,32 @@ DCSIM_DEV void dcsim_handle_finish(dcsim_ctx_t& c, uint64_t r, int d) {
   uint32_t bh = 0x7ff00000u, bl = 0u, bs = 0xffffffffu;
   int bi = -1;
   double psum = 0.0;
-  dcsim_warp_sync(); /* lane 0's reads of record k are done before anybody overwrites slot k */
-  for (int base = 0; base < n1; base += DCSIM_LANES) {
+  bool accounted = false;
+  for (int base = 0; base < n1 || !accounted; base += DCSIM_LANES) {
     const int j = base + c.lane;
     const bool act = j < n1, moved = act && j >= k;
     const int src = moved ? j + 1 : j;
     double a_t = DCSIM_INF, a_pw = 0.0, a_tpt = 0.0, a_start = 0.0, a_size = 0.0, a_f = 0.0, a_done = 0.0, a_upd = 0.0;
     uint32_t a_seq = 0xffffffffu, a_meta = 0u, a_jid = 0u;
-    if (act) { a_t = rt[src]; a_seq = rq[src]; }
-    if (act) a_pw = rp[src];
+    if (act) { a_t = rt[src]; a_seq = rq[src]; a_pw = rp[src]; }
     if (moved) {
       a_tpt = rv[src]; a_start = ra[src]; a_meta = rm[src];
       if (full) { a_size = dcsim_at<double>(c.rec, L.rn_size)[off + src]; a_f = dcsim_at<double>(c.rec, L.rn_f)[off + src];
                   a_jid = dcsim_at<uint32_t>(c.rec, L.rn_jid)[off + src]; }
       if constexpr (CAP) { a_done = dcsim_at<double>(c.rec, L.rn_done)[off + src]; a_upd = dcsim_at<double>(c.rec, L.rn_upd)[off + src]; }
+    }
+    if (!accounted) {
+      /* lane 0 books the finished job (record k) while the loads above are still in flight: when the records live in
+         HBM/L2 the two round trips overlap instead of following each other */
+      if (c.lane == 0) {
+        c.H->ev_fin++;
+        if (DCSIM_PREFETCH_DEQ) { /* the dequeue loop below will want this entry: have the load in flight meanwhile */
+          pre_jt = dcsim_dequeue_pick(c, d);
+          if (pre_jt >= 0) pre = dcsim_queue_base(c, d, pre_jt)[DCI(c, pre_jt ? DI_QH_TRN : DI_QH_INF)[d]];
+        }
+        dcsim_finish_account(c, r, d, k); /* reads record k; writes no record */
+      }
+      accounted = true;
     }
     {
       const int cnt = n1 - base < DCSIM_LANES ? n1 - base : DCSIM_LANES;
@@ -1528,7 +1543,7 @@ DCSIM_DEV void dcsim_handle_finish(dcsim_ctx_t& c, uint64_t r, int d) {
       const uint32_t h = dcsim_hi(a_t), l = dcsim_lo(a_t);
       if (act && (h < bh || (h == bh && (l < bl || (l == bl && a_seq < bs))))) { bh = h; bl = l; bs = a_seq; bi = j; }
     }
-    dcsim_warp_sync(); /* every lane holds its record before the slot it came from is overwritten */
+    dcsim_warp_sync(); /* every lane holds its record — and lane 0 is done with record k — before slots are overwritten */
     if (moved) {
       rt[j] = a_t; rq[j] = a_seq; rp[j] = a_pw; rv[j] = a_tpt; ra[j] = a_start; rm[j] = a_meta;
       if (full) { dcsim_at<double>(c.rec, L.rn_size)[off + j] = a_size; dcsim_at<double>(c.rec, L.rn_f)[off + j] = a_f;
