@@ -1500,6 +1500,14 @@ DCSIM_DEV void dcsim_handle_finish(dcsim_ctx_t& c, uint64_t r, int d) {
   const int k = DCI(c, DI_FMIN_SLOT)[d];
   dcsim_qent_t pre; pre.size = 0.0; pre.jid = 0u; pre.ing = 0u;
   int pre_jt = -1;
+  if (c.lane == 0) {
+    c.H->ev_fin++;
+    if (DCSIM_PREFETCH_DEQ) { /* the dequeue loop below will want this entry: have the load in flight meanwhile */
+      pre_jt = dcsim_dequeue_pick(c, d);
+      if (pre_jt >= 0) pre = dcsim_queue_base(c, d, pre_jt)[DCI(c, pre_jt ? DI_QH_TRN : DI_QH_INF)[d]];
+    }
+    dcsim_finish_account(c, r, d, k); /* reads record k; writes no record */
+  }
   double* rt = dcsim_at<double>(c.rec, L.rn_t) + off; double* rp = dcsim_at<double>(c.rec, L.rn_pw) + off;
   double* rv = dcsim_at<double>(c.rec, L.rn_tpt) + off; double* ra = dcsim_at<double>(c.rec, L.rn_start) + off;
   uint32_t* rq = dcsim_at<uint32_t>(c.rec, L.rn_seq) + off; uint32_t* rm = dcsim_at<uint32_t>(c.rec, L.rn_meta) + off;
@@ -1508,8 +1516,10 @@ DCSIM_DEV void dcsim_handle_finish(dcsim_ctx_t& c, uint64_t r, int d) {
   uint32_t bh = 0x7ff00000u, bl = 0u, bs = 0xffffffffu;
   int bi = -1;
   double psum = 0.0;
-  bool accounted = false;
-  for (int base = 0; base < n1 || !accounted; base += DCSIM_LANES) {
+  dcsim_warp_sync(); /* lane 0's reads of record k are done before anybody overwrites slot k */
+  /* (issuing the pass's loads BEFORE lane 0's accounting, so that the two L2 round trips overlap, measured slower:
+     the loop then carries lane 0's code with every record field live — profiles/r02_variants_ab.md) */
+  for (int base = 0; base < n1; base += DCSIM_LANES) {
     const int j = base + c.lane;
     const bool act = j < n1, moved = act && j >= k;
     const int src = moved ? j + 1 : j;
@@ -1522,19 +1532,6 @@ DCSIM_DEV void dcsim_handle_finish(dcsim_ctx_t& c, uint64_t r, int d) {
                   a_jid = dcsim_at<uint32_t>(c.rec, L.rn_jid)[off + src]; }
       if constexpr (CAP) { a_done = dcsim_at<double>(c.rec, L.rn_done)[off + src]; a_upd = dcsim_at<double>(c.rec, L.rn_upd)[off + src]; }
     }
-    if (!accounted) {
-      /* lane 0 books the finished job (record k) while the loads above are still in flight: when the records live in
-         HBM/L2 the two round trips overlap instead of following each other */
-      if (c.lane == 0) {
-        c.H->ev_fin++;
-        if (DCSIM_PREFETCH_DEQ) { /* the dequeue loop below will want this entry: have the load in flight meanwhile */
-          pre_jt = dcsim_dequeue_pick(c, d);
-          if (pre_jt >= 0) pre = dcsim_queue_base(c, d, pre_jt)[DCI(c, pre_jt ? DI_QH_TRN : DI_QH_INF)[d]];
-        }
-        dcsim_finish_account(c, r, d, k); /* reads record k; writes no record */
-      }
-      accounted = true;
-    }
     {
       const int cnt = n1 - base < DCSIM_LANES ? n1 - base : DCSIM_LANES;
       for (int i = 0; i < cnt; ++i) psum += dcsim_bcast_f64(a_pw, i); /* SIM:168-179: dict order, from 0.0 */
@@ -1543,7 +1540,7 @@ DCSIM_DEV void dcsim_handle_finish(dcsim_ctx_t& c, uint64_t r, int d) {
       const uint32_t h = dcsim_hi(a_t), l = dcsim_lo(a_t);
       if (act && (h < bh || (h == bh && (l < bl || (l == bl && a_seq < bs))))) { bh = h; bl = l; bs = a_seq; bi = j; }
     }
-    dcsim_warp_sync(); /* every lane holds its record — and lane 0 is done with record k — before slots are overwritten */
+    dcsim_warp_sync(); /* every lane holds its record before the slot it came from is overwritten */
     if (moved) {
       rt[j] = a_t; rq[j] = a_seq; rp[j] = a_pw; rv[j] = a_tpt; ra[j] = a_start; rm[j] = a_meta;
       if (full) { dcsim_at<double>(c.rec, L.rn_size)[off + j] = a_size; dcsim_at<double>(c.rec, L.rn_f)[off + j] = a_f;
