@@ -286,6 +286,8 @@ int dcsim_create(const void* spec_blob, size_t spec_bytes, uint64_t n_replicas, 
   if (!spec_blob || spec_bytes != sizeof(dcsim_spec_t))
     return set_err(NULL, DCSIM_E_INVALID, "create: spec blob must be %s%lld bytes", "", (long long)sizeof(dcsim_spec_t));
   if (n_replicas == 0) return set_err(NULL, DCSIM_E_INVALID, "create: n_replicas must be > 0%s%lld");
+  if (n_replicas > 0xffffffffull) /* the event loop keeps the local replica index in 32 bits */
+    return set_err(NULL, DCSIM_E_INVALID, "create: n_replicas must be below 2^32 per handle%s%lld");
   dcsim_spec_t sp;
   memcpy(&sp, spec_blob, sizeof(sp));
   int rc = validate_spec(&sp);

@@ -205,7 +205,7 @@ enum : uint32_t {
 
 enum { /* per-DC f64 arrays inside the state block, each DCSIM_MAX_DC long */
   DF_ENERGY = 0,
-  DF_LAST_T,     /* (kept in a register during a launch: dcsim_ctx_t::last_t; this slot holds it between launches)
+  DF_LAST_T,     /* (kept in a register during a launch: dcsim_ctx_t::now; this slot holds it between launches)
                     util_last_ts (SIM:430-436) AND last_energy_time (models.py:100-106): both are 0.0 until the
                     first event and are set to t on every event, so one slot carries both */
   DF_UTIL_TIME, DF_UTIL_BEGIN, DF_ACC_UNIT, DF_CUR_FREQ, DF_POWER,
@@ -418,7 +418,7 @@ struct dcsim_ctx_t {
   char* blk;             /* this replica's state block (shared memory on the GPU) */
   char* rec;             /* base the running-job record offsets (L.rn_*) apply to: blk when the records are staged with
                             the rest of the block, the block's home in HBM/L2 when only the head is staged */
-  char* q;               /* this replica's FIFOs (HBM) */
+  uint32_t r;            /* local replica index (its FIFOs, list and histogram row are addressed from it on demand) */
   dcsim_hdr_t* H;
   int lane;
   bool is_traced, is_logged;
@@ -426,9 +426,9 @@ struct dcsim_ctx_t {
    * authoritative (only lane 0 runs handlers); the others are warp-uniform. */
   uint32_t seq;          /* successful pushes (SIM:163) */
   uint32_t cursor;       /* next entry of the event list */
-  double now;
-  double last_t;         /* instant of the previous processed event, 0.0 before the first: util_last_ts / last_energy_time
-                            of EVERY data centre (SIM:429-437 touches them all on every event, so they never differ) */
+  double now;            /* instant of the latest processed event, 0.0 before the first.  Until the next event is popped
+                            it is also util_last_ts / last_energy_time of EVERY data centre: SIM:429-437 touches them all
+                            on every event, so they never differ (DF_LAST_T holds it between launches) */
 };
 
 #define DCF(c, which) (dcsim_at<double>((c).blk, DCSIM_OFF_DC_F64 + (which) * DCSIM_MAX_DC * 8))
@@ -1163,7 +1163,7 @@ DCSIM_DEV void dcsim_rescan_dc(dcsim_ctx_t& c, int d) {
 DCSIM_DEV dcsim_qent_t* dcsim_queue_base(const dcsim_ctx_t& c, int d, int jt) {
   const dcsim_layout_t& L = c.P->L;
   const uint64_t per_dc = (uint64_t)L.cap_q[0] + (uint64_t)L.cap_q[1];
-  return reinterpret_cast<dcsim_qent_t*>(c.q) + (uint64_t)d * per_dc + (jt ? (uint64_t)L.cap_q[0] : 0ull);
+  return reinterpret_cast<dcsim_qent_t*>(c.P->queues + (uint64_t)c.r * L.queue_bytes) + (uint64_t)d * per_dc + (jt ? (uint64_t)L.cap_q[0] : 0ull);
 }
 DCSIM_DEV int dcsim_queue_len(dcsim_ctx_t& c, int d, int jt) { return DCI(c, jt ? DI_QN_TRN : DI_QN_INF)[d]; }
 DCSIM_DEV void dcsim_enqueue(dcsim_ctx_t& c, int d, int jt, double size, uint32_t jid, uint32_t ing) {
@@ -1350,8 +1350,8 @@ DCSIM_DEV void dcsim_start_by_rule(dcsim_ctx_t& c, int rule, bool at_xfer, int d
  * warp (all of its lane groups) would otherwise sit out every 16 list events, hides behind the events of the current
  * half; dcsim_list_wait() is called before the first entry of a freshly filled half is looked at.  Slots of list
  * positions at or past the end of the list get (+inf, 0): "no event". */
-DCSIM_DEV void dcsim_list_fill(dcsim_ctx_t& c, uint64_t r, uint32_t first, uint32_t n_entries) {
-  const uint64_t off = r * 2ull * (uint64_t)c.P->cap_arr;
+DCSIM_DEV void dcsim_list_fill(dcsim_ctx_t& c, uint32_t first, uint32_t n_entries) {
+  const uint64_t off = (uint64_t)c.r * 2ull * (uint64_t)c.P->cap_arr;
   const uint32_t count = c.H->ml_count;
   for (uint32_t i = (uint32_t)c.lane; i < n_entries; i += DCSIM_LANES) {
     const uint32_t p = first + i, slot = p & (DCSIM_LIST_WINDOW - 1u);
@@ -1400,7 +1400,7 @@ DCSIM_DEV void dcsim_handle_xfer(dcsim_ctx_t& c, double size, uint32_t meta) {
  * of its two pushes — the xfer_done's goes into the ring slot of that entry's list position, the stream's next
  * arrival's into the stream's pending slot.  xfer_done: dcsim_handle_xfer. */
 template <bool CAP>
-DCSIM_DEV void dcsim_handle_list(dcsim_ctx_t& c, uint64_t r) {
+DCSIM_DEV void dcsim_handle_list(dcsim_ctx_t& c) {
   const uint32_t i = c.cursor & (DCSIM_LIST_WINDOW - 1u);
   if (c.lane == 0) {
     const uint32_t meta = LW_META(c)[i];
@@ -1418,14 +1418,14 @@ DCSIM_DEV void dcsim_handle_list(dcsim_ctx_t& c, uint64_t r) {
   c.cursor += 1u;
   if ((c.cursor & (DCSIM_LIST_HALF - 1u)) == 0u) { /* entering the other half: it was refilled half a ring ago */
     dcsim_list_wait();                              /* (also: lane 0 is done with the half just left) */
-    dcsim_list_fill(c, r, c.cursor + DCSIM_LIST_HALF, DCSIM_LIST_HALF);
+    dcsim_list_fill(c, c.cursor + DCSIM_LIST_HALF, DCSIM_LIST_HALF);
   } else {
     dcsim_warp_sync();
   }
 }
 
 /* SIM:701-927 minus RL/elastic branches (lane 0 part, after the record was read and before it is erased). */
-DCSIM_DEV void dcsim_finish_account(dcsim_ctx_t& c, uint64_t r, int d, int slot) {
+DCSIM_DEV void dcsim_finish_account(dcsim_ctx_t& c, int d, int slot) {
   const dcsim_spec_t& sp = c.P->spec;
   const dcsim_layout_t& L = c.P->L;
   dcsim_hdr_t* H = c.H;
@@ -1439,7 +1439,7 @@ DCSIM_DEV void dcsim_finish_account(dcsim_ctx_t& c, uint64_t r, int d, int slot)
   const double lat = now - dcsim_at<double>(c.rec, L.rn_start)[i]; /* SIM:820 */
   H->lat_sum += lat;
   if (jt == DCSIM_JT_INFERENCE) { H->lat_sum_inf += lat; H->n_fin_inf++; } else { H->lat_sum_trn += lat; H->n_fin_trn++; }
-  if (c.P->lat_hist) dcsim_hist_add(c.P->lat_hist, r, jt, lat);
+  if (c.P->lat_hist) dcsim_hist_add(c.P->lat_hist, (uint64_t)c.r, jt, lat);
   if (L.lean == 0) { /* the readers of a finished job's size / f / jid: job_log.csv and the bandit's reward */
     const double f_used = dcsim_at<double>(c.rec, L.rn_f)[i];
     if (c.is_logged && c.P->rec.jobs)
@@ -1493,7 +1493,7 @@ DCSIM_DEV void dcsim_dequeue_loop(dcsim_ctx_t& c, int d, const dcsim_qent_t& pre
  * The records are touched once per job_finish — one load round trip, stores fire-and-forget — which is what lets them
  * live in HBM/L2 (RECG) when the block is large. */
 template <bool CAP, bool RECG>
-DCSIM_DEV void dcsim_handle_finish(dcsim_ctx_t& c, uint64_t r, int d) {
+DCSIM_DEV void dcsim_handle_finish(dcsim_ctx_t& c, int d) {
   const dcsim_layout_t& L = c.P->L;
   const int off = d * L.cap_run;
   const int n = DCI(c, DI_NRUN)[d];
@@ -1506,7 +1506,7 @@ DCSIM_DEV void dcsim_handle_finish(dcsim_ctx_t& c, uint64_t r, int d) {
       pre_jt = dcsim_dequeue_pick(c, d);
       if (pre_jt >= 0) pre = dcsim_queue_base(c, d, pre_jt)[DCI(c, pre_jt ? DI_QH_TRN : DI_QH_INF)[d]];
     }
-    dcsim_finish_account(c, r, d, k); /* reads record k; writes no record */
+    dcsim_finish_account(c, d, k); /* reads record k; writes no record */
   }
   double* rt = dcsim_at<double>(c.rec, L.rn_t) + off; double* rp = dcsim_at<double>(c.rec, L.rn_pw) + off;
   double* rv = dcsim_at<double>(c.rec, L.rn_tpt) + off; double* ra = dcsim_at<double>(c.rec, L.rn_start) + off;
@@ -1534,7 +1534,15 @@ DCSIM_DEV void dcsim_handle_finish(dcsim_ctx_t& c, uint64_t r, int d) {
     }
     {
       const int cnt = n1 - base < DCSIM_LANES ? n1 - base : DCSIM_LANES;
+#if DCSIM_LANES >= 4
+      /* SIM:168-179: dict order, from 0.0.  Four at a time: lanes at and past cnt hold 0.0, and x + 0.0 == x exactly */
+      for (int i = 0; i < cnt; i += 4) {
+        psum += dcsim_bcast_f64(a_pw, i); psum += dcsim_bcast_f64(a_pw, i + 1);
+        psum += dcsim_bcast_f64(a_pw, i + 2); psum += dcsim_bcast_f64(a_pw, i + 3);
+      }
+#else
       for (int i = 0; i < cnt; ++i) psum += dcsim_bcast_f64(a_pw, i); /* SIM:168-179: dict order, from 0.0 */
+#endif
     }
     {
       const uint32_t h = dcsim_hi(a_t), l = dcsim_lo(a_t);
@@ -1767,7 +1775,7 @@ DCSIM_DEV void dcsim_handle_log(dcsim_ctx_t& c) {
 /* SIM:31-157, the parts that touch simulation state: zeroed DCs at default_freq, one pending arrival per
  * (ingress, job type) in dict order inf-then-trn (drawn by the pre-pass; here they get the constructor's seqs), then
  * the first log tick. */
-DCSIM_DEV void dcsim_replica_init(dcsim_ctx_t& c, uint64_t r) {
+DCSIM_DEV void dcsim_replica_init(dcsim_ctx_t& c) {
   const dcsim_spec_t& sp = c.P->spec;
   const dcsim_layout_t& L = c.P->L;
   /* the head only: with every DI_NRUN at 0 no record is ever read before it was written */
@@ -1780,9 +1788,9 @@ DCSIM_DEV void dcsim_replica_init(dcsim_ctx_t& c, uint64_t r) {
     DCF(c, DF_POWER)[d] = (double)sp.dc[d].total_gpus * (sp.dc[d].power_gating ? sp.dc[d].p_sleep : sp.dc[d].p_idle);
   }
   dcsim_warp_sync();
-  c.seq = 0u; c.now = 0.0; c.last_t = 0.0; c.cursor = 0u;
+  c.seq = 0u; c.now = 0.0; c.cursor = 0u;
   if (c.lane == 0) {
-    const dcsim_arrhdr_t ah = c.P->arr_hdr[r];
+    const dcsim_arrhdr_t ah = c.P->arr_hdr[c.r];
     c.H->ml_count = ah.ml_count; c.H->status |= ah.status;
     c.H->rng_pos = ah.rng_words; /* every draw of the run happened in the pre-pass */
     for (int s = 0; s < 2 * sp.n_ing; ++s) /* SIM:154-156 */
@@ -1792,7 +1800,7 @@ DCSIM_DEV void dcsim_replica_init(dcsim_ctx_t& c, uint64_t r) {
     c.H->initialized = 1u;
   }
   dcsim_warp_sync();
-  dcsim_list_fill(c, r, 0u, DCSIM_LIST_WINDOW);
+  dcsim_list_fill(c, 0u, DCSIM_LIST_WINDOW);
   dcsim_list_wait();
 }
 
@@ -1803,7 +1811,7 @@ DCSIM_DEV void dcsim_replica_tail(dcsim_ctx_t& c) {
   DCSIM_FOR_EACH_DC(d, c, sp.n_dc) {
     const dcsim_dc_t& cfg = sp.dc[d];
     const int busy = DCI(c, DI_BUSY)[d];
-    const double last = c.last_t;
+    const double last = c.now; /* the latest event's instant: every DC's stamp */
     if (0.0 < last && last < end) DCF(c, DF_UTIL_TIME)[d] += (double)busy * (end - last); /* SIM:471-474 */
     if (last != 0.0) { /* models.py:100-106 with power_fn=None */
       double dt = end - last; dt = dt > 0.0 ? dt : 0.0;
@@ -1813,8 +1821,8 @@ DCSIM_DEV void dcsim_replica_tail(dcsim_ctx_t& c) {
       const double p_idle = (double)(cfg.total_gpus - busy) * (cfg.power_gating ? cfg.p_sleep : cfg.p_idle);
       DCF(c, DF_ENERGY)[d] += (p_active + p_idle) * dt;
     }
+    DCF(c, DF_LAST_T)[d] = end;
   }
-  c.last_t = end;
   dcsim_warp_sync();
 }
 
@@ -1824,7 +1832,7 @@ DCSIM_DEV void dcsim_replica_tail(dcsim_ctx_t& c) {
  * writes of the previous event are visible to every lane; inside a branch a sync separates lane 0's handler
  * from the warp-parallel step that reads what it wrote. */
 template <bool CAP, bool RECG>
-DCSIM_DEV uint32_t dcsim_replica_run(dcsim_ctx_t& c, uint64_t r) {
+DCSIM_DEV uint32_t dcsim_replica_run(dcsim_ctx_t& c) {
   const dcsim_spec_t& sp = c.P->spec;
   const uint32_t budget = c.P->budget32; /* per-launch event budget; 0xffffffff = unlimited */
   const bool tracing = c.is_traced && c.P->rec.trace != nullptr;
@@ -1844,16 +1852,15 @@ DCSIM_DEV uint32_t dcsim_replica_run(dcsim_ctx_t& c, uint64_t r) {
 
     /* SIM:429-437 + models.py:100-106, state before the event.  Every DC's "last" stamp is the previous event's instant
      * (one register for all of them); the first event only stamps (0.0 is the reference's "never touched" sentinel). */
-    if (c.last_t == 0.0) {
+    if (c.now == 0.0) {
       DCSIM_FOR_EACH_DC(d, c, sp.n_dc) DCF(c, DF_UTIL_BEGIN)[d] = t;
     } else {
-      double dt = t - c.last_t; dt = dt > 0.0 ? dt : 0.0;
+      double dt = t - c.now; dt = dt > 0.0 ? dt : 0.0;
       DCSIM_FOR_EACH_DC(d, c, sp.n_dc) {
         DCF(c, DF_UTIL_TIME)[d] += (double)DCI(c, DI_BUSY)[d] * dt;
         DCF(c, DF_ENERGY)[d] += DCF(c, DF_POWER)[d] * dt;
       }
     }
-    c.last_t = t;
     dcsim_warp_sync(); /* every lane has read its candidate / busy / power before lane 0's handler rewrites them */
     c.now = t;
     /* dispatch on the winning slot itself; the event kind is only spelled out for the (cold) trace */
@@ -1871,9 +1878,9 @@ DCSIM_DEV uint32_t dcsim_replica_run(dcsim_ctx_t& c, uint64_t r) {
     }
 
     if (win == CAND_LIST(c)) {
-      dcsim_handle_list<CAP>(c, r);
+      dcsim_handle_list<CAP>(c);
     } else if (win < CAND_LIST(c)) {
-      dcsim_handle_finish<CAP, RECG>(c, r, win - CAND_DC0);
+      dcsim_handle_finish<CAP, RECG>(c, win - CAND_DC0);
     } else if (win == CAND_LOG(c)) {
       if (c.lane == 0) c.H->ev_log++;
       dcsim_handle_log<CAP>(c);
@@ -1948,17 +1955,16 @@ template <bool CAP, bool RECG>
 DCSIM_DEV uint32_t dcsim_replica_step(const dcsim_kparams_t* P, uint64_t r, char* blk, char* rec, bool fresh) {
   dcsim_ctx_t c;
   c.P = P; c.blk = blk; c.rec = rec; c.H = reinterpret_cast<dcsim_hdr_t*>(blk); c.lane = dcsim_lane();
-  c.q = P->queues + r * P->L.queue_bytes;
+  c.r = (uint32_t)r; /* n_replicas < 2^32 (checked by dcsim_create) */
   c.is_traced = ((int64_t)r == P->rec.trace_replica);
   c.is_logged = ((int64_t)r == P->rec.log_replica);
   if (fresh) {
-    dcsim_replica_init(c, r);
+    dcsim_replica_init(c);
   } else { /* resume: hot scalars back into registers */
     c.seq = c.H->seq; c.now = c.H->now; c.cursor = c.H->ml_cursor;
-    c.last_t = DCF(c, DF_LAST_T)[0];
   }
   uint32_t n = 0u;
-  if (c.H->done == 0u) n = dcsim_replica_run<CAP, RECG>(c, r);
+  if (c.H->done == 0u) n = dcsim_replica_run<CAP, RECG>(c);
   dcsim_list_wait(); /* a refill still in flight lands before the block is staged out (the ring is part of it) */
   if (c.lane == 0) {
     c.H->ev_xfer = c.cursor - c.H->ev_arr; /* every consumed list entry is an arrival or an xfer_done */
@@ -1966,7 +1972,8 @@ DCSIM_DEV uint32_t dcsim_replica_step(const dcsim_kparams_t* P, uint64_t r, char
     c.H->n_events = c.H->ev_arr + c.H->ev_xfer + c.H->ev_fin + c.H->ev_log; /* every processed event is one of these */
     c.H->seq = c.seq; c.H->now = c.now; c.H->last_t = c.H->n_events ? c.now : 0.0;
     c.H->ml_cursor = c.cursor;
-    for (int d = 0; d < P->spec.n_dc; ++d) DCF(c, DF_LAST_T)[d] = c.last_t;
+    if (c.H->done == 0u) /* (the tail stamped end_time itself) */
+      for (int d = 0; d < P->spec.n_dc; ++d) DCF(c, DF_LAST_T)[d] = c.now;
   }
   dcsim_warp_sync();
   dcsim_write_summary(c, P->summary + r * DCSIM_SUMMARY_K);
