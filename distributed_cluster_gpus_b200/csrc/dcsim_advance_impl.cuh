@@ -43,22 +43,31 @@ __global__ void __launch_bounds__(DCSIM_MAX_WARPS_PER_CTA * 32, DCSIM_MIN_CTAS_P
 DCSIM_ADV(dcsim_advance_kernel)(const __grid_constant__ dcsim_kparams_t P, unsigned long long* __restrict__ events_total) {
   /* one replica per group of DCSIM_LANES lanes: a whole warp, or an aligned quarter / half of one */
   const int grp = (int)(threadIdx.x / DCSIM_LANES), lane = (int)(threadIdx.x & (DCSIM_LANES - 1));
-  const uint64_t r = (uint64_t)blockIdx.x * (uint64_t)(blockDim.x / DCSIM_LANES) + (uint64_t)grp;
-  if (r >= P.n_replicas) return; /* whole groups leave together */
+  const uint64_t r0 = (uint64_t)blockIdx.x * (uint64_t)(blockDim.x / DCSIM_LANES) + (uint64_t)grp;
+#if DCSIM_LANES == 32
+  if (r0 >= P.n_replicas) return;
+  const bool ghost = false;
+#else
+  /* The event loop's collectives span the whole warp (dcsim_event_sync): a warp leaves only as a whole.  In the batch's
+   * last warp a lane group without a replica stays as a GHOST: it runs the loop switched off next to the real ones. */
+  if (r0 - (uint64_t)(grp % DCSIM_REPLICAS_PER_WARP) >= P.n_replicas) return;
+  const bool ghost = r0 >= P.n_replicas;
+#endif
+  const uint64_t r = ghost ? P.n_replicas - 1u : r0; /* (a ghost only ever READS through these pointers) */
   const int bytes = MODE == DCSIM_MODE_HEAD ? P.L.rec_off : P.L.total_bytes; /* what is staged */
   char* home = P.state + r * (uint64_t)P.L.total_bytes;
   char* blk = MODE != DCSIM_MODE_INPLACE ? dcsim_smem + (size_t)grp * (size_t)bytes : home;
   char* rec = MODE == DCSIM_MODE_STAGED ? blk : home;
-  const bool fresh = reinterpret_cast<const dcsim_hdr_t*>(home)->initialized == 0u;
-  if (MODE != DCSIM_MODE_INPLACE && !fresh) { /* resume: coalesced 16-byte loads of the replica's block */
+  const bool fresh = !ghost && reinterpret_cast<const dcsim_hdr_t*>(home)->initialized == 0u;
+  if (MODE != DCSIM_MODE_INPLACE && !fresh && !ghost) { /* resume: coalesced 16-byte loads of the replica's block */
     const uint4* src = reinterpret_cast<const uint4*>(home);
     uint4* dst = reinterpret_cast<uint4*>(blk);
     for (int i = lane; i < bytes / 16; i += DCSIM_LANES) dst[i] = src[i];
   }
   dcsim_warp_sync();
-  const uint32_t n = dcsim_replica_step<CAP, MODE != DCSIM_MODE_STAGED>(&P, r, blk, rec, fresh);
+  const uint32_t n = dcsim_replica_step<CAP, MODE != DCSIM_MODE_STAGED>(&P, r, blk, rec, fresh, ghost);
   dcsim_warp_sync();
-  if (MODE != DCSIM_MODE_INPLACE) {
+  if (MODE != DCSIM_MODE_INPLACE && !ghost) {
     const uint4* src = reinterpret_cast<const uint4*>(blk);
     uint4* dst = reinterpret_cast<uint4*>(home);
     for (int i = lane; i < bytes / 16; i += DCSIM_LANES) dst[i] = src[i];

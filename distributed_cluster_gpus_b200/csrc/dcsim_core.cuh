@@ -67,6 +67,10 @@ static inline uint32_t dcsim_popc(uint32_t x) { return (uint32_t)__builtin_popco
 static inline uint32_t dcsim_lanemask_lt(int) { return 0u; }
 static inline uint32_t dcsim_warp_add_u32(uint32_t x) { return x; }
 static inline uint32_t dcsim_warp_max_u32(uint32_t x) { return x; }
+static inline uint32_t dcsim_pick_u32(bool, uint32_t v) { return v; }
+static inline void dcsim_event_sync() {}
+static inline bool dcsim_event_any(bool p) { return p; }
+static inline uint32_t dcsim_event_min_u32(uint32_t x) { return x; }
 #define DCSIM_INF (__builtin_inf())
 #else
 #define DCSIM_DEV __device__ __forceinline__
@@ -125,6 +129,40 @@ DCSIM_DEV uint32_t dcsim_warp_max_u32(uint32_t x) {
   return x;
 }
 #endif
+/* The value `v` of the ONE lane of the group whose `mine` is set, to every lane of the group.  A ballot with a member
+ * mask that differs between the groups of a warp is executed once per distinct mask (4 serial VOTEs + the bookkeeping
+ * around them: the largest single stall of the 8-lane event loop in the round-2 ncu capture); a min-butterfly is three
+ * converged shuffles. */
+DCSIM_DEV uint32_t dcsim_pick_u32(bool mine, uint32_t v) {
+#if DCSIM_LANES == 32
+  return __shfl_sync(0xffffffffu, v, __ffs((int)__ballot_sync(0xffffffffu, mine)) - 1);
+#else
+  return dcsim_warp_min_u32(mine ? v : 0xffffffffu);
+#endif
+}
+/* EVENT-LEVEL collectives: called at points of the event loop that every lane of the WARP reaches together, whatever
+ * its replica is doing (dcsim_replica_run keeps the loop itself warp-uniform: a replica that is done stays in it,
+ * switched off, until all replicas of the warp are).  The member mask is then the constant full mask even when the
+ * warp carries several replicas — a group-relative mask is a run-time value the hardware cannot know to be uniform,
+ * and every collective under it pays a MATCH.ANY + REDUX.OR + branch to find out.  Shuffles still stay inside the
+ * group: xor distances below DCSIM_LANES never leave an aligned group of DCSIM_LANES lanes. */
+DCSIM_DEV void dcsim_event_sync() { __syncwarp(); }
+DCSIM_DEV bool dcsim_event_any(bool p) {
+#if DCSIM_LANES == 32
+  return p; /* one replica per warp: its own flag */
+#else
+  return __any_sync(0xffffffffu, p) != 0;
+#endif
+}
+DCSIM_DEV uint32_t dcsim_event_min_u32(uint32_t x) {
+#if DCSIM_LANES == 32
+  return __reduce_min_sync(0xffffffffu, x);
+#else
+#pragma unroll
+  for (int o = DCSIM_LANES / 2; o > 0; o >>= 1) { const uint32_t y = __shfl_xor_sync(0xffffffffu, x, o); x = y < x ? y : x; }
+  return x;
+#endif
+}
 #define DCSIM_INF (__longlong_as_double(0x7ff0000000000000LL))
 #endif
 
@@ -1072,10 +1110,10 @@ DCSIM_DEV uint32_t* dcsim_list_seq_slot(dcsim_ctx_t& c, uint32_t m) {
 }
 
 /* Pop-min over the event set itself: one candidate slot per lane (two with 8 lanes per replica), three
- * min-reductions (REDUX.MIN on a whole warp, shuffle butterflies inside a lane group), one ballot.  The lane of slot
- * CAND_LIST(c) takes its candidate straight from the list
- * window (entry c.cursor; the slot behind the window reads +inf), so nothing has to "publish" the next list entry.
- * Returns the winning candidate slot, -1 if all are +inf. */
+ * min-reductions and the pick of the winner (REDUX.MIN + a ballot on a whole warp, shuffle butterflies inside a lane
+ * group).  EVENT-LEVEL: every lane of the warp calls it together (dcsim_event_sync).  The lane of slot CAND_LIST(c)
+ * takes its candidate straight from the list window (entry c.cursor; the slot behind the window reads +inf), so
+ * nothing has to "publish" the next list entry.  Returns the winning candidate slot, -1 if all are +inf. */
 DCSIM_DEV int dcsim_argmin_cand(dcsim_ctx_t& c, double* t_out, uint32_t* seq_out) {
   const uint32_t li = c.cursor & (DCSIM_LIST_WINDOW - 1u); /* entries at and past the end of the list read (+inf, 0) */
   const uint32_t lm = LW_META(c)[li];
@@ -1107,15 +1145,16 @@ DCSIM_DEV int dcsim_argmin_cand(dcsim_ctx_t& c, double* t_out, uint32_t* seq_out
     const uint32_t h = dcsim_hi(t), l = dcsim_lo(t);
     if (i0 == 0 || h < bh || (h == bh && (l < bl || (l == bl && s < bs)))) { bh = h; bl = l; bs = s; bi = i; }
   }
-  const uint32_t mh = dcsim_warp_min_u32(bh);
-  if (mh >= 0x7ff00000u) return -1;
-  const uint32_t ml = dcsim_warp_min_u32(bh == mh ? bl : 0xffffffffu);
+  /* event-level: every lane of the warp is here (no early return before the last collective) */
+  const uint32_t mh = dcsim_event_min_u32(bh);
+  const uint32_t ml = dcsim_event_min_u32(bh == mh ? bl : 0xffffffffu);
   const bool m = (bh == mh) && (bl == ml);
-  const uint32_t ms = dcsim_warp_min_u32(m ? bs : 0xffffffffu);
-  const uint32_t votes = dcsim_warp_ballot(m && bs == ms);
+  const uint32_t ms = dcsim_event_min_u32(m ? bs : 0xffffffffu);
+  const uint32_t win = dcsim_event_min_u32(m && bs == ms ? (uint32_t)bi : 0xffffffffu); /* (t, seq) is unique: one lane */
+  if (mh >= 0x7ff00000u) return -1;
   *t_out = __hiloint2double((int)mh, (int)ml);
   *seq_out = ms;
-  return (int)dcsim_bcast_u32((uint32_t)bi, dcsim_ffs(votes) - 1);
+  return (int)win;
 #else
   CAND_T(c)[CAND_LIST(c)] = LW_T(c)[li];
   CAND_SEQ(c)[CAND_LIST(c)] = *dcsim_list_seq_slot(c, lm);
@@ -1419,10 +1458,8 @@ DCSIM_DEV void dcsim_handle_list(dcsim_ctx_t& c) {
   if ((c.cursor & (DCSIM_LIST_HALF - 1u)) == 0u) { /* entering the other half: it was refilled half a ring ago */
     dcsim_list_wait();                              /* (also: lane 0 is done with the half just left) */
     dcsim_list_fill(c, c.cursor + DCSIM_LIST_HALF, DCSIM_LIST_HALF);
-  } else {
-    dcsim_warp_sync();
   }
-}
+} /* (the event's closing sync follows in dcsim_event_body) */
 
 /* SIM:701-927 minus RL/elastic branches (lane 0 part, after the record was read and before it is erased). */
 DCSIM_DEV void dcsim_finish_account(dcsim_ctx_t& c, int d, int slot) {
@@ -1565,8 +1602,7 @@ DCSIM_DEV void dcsim_handle_finish(dcsim_ctx_t& c, int d) {
     const uint32_t ml = dcsim_warp_min_u32(bh == mh ? bl : 0xffffffffu);
     const bool m = (bh == mh) && (bl == ml);
     ws = dcsim_warp_min_u32(m ? bs : 0xffffffffu);
-    const uint32_t votes = dcsim_warp_ballot(m && bs == ws && bi >= 0);
-    win = (int)dcsim_bcast_u32((uint32_t)bi, dcsim_ffs(votes) - 1);
+    win = (int)dcsim_pick_u32(m && bs == ws && bi >= 0, (uint32_t)bi);
     wt = dcsim_hilo_f64(mh, ml);
   }
   if (c.lane == 0) {
@@ -1576,8 +1612,7 @@ DCSIM_DEV void dcsim_handle_finish(dcsim_ctx_t& c, int d) {
     dcsim_dequeue_loop<CAP>(c, d, pre, pre_jt); /* appends behind the compacted records */
     dcsim_refresh_power(c, d);
   }
-  dcsim_warp_sync();
-}
+} /* (the event's closing sync follows in dcsim_event_body) */
 
 /* Warp.  Earliest superseded job_finish -> candidate slot CAND_STALE(c). */
 DCSIM_DEV void dcsim_rescan_stale(dcsim_ctx_t& c) {
@@ -1766,8 +1801,7 @@ DCSIM_DEV void dcsim_handle_log(dcsim_ctx_t& c) {
     if (dcsim_schedulable(c, t)) { CAND_T(c)[CAND_LOG(c)] = t; CAND_SEQ(c)[CAND_LOG(c)] = c.seq++; }
     else { CAND_T(c)[CAND_LOG(c)] = DCSIM_INF; CAND_SEQ(c)[CAND_LOG(c)] = 0xffffffffu; }
   }
-  dcsim_warp_sync();
-}
+} /* (the event's closing sync follows in dcsim_event_body) */
 
 /* ================================================================================================
  * Replica life cycle
@@ -1826,32 +1860,19 @@ DCSIM_DEV void dcsim_replica_tail(dcsim_ctx_t& c) {
   dcsim_warp_sync();
 }
 
-/* SIM:423-467: the event loop.  Returns the number of events processed by this call.
+/* One popped event (SIM:429-467) of a replica that is `on`: the per-DC accrual with the state before the event, then
+ * the handler of the winning candidate slot.  Called by every lane of the warp (see dcsim_event_sync): a replica that
+ * is switched off passes through the two synchronisation points and touches nothing.
  *
- * Visibility protocol: every branch ends with a warp sync, so at the top of an iteration all shared-memory
- * writes of the previous event are visible to every lane; inside a branch a sync separates lane 0's handler
- * from the warp-parallel step that reads what it wrote. */
+ * Visibility protocol: the second sync ends every event, so at the next pop-min all shared-memory writes of this one
+ * are visible to every lane; inside a handler a (group) sync separates lane 0's part from a lane-parallel step that
+ * reads what it wrote. */
 template <bool CAP, bool RECG>
-DCSIM_DEV uint32_t dcsim_replica_run(dcsim_ctx_t& c) {
+DCSIM_DEV void dcsim_event_body(dcsim_ctx_t& c, bool on, int win, double t, uint32_t seq, bool tracing) {
   const dcsim_spec_t& sp = c.P->spec;
-  const uint32_t budget = c.P->budget32; /* per-launch event budget; 0xffffffff = unlimited */
-  const bool tracing = c.is_traced && c.P->rec.trace != nullptr;
-  uint32_t done_here = 0u;
-  bool finished = false;
-  for (;;) {
-    /* a capacity overflowed (or a sampler ran away): stop and report, never guess.  Polled every 16 events — every
-     * capacity check refuses the write on its own, so a replica that overflowed stays memory-safe until it is seen */
-    if (done_here >= budget || c.H->status != 0u) break;
-    uint32_t chunk = budget - done_here; chunk = chunk < 16u ? chunk : 16u;
-    uint32_t k = 0u;
-    for (; k < chunk; ++k) {
-    double t; uint32_t seq;
-    const int win = dcsim_argmin_cand(c, &t, &seq);
-    if (win < 0) { finished = true; break; }         /* `while self.event_q` */
-    if (t > sp.end_time) { finished = true; break; } /* SIM:427 */
-
-    /* SIM:429-437 + models.py:100-106, state before the event.  Every DC's "last" stamp is the previous event's instant
-     * (one register for all of them); the first event only stamps (0.0 is the reference's "never touched" sentinel). */
+  /* SIM:429-437 + models.py:100-106, state before the event.  Every DC's "last" stamp is the previous event's instant
+   * (one register for all of them); the first event only stamps (0.0 is the reference's "never touched" sentinel). */
+  if (on) {
     if (c.now == 0.0) {
       DCSIM_FOR_EACH_DC(d, c, sp.n_dc) DCF(c, DF_UTIL_BEGIN)[d] = t;
     } else {
@@ -1861,7 +1882,9 @@ DCSIM_DEV uint32_t dcsim_replica_run(dcsim_ctx_t& c) {
         DCF(c, DF_ENERGY)[d] += DCF(c, DF_POWER)[d] * dt;
       }
     }
-    dcsim_warp_sync(); /* every lane has read its candidate / busy / power before lane 0's handler rewrites them */
+  }
+  dcsim_event_sync(); /* every lane has read its candidate / busy / power before lane 0's handler rewrites them */
+  if (on) {
     c.now = t;
     /* dispatch on the winning slot itself; the event kind is only spelled out for the (cold) trace */
     if (tracing && c.lane == 0) {
@@ -1895,10 +1918,59 @@ DCSIM_DEV uint32_t dcsim_replica_run(dcsim_ctx_t& c) {
       dcsim_warp_sync();
       dcsim_rescan_stale(c);
     }
+  }
+  dcsim_event_sync(); /* the handler's writes (lane 0's mostly) are visible to every lane's next pop-min */
+}
+
+/* SIM:423-467: the event loop.  Returns the number of events processed by this call.  `live`: this lane group holds a
+ * replica that has not reached end_time yet (false: it only keeps the warp's other replicas company, see below). */
+template <bool CAP, bool RECG>
+DCSIM_DEV uint32_t dcsim_replica_run(dcsim_ctx_t& c, bool live) {
+  const dcsim_spec_t& sp = c.P->spec;
+  const uint32_t budget = c.P->budget32; /* per-launch event budget; 0xffffffff = unlimited */
+  const bool tracing = c.is_traced && c.P->rec.trace != nullptr;
+  uint32_t done_here = 0u;
+  bool finished = false;
+#if !defined(DCSIM_HOST_EMU) && DCSIM_LANES < 32
+  /* Several replicas per warp: the loop is WARP-uniform.  A replica that ends (end_time, event budget, a status bit)
+   * is switched off and rides along — through at most the rest of a 16-event chunk of no-ops, then idle as its lanes
+   * would be anyway — until every replica of the warp has ended.  That is what lets the pop-min and the two
+   * synchronisation points of an event use the constant full member mask (dcsim_event_sync). */
+  bool on = live;
+  for (;;) {
+    /* a capacity overflowed (or a sampler ran away): stop and report, never guess.  Polled every 16 events — every
+     * capacity check refuses the write on its own, so a replica that overflowed stays memory-safe until it is seen */
+    if (on && c.H->status != 0u) on = false;
+    if (!dcsim_event_any(on && done_here < budget)) break;
+#pragma unroll 1
+    for (int k = 0; k < 16; ++k) {
+      if (done_here >= budget) on = false;
+      double t = 0.0; uint32_t seq = 0u;
+      const int win = dcsim_argmin_cand(c, &t, &seq);
+      if (on && (win < 0 || t > sp.end_time)) { finished = true; on = false; } /* `while self.event_q` / SIM:427 */
+      dcsim_event_body<CAP, RECG>(c, on, win, t, seq, tracing);
+      if (on) ++done_here;
+    }
+  }
+#else
+  if (!live) return 0u;
+  for (;;) {
+    /* a capacity overflowed (or a sampler ran away): stop and report, never guess.  Polled every 16 events — every
+     * capacity check refuses the write on its own, so a replica that overflowed stays memory-safe until it is seen */
+    if (done_here >= budget || c.H->status != 0u) break;
+    uint32_t chunk = budget - done_here; chunk = chunk < 16u ? chunk : 16u;
+    uint32_t k = 0u;
+    for (; k < chunk; ++k) {
+      double t; uint32_t seq;
+      const int win = dcsim_argmin_cand(c, &t, &seq);
+      if (win < 0) { finished = true; break; }         /* `while self.event_q` */
+      if (t > sp.end_time) { finished = true; break; } /* SIM:427 */
+      dcsim_event_body<CAP, RECG>(c, true, win, t, seq, tracing);
     } /* 16-event chunk */
     done_here += k;
     if (finished) break;
   }
+#endif
   if (finished && c.H->done == 0u) {
     dcsim_replica_tail(c);
     if (c.lane == 0) c.H->done = 1u;
@@ -1952,19 +2024,22 @@ DCSIM_DEV void dcsim_write_summary(dcsim_ctx_t& c, double* out) {
  * block (shared memory on the GPU), already loaded unless `fresh`; `rec` is the base the running-job record offsets
  * apply to (== blk when the records were staged with it, the block's home in HBM when only the head was: RECG). */
 template <bool CAP, bool RECG>
-DCSIM_DEV uint32_t dcsim_replica_step(const dcsim_kparams_t* P, uint64_t r, char* blk, char* rec, bool fresh) {
+DCSIM_DEV uint32_t dcsim_replica_step(const dcsim_kparams_t* P, uint64_t r, char* blk, char* rec, bool fresh, bool ghost = false) {
   dcsim_ctx_t c;
   c.P = P; c.blk = blk; c.rec = rec; c.H = reinterpret_cast<dcsim_hdr_t*>(blk); c.lane = dcsim_lane();
   c.r = (uint32_t)r; /* n_replicas < 2^32 (checked by dcsim_create) */
-  c.is_traced = ((int64_t)r == P->rec.trace_replica);
-  c.is_logged = ((int64_t)r == P->rec.log_replica);
+  c.is_traced = !ghost && ((int64_t)r == P->rec.trace_replica);
+  c.is_logged = !ghost && ((int64_t)r == P->rec.log_replica);
+  if (ghost) { /* a lane group without a replica (the batch's last warp): reads whatever is there, writes nothing */
+    c.seq = 0u; c.now = 0.0; c.cursor = 0u;
+    return dcsim_replica_run<CAP, RECG>(c, false);
+  }
   if (fresh) {
     dcsim_replica_init(c);
   } else { /* resume: hot scalars back into registers */
     c.seq = c.H->seq; c.now = c.H->now; c.cursor = c.H->ml_cursor;
   }
-  uint32_t n = 0u;
-  if (c.H->done == 0u) n = dcsim_replica_run<CAP, RECG>(c);
+  const uint32_t n = dcsim_replica_run<CAP, RECG>(c, c.H->done == 0u);
   dcsim_list_wait(); /* a refill still in flight lands before the block is staged out (the ring is part of it) */
   if (c.lane == 0) {
     c.H->ev_xfer = c.cursor - c.H->ev_arr; /* every consumed list entry is an arrival or an xfer_done */
