@@ -224,6 +224,8 @@ enum {
      n_dc + 2 earliest superseded job_finish (cap_greedy re-scheduling leaves the old event in the heap, SIM:330-338) */
   CAND_N = 16        /* slots allocated (DCSIM_MAX_DC + 3 used at most); unused ones stay +inf */
 };
+#define DCSIM_CAND_N 16 /* == CAND_N, for the preprocessor (an enumerator reads as 0 in #if) */
+static_assert(DCSIM_CAND_N == CAND_N, "DCSIM_CAND_N");
 #define CAND_LIST(c) ((c).P->spec.n_dc)
 #define CAND_LOG(c) ((c).P->spec.n_dc + 1)
 #define CAND_STALE(c) ((c).P->spec.n_dc + 2)
@@ -1117,44 +1119,45 @@ DCSIM_DEV uint32_t* dcsim_list_seq_slot(dcsim_ctx_t& c, uint32_t m) {
 DCSIM_DEV int dcsim_argmin_cand(dcsim_ctx_t& c, double* t_out, uint32_t* seq_out) {
   const uint32_t li = c.cursor & (DCSIM_LIST_WINDOW - 1u); /* entries at and past the end of the list read (+inf, 0) */
   const uint32_t lm = LW_META(c)[li];
-#if !defined(DCSIM_HOST_EMU) && DCSIM_LANES >= CAND_N
-  /* one slot per lane, no loop; the surplus lanes all look at the last slot, which is never used (+inf) */
-  const int i = c.lane < CAND_N ? c.lane : CAND_N - 1;
+#if !defined(DCSIM_HOST_EMU)
+  /* slot == lane, no loop; surplus lanes all look at the last slot, which is never used (+inf) */
+  const int i = c.lane < DCSIM_CAND_N ? c.lane : DCSIM_CAND_N - 1;
   const bool list = i == c.P->spec.n_dc;
-  const double t = *(list ? LW_T(c) + li : CAND_T(c) + i);
-  const uint32_t s = *(list ? dcsim_list_seq_slot(c, lm) : CAND_SEQ(c) + i);
-  const uint32_t h = dcsim_hi(t), l = dcsim_lo(t);
-  const uint32_t mh = dcsim_warp_min_u32(h);
-  if (mh >= 0x7ff00000u) return -1;
-  const uint32_t ml = dcsim_warp_min_u32(h == mh ? l : 0xffffffffu);
-  const bool m = (h == mh) && (l == ml);
-  const uint32_t ms = dcsim_warp_min_u32(m ? s : 0xffffffffu);
-  const uint32_t votes = dcsim_warp_ballot(m && s == ms);
-  *t_out = __hiloint2double((int)mh, (int)ml);
-  *seq_out = ms;
-  return dcsim_ffs(votes) - 1; /* slot == lane */
-#elif !defined(DCSIM_HOST_EMU)
-  uint32_t bh = 0x7ff00000u, bl = 0u, bs = 0xffffffffu;
-  int bi = -1;
-  const int n_slots = c.P->spec.n_dc + 3, slot_list = c.P->spec.n_dc;
-  for (int i0 = 0; i0 < n_slots; i0 += DCSIM_LANES) { /* with 8 lanes: one round up to 5 DCs, else two */
-    const int i = i0 + c.lane; /* < CAND_N: unused slots read +inf */
-    const bool list = i == slot_list;
-    const double t = *(list ? LW_T(c) + li : CAND_T(c) + i);
-    const uint32_t s = *(list ? dcsim_list_seq_slot(c, lm) : CAND_SEQ(c) + i);
-    const uint32_t h = dcsim_hi(t), l = dcsim_lo(t);
-    if (i0 == 0 || h < bh || (h == bh && (l < bl || (l == bl && s < bs)))) { bh = h; bl = l; bs = s; bi = i; }
+  double t = *(list ? LW_T(c) + li : CAND_T(c) + i);
+  uint32_t s = *(list ? dcsim_list_seq_slot(c, lm) : CAND_SEQ(c) + i);
+  uint32_t h = dcsim_hi(t), l = dcsim_lo(t);
+#if DCSIM_LANES < DCSIM_CAND_N
+  /* fewer lanes than slots (8 lanes): the event set of up to 5 DCs (n_dc + 3 slots) still fits one round; beyond, each
+   * lane also looks at slot lane + DCSIM_LANES and keeps the earlier of its two (a scenario constant: no divergence) */
+  int slot = i;
+  if (c.P->spec.n_dc + 3 > DCSIM_LANES) {
+    const int i2 = c.lane + DCSIM_LANES;
+    const bool list2 = i2 == c.P->spec.n_dc;
+    const double t2 = *(list2 ? LW_T(c) + li : CAND_T(c) + i2);
+    const uint32_t s2 = *(list2 ? dcsim_list_seq_slot(c, lm) : CAND_SEQ(c) + i2);
+    const uint32_t h2 = dcsim_hi(t2), l2 = dcsim_lo(t2);
+    if (h2 < h || (h2 == h && (l2 < l || (l2 == l && s2 < s)))) { h = h2; l = l2; s = s2; slot = i2; }
   }
-  /* event-level: every lane of the warp is here (no early return before the last collective) */
-  const uint32_t mh = dcsim_event_min_u32(bh);
-  const uint32_t ml = dcsim_event_min_u32(bh == mh ? bl : 0xffffffffu);
-  const bool m = (bh == mh) && (bl == ml);
-  const uint32_t ms = dcsim_event_min_u32(m ? bs : 0xffffffffu);
-  const uint32_t win = dcsim_event_min_u32(m && bs == ms ? (uint32_t)bi : 0xffffffffu); /* (t, seq) is unique: one lane */
+#endif
+  /* event-level collectives: every lane of the warp is here, so a lane group never returns before the last one */
+  const uint32_t mh = dcsim_event_min_u32(h);
+#if DCSIM_LANES == 32
+  if (mh >= 0x7ff00000u) return -1; /* (one replica per warp: the whole warp returns) */
+#endif
+  const uint32_t ml = dcsim_event_min_u32(h == mh ? l : 0xffffffffu);
+  const bool m = (h == mh) && (l == ml);
+  const uint32_t ms = dcsim_event_min_u32(m ? s : 0xffffffffu);
+#if DCSIM_LANES == 32
+  const int win = dcsim_ffs(__ballot_sync(0xffffffffu, m && s == ms)) - 1; /* slot == lane */
+#elif DCSIM_LANES >= DCSIM_CAND_N
+  const int win = (int)dcsim_event_min_u32(m && s == ms ? (uint32_t)i : 0xffffffffu); /* (t, seq) is unique: one lane */
+#else
+  const int win = (int)dcsim_event_min_u32(m && s == ms ? (uint32_t)slot : 0xffffffffu);
+#endif
   if (mh >= 0x7ff00000u) return -1;
   *t_out = __hiloint2double((int)mh, (int)ml);
   *seq_out = ms;
-  return (int)win;
+  return win;
 #else
   CAND_T(c)[CAND_LIST(c)] = LW_T(c)[li];
   CAND_SEQ(c)[CAND_LIST(c)] = *dcsim_list_seq_slot(c, lm);
