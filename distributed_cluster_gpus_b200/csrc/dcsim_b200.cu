@@ -232,11 +232,12 @@ static cudaError_t size_launch(dcsim_t* h) {
   int smem_optin = 0, smem_sm = 0;
   if ((e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device)) != cudaSuccess) return e;
   if ((e = cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, h->device)) != cudaSuccess) return e;
-  /* Lanes per replica.  Four replicas per warp pay when an event's warp-wide part (pop-min, DC sweep, lane-0 handler)
-   * dominates: few DCs (their finish slots + list + log fit one round of 8 lanes) and short running sets (a job_finish
-   * walks the DC's records 8 at a time).  Measured (profiles/r02_ab_lane_groups.jsonl): 4 DC x 64 +20 %, 1 DC x 64 +10 %,
-   * but 8 DC x 256 -16 % and joint_nf (up to 64 running jobs per DC) -23 % — those keep the whole warp. */
-  int lanes = (h->spec.n_dc <= 5 && h->L.cap_run <= 16) ? 8 : 32;
+  /* Lanes per replica.  Four replicas per warp share everything warp-wide in an event (pop-min, DC sweep, the lane-0
+   * handler's issue slots) and pay whenever the event set fits one round of 8 lanes: up to 5 DCs (n_dc finish slots +
+   * list + log + stale).  Measured with the event-level pop-min (profiles/r02_ab_s17_*): 4 DC x 64 +35 % over the
+   * 32-lane build, debug n=2 +34 %, joint_nf / carbon_cost (up to 64 running jobs per DC: a job_finish walks them 8
+   * at a time) +2..3 %; 8 DC x 256 (two slots per lane, all 8 lanes in the sweep) -10 %: it keeps the whole warp. */
+  int lanes = h->spec.n_dc <= 5 ? 8 : 32;
   { const char* g = getenv("DCSIM_GROUP"); if (g) { const int v = atoi(g); if (v == 8 || v == 16 || v == 32) lanes = v; } }
   const int rpw = 32 / lanes; /* replicas per warp */
   const int max_warps = min_ctas_for(lanes) * DCSIM_MAX_WARPS_PER_CTA;

@@ -71,6 +71,10 @@ static inline uint32_t dcsim_pick_u32(bool, uint32_t v) { return v; }
 static inline void dcsim_event_sync() {}
 static inline bool dcsim_event_any(bool p) { return p; }
 static inline uint32_t dcsim_event_min_u32(uint32_t x) { return x; }
+static inline bool dcsim_event_any_full(bool p) { return p; }
+static inline void dcsim_sync_full() {}
+static inline uint32_t dcsim_event_bcast_u32(uint32_t x, int) { return x; }
+static inline uint32_t dcsim_event_pick_u32(bool, uint32_t v) { return v; }
 #define DCSIM_INF (__builtin_inf())
 #else
 #define DCSIM_DEV __device__ __forceinline__
@@ -163,6 +167,17 @@ DCSIM_DEV uint32_t dcsim_event_min_u32(uint32_t x) {
   return x;
 #endif
 }
+/* Thread-per-replica kernels (the arrival pre-pass): all 32 lanes of the warp, each with its own replica. */
+DCSIM_DEV bool dcsim_event_any_full(bool p) { return __any_sync(0xffffffffu, p) != 0; }
+DCSIM_DEV void dcsim_sync_full() { __syncwarp(); }
+DCSIM_DEV uint32_t dcsim_event_bcast_u32(uint32_t x, int src) { return __shfl_sync(0xffffffffu, x, src, DCSIM_LANES); }
+DCSIM_DEV uint32_t dcsim_event_pick_u32(bool mine, uint32_t v) { /* dcsim_pick_u32 at an event-level point */
+#if DCSIM_LANES == 32
+  return dcsim_pick_u32(mine, v);
+#else
+  return dcsim_event_min_u32(mine ? v : 0xffffffffu);
+#endif
+}
 #define DCSIM_INF (__longlong_as_double(0x7ff0000000000000LL))
 #endif
 
@@ -179,6 +194,13 @@ DCSIM_DEV double dcsim_bcast_f64(double x, int src) {
   (void)src; return x;
 #else
   return __hiloint2double((int)dcsim_bcast_u32(dcsim_hi(x), src), (int)dcsim_bcast_u32(dcsim_lo(x), src));
+#endif
+}
+DCSIM_DEV double dcsim_event_bcast_f64(double x, int src) {
+#ifdef DCSIM_HOST_EMU
+  (void)src; return x;
+#else
+  return __hiloint2double((int)dcsim_event_bcast_u32(dcsim_hi(x), src), (int)dcsim_event_bcast_u32(dcsim_lo(x), src));
 #endif
 }
 
@@ -636,19 +658,30 @@ DCSIM_DEV void dcsim_trng_topup(dcsim_trng_t<MT>& g, uint32_t* ring, int stride)
      SLOWER — the longer live ranges cost more than the overlap gains (profiles/r02_variants_ab.md) */
   while (g.filled - g.pos <= DCSIM_TRNG_RING - 4u) dcsim_trng_block(g, ring, stride);
 }
-template <bool MT>
+/* A sampler out-ran the ring (a long rejection run): one more block, out of line.  The Philox flavour takes the
+ * generator's fields BY VALUE — handing out &g would pin the whole generator (pos, filled) in local memory for the
+ * entire kernel, a load and a store around every word drawn. */
 #ifndef DCSIM_HOST_EMU
-__device__ __noinline__
+static __device__ __noinline__
 #else
 static
 #endif
-void dcsim_trng_dry(dcsim_trng_t<MT>* g, uint32_t* ring, int stride) { dcsim_trng_block(*g, ring, stride); } /* a sampler out-ran the ring (long rejection run) */
+void dcsim_trng_dry_philox(uint32_t k0, uint32_t k1, uint32_t filled, uint32_t* ring, int stride) {
+  uint32_t w[4];
+  dcsim_philox_block(k0, k1, filled >> 2, w);
+  const uint32_t i = filled & (DCSIM_TRNG_RING - 1u);
+  ring[(i + 0u) * stride] = w[0]; ring[(i + 1u) * stride] = w[1];
+  ring[(i + 2u) * stride] = w[2]; ring[(i + 3u) * stride] = w[3];
+}
 /* The samplers call dcsim_trng_need(n) once where they are about to draw n words (n <= 4: one block refills the ring
  * by that much) and then take the words without a check each.  After the per-arrival top-up the ring holds >= 29 words,
  * so only long rejection runs ever refill here. */
 template <bool MT>
 DCSIM_DEV void dcsim_trng_need(dcsim_trng_t<MT>& g, uint32_t* ring, int stride, uint32_t n) {
-  if (g.filled - g.pos < n) dcsim_trng_dry(&g, ring, stride);
+  if (g.filled - g.pos < n) {
+    if constexpr (MT) dcsim_trng_block(g, ring, stride);
+    else { dcsim_trng_dry_philox(g.k0, g.k1, g.filled, ring, stride); g.filled += 4u; }
+  }
 }
 template <bool MT>
 DCSIM_DEV uint32_t dcsim_trng_word(dcsim_trng_t<MT>& g, uint32_t* ring, int stride) { /* after dcsim_trng_need */
@@ -703,43 +736,50 @@ DCSIM_DEV double dcsim_sin_phase_approx(double t, double inv_period, double two_
  * accepts and U2 > p0 + eps rejects exactly as the full formula would; only candidates inside the +-eps band (or with
  * a very long gap) evaluate the reference's expression.  Same words consumed, same decisions, same w — but a thread
  * spends ~20 instructions instead of ~500 on a rejected candidate, which matters because a warp's lanes all wait
- * for the lane with the longest rejection run.  The accepted candidate's gap -log(1-U1)/max_rate is evaluated AFTER the
- * loop, at the same program point as a Poisson stream's -log(1-U)/rate: one converged log() per arrival and warp. */
+ * for the lane with the longest rejection run.  The accepted candidate's gap -log(1-U1)/max_rate is left to
+ * dcsim_t_gap_finish(), which the arrival loop calls behind a warp-wide reconvergence point: written after the loop
+ * in the same function, the compiler duplicated the log() into every loop exit and the lanes ran it one exit at a
+ * time (ncu: 18 % of the kernel's instructions at a third of the lanes). */
+/* What the draws of one inter-arrival gap leave to be done: gap = is_w ? v : -log(v) / rate. */
+struct dcsim_gap_draw_t { double v, rate; bool is_w; };
 template <bool MT>
-DCSIM_DEV double dcsim_t_gap(dcsim_trng_t<MT>& g, uint32_t* ring, int stride, const dcsim_spec_t& sp, const dcsim_squeeze_t& q, int jt,
-                             double t, uint32_t* status) {
+DCSIM_DEV dcsim_gap_draw_t dcsim_t_gap_draw(dcsim_trng_t<MT>& g, uint32_t* ring, int stride, const dcsim_spec_t& sp, const dcsim_squeeze_t& q,
+                                            int jt, double t, uint32_t* status) {
   const dcsim_arrival_t& a = sp.arr[jt];
-  double x, rate;
+  dcsim_gap_draw_t out;
+  out.v = DCSIM_INF; out.rate = 1.0; out.is_w = true; /* a dead stream */
   if (a.mode == DCSIM_ARR_POISSON) {
-    if (a.rate <= 0.0) return DCSIM_INF;
+    if (a.rate <= 0.0) return out;
     dcsim_trng_need(g, ring, stride, 2u);
-    x = 1.0 - dcsim_trng_random(g, ring, stride);
-    rate = a.rate;
+    out.v = 1.0 - dcsim_trng_random(g, ring, stride); out.rate = a.rate; out.is_w = false;
   } else if (a.mode == DCSIM_ARR_SINUSOID) {
     const double max_rate = q.max_rate;
     double lam0 = a.rate * (1.0 + a.amp * dcsim_sin_phase_approx(t, q.inv_period, sp.two_pi));
     lam0 = lam0 > 0.0 ? lam0 : 0.0;
     const double p0 = lam0 / max_rate, p_lo = p0 - q.eps, p_hi = p0 + q.eps;
     for (int it = 0;; ++it) {
-      if (it >= DCSIM_REJECTION_LIMIT) { *status |= DCSIM_ST_RNG_RUNAWAY; return DCSIM_INF; }
+      if (it >= DCSIM_REJECTION_LIMIT) { *status |= DCSIM_ST_RNG_RUNAWAY; return out; }
       dcsim_trng_need(g, ring, stride, 4u);
       const double x1 = 1.0 - dcsim_trng_random(g, ring, stride);
       const double u2 = dcsim_trng_random(g, ring, stride);
       if (x1 >= q.x1_min) {
-        if (u2 > p_hi) continue;                          /* certainly rejected */
-        if (u2 <= p_lo) { x = x1; break; }                /* certainly accepted */
+        if (u2 > p_hi) continue;                                                        /* certainly rejected */
+        if (u2 <= p_lo) { out.v = x1; out.rate = max_rate; out.is_w = false; break; }   /* certainly accepted */
       }
       const double w = -log(x1) / max_rate;               /* in the band: the reference's expression */
       const double tc = t + w;
       double lam = a.rate * (1.0 + a.amp * sin(sp.two_pi * dcsim_mod_pos(tc, a.period) / a.period));
       lam = lam > 0.0 ? lam : 0.0;
-      if (u2 <= lam / max_rate) return w;
+      if (u2 <= lam / max_rate) { out.v = w; break; }
     }
-    rate = max_rate;
-  } else {
-    return DCSIM_INF;
   }
-  return -log(x) / rate;
+  return out;
+}
+DCSIM_DEV double dcsim_t_gap_finish(const dcsim_gap_draw_t& d) { return d.is_w ? d.v : -log(d.v) / d.rate; }
+template <bool MT>
+DCSIM_DEV double dcsim_t_gap(dcsim_trng_t<MT>& g, uint32_t* ring, int stride, const dcsim_spec_t& sp, const dcsim_squeeze_t& q, int jt,
+                             double t, uint32_t* status) {
+  return dcsim_t_gap_finish(dcsim_t_gap_draw(g, ring, stride, sp, q, jt, t, status));
 }
 
 /* arrivals.py:5-11 with random.py:541-549, 597: draws what the job size is a function of — the clamped uniform of the
@@ -822,7 +862,7 @@ DCSIM_DEV void dcsim_generate_arrivals(const dcsim_kparams_t* P, uint64_t r, dou
   sq[1] = dcsim_squeeze_setup(sp.arr[1], sp.two_pi);
   for (int s = 0; s < n_streams; ++s) { /* SIM:154-156 */
     dcsim_trng_topup(g, ring, stride);
-    const double t = dcsim_test_quantize(0.0 + dcsim_t_gap(g, ring, stride, sp, sq[s & 1], s & 1, 0.0, &status));
+    const double t = dcsim_test_quantize(0.0 + dcsim_t_gap(g, ring, stride, sp, (s & 1) ? sq[1] : sq[0], s & 1, 0.0, &status));
     const bool ok = !(t == DCSIM_INF) && !(t > end_eps);
     next_t[s * stride] = ok ? t : DCSIM_INF;
     last_idx[s * stride] = DCSIM_NO_PRED;
@@ -833,53 +873,74 @@ DCSIM_DEV void dcsim_generate_arrivals(const dcsim_kparams_t* P, uint64_t r, dou
   uint32_t* out_meta = P->arr_meta + r * (uint64_t)P->cap_arr;
   uint32_t* out_pred = P->arr_pred + r * (uint64_t)P->cap_arr;
   const int k_bits = dcsim_bit_length((uint32_t)sp.n_dc);
+  /* The loop is WARP-uniform: a replica that has ended (end_time, an overflow) stays in it, switched off, until the
+   * warp's last one has — so that the lanes can be made to reconverge (a full-mask __syncwarp) between the divergent
+   * part of an arrival (rejection loops of different lengths) and the part all of them share (the log of the gap). */
+  bool alive = true;
   for (;;) {
     int s = -1;
     double t = DCSIM_INF;
     bool tie = false;
-    for (int q = 0; q < n_streams; ++q) {
-      const double tq = next_t[q * stride];
-      if (tq < t) { t = tq; s = q; tie = false; } else if (tq == t) tie = true;
+    if (alive) {
+      for (int q = 0; q < n_streams; ++q) {
+        const double tq = next_t[q * stride];
+        if (tq < t) { t = tq; s = q; tie = false; } else if (tq == t) tie = true;
+      }
+      if (s < 0 || t > sp.end_time) alive = false; /* heap empty / SIM:427 */
+      else if (tie) { /* heap order is (t, seq): pending arrivals at the same instant pop in push order (rare: ~rate * ulp(t)) */
+        for (int q = s + 1; q < n_streams; ++q)
+          if (next_t[q * stride] == t && dcsim_stream_rank(last_idx[q * stride], q) < dcsim_stream_rank(last_idx[s * stride], s)) s = q;
+      }
+      if (status) alive = false;
     }
-    if (s < 0 || t > sp.end_time) break; /* heap empty / SIM:427 */
-    if (tie) { /* heap order is (t, seq): pending arrivals at the same instant pop in push order (rare: ~rate * ulp(t)) */
-      for (int q = s + 1; q < n_streams; ++q)
-        if (next_t[q * stride] == t && dcsim_stream_rank(last_idx[q * stride], q) < dcsim_stream_rank(last_idx[s * stride], s)) s = q;
-    }
-    if (status) break;
-    dcsim_trng_topup(g, ring, stride); /* all lanes refill here, together */
+    if (!dcsim_event_any_full(alive)) break;
     const int jt = s & 1;
-    double raw = dcsim_t_size_raw(g, ring, stride, sp, jt, &status); /* draw order: size -> route -> next gap (SIM:540,576,591) */
+    double raw = 0.0;
     int dc_sel = 0;
     uint32_t raw_is_size = 0u;
-    if (sp.route_rule == DCSIM_ROUTE_ECO) { /* SIM:544-553: routes by E_unit * size, so the size is needed here */
-      const double size = dcsim_size_from_raw(sp, raw, jt);
-      double best = sp.dc[0].eco_e_unit[jt] * size;
-      for (int d = 1; d < sp.n_dc; ++d) {
-        const double score = sp.dc[d].eco_e_unit[jt] * size;
-        if (score < best) { best = score; dc_sel = d; }
-      }
-      raw = size; raw_is_size = 0x100u;
-    } else { /* random.choice: random.py:242-250 */
-      dcsim_trng_need(g, ring, stride, 1u);
-      uint32_t v = dcsim_trng_word(g, ring, stride) >> (32 - k_bits);
-      for (int it = 0; v >= (uint32_t)sp.n_dc; ++it) {
-        if (it >= DCSIM_REJECTION_LIMIT) { status |= DCSIM_ST_RNG_RUNAWAY; v = 0u; break; }
+    dcsim_gap_draw_t gd;
+    gd.v = DCSIM_INF; gd.rate = 1.0; gd.is_w = true;
+    if (alive) {
+      dcsim_trng_topup(g, ring, stride);
+      raw = dcsim_t_size_raw(g, ring, stride, sp, jt, &status); /* draw order: size -> route -> next gap (SIM:540,576,591) */
+      if (sp.route_rule == DCSIM_ROUTE_ECO) { /* SIM:544-553: routes by E_unit * size, so the size is needed here */
+        const double size = dcsim_size_from_raw(sp, raw, jt);
+        double best = sp.dc[0].eco_e_unit[jt] * size;
+        for (int d = 1; d < sp.n_dc; ++d) {
+          const double score = sp.dc[d].eco_e_unit[jt] * size;
+          if (score < best) { best = score; dc_sel = d; }
+        }
+        raw = size; raw_is_size = 0x100u;
+      } else { /* random.choice: random.py:242-250 */
         dcsim_trng_need(g, ring, stride, 1u);
-        v = dcsim_trng_word(g, ring, stride) >> (32 - k_bits);
+        uint32_t v = dcsim_trng_word(g, ring, stride) >> (32 - k_bits);
+        for (int it = 0; v >= (uint32_t)sp.n_dc; ++it) {
+          if (it >= DCSIM_REJECTION_LIMIT) { status |= DCSIM_ST_RNG_RUNAWAY; v = 0u; break; }
+          dcsim_trng_need(g, ring, stride, 1u);
+          v = dcsim_trng_word(g, ring, stride) >> (32 - k_bits);
+        }
+        dc_sel = (int)v;
       }
-      dc_sel = (int)v;
+      dcsim_squeeze_t q; /* selected field by field: indexing sq[] with jt would put the array in local memory */
+      q.max_rate = jt ? sq[1].max_rate : sq[0].max_rate; q.x1_min = jt ? sq[1].x1_min : sq[0].x1_min;
+      q.eps = jt ? sq[1].eps : sq[0].eps; q.inv_period = jt ? sq[1].inv_period : sq[0].inv_period;
+      gd = dcsim_t_gap_draw(g, ring, stride, sp, q, jt, t, &status);
     }
-    const double tn = dcsim_test_quantize(t + dcsim_t_gap(g, ring, stride, sp, jt ? sq[1] : sq[0], jt, t, &status));
-    const bool has_next = !(tn == DCSIM_INF) && !(tn > end_eps);
-    next_t[s * stride] = has_next ? tn : DCSIM_INF;
-    if (count >= P->cap_arr) { status |= DCSIM_ST_ARRIVALS_OVERFLOW; break; }
-    out_t[count] = t;
-    out_raw[count] = raw;
-    out_meta[count] = (uint32_t)s | ((uint32_t)dc_sel << 4) | (has_next ? 0x80u : 0u) | raw_is_size;
-    out_pred[count] = last_idx[s * stride];
-    last_idx[s * stride] = count;
-    ++count;
+    dcsim_sync_full(); /* every lane is back from its rejection loops */
+    if (alive) {
+      const double tn = dcsim_test_quantize(t + dcsim_t_gap_finish(gd));
+      const bool has_next = !(tn == DCSIM_INF) && !(tn > end_eps);
+      next_t[s * stride] = has_next ? tn : DCSIM_INF;
+      if (count >= P->cap_arr) { status |= DCSIM_ST_ARRIVALS_OVERFLOW; alive = false; }
+      else {
+        out_t[count] = t;
+        out_raw[count] = raw;
+        out_meta[count] = (uint32_t)s | ((uint32_t)dc_sel << 4) | (has_next ? 0x80u : 0u) | raw_is_size;
+        out_pred[count] = last_idx[s * stride];
+        last_idx[s * stride] = count;
+        ++count;
+      }
+    }
   }
   dcsim_arrhdr_t h;
   h.count = count; h.first_mask = first_mask; h.rng_words = g.pos; h.status = status;
@@ -1869,7 +1930,13 @@ DCSIM_DEV void dcsim_replica_tail(dcsim_ctx_t& c) {
  *
  * Visibility protocol: the second sync ends every event, so at the next pop-min all shared-memory writes of this one
  * are visible to every lane; inside a handler a (group) sync separates lane 0's part from a lane-parallel step that
- * reads what it wrote. */
+ * reads what it wrote.
+ *
+ * Only the pop-min and these two syncs are event-level.  Making the HANDLERS event-level too (every replica of the
+ * warp walks through job_finish, or through the list ring's refill, as soon as one of them has to — so that their
+ * collectives also get the full mask) measured 10 % SLOWER (profiles/r02_ab_s16_*): handlers of different replicas
+ * are divergent paths of one warp, the scheduler interleaves them, and one replica's L2 round trip hides behind
+ * another's arithmetic; a warp-wide sync inside a handler takes that away. */
 template <bool CAP, bool RECG>
 DCSIM_DEV void dcsim_event_body(dcsim_ctx_t& c, bool on, int win, double t, uint32_t seq, bool tracing) {
   const dcsim_spec_t& sp = c.P->spec;
