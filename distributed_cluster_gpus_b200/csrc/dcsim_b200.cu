@@ -238,7 +238,16 @@ static cudaError_t size_launch(dcsim_t* h) {
    * 32-lane build, debug n=2 +34 %, joint_nf / carbon_cost (up to 64 running jobs per DC: a job_finish walks them 8
    * at a time) +2..3 %; 8 DC x 256 (two slots per lane, all 8 lanes in the sweep) -10 %: it keeps the whole warp. */
   int lanes = h->spec.n_dc <= 5 ? 8 : 32;
-  { const char* g = getenv("DCSIM_GROUP"); if (g) { const int v = atoi(g); if (v == 8 || v == 16 || v == 32) lanes = v; } }
+  if (lanes == 8) {
+    /* ... unless four blocks per warp leave the SM with hardly more resident REPLICAS than one per warp would (very
+     * large heads: the power-cap controller's pools — cap_greedy 4 x 64: 12 vs 14 replicas per SM, and the 32-lane
+     * build is 1.6x faster there, profiles/r02_ab_s19_*; the bandit's tables: 52 vs 32, 8 lanes 18 % faster) */
+    int w8 = 0, w32 = 0, unused = 0;
+    const int bytes8 = 4 * h->L.rec_off, bytes32 = h->L.rec_off; /* head-staged: the smallest footprint of each */
+    w8 = resident_warps_for(bytes8, smem_optin, smem_sm, min_ctas_for(8) * DCSIM_MAX_WARPS_PER_CTA, &unused);
+    w32 = resident_warps_for(bytes32, smem_optin, smem_sm, min_ctas_for(32) * DCSIM_MAX_WARPS_PER_CTA, &unused);
+    if (2 * (4 * w8) < 3 * w32) lanes = 32; /* fewer than 1.5x the replicas per SM */
+  }
   const int rpw = 32 / lanes; /* replicas per warp */
   const int max_warps = min_ctas_for(lanes) * DCSIM_MAX_WARPS_PER_CTA;
   int wpc_full = 0, wpc_head = 0;

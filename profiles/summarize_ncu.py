@@ -61,7 +61,11 @@ def main():
                 line = int(r[0])
             except ValueError:
                 continue
-            g = lambda name: int(r[col[name]]) if name in col and r[col[name]] not in ("", "-") else 0  # noqa: E731
+            def g(name):
+                try:
+                    return int(r[col[name]].replace(",", ""))
+                except (KeyError, IndexError, ValueError):  # a source line with commas and quotes shifts the row
+                    return 0
             a = agg[(cur, line)]
             a[0] += g("Instructions Executed")
             a[1] += g("Warp Stall Sampling (All Samples)")
