@@ -248,6 +248,7 @@ static cudaError_t size_launch(dcsim_t* h) {
     w32 = resident_warps_for(bytes32, smem_optin, smem_sm, min_ctas_for(32) * DCSIM_MAX_WARPS_PER_CTA, &unused);
     if (2 * (4 * w8) < 3 * w32) lanes = 32; /* fewer than 1.5x the replicas per SM */
   }
+  { const char* g = getenv("DCSIM_GROUP"); if (g) { const int v = atoi(g); if (v == 8 || v == 16 || v == 32) lanes = v; } }
   const int rpw = 32 / lanes; /* replicas per warp */
   const int max_warps = min_ctas_for(lanes) * DCSIM_MAX_WARPS_PER_CTA;
   int wpc_full = 0, wpc_head = 0;

@@ -247,6 +247,7 @@ enum {
   CAND_N = 16        /* slots allocated (DCSIM_MAX_DC + 3 used at most); unused ones stay +inf */
 };
 #define DCSIM_CAND_N 16 /* == CAND_N, for the preprocessor (an enumerator reads as 0 in #if) */
+#define DCSIM_SEQ_LIMIT ((1u << 28) - (1u << 20)) /* lane-group builds: see dcsim_argmin_cand */
 static_assert(DCSIM_CAND_N == CAND_N, "DCSIM_CAND_N");
 #define CAND_LIST(c) ((c).P->spec.n_dc)
 #define CAND_LOG(c) ((c).P->spec.n_dc + 1)
@@ -295,11 +296,12 @@ enum { /* per-DC i32 arrays; FIFO rings are (head index, length) so no modulo is
 /* Persistent scalars of a replica (first bytes of its state block). */
 struct dcsim_hdr_t {
   double now, lat_sum, lat_sum_inf, lat_sum_trn, last_t;
+  double omin_t;        /* the earliest of the candidates OTHER than the list entry: (omin_t, omin_seq) in slot omin_slot, */
   uint32_t n_events, seq, jid, rng_pos;
-  uint32_t _r0, status, done, initialized;
+  uint32_t cand_dirty, status, done, initialized; /* ... valid while cand_dirty == 0 (dcsim_argmin_cand) */
   uint32_t n_fin_inf, n_fin_trn, ev_arr, ev_xfer;
-  uint32_t ev_fin, ev_log, _r1, max_run;
-  uint32_t max_q, _r2, bandit_t, n_stale;
+  uint32_t ev_fin, ev_log, omin_seq, max_run;
+  uint32_t max_q, omin_slot, bandit_t, n_stale;
   uint32_t smin_slot, ml_cursor, ml_count, _r3; /* event-list cursor / length */
 };
 
@@ -1172,58 +1174,104 @@ DCSIM_DEV uint32_t* dcsim_list_seq_slot(dcsim_ctx_t& c, uint32_t m) {
   return (m & ML_XFER) ? XRING(c) + (c.cursor & (uint32_t)c.P->L.xring_mask) : PEND_SEQ(c) + ((m >> 1) & 15u);
 }
 
-/* Pop-min over the event set itself: one candidate slot per lane (two with 8 lanes per replica), three
- * min-reductions and the pick of the winner (REDUX.MIN + a ballot on a whole warp, shuffle butterflies inside a lane
- * group).  EVENT-LEVEL: every lane of the warp calls it together (dcsim_event_sync).  The lane of slot CAND_LIST(c)
- * takes its candidate straight from the list window (entry c.cursor; the slot behind the window reads +inf), so
- * nothing has to "publish" the next list entry.  Returns the winning candidate slot, -1 if all are +inf. */
-DCSIM_DEV int dcsim_argmin_cand(dcsim_ctx_t& c, double* t_out, uint32_t* seq_out) {
+/* Pop-min over the event set.  Two halves:
+ *
+ *  (1) the earliest of the candidates OTHER than the list entry — per DC the earliest job_finish, the log tick, (power-cap
+ *      controller) the earliest superseded job_finish: one slot per lane (two with 8 lanes and more than 5 DCs) and
+ *      three min-reductions.  A warp per replica: REDUX.MIN over hi, lo, seq and a ballot.  Several replicas per warp:
+ *      shuffle butterflies inside the lane group over hi, lo and (seq << 4 | slot) under the constant full mask — this is
+ *      an EVENT-LEVEL point, every lane of the warp is here (dcsim_event_sync);
+ *  (2) that minimum against the next list entry, read straight from the list window (entry c.cursor; the slot behind
+ *      the window reads +inf), so nothing has to "publish" the next list entry: a compare on every lane.
+ *
+ * With several replicas per warp (1) is CACHED in the header: it changes only when one of those slots is written (a
+ * job_finish, a start that becomes its DC's earliest finish, a log tick, the cap controller), whoever writes one raises
+ * cand_dirty, and the reduction only runs when some replica of the warp is dirty (a clean one next to it recomputes what
+ * it had).  In a saturated cluster most events are arrivals and transfers that queue: the 4 DC x 64 bench batch
+ * re-reduces on a few percent of its events (event loop 126.8 -> 119.3 ms); a lightly loaded single DC is dirty on most
+ * and pays for the bookkeeping (268 -> 279 ms) — profiles/r02_ab_s21_*.  What else was tried for (1), all slower: one
+ * butterfly over the whole tuple (fewer dependent round trips, more instructions), every lane scanning the slots itself
+ * (no shuffles at all: +20 %), probing chunks that switch the cache off when it misses (the switch costs what it saves).
+ * With a warp per replica three REDUX.MIN are cheaper than the bookkeeping: no cache.
+ *
+ * The list's slot of the event set is never written: it stays +inf and takes part in (1) harmlessly.
+ * Returns the winning candidate slot, -1 if all are +inf. */
+struct dcsim_omin_t { uint32_t hi, lo, seq; int slot; bool fresh; }; /* (1); fresh: just reduced, not yet in the header */
+/* Lane 0, after the event's first sync (every lane has read the header's copy by then): publishes a fresh (1). */
+DCSIM_DEV void dcsim_omin_publish(dcsim_ctx_t& c, const dcsim_omin_t& o) {
+  if (o.fresh && c.lane == 0) {
+    c.H->omin_t = dcsim_hilo_f64(o.hi, o.lo); c.H->omin_seq = o.seq; c.H->omin_slot = (uint32_t)o.slot; c.H->cand_dirty = 0u;
+  }
+}
+DCSIM_DEV int dcsim_argmin_cand(dcsim_ctx_t& c, dcsim_omin_t& om, double* t_out, uint32_t* seq_out) {
   const uint32_t li = c.cursor & (DCSIM_LIST_WINDOW - 1u); /* entries at and past the end of the list read (+inf, 0) */
   const uint32_t lm = LW_META(c)[li];
+  uint32_t oh, ol, os;
+  int oslot;
+  om.fresh = false;
+#if !defined(DCSIM_HOST_EMU) && DCSIM_LANES == 32
+  {
+    /* slot == lane, no loop; surplus lanes all look at the last slot, which is never used (+inf) */
+    const int i = c.lane < DCSIM_CAND_N ? c.lane : DCSIM_CAND_N - 1;
+    const double t = CAND_T(c)[i];
+    const uint32_t s = CAND_SEQ(c)[i];
+    const uint32_t h = dcsim_hi(t), l = dcsim_lo(t);
+    oh = dcsim_event_min_u32(h);
+    ol = dcsim_event_min_u32(h == oh ? l : 0xffffffffu);
+    const bool m = (h == oh) && (l == ol);
+    os = dcsim_event_min_u32(m ? s : 0xffffffffu);
+    oslot = dcsim_ffs(__ballot_sync(0xffffffffu, m && s == os)) - 1;
+  }
+#else
+  if (dcsim_event_any(c.H->cand_dirty != 0u)) {
 #if !defined(DCSIM_HOST_EMU)
-  /* slot == lane, no loop; surplus lanes all look at the last slot, which is never used (+inf) */
-  const int i = c.lane < DCSIM_CAND_N ? c.lane : DCSIM_CAND_N - 1;
-  const bool list = i == c.P->spec.n_dc;
-  double t = *(list ? LW_T(c) + li : CAND_T(c) + i);
-  uint32_t s = *(list ? dcsim_list_seq_slot(c, lm) : CAND_SEQ(c) + i);
-  uint32_t h = dcsim_hi(t), l = dcsim_lo(t);
+    const int i = c.lane < DCSIM_CAND_N ? c.lane : DCSIM_CAND_N - 1; /* slot == lane */
+    double t = CAND_T(c)[i];
+    uint32_t s = CAND_SEQ(c)[i];
+    uint32_t h = dcsim_hi(t), l = dcsim_lo(t);
+    uint32_t slot = (uint32_t)i;
 #if DCSIM_LANES < DCSIM_CAND_N
-  /* fewer lanes than slots (8 lanes): the event set of up to 5 DCs (n_dc + 3 slots) still fits one round; beyond, each
-   * lane also looks at slot lane + DCSIM_LANES and keeps the earlier of its two (a scenario constant: no divergence) */
-  int slot = i;
-  if (c.P->spec.n_dc + 3 > DCSIM_LANES) {
-    const int i2 = c.lane + DCSIM_LANES;
-    const bool list2 = i2 == c.P->spec.n_dc;
-    const double t2 = *(list2 ? LW_T(c) + li : CAND_T(c) + i2);
-    const uint32_t s2 = *(list2 ? dcsim_list_seq_slot(c, lm) : CAND_SEQ(c) + i2);
-    const uint32_t h2 = dcsim_hi(t2), l2 = dcsim_lo(t2);
-    if (h2 < h || (h2 == h && (l2 < l || (l2 == l && s2 < s)))) { h = h2; l = l2; s = s2; slot = i2; }
+    /* fewer lanes than slots (8 lanes): the event set of up to 5 DCs (n_dc + 3 slots) still fits one round; beyond,
+     * each lane also looks at slot lane + DCSIM_LANES and keeps the earlier of its two (a scenario constant) */
+    if (c.P->spec.n_dc + 3 > DCSIM_LANES) {
+      const int i2 = c.lane + DCSIM_LANES;
+      const double t2 = CAND_T(c)[i2];
+      const uint32_t s2 = CAND_SEQ(c)[i2];
+      const uint32_t h2 = dcsim_hi(t2), l2 = dcsim_lo(t2);
+      if (h2 < h || (h2 == h && (l2 < l || (l2 == l && s2 < s)))) { h = h2; l = l2; s = s2; slot = (uint32_t)i2; }
+    }
+#endif
+    oh = dcsim_event_min_u32(h);
+    ol = dcsim_event_min_u32(h == oh ? l : 0xffffffffu);
+    const bool m = (h == oh) && (l == ol);
+    /* seq and slot in ONE reduction, as (seq << 4) | slot: the slot is 4 bits (CAND_N == 16), and a replica that ever
+     * hands out seq 2^28 stops with DCSIM_ST_SEQ_OVERFLOW (dcsim_event_body) — 2^28 pushes are ~10^8 events, a thousand
+     * times the longest configuration of BASELINE.json.  (t, seq) is unique, so this only spares the pick a butterfly. */
+    const uint32_t mk = dcsim_event_min_u32(m ? ((s << 4) | slot) : 0xffffffffu);
+    os = oh >= 0x7ff00000u ? 0xffffffffu : mk >> 4;
+    oslot = (int)(mk & 15u);
+#else
+    double ot = DCSIM_INF;
+    os = 0xffffffffu;
+    oslot = dcsim_argmin_ts(CAND_T(c), CAND_SEQ(c), CAND_N, c.lane, &ot, &os);
+    if (oslot < 0) { ot = DCSIM_INF; os = 0xffffffffu; oslot = 0; }
+    oh = dcsim_hi(ot); ol = dcsim_lo(ot);
+#endif
+    om.hi = oh; om.lo = ol; om.seq = os; om.slot = oslot; om.fresh = true;
+  } else {
+    const double ot = c.H->omin_t;
+    oh = dcsim_hi(ot); ol = dcsim_lo(ot); os = c.H->omin_seq; oslot = (int)c.H->omin_slot;
   }
 #endif
-  /* event-level collectives: every lane of the warp is here, so a lane group never returns before the last one */
-  const uint32_t mh = dcsim_event_min_u32(h);
-#if DCSIM_LANES == 32
-  if (mh >= 0x7ff00000u) return -1; /* (one replica per warp: the whole warp returns) */
-#endif
-  const uint32_t ml = dcsim_event_min_u32(h == mh ? l : 0xffffffffu);
-  const bool m = (h == mh) && (l == ml);
-  const uint32_t ms = dcsim_event_min_u32(m ? s : 0xffffffffu);
-#if DCSIM_LANES == 32
-  const int win = dcsim_ffs(__ballot_sync(0xffffffffu, m && s == ms)) - 1; /* slot == lane */
-#elif DCSIM_LANES >= DCSIM_CAND_N
-  const int win = (int)dcsim_event_min_u32(m && s == ms ? (uint32_t)i : 0xffffffffu); /* (t, seq) is unique: one lane */
-#else
-  const int win = (int)dcsim_event_min_u32(m && s == ms ? (uint32_t)slot : 0xffffffffu);
-#endif
-  if (mh >= 0x7ff00000u) return -1;
-  *t_out = __hiloint2double((int)mh, (int)ml);
-  *seq_out = ms;
-  return win;
-#else
-  CAND_T(c)[CAND_LIST(c)] = LW_T(c)[li];
-  CAND_SEQ(c)[CAND_LIST(c)] = *dcsim_list_seq_slot(c, lm);
-  return dcsim_argmin_ts(CAND_T(c), CAND_SEQ(c), CAND_N, c.lane, t_out, seq_out);
-#endif
+  const double lt = LW_T(c)[li];
+  const uint32_t lh = dcsim_hi(lt), ll = dcsim_lo(lt);
+  const uint32_t ls = *dcsim_list_seq_slot(c, lm);
+  const bool list_first = lh < oh || (lh == oh && (ll < ol || (ll == ol && ls < os)));
+  const uint32_t wh = list_first ? lh : oh;
+  if (wh >= 0x7ff00000u) return -1;
+  *t_out = dcsim_hilo_f64(wh, list_first ? ll : ol);
+  *seq_out = list_first ? ls : os;
+  return list_first ? CAND_LIST(c) : oslot;
 }
 
 /* SIM:160-163: an event later than end_time + 1e-9 (or at +inf) is never scheduled and takes no seq. */
@@ -1257,6 +1305,7 @@ DCSIM_DEV void dcsim_rescan_dc(dcsim_ctx_t& c, int d) {
   if (c.lane == 0) {
     CAND_T(c)[CAND_DC0 + d] = k >= 0 ? t : DCSIM_INF;
     CAND_SEQ(c)[CAND_DC0 + d] = k >= 0 ? s : 0xffffffffu;
+    c.H->cand_dirty = 1u;
     DCI(c, DI_FMIN_SLOT)[d] = k;
   }
   dcsim_warp_sync();
@@ -1411,6 +1460,7 @@ DCSIM_DEV void dcsim_start_job(dcsim_ctx_t& c, int d, int jt, double size, uint3
     const double ct = CAND_T(c)[CAND_DC0 + d];
     if (t_fin < ct || (t_fin == ct && seq < CAND_SEQ(c)[CAND_DC0 + d])) {
       CAND_T(c)[CAND_DC0 + d] = t_fin; CAND_SEQ(c)[CAND_DC0 + d] = seq; DCI(c, DI_FMIN_SLOT)[d] = slot;
+      c.H->cand_dirty = 1u; /* (a start that is not its DC's earliest finish leaves the event set's minimum alone) */
     }
   }
 }
@@ -1671,6 +1721,7 @@ DCSIM_DEV void dcsim_handle_finish(dcsim_ctx_t& c, int d) {
   }
   if (c.lane == 0) {
     CAND_T(c)[CAND_DC0 + d] = wt; CAND_SEQ(c)[CAND_DC0 + d] = ws; DCI(c, DI_FMIN_SLOT)[d] = win;
+    c.H->cand_dirty = 1u;
     DCI(c, DI_NRUN)[d] = n1;
     DCF(c, DF_PSUM)[d] = psum;
     dcsim_dequeue_loop<CAP>(c, d, pre, pre_jt); /* appends behind the compacted records */
@@ -1686,6 +1737,7 @@ DCSIM_DEV void dcsim_rescan_stale(dcsim_ctx_t& c) {
   if (c.lane == 0) {
     CAND_T(c)[CAND_STALE(c)] = k >= 0 ? t : DCSIM_INF;
     CAND_SEQ(c)[CAND_STALE(c)] = k >= 0 ? s : 0xffffffffu;
+    c.H->cand_dirty = 1u;
     c.H->smin_slot = (uint32_t)k;
   }
   dcsim_warp_sync();
@@ -1864,6 +1916,7 @@ DCSIM_DEV void dcsim_handle_log(dcsim_ctx_t& c) {
     const double t = c.now + interval; /* SIM:949 */
     if (dcsim_schedulable(c, t)) { CAND_T(c)[CAND_LOG(c)] = t; CAND_SEQ(c)[CAND_LOG(c)] = c.seq++; }
     else { CAND_T(c)[CAND_LOG(c)] = DCSIM_INF; CAND_SEQ(c)[CAND_LOG(c)] = 0xffffffffu; }
+    c.H->cand_dirty = 1u;
   }
 } /* (the event's closing sync follows in dcsim_event_body) */
 
@@ -1895,6 +1948,7 @@ DCSIM_DEV void dcsim_replica_init(dcsim_ctx_t& c) {
       if ((ah.first_mask >> s) & 1u) PEND_SEQ(c)[s] = c.seq++;
     const double t = 0.0 + sp.log_interval; /* SIM:157 */
     if (dcsim_schedulable(c, t)) { CAND_T(c)[CAND_LOG(c)] = t; CAND_SEQ(c)[CAND_LOG(c)] = c.seq++; }
+    c.H->cand_dirty = 1u;
     c.H->initialized = 1u;
   }
   dcsim_warp_sync();
@@ -1938,7 +1992,7 @@ DCSIM_DEV void dcsim_replica_tail(dcsim_ctx_t& c) {
  * are divergent paths of one warp, the scheduler interleaves them, and one replica's L2 round trip hides behind
  * another's arithmetic; a warp-wide sync inside a handler takes that away. */
 template <bool CAP, bool RECG>
-DCSIM_DEV void dcsim_event_body(dcsim_ctx_t& c, bool on, int win, double t, uint32_t seq, bool tracing) {
+DCSIM_DEV void dcsim_event_body(dcsim_ctx_t& c, bool on, int win, double t, uint32_t seq, bool tracing, const dcsim_omin_t& om) {
   const dcsim_spec_t& sp = c.P->spec;
   /* SIM:429-437 + models.py:100-106, state before the event.  Every DC's "last" stamp is the previous event's instant
    * (one register for all of them); the first event only stamps (0.0 is the reference's "never touched" sentinel). */
@@ -1954,6 +2008,7 @@ DCSIM_DEV void dcsim_event_body(dcsim_ctx_t& c, bool on, int win, double t, uint
     }
   }
   dcsim_event_sync(); /* every lane has read its candidate / busy / power before lane 0's handler rewrites them */
+  dcsim_omin_publish(c, om); /* (before the handler: it may dirty the event set again) */
   if (on) {
     c.now = t;
     /* dispatch on the winning slot itself; the event kind is only spelled out for the (cold) trace */
@@ -1989,6 +2044,10 @@ DCSIM_DEV void dcsim_event_body(dcsim_ctx_t& c, bool on, int win, double t, uint
       dcsim_rescan_stale(c);
     }
   }
+#if !defined(DCSIM_HOST_EMU) && DCSIM_LANES < 32
+  /* (lane 0 hands out the seqs; one event pushes far fewer than the 2^20 of slack; the status is polled per chunk) */
+  if (on && c.lane == 0 && c.seq >= DCSIM_SEQ_LIMIT) c.H->status |= DCSIM_ST_SEQ_OVERFLOW;
+#endif
   dcsim_event_sync(); /* the handler's writes (lane 0's mostly) are visible to every lane's next pop-min */
 }
 
@@ -2016,9 +2075,10 @@ DCSIM_DEV uint32_t dcsim_replica_run(dcsim_ctx_t& c, bool live) {
     for (int k = 0; k < 16; ++k) {
       if (done_here >= budget) on = false;
       double t = 0.0; uint32_t seq = 0u;
-      const int win = dcsim_argmin_cand(c, &t, &seq);
+      dcsim_omin_t om;
+      const int win = dcsim_argmin_cand(c, om, &t, &seq);
       if (on && (win < 0 || t > sp.end_time)) { finished = true; on = false; } /* `while self.event_q` / SIM:427 */
-      dcsim_event_body<CAP, RECG>(c, on, win, t, seq, tracing);
+      dcsim_event_body<CAP, RECG>(c, on, win, t, seq, tracing, om);
       if (on) ++done_here;
     }
   }
@@ -2032,10 +2092,11 @@ DCSIM_DEV uint32_t dcsim_replica_run(dcsim_ctx_t& c, bool live) {
     uint32_t k = 0u;
     for (; k < chunk; ++k) {
       double t; uint32_t seq;
-      const int win = dcsim_argmin_cand(c, &t, &seq);
+      dcsim_omin_t om;
+      const int win = dcsim_argmin_cand(c, om, &t, &seq);
       if (win < 0) { finished = true; break; }         /* `while self.event_q` */
       if (t > sp.end_time) { finished = true; break; } /* SIM:427 */
-      dcsim_event_body<CAP, RECG>(c, true, win, t, seq, tracing);
+      dcsim_event_body<CAP, RECG>(c, true, win, t, seq, tracing, om);
     } /* 16-event chunk */
     done_here += k;
     if (finished) break;

@@ -36,7 +36,7 @@ S_DC0, S_DC_STRIDE = 24, 8
 SUMMARY_K = 24 + 8 * MAX_DC
 SD_ENERGY_J, SD_UTIL_GPU_TIME, SD_ACC_JOB_UNIT, SD_BUSY, SD_CURRENT_FREQ, SD_Q_INF, SD_Q_TRN, SD_RUNNING = range(8)
 ST_XFER_OVERFLOW, ST_RUN_OVERFLOW, ST_QUEUE_OVERFLOW, ST_STALE_OVERFLOW, ST_RNG_RUNAWAY = 1, 2, 4, 8, 16
-ST_ARRIVALS_OVERFLOW, ST_ARRIVAL_TIE = 32, 64
+ST_ARRIVALS_OVERFLOW, ST_ARRIVAL_TIE, ST_SEQ_OVERFLOW = 32, 64, 128
 A_REPLICAS, A_FAILED, A_EVENTS, A_JOBS, A_ENERGY, A_ENERGY_SQ, A_LAT_SUM, A_MEANLAT_SUM, A_MEANLAT_SQ, A_RNG_WORDS = range(10)
 A_RUNNING = 11
 AGG_K = 16

@@ -173,8 +173,9 @@ enum { /* offsets inside a per-DC group */
 enum { /* status bits: a replica that overflowed a capacity stops and says so — never silently */
   DCSIM_ST_XFER_OVERFLOW = 1, DCSIM_ST_RUN_OVERFLOW = 2, DCSIM_ST_QUEUE_OVERFLOW = 4,
   DCSIM_ST_STALE_OVERFLOW = 8, DCSIM_ST_RNG_RUNAWAY = 16, DCSIM_ST_ARRIVALS_OVERFLOW = 32,
-  DCSIM_ST_ARRIVAL_TIE = 64 /* two streams drew the very same arrival instant: their order needs the heap's seq,
-                               which the state-independent pre-pass cannot know (probability ~2^-52 per pair) */
+  DCSIM_ST_ARRIVAL_TIE = 64,  /* (unused since ABI 2: arrivals at the same instant are ordered by push rank, as the heap does) */
+  DCSIM_ST_SEQ_OVERFLOW = 128 /* a replica pushed more than 2^28 events: the builds that carry several replicas per warp
+                                 pack the pop-min's (seq, slot) in one word */
 };
 
 /* aggregate vector produced by dcsim_reduce_summary(); the only thing that crosses NVLink */
