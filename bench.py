@@ -536,13 +536,19 @@ def main():
         run_reference_arm(args, world, rank)
         return
     if world > 1:
-        # BEFORE torch is imported (NCCL reads its environment once): the communicator's init lines (nranks, NVLS, ...) are
-        # wanted as evidence that N ranks really talk, but stdout must stay ONE JSON line — so they go to stderr unless the
-        # caller routed them somewhere itself.  A caller's own NCCL_DEBUG level is respected.
-        if "NCCL_DEBUG" not in os.environ:
+        # stdout must stay ONE JSON line, whatever the libraries underneath write to file descriptor 1 (NCCL prints its
+        # version banner and its INFO lines there): fd 1 is pointed at stderr for the rest of the process and Python's own
+        # sys.stdout keeps the real stdout.
+        sys.stdout.flush()
+        real_stdout = os.dup(1)
+        os.dup2(2, 1)
+        sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
+        # BEFORE torch is imported: the communicator's init lines (nranks, NVLS, ...) are wanted as evidence that N ranks
+        # really talk.  An INFO / TRACE level chosen by the caller is respected, a quieter one (images often export
+        # NCCL_DEBUG=VERSION or WARN) is raised to INFO for the INIT subsystem; the lines end up on stderr (see above).
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
             os.environ["NCCL_DEBUG"] = "INFO"
-            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+            os.environ["NCCL_DEBUG_SUBSYS"] = "INIT"
     run_b200(args, world, rank, local_rank)
 
 

@@ -79,6 +79,27 @@ def test_kernel_matches_reference_fixture(name):
             assert abs(got[r, S.S_LAT_SUM] / got[r, S.S_JOBS_FINISHED] - m_ref) <= RTOL * abs(m_ref)
 
 
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 6, 7, 37])
+def test_partially_filled_last_warp(oracle, n):
+    """Replica counts that are not a multiple of the replicas a warp carries: in the lane-group builds the event loop's
+    collectives span the warp, so the lane groups without a replica stay in the loop as ghosts (dcsim_advance_impl.cuh)
+    — they must neither hang the warp nor touch anything; also with a per-launch event budget (resume)."""
+    sp = SC.to_spec(dict(SC.CFG3, duration=15.0))
+    want, want_total = oracle.run_batch(sp.to_bytes(), n, 77, 0, n_threads=os.cpu_count() or 1)
+    with engine_cls()(sp, n, base_seed=77) as eng:
+        assert eng.advance(0) == want_total
+        assert_rows_match(eng.summary(), want, 4)
+        lanes = eng.launch_info()["lanes_per_replica"]
+    with engine_cls()(sp, n, base_seed=77) as eng:
+        guard = 0
+        while not eng.all_done():
+            eng.advance(257)
+            guard += 1
+            assert guard < 2000
+        assert_rows_match(eng.summary(), want, 4)
+    print(f"{n} replicas on {lanes} lanes each")
+
+
 @pytest.mark.parametrize("chunk", [1, 13, 4096])
 def test_resume_is_invariant_on_device(chunk):
     sp = SC.to_spec(dict(SC.CFG3, duration=10.0 if chunk == 1 else 40.0))
