@@ -262,6 +262,7 @@ def test_parked_engine_is_reseeded_correctly(tmp_path, oracle):
     sc = SC.BY_NAME["ragged_3dc_12_5_40"]
     blob = SC.to_spec(sc).to_bytes()
     E.free_cached_engine()
+    logs = {}
     for seed in (5, 900, 5):
         kw = SC.build_inputs(sc)
         sim = MultiIngressPaperSimulator(router_policy=pc.build_router_policy(), logger=logging.getLogger("t"),
@@ -273,8 +274,12 @@ def test_parked_engine_is_reseeded_correctly(tmp_path, oracle):
         rows = list(csv.reader(open(sim.job_log_path)))
         assert len(rows) - 1 == int(want[0, S.S_JOBS_FINISHED])
         assert E._CACHED["engine"] is not None                      # parked for the next run
+        assert E._CACHED_LOGGED["engine"] is not None               # ... and so is the one-replica companion (CSV rows)
+        logs[seed] = logs.get(seed, []) + [(open(sim.job_log_path).read(), open(sim.cluster_log_path).read())]
+    assert logs[5][0] == logs[5][1]      # same seed on a re-seeded companion: the same CSV bytes as on the fresh one
+    assert logs[5][0] != logs[900][0]
     E.free_cached_engine()
-    assert E._CACHED["engine"] is None
+    assert E._CACHED["engine"] is None and E._CACHED_LOGGED["engine"] is None
 
 
 def test_latency_histogram_on_device(oracle):
