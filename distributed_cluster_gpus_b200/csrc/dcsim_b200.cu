@@ -339,6 +339,12 @@ int dcsim_create(const void* spec_blob, size_t spec_bytes, uint64_t n_replicas, 
   CREATE_TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   h->stream = h->own_stream;
   const size_t state_bytes = (size_t)n_replicas * (size_t)h->L.total_bytes;
+  if (h->L.queue_bytes >= (1ull << 32)) /* the event loop addresses inside one replica's FIFOs with 32 bits */
+  {
+    rc = set_err(NULL, DCSIM_E_INVALID, "create: one replica's FIFO queues exceed 4 GB (cap_q_inf / cap_q_trn too large)%s%lld");
+    dcsim_destroy(h);
+    return rc;
+  }
   const size_t queue_bytes = (size_t)n_replicas * (size_t)h->L.queue_bytes;
   CREATE_TRY(cudaMalloc(&h->d_state, state_bytes));
   CREATE_TRY(cudaMalloc(&h->d_queues, queue_bytes ? queue_bytes : 16));

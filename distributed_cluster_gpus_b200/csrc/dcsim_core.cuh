@@ -1245,7 +1245,7 @@ DCSIM_DEV int dcsim_argmin_cand(dcsim_ctx_t& c, dcsim_omin_t& om, double* t_out,
     ol = dcsim_event_min_u32(h == oh ? l : 0xffffffffu);
     const bool m = (h == oh) && (l == ol);
     /* seq and slot in ONE reduction, as (seq << 4) | slot: the slot is 4 bits (CAND_N == 16), and a replica that ever
-     * hands out seq 2^28 stops with DCSIM_ST_SEQ_OVERFLOW (dcsim_event_body) — 2^28 pushes are ~10^8 events, a thousand
+     * hands out seq 2^28 stops with DCSIM_ST_SEQ_OVERFLOW (dcsim_replica_run) — 2^28 pushes are ~10^8 events, a thousand
      * times the longest configuration of BASELINE.json.  (t, seq) is unique, so this only spares the pick a butterfly. */
     const uint32_t mk = dcsim_event_min_u32(m ? ((s << 4) | slot) : 0xffffffffu);
     os = oh >= 0x7ff00000u ? 0xffffffffu : mk >> 4;
@@ -1312,10 +1312,13 @@ DCSIM_DEV void dcsim_rescan_dc(dcsim_ctx_t& c, int d) {
 }
 
 /* ---- HBM FIFOs (dc.q_inf / dc.q_train, models.py:61-62) --------------------------------------- */
-DCSIM_DEV dcsim_qent_t* dcsim_queue_base(const dcsim_ctx_t& c, int d, int jt) {
+/* Entry `idx` of DC d's FIFO of job type jt.  One replica's FIFOs are below 4 GB (dcsim_create checks), so everything
+ * but the replica's own offset is 32-bit arithmetic: one widening multiply-add instead of a chain of 64-bit ones. */
+DCSIM_DEV dcsim_qent_t* dcsim_queue_at(const dcsim_ctx_t& c, int d, int jt, int idx) {
   const dcsim_layout_t& L = c.P->L;
-  const uint64_t per_dc = (uint64_t)L.cap_q[0] + (uint64_t)L.cap_q[1];
-  return reinterpret_cast<dcsim_qent_t*>(c.P->queues + (uint64_t)c.r * L.queue_bytes) + (uint64_t)d * per_dc + (jt ? (uint64_t)L.cap_q[0] : 0ull);
+  const uint32_t per_dc = (uint32_t)L.cap_q[0] + (uint32_t)L.cap_q[1];
+  const uint32_t inner = ((uint32_t)d * per_dc + (jt ? (uint32_t)L.cap_q[0] : 0u) + (uint32_t)idx) * (uint32_t)sizeof(dcsim_qent_t);
+  return reinterpret_cast<dcsim_qent_t*>(c.P->queues + ((uint64_t)c.r * (uint64_t)(uint32_t)L.queue_bytes + (uint64_t)inner));
 }
 DCSIM_DEV int dcsim_queue_len(dcsim_ctx_t& c, int d, int jt) { return DCI(c, jt ? DI_QN_TRN : DI_QN_INF)[d]; }
 DCSIM_DEV void dcsim_enqueue(dcsim_ctx_t& c, int d, int jt, double size, uint32_t jid, uint32_t ing) {
@@ -1326,14 +1329,14 @@ DCSIM_DEV void dcsim_enqueue(dcsim_ctx_t& c, int d, int jt, double size, uint32_
   int tail = DCI(c, jt ? DI_QH_TRN : DI_QH_INF)[d] + n;
   if (tail >= cap) tail -= cap;
   dcsim_qent_t e; e.size = size; e.jid = jid; e.ing = ing;
-  dcsim_queue_base(c, d, jt)[tail] = e;
+  *dcsim_queue_at(c, d, jt, tail) = e;
   *len = n + 1;
   if ((uint32_t)(n + 1) > c.H->max_q) c.H->max_q = (uint32_t)(n + 1);
 }
 DCSIM_DEV dcsim_qent_t dcsim_dequeue(dcsim_ctx_t& c, int d, int jt) {
   int32_t* head = DCI(c, jt ? DI_QH_TRN : DI_QH_INF) + d;
   const int h = *head;
-  const dcsim_qent_t e = dcsim_queue_base(c, d, jt)[h];
+  const dcsim_qent_t e = *dcsim_queue_at(c, d, jt, h);
   *head = h + 1 >= c.P->L.cap_q[jt] ? 0 : h + 1;
   DCI(c, jt ? DI_QN_TRN : DI_QN_INF)[d] -= 1;
   return e;
@@ -1655,7 +1658,7 @@ DCSIM_DEV void dcsim_handle_finish(dcsim_ctx_t& c, int d) {
     c.H->ev_fin++;
     if (DCSIM_PREFETCH_DEQ) { /* the dequeue loop below will want this entry: have the load in flight meanwhile */
       pre_jt = dcsim_dequeue_pick(c, d);
-      if (pre_jt >= 0) pre = dcsim_queue_base(c, d, pre_jt)[DCI(c, pre_jt ? DI_QH_TRN : DI_QH_INF)[d]];
+      if (pre_jt >= 0) pre = *dcsim_queue_at(c, d, pre_jt, DCI(c, pre_jt ? DI_QH_TRN : DI_QH_INF)[d]);
     }
     dcsim_finish_account(c, d, k); /* reads record k; writes no record */
   }
@@ -2044,10 +2047,6 @@ DCSIM_DEV void dcsim_event_body(dcsim_ctx_t& c, bool on, int win, double t, uint
       dcsim_rescan_stale(c);
     }
   }
-#if !defined(DCSIM_HOST_EMU) && DCSIM_LANES < 32
-  /* (lane 0 hands out the seqs; one event pushes far fewer than the 2^20 of slack; the status is polled per chunk) */
-  if (on && c.lane == 0 && c.seq >= DCSIM_SEQ_LIMIT) c.H->status |= DCSIM_ST_SEQ_OVERFLOW;
-#endif
   dcsim_event_sync(); /* the handler's writes (lane 0's mostly) are visible to every lane's next pop-min */
 }
 
@@ -2069,6 +2068,12 @@ DCSIM_DEV uint32_t dcsim_replica_run(dcsim_ctx_t& c, bool live) {
   for (;;) {
     /* a capacity overflowed (or a sampler ran away): stop and report, never guess.  Polled every 16 events — every
      * capacity check refuses the write on its own, so a replica that overflowed stays memory-safe until it is seen */
+    {
+      /* lane 0 hands out the seqs; the packed (seq, slot) reduction of the pop-min needs them below 2^28.  Checked once
+       * per chunk with 2^20 of slack (one event pushes a few; the cap controller at most a job_finish per running job) */
+      const uint32_t seq0 = dcsim_event_bcast_u32(c.seq, 0);
+      if (on && seq0 >= DCSIM_SEQ_LIMIT) { if (c.lane == 0) c.H->status |= DCSIM_ST_SEQ_OVERFLOW; on = false; }
+    }
     if (on && c.H->status != 0u) on = false;
     if (!dcsim_event_any(on && done_here < budget)) break;
 #pragma unroll 1
