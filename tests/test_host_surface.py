@@ -176,3 +176,26 @@ def test_shard_covers_every_replica_once():
         assert spans[0][0] == 0 and sum(c for _, c in spans) == total
         for (f0, c0), (f1, _c1) in zip(spans, spans[1:]):
             assert f0 + c0 == f1
+
+
+def test_summary_copy_helper_is_exact_for_small_and_large_arrays():
+    """engine._copy_rows: the (threaded, for large arrays) private copy of the page-locked summary mirror."""
+    import numpy as np
+    from distributed_cluster_gpus_b200 import engine as E
+    rng = np.random.default_rng(3)
+    for rows in (1, 7, 4096, 65536, 65537):
+        src = rng.random((rows, S.SUMMARY_K))
+        dst = E._copy_rows(src)
+        assert dst is not src and dst.flags["C_CONTIGUOUS"] and not np.shares_memory(dst, src)
+        assert np.array_equal(dst, src)
+
+
+def test_status_bits_of_header_and_python_mirror_agree():
+    """include/dcsim_b200.h DCSIM_ST_* against spec.ST_* and the engine's descriptions (every bit has a name)."""
+    import re
+    from distributed_cluster_gpus_b200 import engine as E
+    text = open(os.path.join(ROOT, "include", "dcsim_b200.h")).read()
+    bits = {name: int(val) for name, val in re.findall(r"DCSIM_(ST_[A-Z_]+)\s*=\s*(\d+)", text)}
+    assert bits and all(getattr(S, name) == val for name, val in bits.items())
+    assert set(E.STATUS_NAMES) == set(bits.values())
+    assert E.describe_status(0) == "ok" and "2^28" in E.describe_status(S.ST_SEQ_OVERFLOW)
