@@ -240,6 +240,26 @@ def test_conditioning_probe_separates_chaotic_scenarios(oracle, hostemu):
     assert moved(case["scenario"], case["seed"]) >= 1e-7
 
 
+def test_round2_gpu_fuzz_flags_are_conditioning_not_logic(hostemu, oracle):
+    """The two scenarios (of 7000) on which the final GPU build's event counts differ from the oracle's — both cap_greedy,
+    one replica of seven each (profiles/r02_fuzz_gpu_6000cases_f3.json): the host build of the same device source agrees
+    with the oracle on every count and every float, so the handler logic is the oracle's; every GPU build, round 1's
+    included, returns the same deviating answer (profiles/r02_fuzz_recheck_f3.jsonl) — libdevice vs glibc in the last
+    bit, amplified by the controller's threshold decisions."""
+    import json
+    from conftest import GOLDEN_DIR
+    with open(os.path.join(GOLDEN_DIR, "ill_conditioned_cap_greedy_cases_r2.json")) as f:
+        spec = json.load(f)
+    for case in spec["cases"]:
+        assert case["scenario"]["algo"] == "cap_greedy"
+        blob = SC.to_spec(case["scenario"]).to_bytes()
+        want, want_total = oracle.run_batch(blob, spec["replicas"], case["seed"], 0)
+        got = hostemu.run_batch(blob, spec["replicas"], case["seed"])
+        assert got["events"] == want_total
+        cols = [c for c in range(want.shape[1]) if c != S.S_MAX_XFER]   # (the device keeps no in-flight-transfer pool any more)
+        assert np.array_equal(got["summary"][:, cols], want[:, cols])
+
+
 def test_device_core_mt_mode_against_stock_reference_on_random_scenarios(hostemu):
     """rng = MT19937 of the device core (host build) against the reference as shipped on the 160 random scenarios."""
     from conftest import load_fuzz_reference
