@@ -2059,7 +2059,7 @@ DCSIM_DEV uint32_t dcsim_replica_run(dcsim_ctx_t& c, bool live) {
   const bool tracing = c.is_traced && c.P->rec.trace != nullptr;
   uint32_t done_here = 0u;
   bool finished = false;
-#if !defined(DCSIM_HOST_EMU) && DCSIM_LANES < 32
+#if (!defined(DCSIM_HOST_EMU) && DCSIM_LANES < 32) || defined(DCSIM_HOST_UNIFORM_LOOP) /* (the latter: a test-only host build of THIS skeleton) */
   /* Several replicas per warp: the loop is WARP-uniform.  A replica that ends (end_time, event budget, a status bit)
    * is switched off and rides along — through at most the rest of a 16-event chunk of no-ops, then idle as its lanes
    * would be anyway — until every replica of the warp has ended.  That is what lets the pop-min and the two

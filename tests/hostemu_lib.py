@@ -14,7 +14,9 @@ SUMMARY_K = 24 + 8 * 8
 TRACE_DTYPE = np.dtype([("t", "<f8"), ("seq", "<u4"), ("kind", "<u4")])
 _SO_PERTURBED = os.path.join(_DIR, "_build", "libdcsim_hostemu_perturbed.so")
 _SO_SMALLRING = os.path.join(_DIR, "_build", "libdcsim_hostemu_smallring.so")
+_SO_UNIFORM = os.path.join(_DIR, "_build", "libdcsim_hostemu_uniform.so")
 _lib_smallring = None
+_lib_uniform = None
 _lib = None
 _lib_perturbed = None
 
@@ -32,20 +34,21 @@ def _bind(path):
 
 def _ensure_built():
     srcs = (os.path.join(_DIR, "hostemu.cpp"), os.path.join(_DIR, "build.sh"), _CORE, _HDR)
-    for so in (_SO, _SO_PERTURBED, _SO_SMALLRING):
+    for so in (_SO, _SO_PERTURBED, _SO_SMALLRING, _SO_UNIFORM):
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
             subprocess.run([os.path.join(_DIR, "build.sh")], check=True, capture_output=True)
             return
 
 
-def lib(perturbed=False, smallring=False):
+def lib(perturbed=False, smallring=False, uniform=False):
     """perturbed=True: the conditioning probe (every 5th pow() result moved by one ulp, see hostemu.cpp);
-    smallring=True: the list merge built with a one-chunk ring (its HBM fall-back paths do all the work)."""
-    global _lib, _lib_perturbed, _lib_smallring
+    smallring=True: the list merge built with a one-chunk ring (its HBM fall-back paths do all the work);
+    uniform=True: the event-loop skeleton of the lane-group GPU builds (replicas switched off instead of leaving)."""
+    global _lib, _lib_perturbed, _lib_smallring, _lib_uniform
     if _lib is None:
         _ensure_built()
-        _lib, _lib_perturbed, _lib_smallring = _bind(_SO), _bind(_SO_PERTURBED), _bind(_SO_SMALLRING)
-    return _lib_smallring if smallring else (_lib_perturbed if perturbed else _lib)
+        _lib, _lib_perturbed, _lib_smallring, _lib_uniform = _bind(_SO), _bind(_SO_PERTURBED), _bind(_SO_SMALLRING), _bind(_SO_UNIFORM)
+    return _lib_uniform if uniform else (_lib_smallring if smallring else (_lib_perturbed if perturbed else _lib))
 
 
 def set_test_time_quantum(q):
@@ -53,10 +56,11 @@ def set_test_time_quantum(q):
     lib().hostemu_set_test_time_quantum(float(q))
     lib(perturbed=True).hostemu_set_test_time_quantum(float(q))
     lib(smallring=True).hostemu_set_test_time_quantum(float(q))
+    lib(uniform=True).hostemu_set_test_time_quantum(float(q))
 
 
 def run_batch(spec_bytes, n_replicas, seed0, chunk_events=0, trace_cap=0, rec_replica=-1, job_dtype=None,
-              jobs_cap=0, cluster_dtype=None, cluster_cap=0, rng_kind=0, perturbed=False, smallring=False):
+              jobs_cap=0, cluster_dtype=None, cluster_cap=0, rng_kind=0, perturbed=False, smallring=False, uniform=False):
     out = np.zeros((n_replicas, SUMMARY_K))
     buf = C.create_string_buffer(spec_bytes, len(spec_bytes))
     trace = np.zeros(max(trace_cap, 1), dtype=TRACE_DTYPE)
@@ -65,7 +69,7 @@ def run_batch(spec_bytes, n_replicas, seed0, chunk_events=0, trace_cap=0, rec_re
     counts = np.zeros(4, dtype=np.uint32)
     layout = np.zeros(8, dtype=np.int32)
     hist = np.zeros((n_replicas, 2, 128), dtype=np.uint32)
-    total = lib(perturbed, smallring).hostemu_run_batch(buf, len(spec_bytes), n_replicas, seed0 & (2**64 - 1), chunk_events,
+    total = lib(perturbed, smallring, uniform).hostemu_run_batch(buf, len(spec_bytes), n_replicas, seed0 & (2**64 - 1), chunk_events,
                                     out.ctypes.data, rec_replica,
                                     trace.ctypes.data if trace_cap else None, trace_cap,
                                     jobs.ctypes.data if jobs is not None and jobs_cap else None, jobs_cap,

@@ -51,6 +51,23 @@ def test_head_staged_mode_equals_oracle(oracle, hostemu, monkeypatch, name):
         assert got["events"] == total and _same(got["summary"], want), (name, chunk)
 
 
+@pytest.mark.parametrize("name", DEVICE_SUPPORTED)
+def test_lane_group_loop_skeleton_equals_oracle(oracle, hostemu, name):
+    """The event-loop skeleton the GPU builds with several replicas per warp use (dcsim_replica_run: the loop is
+    warp-uniform, a replica that ends — end_time, event budget, status bit — is switched off instead of leaving), compiled
+    for the host's single lane (build `uniform`): one shot and in chunks of 1 / 61 events per launch."""
+    sc = SC.BY_NAME[name]
+    if sc["duration"] > 200 and sc["n_dc"] >= 4:
+        sc = dict(sc, duration=100.0)
+    blob = SC.to_spec(sc).to_bytes()
+    want, total = oracle.run_batch(blob, 2, 77, 1)
+    chunks = (0, 61) if total > 40000 else (0, 61, 1)
+    for chunk in chunks:
+        got = hostemu.run_batch(blob, 2, 77 + 1, chunk_events=chunk, uniform=True)
+        assert got["events"] == total and np.all(got["summary"][:, S.S_STATUS] == 0), (name, chunk)
+        assert _same(got["summary"], want), (name, chunk, np.argwhere(got["summary"] != want)[:10])
+
+
 @pytest.mark.parametrize("chunk", [1, 7, 1000])
 def test_resume_is_invariant(oracle, hostemu, chunk):
     """advance() in chunks (state block staged out and in between launches) == one advance to the end."""
